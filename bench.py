@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the phaneron_b200 hot path (BASELINE.json):
+
+  metric  : 2160p50 v210 4-layer composite frames/sec (+ achieved HBM GB/s vs roofline)
+  workload: BASELINE.json configs[2]: 3840x2160 v210, 4 layers (L1 identity full frame,
+            L2-L4 MIXER FILL 0.5 picture-in-picture, top layer in a dissolve at mix 0.5
+            with a 5th source), BT.709 sources -> BT.2020 working space -> v210 BT.2020 out
+
+A "step" is a batch of FRAMES_PER_STEP frames.  `value` times the fused launches with
+inputs resident in HBM (recorded once through the public operator API, then replayed),
+rotating over enough input sets to exceed L2.  `e2e` runs every frame through the public
+API (ToRGBA.loadFrame H2D from pinned host memory -> operators -> FromRGBA.saveFrame D2H).
+One process per GPU; N>1 = N independent channels (weak scaling, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--inputs ramp|noise] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, LAYERS, VARIANT = 3840, 2160, 4, "mix"
+COL_READ, COL_WORK = "709", "2020"
+FRAMES_PER_STEP = 240          # device-resident leg
+E2E_FRAMES_PER_STEP = 8        # public-API leg (PCIe bound: ~133 MB H2D + 22 MB D2H per frame)
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "2160p50 v210 4-layer composite frames/sec"
+REF_SAMPLE_LINES = 144         # --impl reference: each step composites a 3840x144 band (1/15 frame)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag, self.proc = gpu_index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self, t0, t1):
+        self.stop_flag = True
+        time.sleep(0.15)
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for t, r in self.samples if t0 <= t <= t1] or [r for _, r in self.samples[-3:]]
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows)}
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = max(float(r[1]) for r in rows)
+            out["power_w_max"] = max(float(r[2]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        except Exception:
+            pass
+        return out
+
+
+def pinned_copy(lib, arr: np.ndarray) -> np.ndarray:
+    import ctypes as C
+    p = lib.pb_host_alloc(arr.nbytes)
+    if not p:
+        raise RuntimeError("pb_host_alloc failed")
+    out = np.ctypeslib.as_array((C.c_uint8 * arr.nbytes).from_address(p))
+    out[:] = arr.view(np.uint8).reshape(-1)
+    return out
+
+
+def pin_scene(lib, scene):
+    for L in scene["layers"]:
+        L["src"] = pinned_copy(lib, L["src"])
+        t = L.get("transition")
+        if t:
+            t["src"] = pinned_copy(lib, t["src"])
+            if "mask" in t:
+                t["mask"] = pinned_copy(lib, t["mask"])
+    return scene
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_fps(steps, warmup, inputs, threads):
+    """the reference's unfused stage sequence as restated in oracle/ on the host cores"""
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from scene_oracle import SceneOracle
+    from phaneron_b200.scenes import layered_scene
+    oracle.set_threads(threads)
+    scene = layered_scene(WIDTH, REF_SAMPLE_LINES, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
+    so = SceneOracle(scene)
+    for _ in range(warmup):
+        so.packed()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        so.packed()
+    dt = time.perf_counter() - t0
+    frames = steps * REF_SAMPLE_LINES / HEIGHT
+    return frames / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    fps, dt = cpu_reference_fps(args.steps, max(args.warmup, 1), args.inputs, threads)
+    sample = (f"{args.steps} steps, each the full unfused chain (5x v210 read, 5x transform, dissolve, combine_4, v210 write, "
+              f"RGBA-f32 intermediates) on a {WIDTH}x{REF_SAMPLE_LINES} band = {REF_SAMPLE_LINES}/{HEIGHT} of a frame; fps scaled to whole frames")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.inputs), "host": "CPU restatement of the reference's OpenCL kernels (oracle/), not POCL"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(inputs):
+    return (f"{WIDTH}x{HEIGHT} v210, {LAYERS}-layer composite (L1 identity, L2-L4 MIXER FILL 0.5 PiP, top layer dissolve mix=0.5 "
+            f"with a 5th source), {COL_READ}->{COL_WORK}, inputs={inputs}")
+
+
+# ------------------------------------------------------------------------------------------
+async def run_ours(args, rank, world, local_rank):
+    from phaneron_b200 import _lib, clContext
+    from phaneron_b200.harness import ChannelHarness
+    from phaneron_b200.scenes import layered_scene
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local_rank)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    lib = _lib.lib()
+    ctx = clContext({"platformIndex": 0, "deviceIndex": local_rank, "overlapping": True})
+    await ctx.initialise()
+
+    # ---- scenes: enough distinct input sets that a replay never finds its inputs in L2 ----
+    frame_bytes = (WIDTH // 48) * 128 * HEIGHT
+    n_in = LAYERS + (1 if VARIANT == "mix" else 2 if VARIANT == "wipe" else 0)
+    set_bytes = (n_in + 1) * frame_bytes
+    n_sets = max(3, -(-2 * L2_BYTES // set_bytes) + 1)
+    harnesses, chains, keep = [], [], []
+    for s in range(n_sets):
+        scene = layered_scene(WIDTH, HEIGHT, LAYERS, args.inputs, VARIANT, COL_READ, COL_WORK, frame_set=s + rank * n_sets)
+        h = ChannelHarness(ctx, scene, chanID=f"ch{rank}s{s}")
+        await h.init()
+        chain, dests = await h.record_chain()
+        if not chain.complete:
+            raise RuntimeError("recorded chain is not replayable")
+        harnesses.append(h)
+        chains.append(chain)
+        keep.append(dests)
+    alg_bytes = harnesses[0].algorithmic_bytes()
+    launches_per_frame = chains[0].launches
+    await ctx.waitFinish(ctx.queue.process)
+
+    def replay_step(step_index):
+        base = step_index * FRAMES_PER_STEP
+        for f in range(FRAMES_PER_STEP):
+            chains[(base + f) % n_sets].replay()
+
+    # ---- device-resident leg ----------------------------------------------------------------
+    for w in range(args.warmup):
+        replay_step(w)
+    await ctx.waitFinish(ctx.queue.process)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = ctx.createEvent(), ctx.createEvent()
+    st0 = ctx.stats()
+    barrier()
+    await ctx.waitFinish(ctx.queue.process)
+    t0 = time.perf_counter()
+    ev0.record()
+    for k in range(args.steps):
+        replay_step(k)
+    ev1.record()
+    ev1.synchronize()
+    t1 = time.perf_counter()
+    barrier()
+    st1 = ctx.stats()
+    ms = ev0.elapsed_ms(ev1)
+    clocks = sampler.finish(t0, t1)
+    if dist:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames = args.steps * FRAMES_PER_STEP
+    fps_rank = frames / (ms * 1e-3)
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+
+    # ---- end-to-end leg through the public API ------------------------------------------------
+    e2e_scene = pin_scene(lib, layered_scene(WIDTH, HEIGHT, LAYERS, args.inputs, VARIANT, COL_READ, COL_WORK, frame_set=rank * n_sets))
+    he = ChannelHarness(ctx, e2e_scene, chanID=f"e2e{rank}")
+    await he.init()
+    for _ in range(3):
+        await he.run_frame()
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    await ctx.waitFinish(ctx.queue.process)
+    s0 = ctx.stats()
+    te0 = time.perf_counter()
+    checksum = 0
+    for i in range(e2e_steps * E2E_FRAMES_PER_STEP):
+        ups = await he.upload_all(1000 + i)              # H2D of every source frame, from pinned host memory
+        frame = await he.compose(ups, 1000 + i)          # operators + job queue (records the expression)
+        dests = await he.consume(frame, download=True)   # fused launch + D2H of the packed result
+        checksum ^= int(dests[0].host[:64].view(np.uint64).sum())
+        for d in dests:
+            d.release()
+    te1 = time.perf_counter()
+    s1 = ctx.stats()
+    e2e_dt = te1 - te0
+    if dist:
+        import torch
+        t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_fps = world * e2e_steps * E2E_FRAMES_PER_STEP / e2e_dt
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        launch_ms = ms / (frames * launches_per_frame)
+        achieved = alg_bytes / launches_per_frame / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": fps_rank * world, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.inputs), "frames_per_step": FRAMES_PER_STEP, "input_sets": n_sets,
+                       "l2_policy": f"inputs larger than L2: {n_sets} rotating sets x {set_bytes} B = {n_sets * set_bytes} B > 126 MiB",
+                       "channels": world, "parallelism": f"{world} independent channel(s), one per GPU",
+                       "launches_per_frame": launches_per_frame, "occlusion_culling": False},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": f"of {peak_kind}", "frac_of_nominal_8TBps": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": alg_bytes // launches_per_frame, "launch_us": launch_ms * 1e3},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // e2e_steps,
+                    "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // e2e_steps, "frames_per_step": E2E_FRAMES_PER_STEP,
+                    "steps": e2e_steps, "checksum": checksum & 0xFFFFFFFF},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n = 20
+            fps, dt = cpu_reference_fps(n, 1, args.inputs, threads)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n} x {WIDTH}x{REF_SAMPLE_LINES} bands ({REF_SAMPLE_LINES}/{HEIGHT} frame each) of the same scene, "
+                                              f"oracle/ unfused chain, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    barrier()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--inputs", default="noise", choices=["ramp", "noise"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun like the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    asyncio.run(run_ours(args, rank, world, local_rank))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+/*
+ * phaneron_b200.h -- C ABI of libphaneron_b200.so, the B200 (sm_100a) replacement
+ * for the `nodencl` OpenCL addon that Streampunk/phaneron's src/process/*.ts and
+ * src/clJobQueue.ts bind to.
+ *
+ * Every entry point cites the nodencl call (by its call sites in the reference,
+ * paths under /root/reference/) that it replaces.  Plain pointers and sizes only;
+ * no C++/torch types.  Thread-safe per context (one mutex per pb_ctx); every call
+ * returns PB_OK or a negative pb_status, with the message in pb_last_error()
+ * (thread-local).  Intended callers: the N-API shim (napi/phaneron_napi.cc, one
+ * async work item per call, mirroring nodencl's Promises) and Python ctypes
+ * (phaneron_b200/_lib.py).
+ *
+ * There is NO CPU fallback: pb_ctx_create fails when no CUDA device is present.
+ */
+#ifndef PHANERON_B200_H
+#define PHANERON_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;   /* nodencl clContext           (index.ts:94-102)  */
+typedef struct pb_buf pb_buf;   /* nodencl OpenCLBuffer        (io.ts:61-77)      */
+typedef struct pb_prog pb_prog; /* nodencl OpenCLProgram       (packer.ts:97-103) */
+
+typedef enum pb_status {
+	PB_OK = 0,
+	PB_ERR_CUDA = -1,     /* a CUDA runtime call failed */
+	PB_ERR_ARG = -2,      /* bad argument / missing kernel parameter */
+	PB_ERR_NO_DEVICE = -3,
+	PB_ERR_STATE = -4     /* e.g. running a program on a released buffer */
+} pb_status;
+
+/* clContext.queue.{load,process,unload} (clJobQueue.ts:126,131; transform.ts:100) */
+typedef enum pb_queue { PB_QUEUE_LOAD = 0, PB_QUEUE_PROCESS = 1, PB_QUEUE_UNLOAD = 2 } pb_queue;
+/* createBuffer(numBytes, 'readonly'|'writeonly'|'readwrite', 'none'|'coarse'|'fine', ...) */
+typedef enum pb_dir { PB_DIR_READONLY = 0, PB_DIR_WRITEONLY = 1, PB_DIR_READWRITE = 2 } pb_dir;
+typedef enum pb_svm { PB_SVM_NONE = 0, PB_SVM_COARSE = 1, PB_SVM_FINE = 2 } pb_svm;
+/* buffer.hostAccess('none'|'readonly'|'writeonly', queue?, src?) */
+typedef enum pb_access { PB_ACCESS_NONE = 0, PB_ACCESS_READONLY = 1, PB_ACCESS_WRITEONLY = 2 } pb_access;
+
+/* What createProgram's OpenCL source string + entry name selected in the reference.
+   ('read'/'write' are reused by all packers, so identity comes from the op.) */
+typedef enum pb_op {
+	PB_OP_V210_READ = 1,    /* v210.ts:25-111    */
+	PB_OP_V210_WRITE = 2,   /* v210.ts:113-195   */
+	PB_OP_RGBA8_READ = 3,   /* rgba8.ts:25-67    */
+	PB_OP_RGBA8_WRITE = 4,  /* rgba8.ts:69-103   */
+	PB_OP_BGRA8_READ = 5,   /* bgra8.ts:25-67    */
+	PB_OP_BGRA8_WRITE = 6,  /* bgra8.ts:69-103   */
+	PB_OP_COMBINE = 10,     /* combine.ts:24-68  (N from the lKIn params bound) */
+	PB_OP_DISSOLVE = 11,    /* transition.ts:60-65 */
+	PB_OP_WIPE_MASK = 12,   /* transition.ts:66-73 */
+	PB_OP_TRANSFORM = 13,   /* transform.ts:36-59 */
+	PB_OP_YADIF = 14,       /* yadifCl.ts:105-167 */
+	PB_OP_MIX = 15,         /* mix.ts:30-45 */
+	PB_OP_WIPE = 16,        /* wipe.ts:30-47 */
+	PB_OP_RESIZE = 17       /* resize.ts:35-59 */
+} pb_op;
+
+/* One kernel argument, bound BY KERNEL PARAMETER NAME as nodencl's runProgram
+   does (clJobQueue.ts:126; names from each getKernelParams, e.g. v210.ts:297-309). */
+typedef enum pb_param_kind { PB_PARAM_BUF = 0, PB_PARAM_NUM = 1 } pb_param_kind;
+typedef struct pb_param {
+	const char *name;
+	int kind;     /* pb_param_kind */
+	pb_buf *buf;  /* PB_PARAM_BUF */
+	double num;   /* PB_PARAM_NUM: numbers and booleans */
+} pb_param;
+
+/* nodencl RunTimings, microseconds (clJobQueue.ts:183-190) */
+typedef struct pb_timings {
+	uint32_t dataToKernel;
+	uint32_t kernelExec;
+	uint32_t totalTime;
+} pb_timings;
+
+typedef struct pb_stats {
+	uint64_t kernel_launches;   /* every CUDA kernel this context launched */
+	uint64_t fused_launches;    /* of which: fused chain launches */
+	uint64_t deferred_nodes;    /* jobs recorded into the frame-expression DAG */
+	uint64_t materialised;      /* deferred RGBA frames that had to be written to HBM */
+	uint64_t h2d_bytes, d2h_bytes;
+	uint64_t dev_bytes_live, dev_bytes_pooled;
+} pb_stats;
+
+const char *pb_last_error(void);
+const char *pb_version(void);
+
+/* new clContext({platformIndex, deviceIndex, overlapping}) + initialise()
+   (index.ts:94-102).  flags: bit0 = defer RGBA intermediates and fuse at sinks
+   (default behaviour of the product); 0 = eager, one launch per job. */
+#define PB_CTX_DEFER 1u
+int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out);
+int pb_ctx_destroy(pb_ctx *ctx);
+/* getPlatformInfo() (index.ts:103-107): JSON text into buf */
+int pb_ctx_info(pb_ctx *ctx, char *buf, size_t buf_len);
+int pb_ctx_stats(pb_ctx *ctx, pb_stats *out);
+int pb_ctx_set_flags(pb_ctx *ctx, unsigned flags);
+
+/* createBuffer(numBytes, dir, svm, imageDims?, owner?) (io.ts:61-77; mixer.ts:196-207) */
+int pb_buf_create(pb_ctx *ctx, size_t bytes, int dir, int svm, int image_w, int image_h,
+                  const char *owner, pb_buf **out);
+/* wrap device memory owned by the caller (ROUTE frames received over NCCL) */
+int pb_buf_wrap(pb_ctx *ctx, void *dev_ptr, size_t bytes, int image_w, int image_h, pb_buf **out);
+int pb_buf_addref(pb_buf *buf);   /* OpenCLBuffer.addRef()  */
+int pb_buf_release(pb_buf *buf);  /* OpenCLBuffer.release() */
+int pb_buf_refs(pb_buf *buf);
+size_t pb_buf_bytes(pb_buf *buf);
+/* host-addressable storage of the Buffer subclass (pinned); valid until release */
+void *pb_buf_host_ptr(pb_buf *buf);
+/* device pointer; materialises a deferred frame.  NULL on error. */
+void *pb_buf_dev_ptr(pb_buf *buf);
+/* 1 if the frame currently exists only as a deferred expression (no HBM copy) */
+int pb_buf_is_deferred(pb_buf *buf);
+/* hostAccess(mode, queue, src): WRITEONLY+src = H2D copy of src; WRITEONLY w/o src = map
+   for host writes (flushed to the device before the next use); READONLY = D2H into the
+   host storage (materialising if deferred); NONE = hand back to the device.  Blocks
+   until the copy on `queue` is complete, like the resolved Promise. */
+int pb_buf_host_access(pb_buf *buf, int mode, int queue, const void *src, size_t src_bytes);
+/* async variants for callers that pipeline (bench e2e, ROUTE): enqueue only */
+int pb_buf_upload_async(pb_buf *buf, int queue, const void *pinned_src, size_t bytes);
+int pb_buf_download_async(pb_buf *buf, int queue, void *pinned_dst, size_t bytes);
+/* pinned host allocations for callers' staging rings */
+void *pb_host_alloc(size_t bytes);
+void pb_host_free(void *p);
+
+/* createProgram(source, {name, globalWorkItems, workItemsPerGroup}) (packer.ts:97-103,
+   imageProcess.ts:68-74): the op enum stands in for the OpenCL source. */
+int pb_prog_create(pb_ctx *ctx, int op, int width, int height, pb_prog **out);
+int pb_prog_destroy(pb_prog *prog);
+
+/* runProgram(program, params, queue) (clJobQueue.ts:122-128).  In PB_CTX_DEFER mode a
+   job whose output is an RGBA frame is only RECORDED (timings zero); a packed sink
+   (any *_WRITE op) compiles the recorded expression into one fused launch. */
+int pb_run_program(pb_ctx *ctx, pb_prog *prog, const pb_param *params, int num_params, int queue,
+                   pb_timings *timings);
+/* waitFinish(queue) (clJobQueue.ts:131) */
+int pb_wait_finish(pb_ctx *ctx, int queue);
+/* make `queue` wait (device-side) for everything enqueued so far on `on_queue` */
+int pb_queue_wait_queue(pb_ctx *ctx, int queue, int on_queue);
+/* the CUDA stream behind a queue id (for event timing by the caller) */
+void *pb_ctx_stream(pb_ctx *ctx, int queue);
+
+/* CUDA-event timing on a queue's stream (the device-side replacement for the hrtime
+   bookkeeping in clJobQueue.ts:159-215); used by bench.py */
+typedef struct pb_event pb_event;
+int pb_event_create(pb_ctx *ctx, pb_event **out);
+int pb_event_record(pb_event *ev, int queue);
+int pb_event_sync(pb_event *ev);
+int pb_event_elapsed_ms(pb_event *start, pb_event *stop, float *ms);
+int pb_event_destroy(pb_event *ev);
+
+/* Record / replay of fused launches.  phaneron re-issues an identical job list every
+   frame (same programs, same buffer roles); a host that recycles its buffers can record
+   the launches of one frame and replay them without re-walking the job queue.  bench.py
+   uses this to time the device path without Python in the loop.  Buffers referenced by
+   a chain stay alive until pb_chain_destroy. */
+typedef struct pb_chain pb_chain;
+int pb_chain_begin(pb_ctx *ctx);
+int pb_chain_end(pb_ctx *ctx, pb_chain **out);
+/* launches in the chain; *complete = 0 if a non-replayable (stand-alone) kernel ran while recording */
+int pb_chain_info(pb_chain *chain, int *launches, int *complete);
+int pb_chain_replay(pb_chain *chain, int queue);
+int pb_chain_destroy(pb_chain *chain);
+
+/* colourMaths.ts exports, so hosts without colourMaths.ts (Python, C++) agree with the
+   TypeScript bit for bit.  Return 1 if colspec was known, 0 if it fell back to '709'. */
+int pb_gamma2linear_lut(const char *colspec, float *out65536);   /* colourMaths.ts:130-149 */
+int pb_linear2gamma_lut(const char *colspec, float *out65536);   /* colourMaths.ts:151-169 */
+int pb_ycbcr2rgb_matrix(const char *colspec, int num_bits, int luma_black, int luma_white,
+                        int chr_range, float *out12);              /* colourMaths.ts:276-332 */
+int pb_rgb2ycbcr_matrix(const char *colspec, int num_bits, int luma_black, int luma_white,
+                        int chr_range, float *out12);              /* colourMaths.ts:334-390 */
+int pb_rgb2rgb_matrix(const char *src, const char *dst, float *out9); /* colourMaths.ts:392-394 */
+/* Transform.getKernelParams matrix build (transform.ts:119-171) */
+int pb_transform_matrix(int width, int height, int flip_h, int flip_v, double anchor_x,
+                        double anchor_y, double scale_x, double scale_y, double offset_x,
+                        double offset_y, double rotate_turns, float *out9);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,62 @@
+// pb_desc.h -- launch descriptors shared by the runtime (host) and the kernels.
+//
+// A "frame expression" is what phaneron's layer graph computes for one output
+// frame: leaves are packed source frames (or RGBA-f32 frames that had to be
+// materialised), inner nodes are Transform / Transition / Combine, the root is a
+// packed writer.  The runtime flattens an expression into a FusedDesc and hands it
+// to ONE kernel launch (pb_fused.cu).
+#pragma once
+#include <stdint.h>
+
+namespace pb {
+
+constexpr int kMaxLayers = 8;   // combine_N inputs (combiner.ts builds N = number of layers)
+constexpr int kMaxReadConsts = 8;
+
+enum LeafKind : int { LEAF_NONE = 0, LEAF_V210 = 1, LEAF_RGBA_F32 = 2 };
+enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
+
+// Loader constants (loadSave.ts:41-64): YCbCr->RGB 3x4, gamma->linear LUT, gamut 3x3
+struct ReadConsts {
+	float cm[12];
+	float gamut[9];
+	const float *lut;
+	const uint8_t *lut_res;   // optional smem-residual form (see pb_lut.cuh); may be null
+};
+
+// Saver constants (loadSave.ts:130-150): linear->gamma LUT, RGB->YCbCr 3x4
+struct WriteConsts {
+	float cm[12];
+	const float *lut;
+};
+
+struct Leaf {
+	const void *ptr;
+	int kind;          // LeafKind
+	int w, h;          // source dimensions in pixels
+	int pitch;         // bytes per line (v210) / unused for RGBA (w*16)
+	int rc;            // index into FusedDesc::rc (v210 leaves)
+	int has_xf;        // 0: sample texel (x,y) directly; 1: Transform (transform.ts:36-59)
+	int xf_w, xf_h;    // dimensions of the Transform's output image
+	float m[6];        // rows 0 and 1 of the 3x3 transformMatrix
+};
+
+struct Layer {
+	int kind;          // LayerKind
+	float mix;         // dissolve
+	Leaf a, b, mask;
+};
+
+struct FusedDesc {
+	int n_layers;
+	int out_w, out_h;
+	int interlace;     // packer.ts:24-28 Interlace enum: 0, 1 (top), 3 (bottom)
+	int out_pitch;     // bytes per output line
+	int n_rc;
+	void *out;
+	WriteConsts wc;
+	ReadConsts rc[kMaxReadConsts];
+	Layer layers[kMaxLayers];
+};
+
+}  // namespace pb

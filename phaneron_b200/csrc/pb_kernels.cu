@@ -1,0 +1,348 @@
+// pb_kernels.cu -- stand-alone ("materialising") kernels, one per reference kernel.
+// They are what runs in eager mode and whenever a deferred RGBA frame must really exist
+// in HBM (host read-back, ROUTE hand-off, yadif history, rotated transforms).  The fused
+// chain lives in pb_fused.cu.
+#include "pb_device.cuh"
+#include "pb_launch.h"
+
+namespace pb {
+
+constexpr int kThreads = 256;
+static inline unsigned blocks_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+// ---- v210 read: v210.ts:25-111 --------------------------------------------------------
+// one thread per 16-byte group (6 pixels)
+__global__ void __launch_bounds__(kThreads) k_v210_read(const uint4 *__restrict__ in, float4 *__restrict__ out,
+                                                        int width, int height, int pitch16,
+                                                        const __grid_constant__ ReadConsts rc) {
+	const int groups = (width + 5) / 6;
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)groups * height) return;
+	const int line = (int)(tid / groups), g = (int)(tid - (size_t)line * groups);
+	const uint4 w = ld_stream(in + (size_t)line * pitch16 + g);
+	const int x0 = g * 6;
+	const int n = min(6, width - x0);
+	const float alpha = (n < 6) ? 0.0f : 1.0f;   // Q1
+	float4 *o = out + (size_t)line * width + x0;
+#pragma unroll
+	for (int p = 0; p < 6; ++p) {
+		if (p < n) {
+			const float3 rgb = ycc_to_linear(v210_px(w, p), alpha, rc);
+			o[p] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+		}
+	}
+}
+
+// ---- v210 write: v210.ts:113-195 ------------------------------------------------------
+// one thread per 16-byte group of the destination pitch (padding groups are cleared as
+// the reference's partial last work-item does, v210.ts:131-136)
+__global__ void __launch_bounds__(kThreads) k_v210_write(const float4 *__restrict__ in, uint4 *__restrict__ out,
+                                                         int width, int lines, int pitch16, int interlace,
+                                                         const __grid_constant__ WriteConsts wc) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)pitch16 * lines) return;
+	const int gl = (int)(tid / pitch16), g = (int)(tid - (size_t)gl * pitch16);
+	const int line = gl * (interlace == 0 ? 1 : 2) + (interlace == 3 ? 1 : 0);
+	const int x0 = g * 6;
+	uint4 w = make_uint4(0, 0, 0, 0);
+	if (x0 < width) {
+		const float4 *src = in + (size_t)line * width + x0;
+		const int n = min(6, width - x0);
+		Ycc px[6];
+#pragma unroll
+		for (int p = 0; p < 6; ++p) {
+			px[p].y = px[p].cb = px[p].cr = 0;
+			if (p < n) {
+				const float4 v = __ldg(src + p);
+				px[p] = (n == 6) ? linear_to_ycc(v.x, v.y, v.z, wc) : linear_to_ycc_tail(v.x, v.y, v.z, wc);
+			}
+		}
+		if (n == 6) {
+			w = v210_pack(px);
+		} else {
+			// v210.ts:186-192
+			w.x = px[0].cr << 20 | px[0].y << 10 | px[0].cb;
+			if (n == 2) w.y = px[1].y;
+			else if (n == 4) {
+				w.y = px[2].y << 20 | px[2].cb << 10 | px[1].y;
+				w.z = px[3].y << 10 | px[2].cr;
+			}
+		}
+	} else if (width % 48 == 0) {
+		return;   // no padding exists
+	}
+	st_stream(out + (size_t)line * pitch16 + g, w);
+}
+
+// ---- rgba8 / bgra8: rgba8.ts:25-103, bgra8.ts:25-103 ------------------------------------
+__global__ void __launch_bounds__(kThreads) k_rgba8_read(const uchar4 *__restrict__ in, float4 *__restrict__ out,
+                                                         size_t n, int bgra, const __grid_constant__ ReadConsts rc) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= n) return;
+	const uchar4 v = in[tid];
+	const float c0 = u2f(bgra ? v.z : v.x), c1 = u2f(v.y), c2 = u2f(bgra ? v.x : v.z), c3 = u2f(v.w);
+	const float r = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c0, 65535.0f), 255.0f)));
+	const float g = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c1, 65535.0f), 255.0f)));
+	const float b = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c2, 65535.0f), 255.0f)));
+	float4 o;
+	o.x = dot3(r, g, b, rc.gamut + 0);
+	o.y = dot3(r, g, b, rc.gamut + 3);
+	o.z = dot3(r, g, b, rc.gamut + 6);
+	o.w = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c3, 65535.0f), 255.0f)));   // alpha goes through the LUT (rgba8.ts:61)
+	out[tid] = o;
+}
+
+__global__ void __launch_bounds__(kThreads) k_rgba8_write(const float4 *__restrict__ in, uchar4 *__restrict__ out,
+                                                          int width, int lines, int interlace, int bgra,
+                                                          const __grid_constant__ WriteConsts wc) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)width * lines) return;
+	const int gl = (int)(tid / width), x = (int)(tid - (size_t)gl * width);
+	const int line = gl * (interlace == 0 ? 1 : 2) + (interlace == 3 ? 1 : 0);
+	const float4 v = __ldg(in + (size_t)line * width + x);
+	const float r = __ldg(wc.lut + sat_rte_u16(mul(v.x, 65535.0f)));
+	const float g = __ldg(wc.lut + sat_rte_u16(mul(v.y, 65535.0f)));
+	const float b = __ldg(wc.lut + sat_rte_u16(mul(v.z, 65535.0f)));
+	uchar4 o;
+	const unsigned char r8 = (unsigned char)sat_rte_u8(mul(r, 255.0f)), g8 = (unsigned char)sat_rte_u8(mul(g, 255.0f)),
+	                    b8 = (unsigned char)sat_rte_u8(mul(b, 255.0f));
+	o.x = bgra ? b8 : r8;
+	o.y = g8;
+	o.z = bgra ? r8 : b8;
+	o.w = 255;
+	out[(size_t)line * width + x] = o;
+}
+
+// ---- combine_N: combine.ts:24-68 --------------------------------------------------------
+struct CombineArgs {
+	const float4 *in[kMaxLayers];
+	int n;
+};
+__global__ void __launch_bounds__(kThreads) k_combine(const __grid_constant__ CombineArgs a, float4 *__restrict__ out, size_t npx) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= npx) return;
+	float4 acc = __ldg(a.in[0] + tid);
+	for (int i = 1; i < a.n; ++i) acc = over4(acc, __ldg(a.in[i] + tid));
+	out[tid] = acc;
+}
+
+// ---- transition_dissolve / mixer: transition.ts:60-65, mix.ts:30-45 -----------------------
+__global__ void __launch_bounds__(kThreads) k_dissolve(const float4 *__restrict__ in0, const float4 *__restrict__ in1, float mix,
+                                                       float4 *__restrict__ out, size_t npx) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= npx) return;
+	out[tid] = dissolve4(__ldg(in0 + tid), __ldg(in1 + tid), mix);
+}
+
+// ---- transition_wipe: transition.ts:66-73 ---------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_wipe_mask(const float4 *__restrict__ in0, const float4 *__restrict__ in1,
+                                                        const float4 *__restrict__ mask, float4 *__restrict__ out, size_t npx) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= npx) return;
+	out[tid] = wipe_mask4(__ldg(in0 + tid), __ldg(in1 + tid), __ldg(mask + tid).x);
+}
+
+// ---- wipe: wipe.ts:30-47 ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_wipe(const float4 *__restrict__ in0, const float4 *__restrict__ in1, float wipe,
+                                                   float4 *__restrict__ out, int w, int h) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)w * h) return;
+	const int x = (int)(tid % w);
+	out[tid] = ((float)x > mul((float)w, wipe)) ? __ldg(in1 + tid) : __ldg(in0 + tid);
+}
+
+// ---- transform: transform.ts:36-59 -------------------------------------------------------------
+struct Mat6 {
+	float m[6];
+};
+__global__ void __launch_bounds__(kThreads) k_transform(const float4 *__restrict__ in, int sw, int sh, const __grid_constant__ Mat6 mat,
+                                                        float4 *__restrict__ out, int w, int h) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)w * h) return;
+	const int y = (int)(tid / w), x = (int)(tid - (size_t)y * w);
+	const float2 p = transform_pos(mat.m, x, y, w, h);
+	out[tid] = sample_linear_clamp(sw, sh, p.x, p.y, [&](int i, int j) {
+		if (i < 0 || j < 0 || i >= sw || j >= sh) return make_float4(0.f, 0.f, 0.f, 0.f);
+		return __ldg(in + (size_t)j * sw + i);
+	});
+}
+
+// ---- resize: resize.ts:35-59 ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_resize(const float4 *__restrict__ in, int sw, int sh, float scale, float offsetX,
+                                                     float offsetY, float f0, float f1, float f2, float f3,
+                                                     float4 *__restrict__ out, int w, int h) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)w * h) return;
+	const int y = (int)(tid / w), x = (int)(tid - (size_t)y * w);
+	const float cx = add(__fdiv_rn(sub(-0.5f, offsetX), scale), 0.5f);
+	const float cy = add(__fdiv_rn(sub(-0.5f, offsetY), scale), 0.5f);
+	const float offX = fma_(cx, f1, f0), offY = fma_(cy, f3, f2);
+	const float mulX = __fdiv_rn(f1, scale), mulY = __fdiv_rn(f3, scale);
+	const float px = fma_(__fdiv_rn((float)x, (float)w), mulX, offX);
+	const float py = fma_(__fdiv_rn((float)y, (float)h), mulY, offY);
+	out[tid] = sample_linear_clamp(sw, sh, px, py, [&](int i, int j) {
+		if (i < 0 || j < 0 || i >= sw || j >= sh) return make_float4(0.f, 0.f, 0.f, 0.f);
+		return __ldg(in + (size_t)j * sw + i);
+	});
+}
+
+// ---- yadif: yadifCl.ts:28-167 ------------------------------------------------------------------------
+__device__ __forceinline__ float half_sum(float a, float b) { return mul(add(a, b), 0.5f); }   // (a + b) / 2.0f, exact
+__device__ __forceinline__ float ad(float a, float b) { return fabsf(sub(a, b)); }
+
+__device__ __forceinline__ float spatial_predictor(float a, float b, float c, float d, float e, float f, float g, float h,
+                                                    float i, float j, float k, float l, float m, float n) {
+	float pred = half_sum(d, k);
+	float best = add(add(ad(c, j), ad(d, k)), ad(e, l));
+	float score = add(add(ad(b, k), ad(c, l)), ad(d, m));
+	bool cmp = score < best;
+	pred = cmp ? half_sum(c, l) : pred;
+	best = cmp ? score : best;
+	score = cmp ? add(add(ad(a, l), ad(b, m)), ad(c, n)) : score;
+	cmp = cmp && (score < best);
+	pred = cmp ? half_sum(b, m) : pred;
+	best = cmp ? score : best;
+	score = add(add(ad(d, i), ad(e, j)), ad(f, k));
+	cmp = score < best;
+	pred = cmp ? half_sum(e, j) : pred;
+	best = cmp ? score : best;
+	score = cmp ? add(add(ad(e, h), ad(f, i)), ad(g, j)) : score;
+	cmp = cmp && (score < best);
+	pred = cmp ? half_sum(f, i) : pred;
+	return pred;
+}
+
+__device__ __forceinline__ float temporal_predictor(float A, float B, float C, float D, float E, float F, float G, float H,
+                                                     float I, float J, float K, float L, float pred, int skip) {
+	const float p0 = half_sum(C, H), p1 = F, p2 = half_sum(D, I), p3 = G, p4 = half_sum(E, J);
+	const float t0 = ad(D, I);
+	const float t1 = mul(add(ad(A, F), ad(B, G)), 0.5f);
+	const float t2 = mul(add(ad(K, F), ad(G, L)), 0.5f);
+	float diff = fmaxf(fmaxf(t0, t1), t2);
+	if (!skip) {
+		const float p2mp3 = sub(p2, p3), p2mp1 = sub(p2, p1), p0mp1 = sub(p0, p1), p4mp3 = sub(p4, p3);
+		const float maxi = fmaxf(fmaxf(p2mp3, p2mp1), fminf(p0mp1, p4mp3));
+		const float mini = fminf(fminf(p2mp3, p2mp1), fmaxf(p0mp1, p4mp3));
+		diff = fmaxf(fmaxf(diff, mini), -maxi);
+	}
+	const float hi = add(p2, diff), lo = sub(p2, diff);
+	pred = (pred > hi) ? hi : pred;
+	pred = (pred < lo) ? lo : pred;
+	return pred;
+}
+
+__global__ void __launch_bounds__(kThreads) k_yadif(const float4 *__restrict__ prev, const float4 *__restrict__ cur,
+                                                    const float4 *__restrict__ next, int parity, int tff, int skip,
+                                                    float4 *__restrict__ out, int w, int h) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)w * h) return;
+	const int yo = (int)(tid / w), xo = (int)(tid - (size_t)yo * w);
+	auto px = [&](const float4 *img, int x, int y) {
+		x = min(max(x, 0), w - 1);
+		y = min(max(y, 0), h - 1);
+		return __ldg(img + (size_t)y * w + x);
+	};
+	if ((yo & 1) == parity) {
+		out[tid] = px(cur, xo, yo);
+		return;
+	}
+	const int second = !(parity ^ tff);
+	const float4 a = px(cur, xo - 3, yo - 1), b = px(cur, xo - 2, yo - 1), c = px(cur, xo - 1, yo - 1), d = px(cur, xo, yo - 1),
+	             e = px(cur, xo + 1, yo - 1), f = px(cur, xo + 2, yo - 1), g = px(cur, xo + 3, yo - 1);
+	const float4 hh = px(cur, xo - 3, yo + 1), i = px(cur, xo - 2, yo + 1), j = px(cur, xo - 1, yo + 1), k = px(cur, xo, yo + 1),
+	             l = px(cur, xo + 1, yo + 1), m = px(cur, xo + 2, yo + 1), n = px(cur, xo + 3, yo + 1);
+	const float4 A = px(prev, xo, yo - 1), B = px(prev, xo, yo + 1);
+	const float4 C = px(second ? cur : prev, xo, yo - 2), D = px(second ? cur : prev, xo, yo), E = px(second ? cur : prev, xo, yo + 2);
+	const float4 F = d, G = k;
+	const float4 H = px(second ? next : cur, xo, yo - 2), I = px(second ? next : cur, xo, yo), J = px(second ? next : cur, xo, yo + 2);
+	const float4 K = px(next, xo, yo - 1), L = px(next, xo, yo + 1);
+	float4 o;
+#define YADIF_CH(ch) \
+	o.ch = temporal_predictor(A.ch, B.ch, C.ch, D.ch, E.ch, F.ch, G.ch, H.ch, I.ch, J.ch, K.ch, L.ch, \
+	                          spatial_predictor(a.ch, b.ch, c.ch, d.ch, e.ch, f.ch, g.ch, hh.ch, i.ch, j.ch, k.ch, l.ch, m.ch, n.ch), skip)
+	YADIF_CH(x);
+	YADIF_CH(y);
+	YADIF_CH(z);
+#undef YADIF_CH
+	o.w = px(cur, xo, yo).w;   // "Reset Alpha" (yadifCl.ts:164): the w channel's prediction is discarded
+	out[tid] = o;
+}
+
+// ---- launchers -----------------------------------------------------------------------------------------
+#define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t launch_v210_read(cudaStream_t s, const void *in, void *out, int w, int h, const ReadConsts &rc) {
+	const int pitch16 = ((w + 47) / 48) * 8;
+	const size_t n = (size_t)((w + 5) / 6) * h;
+	k_v210_read<<<blocks_for(n), kThreads, 0, s>>>((const uint4 *)in, (float4 *)out, w, h, pitch16, rc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_v210_write(cudaStream_t s, const void *in, void *out, int w, int h, int interlace, const WriteConsts &wc) {
+	const int pitch16 = ((w + 47) / 48) * 8;
+	const int lines = interlace == 0 ? h : h / 2;
+	k_v210_write<<<blocks_for((size_t)pitch16 * lines), kThreads, 0, s>>>((const float4 *)in, (uint4 *)out, w, lines, pitch16, interlace, wc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_rgba8_read(cudaStream_t s, const void *in, void *out, int w, int h, int bgra, const ReadConsts &rc) {
+	const size_t n = (size_t)w * h;
+	k_rgba8_read<<<blocks_for(n), kThreads, 0, s>>>((const uchar4 *)in, (float4 *)out, n, bgra, rc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_rgba8_write(cudaStream_t s, const void *in, void *out, int w, int h, int interlace, int bgra, const WriteConsts &wc) {
+	const int lines = interlace == 0 ? h : h / 2;
+	k_rgba8_write<<<blocks_for((size_t)w * lines), kThreads, 0, s>>>((const float4 *)in, (uchar4 *)out, w, lines, interlace, bgra, wc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_combine(cudaStream_t s, const void *const *in, int n, void *out, int w, int h) {
+	CombineArgs a;
+	a.n = n;
+	for (int i = 0; i < kMaxLayers; ++i) a.in[i] = (const float4 *)(i < n ? in[i] : nullptr);
+	const size_t npx = (size_t)w * h;
+	k_combine<<<blocks_for(npx), kThreads, 0, s>>>(a, (float4 *)out, npx);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_dissolve(cudaStream_t s, const void *in0, const void *in1, float mix, void *out, int w, int h) {
+	const size_t npx = (size_t)w * h;
+	k_dissolve<<<blocks_for(npx), kThreads, 0, s>>>((const float4 *)in0, (const float4 *)in1, mix, (float4 *)out, npx);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_wipe_mask(cudaStream_t s, const void *in0, const void *in1, const void *mask, void *out, int w, int h) {
+	const size_t npx = (size_t)w * h;
+	k_wipe_mask<<<blocks_for(npx), kThreads, 0, s>>>((const float4 *)in0, (const float4 *)in1, (const float4 *)mask, (float4 *)out, npx);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_wipe(cudaStream_t s, const void *in0, const void *in1, float wipe, void *out, int w, int h) {
+	k_wipe<<<blocks_for((size_t)w * h), kThreads, 0, s>>>((const float4 *)in0, (const float4 *)in1, wipe, (float4 *)out, w, h);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_transform(cudaStream_t s, const void *in, int sw, int sh, const float *mat6, void *out, int w, int h) {
+	Mat6 m;
+	for (int i = 0; i < 6; ++i) m.m[i] = mat6[i];
+	k_transform<<<blocks_for((size_t)w * h), kThreads, 0, s>>>((const float4 *)in, sw, sh, m, (float4 *)out, w, h);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_resize(cudaStream_t s, const void *in, int sw, int sh, float scale, float ox, float oy, const float *flip4,
+                          void *out, int w, int h) {
+	k_resize<<<blocks_for((size_t)w * h), kThreads, 0, s>>>((const float4 *)in, sw, sh, scale, ox, oy, flip4[0], flip4[1], flip4[2],
+	                                                        flip4[3], (float4 *)out, w, h);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_yadif(cudaStream_t s, const void *prev, const void *cur, const void *next, int parity, int tff, int skip,
+                         void *out, int w, int h) {
+	k_yadif<<<blocks_for((size_t)w * h), kThreads, 0, s>>>((const float4 *)prev, (const float4 *)cur, (const float4 *)next, parity, tff,
+	                                                       skip, (float4 *)out, w, h);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+
+}  // namespace pb

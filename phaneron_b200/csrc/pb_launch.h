@@ -1,0 +1,29 @@
+// pb_launch.h -- host-callable launchers (defined in pb_kernels.cu / pb_fused.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pb_desc.h"
+
+namespace pb {
+
+cudaError_t launch_v210_read(cudaStream_t s, const void *in, void *out, int w, int h, const ReadConsts &rc);
+cudaError_t launch_v210_write(cudaStream_t s, const void *in, void *out, int w, int h, int interlace, const WriteConsts &wc);
+cudaError_t launch_rgba8_read(cudaStream_t s, const void *in, void *out, int w, int h, int bgra, const ReadConsts &rc);
+cudaError_t launch_rgba8_write(cudaStream_t s, const void *in, void *out, int w, int h, int interlace, int bgra, const WriteConsts &wc);
+cudaError_t launch_combine(cudaStream_t s, const void *const *in, int n, void *out, int w, int h);
+cudaError_t launch_dissolve(cudaStream_t s, const void *in0, const void *in1, float mix, void *out, int w, int h);
+cudaError_t launch_wipe_mask(cudaStream_t s, const void *in0, const void *in1, const void *mask, void *out, int w, int h);
+cudaError_t launch_wipe(cudaStream_t s, const void *in0, const void *in1, float wipe, void *out, int w, int h);
+cudaError_t launch_transform(cudaStream_t s, const void *in, int sw, int sh, const float *mat6, void *out, int w, int h);
+cudaError_t launch_resize(cudaStream_t s, const void *in, int sw, int sh, float scale, float ox, float oy, const float *flip4,
+                          void *out, int w, int h);
+cudaError_t launch_yadif(cudaStream_t s, const void *prev, const void *cur, const void *next, int parity, int tff, int skip,
+                         void *out, int w, int h);
+
+// Fused chain: N layers of (leaf | dissolve | wipe) -> combine -> v210 pack, one launch.
+// out_rgba != nullptr writes the composite as RGBA-f32 instead of packing (materialise).
+cudaError_t launch_fused(cudaStream_t s, const FusedDesc &d, void *out_rgba);
+// name of the kernel variant launch_fused would pick (for stats / tests)
+const char *fused_variant(const FusedDesc &d);
+
+}  // namespace pb

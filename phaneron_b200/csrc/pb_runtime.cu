@@ -1,0 +1,1185 @@
+// pb_runtime.cu -- the C ABI (include/phaneron_b200.h): contexts, refcounted buffers with a
+// pinned host face, op-enum "programs", and the frame-expression recorder that turns
+// phaneron's per-stage jobs (clJobQueue.ts:122-128) into one fused launch per output frame.
+//
+// Design: in PB_CTX_DEFER mode a job whose output is an RGBA-f32 image
+// is not executed; its output buffer gets an expression node that references the input
+// expressions (and holds references on the packed leaves).  A packed writer is a sink: it
+// flattens the expression into a pb::FusedDesc and launches once.  Anything the fused kernel
+// cannot express is materialised bottom-up with the stand-alone kernels and re-enters as an
+// RGBA leaf.  Host reads of a deferred frame materialise it on demand.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/phaneron_b200.h"
+#include "pb_desc.h"
+#include "pb_launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+	char tmp[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(tmp, sizeof tmp, fmt, ap);
+	va_end(ap);
+	g_err = tmp;
+	return code;
+}
+
+#define CU(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if (e__ != cudaSuccess) return fail(PB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+	} while (0)
+
+struct Node;
+using NodeP = std::shared_ptr<Node>;
+
+// size-keyed free lists; frames of one format recycle the same few blocks, so steady state
+// performs no cudaMalloc/cudaFree (the reference allocates a fresh SVM buffer per stage per
+// frame: mixer.ts:196, transitioner.ts:152, combiner.ts:230)
+struct Pool {
+	std::unordered_map<size_t, std::vector<void *>> dev, host;
+	size_t dev_pooled = 0, dev_live = 0;
+	static constexpr size_t kMaxPooled = size_t(24) << 30;
+
+	cudaError_t dev_get(size_t n, void **p) {
+		auto &v = dev[n];
+		if (!v.empty()) {
+			*p = v.back();
+			v.pop_back();
+			dev_pooled -= n;
+			dev_live += n;
+			return cudaSuccess;
+		}
+		cudaError_t e = cudaMalloc(p, n);
+		if (e != cudaSuccess) {   // give pooled memory back and retry once
+			trim();
+			e = cudaMalloc(p, n);
+		}
+		if (e == cudaSuccess) dev_live += n;
+		return e;
+	}
+	void dev_put(size_t n, void *p) {
+		if (!p) return;
+		dev_live -= n;
+		if (dev_pooled + n > kMaxPooled) {
+			cudaFree(p);
+			return;
+		}
+		dev[n].push_back(p);
+		dev_pooled += n;
+	}
+	cudaError_t host_get(size_t n, void **p) {
+		auto &v = host[n];
+		if (!v.empty()) {
+			*p = v.back();
+			v.pop_back();
+			return cudaSuccess;
+		}
+		return cudaMallocHost(p, n);
+	}
+	void host_put(size_t n, void *p) {
+		if (p) host[n].push_back(p);
+	}
+	void trim() {
+		for (auto &kv : dev)
+			for (void *p : kv.second) cudaFree(p);
+		dev.clear();
+		dev_pooled = 0;
+	}
+	void destroy() {
+		trim();
+		for (auto &kv : host)
+			for (void *p : kv.second) cudaFreeHost(p);
+		host.clear();
+	}
+};
+
+}  // namespace
+
+struct pb_ctx {
+	int dev = 0;
+	unsigned flags = 0;
+	cudaStream_t q[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_x = nullptr;
+	std::recursive_mutex mu;
+	Pool pool;
+	pb_stats stats{};
+	cudaDeviceProp prop{};
+	struct pb_chain *recording = nullptr;
+};
+
+struct pb_buf {
+	pb_ctx *ctx = nullptr;
+	size_t bytes = 0;
+	int dir = 0, svm = 0, w = 0, h = 0;
+	std::atomic<int> refs{1};
+	void *dev = nullptr;
+	bool dev_external = false;
+	void *host = nullptr;
+	bool host_dirty = false;   // host face written since the last upload
+	NodeP expr;                // non-null: frame exists only as an expression
+	std::string owner;
+};
+
+struct pb_prog {
+	pb_ctx *ctx;
+	int op, w, h;
+};
+
+struct pb_chain {
+	pb_ctx *ctx = nullptr;
+	struct Item {
+		pb::FusedDesc d;
+		void *out_rgba;
+		std::vector<std::shared_ptr<void>> keep;   // expression nodes (hold the leaf buffers)
+		pb_buf *out_buf;                           // addref'd destination
+	};
+	std::vector<Item> items;
+	bool complete = true;
+};
+
+namespace {
+
+enum NodeKind { N_LEAF_V210, N_LEAF_RGBA, N_TRANSFORM, N_DISSOLVE, N_WIPE_MASK, N_COMBINE };
+
+struct Node {
+	NodeKind kind;
+	pb_ctx *ctx;
+	int w = 0, h = 0;            // dimensions of the image this node produces
+	std::vector<NodeP> in;
+	pb_buf *src = nullptr;       // leaves: referenced source buffer
+	pb_buf *lut_buf = nullptr;   // v210 leaves: referenced gamma LUT buffer
+	pb::ReadConsts rc{};         // v210 leaves
+	float mat[6] = {0};          // transform
+	float mix = 0.f;             // dissolve
+	void *mat_dev = nullptr;     // RGBA-f32 copy if this node had to be materialised
+	~Node();
+};
+
+void buf_release_locked(pb_buf *b);
+
+Node::~Node() {
+	std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+	if (mat_dev) ctx->pool.dev_put((size_t)w * h * 16, mat_dev);
+	if (src) buf_release_locked(src);
+	if (lut_buf) buf_release_locked(lut_buf);
+}
+
+void buf_free(pb_buf *b) {
+	pb_ctx *c = b->ctx;
+	b->expr.reset();
+	if (b->dev && !b->dev_external) c->pool.dev_put(b->bytes, b->dev);
+	if (b->host) c->pool.host_put(b->bytes, b->host);
+	delete b;
+}
+
+void buf_release_locked(pb_buf *b) {
+	if (b->refs.fetch_sub(1) == 1) buf_free(b);
+}
+
+int ensure_dev(pb_buf *b) {
+	if (b->dev) return PB_OK;
+	CU(b->ctx->pool.dev_get(b->bytes, &b->dev));
+	return PB_OK;
+}
+
+int ensure_host(pb_buf *b) {
+	if (b->host) return PB_OK;
+	CU(b->ctx->pool.host_get(b->bytes, &b->host));
+	return PB_OK;
+}
+
+// push pending host writes (hostAccess('writeonly') without a source) to the device
+int flush_host(pb_buf *b, cudaStream_t s) {
+	if (!b->host_dirty) return PB_OK;
+	int r = ensure_dev(b);
+	if (r) return r;
+	CU(cudaMemcpyAsync(b->dev, b->host, b->bytes, cudaMemcpyHostToDevice, s));
+	b->ctx->stats.h2d_bytes += b->bytes;
+	b->host_dirty = false;
+	return PB_OK;
+}
+
+const pb_param *find(const pb_param *p, int n, const char *name) {
+	for (int i = 0; i < n; ++i)
+		if (p[i].name && 0 == strcmp(p[i].name, name)) return &p[i];
+	return nullptr;
+}
+
+int need_buf(const pb_param *p, int n, const char *name, pb_buf **out) {
+	const pb_param *q = find(p, n, name);
+	if (!q || q->kind != PB_PARAM_BUF || !q->buf) return fail(PB_ERR_ARG, "missing buffer parameter '%s'", name);
+	if (q->buf->refs.load() <= 0) return fail(PB_ERR_STATE, "parameter '%s' is a released buffer", name);
+	*out = q->buf;
+	return PB_OK;
+}
+
+int need_num(const pb_param *p, int n, const char *name, double *out) {
+	const pb_param *q = find(p, n, name);
+	if (!q || q->kind != PB_PARAM_NUM) return fail(PB_ERR_ARG, "missing numeric parameter '%s'", name);
+	*out = q->num;
+	return PB_OK;
+}
+
+// small constant buffers (matrices) are read from their host face
+int host_floats(pb_buf *b, int count, float *out, const char *what) {
+	if (b->bytes < (size_t)count * 4) return fail(PB_ERR_ARG, "%s buffer holds %zu bytes, need %d", what, b->bytes, count * 4);
+	if (!b->host) return fail(PB_ERR_STATE, "%s buffer was never written by the host", what);
+	memcpy(out, b->host, (size_t)count * 4);
+	return PB_OK;
+}
+
+int make_read_consts(pb_ctx *c, const pb_param *p, int n, bool ycbcr, pb::ReadConsts *rc, pb_buf **lut_out) {
+	pb_buf *lut, *gamut, *cm = nullptr;
+	int r;
+	if ((r = need_buf(p, n, "gammaLut", &lut))) return r;
+	if ((r = need_buf(p, n, "gamutMatrix", &gamut))) return r;
+	if (ycbcr && (r = need_buf(p, n, "colMatrix", &cm))) return r;
+	memset(rc, 0, sizeof *rc);
+	if (cm && (r = host_floats(cm, 12, rc->cm, "colMatrix"))) return r;
+	if ((r = host_floats(gamut, 9, rc->gamut, "gamutMatrix"))) return r;   // Q4: only 9 floats are meaningful
+	if (lut->bytes < 65536 * 4) return fail(PB_ERR_ARG, "gammaLut must hold 65536 floats");
+	if ((r = flush_host(lut, c->q[PB_QUEUE_PROCESS]))) return r;
+	if (!lut->dev) return fail(PB_ERR_STATE, "gammaLut was never written");
+	rc->lut = (const float *)lut->dev;
+	*lut_out = lut;
+	return PB_OK;
+}
+
+int make_write_consts(pb_ctx *c, const pb_param *p, int n, bool ycbcr, pb::WriteConsts *wc) {
+	pb_buf *lut, *cm = nullptr;
+	int r;
+	if ((r = need_buf(p, n, "gammaLut", &lut))) return r;
+	if (ycbcr && (r = need_buf(p, n, "colMatrix", &cm))) return r;
+	memset(wc, 0, sizeof *wc);
+	if (cm && (r = host_floats(cm, 12, wc->cm, "colMatrix"))) return r;
+	if (lut->bytes < 65536 * 4) return fail(PB_ERR_ARG, "gammaLut must hold 65536 floats");
+	if ((r = flush_host(lut, c->q[PB_QUEUE_PROCESS]))) return r;
+	if (!lut->dev) return fail(PB_ERR_STATE, "gammaLut was never written");
+	wc->lut = (const float *)lut->dev;
+	return PB_OK;
+}
+
+inline int v210_pitch_bytes(int w) { return ((w + 47) / 48) * 128; }
+
+// ---- expression handling -------------------------------------------------------------------
+
+// the expression an RGBA input buffer stands for (its recorded node, or itself as a leaf)
+int input_expr(pb_buf *b, NodeP *out) {
+	if (b->expr) {
+		*out = b->expr;
+		return PB_OK;
+	}
+	if (b->w <= 0 || b->h <= 0) return fail(PB_ERR_ARG, "image input '%s' was created without imageDims", b->owner.c_str());
+	int r = flush_host(b, b->ctx->q[PB_QUEUE_PROCESS]);
+	if (r) return r;
+	if (!b->dev) return fail(PB_ERR_STATE, "image input '%s' has no contents", b->owner.c_str());
+	auto n = std::make_shared<Node>();
+	n->kind = N_LEAF_RGBA;
+	n->ctx = b->ctx;
+	n->w = b->w;
+	n->h = b->h;
+	n->src = b;
+	b->refs.fetch_add(1);
+	*out = n;
+	return PB_OK;
+}
+
+int materialise_node(pb_ctx *c, const NodeP &n, const void **dev_out);
+
+struct Compiler {
+	pb_ctx *c;
+	pb::FusedDesc d;
+	std::vector<NodeP> keep;
+
+	int rc_index(const pb::ReadConsts &rc, int *idx) {
+		for (int i = 0; i < d.n_rc; ++i)
+			if (0 == memcmp(&d.rc[i], &rc, sizeof rc)) {
+				*idx = i;
+				return PB_OK;
+			}
+		if (d.n_rc >= pb::kMaxReadConsts) return 1;   // caller materialises instead
+		d.rc[d.n_rc] = rc;
+		*idx = d.n_rc++;
+		return PB_OK;
+	}
+
+	int set_basic_leaf(const NodeP &n, pb::Leaf *lf) {
+		if (n->kind == N_LEAF_V210) {
+			int idx;
+			if (rc_index(n->rc, &idx)) return 1;
+			lf->kind = pb::LEAF_V210;
+			lf->ptr = n->src->dev;
+			lf->w = n->w;
+			lf->h = n->h;
+			lf->pitch = v210_pitch_bytes(n->w);
+			lf->rc = idx;
+			return PB_OK;
+		}
+		if (n->kind == N_LEAF_RGBA) {
+			lf->kind = pb::LEAF_RGBA_F32;
+			lf->ptr = n->src->dev;
+			lf->w = n->w;
+			lf->h = n->h;
+			lf->pitch = n->w * 16;
+			return PB_OK;
+		}
+		return 1;
+	}
+
+	int as_rgba_leaf(const NodeP &n, pb::Leaf *lf) {
+		const void *p;
+		int r = materialise_node(c, n, &p);
+		if (r) return r;
+		lf->kind = pb::LEAF_RGBA_F32;
+		lf->ptr = p;
+		lf->w = n->w;
+		lf->h = n->h;
+		lf->pitch = n->w * 16;
+		return PB_OK;
+	}
+
+	int leaf_spec(const NodeP &n, pb::Leaf *lf) {
+		memset(lf, 0, sizeof *lf);
+		keep.push_back(n);
+		if (0 == set_basic_leaf(n, lf)) return PB_OK;
+		if (n->kind == N_TRANSFORM) {
+			const NodeP &child = n->in[0];
+			if (0 != set_basic_leaf(child, lf)) {
+				int r = as_rgba_leaf(child, lf);
+				if (r) return r;
+			}
+			lf->has_xf = 1;
+			lf->xf_w = n->w;
+			lf->xf_h = n->h;
+			memcpy(lf->m, n->mat, sizeof lf->m);
+			return PB_OK;
+		}
+		return as_rgba_leaf(n, lf);
+	}
+
+	int layer_spec(const NodeP &n, pb::Layer *ly) {
+		memset(ly, 0, sizeof *ly);
+		int r;
+		if (n->kind == N_DISSOLVE) {
+			ly->kind = pb::LAYER_DISSOLVE;
+			ly->mix = n->mix;
+			if ((r = leaf_spec(n->in[0], &ly->a))) return r;
+			return leaf_spec(n->in[1], &ly->b);
+		}
+		if (n->kind == N_WIPE_MASK) {
+			ly->kind = pb::LAYER_WIPE_MASK;
+			if ((r = leaf_spec(n->in[0], &ly->a))) return r;
+			if ((r = leaf_spec(n->in[1], &ly->b))) return r;
+			return leaf_spec(n->in[2], &ly->mask);
+		}
+		ly->kind = pb::LAYER_DIRECT;
+		return leaf_spec(n, &ly->a);
+	}
+
+	int compile(const NodeP &root) {
+		memset(&d, 0, sizeof d);
+		d.out_w = root->w;
+		d.out_h = root->h;
+		if (root->kind == N_COMBINE) {
+			std::vector<NodeP> layers = root->in;
+			// combine_N with N > kMaxLayers: fold the bottom layers first
+			while ((int)layers.size() > pb::kMaxLayers) {
+				auto sub = std::make_shared<Node>();
+				sub->kind = N_COMBINE;
+				sub->ctx = c;
+				sub->w = root->w;
+				sub->h = root->h;
+				sub->in.assign(layers.begin(), layers.begin() + pb::kMaxLayers);
+				layers.erase(layers.begin(), layers.begin() + pb::kMaxLayers);
+				layers.insert(layers.begin(), sub);
+			}
+			d.n_layers = (int)layers.size();
+			for (int i = 0; i < d.n_layers; ++i) {
+				int r = layer_spec(layers[i], &d.layers[i]);
+				if (r) return r;
+			}
+		} else {
+			d.n_layers = 1;
+			int r = layer_spec(root, &d.layers[0]);
+			if (r) return r;
+		}
+		return PB_OK;
+	}
+};
+
+void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf) {
+	if (!c->recording) return;
+	pb_chain::Item it;
+	it.d = cc.d;
+	it.out_rgba = out_rgba;
+	for (const auto &k : cc.keep) it.keep.push_back(std::static_pointer_cast<void>(k));
+	it.out_buf = out_buf;
+	if (out_buf) out_buf->refs.fetch_add(1);
+	c->recording->items.push_back(std::move(it));
+}
+
+// write node n as RGBA-f32 into HBM (cached on the node)
+int materialise_node(pb_ctx *c, const NodeP &n, const void **dev_out) {
+	if (n->kind == N_LEAF_RGBA) {
+		*dev_out = n->src->dev;
+		return PB_OK;
+	}
+	if (!n->mat_dev) {
+		void *p;
+		CU(c->pool.dev_get((size_t)n->w * n->h * 16, &p));
+		Compiler cc{c};
+		int r = cc.compile(n);
+		if (r) {
+			c->pool.dev_put((size_t)n->w * n->h * 16, p);
+			return r;
+		}
+		cudaError_t e = pb::launch_fused(c->q[PB_QUEUE_PROCESS], cc.d, p);
+		if (e != cudaSuccess) {
+			c->pool.dev_put((size_t)n->w * n->h * 16, p);
+			return fail(PB_ERR_CUDA, "fused materialise launch: %s", cudaGetErrorString(e));
+		}
+		c->stats.kernel_launches++;
+		c->stats.fused_launches++;
+		c->stats.materialised++;
+		n->mat_dev = p;
+		cc.keep.push_back(n);   // a recorded chain must keep the node (and its mat_dev) alive
+		record_launch(c, cc, p, nullptr);
+	}
+	*dev_out = n->mat_dev;
+	return PB_OK;
+}
+
+// make a deferred buffer real
+int materialise_buf(pb_buf *b) {
+	if (!b->expr) return PB_OK;
+	pb_ctx *c = b->ctx;
+	NodeP n = b->expr;
+	int r = ensure_dev(b);
+	if (r) return r;
+	if (n->kind == N_LEAF_RGBA) {
+		CU(cudaMemcpyAsync(b->dev, n->src->dev, b->bytes, cudaMemcpyDeviceToDevice, c->q[PB_QUEUE_PROCESS]));
+	} else if (n->mat_dev) {
+		CU(cudaMemcpyAsync(b->dev, n->mat_dev, b->bytes, cudaMemcpyDeviceToDevice, c->q[PB_QUEUE_PROCESS]));
+	} else {
+		Compiler cc{c};
+		if ((r = cc.compile(n))) return r;
+		cudaError_t e = pb::launch_fused(c->q[PB_QUEUE_PROCESS], cc.d, b->dev);
+		if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused materialise launch: %s", cudaGetErrorString(e));
+		c->stats.kernel_launches++;
+		c->stats.fused_launches++;
+		c->stats.materialised++;
+		record_launch(c, cc, b->dev, b);
+	}
+	b->expr.reset();
+	return PB_OK;
+}
+
+// RGBA input that must be real memory for a stand-alone kernel
+int real_input(pb_buf *b, const void **p) {
+	int r = materialise_buf(b);
+	if (r) return r;
+	if ((r = flush_host(b, b->ctx->q[PB_QUEUE_PROCESS]))) return r;
+	if (!b->dev) {
+		// Never written.  The reference reads whatever the fresh SVM allocation holds (this
+		// really happens: Yadif runs with a `next` frame whose ToRGBA job is still queued,
+		// yadif.ts:88-113 vs macadamProducer.ts:193-227).  We define it as zeros.
+		if ((r = ensure_dev(b))) return r;
+		CU(cudaMemsetAsync(b->dev, 0, b->bytes, b->ctx->q[PB_QUEUE_PROCESS]));
+	}
+	*p = b->dev;
+	return PB_OK;
+}
+
+int real_output(pb_buf *b, void **p) {
+	b->expr.reset();
+	b->host_dirty = false;
+	int r = ensure_dev(b);
+	if (r) return r;
+	*p = b->dev;
+	return PB_OK;
+}
+
+NodeP new_node(pb_ctx *c, NodeKind k, int w, int h) {
+	auto n = std::make_shared<Node>();
+	n->kind = k;
+	n->ctx = c;
+	n->w = w;
+	n->h = h;
+	return n;
+}
+
+void set_deferred(pb_buf *out, NodeP n) {
+	pb_ctx *c = out->ctx;
+	if (out->dev && !out->dev_external) {   // drop stale storage: the frame lives in the expression now
+		c->pool.dev_put(out->bytes, out->dev);
+		out->dev = nullptr;
+	}
+	out->host_dirty = false;
+	out->expr = std::move(n);
+	c->stats.deferred_nodes++;
+}
+
+int check_image(pb_buf *b, int w, int h, const char *what) {
+	if (b->bytes < (size_t)w * h * 16) return fail(PB_ERR_ARG, "%s buffer too small for %dx%d RGBA-f32", what, w, h);
+	return PB_OK;
+}
+
+int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) {
+	const bool defer = (c->flags & PB_CTX_DEFER) != 0;
+	const int W = g->w, H = g->h;
+	int r;
+	bool fused_launch = false;
+	cudaError_t e = cudaSuccess;
+	switch (g->op) {
+		case PB_OP_V210_READ: {
+			pb_buf *in, *out, *lut;
+			pb::ReadConsts rc;
+			if ((r = need_buf(p, n, "input", &in)) || (r = need_buf(p, n, "output", &out))) return r;
+			if ((r = make_read_consts(c, p, n, true, &rc, &lut))) return r;
+			if (in->bytes < (size_t)v210_pitch_bytes(W) * H) return fail(PB_ERR_ARG, "v210 input buffer too small");
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if ((r = flush_host(in, s))) return r;
+			if (!in->dev) return fail(PB_ERR_STATE, "v210 input has no contents");
+			if (defer) {
+				NodeP nd = new_node(c, N_LEAF_V210, W, H);
+				nd->src = in;
+				in->refs.fetch_add(1);
+				nd->lut_buf = lut;
+				lut->refs.fetch_add(1);
+				nd->rc = rc;
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
+			void *o;
+			if ((r = real_output(out, &o))) return r;
+			e = pb::launch_v210_read(s, in->dev, o, W, H, rc);
+			break;
+		}
+		case PB_OP_RGBA8_READ:
+		case PB_OP_BGRA8_READ: {
+			pb_buf *in, *out, *lut;
+			pb::ReadConsts rc;
+			if ((r = need_buf(p, n, "input", &in)) || (r = need_buf(p, n, "output", &out))) return r;
+			if ((r = make_read_consts(c, p, n, false, &rc, &lut))) return r;
+			if (in->bytes < (size_t)W * H * 4) return fail(PB_ERR_ARG, "rgba8 input buffer too small");
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if ((r = flush_host(in, s))) return r;
+			if (!in->dev) return fail(PB_ERR_STATE, "rgba8 input has no contents");
+			void *o;
+			if ((r = real_output(out, &o))) return r;
+			e = pb::launch_rgba8_read(s, in->dev, o, W, H, g->op == PB_OP_BGRA8_READ, rc);
+			break;
+		}
+		case PB_OP_V210_WRITE:
+		case PB_OP_RGBA8_WRITE:
+		case PB_OP_BGRA8_WRITE: {
+			pb_buf *in, *out;
+			pb::WriteConsts wc;
+			double il = 0;
+			const bool v210 = g->op == PB_OP_V210_WRITE;
+			if ((r = need_buf(p, n, "input", &in)) || (r = need_buf(p, n, "output", &out))) return r;
+			if ((r = make_write_consts(c, p, n, v210, &wc))) return r;
+			if (find(p, n, "interlace") && (r = need_num(p, n, "interlace", &il))) return r;
+			const int interlace = (int)il;
+			if (interlace != 0 && interlace != 1 && interlace != 3) return fail(PB_ERR_ARG, "interlace must be 0, 1 or 3");
+			const size_t need = v210 ? (size_t)v210_pitch_bytes(W) * H : (size_t)W * H * 4;
+			if (out->bytes < need) return fail(PB_ERR_ARG, "packed output buffer too small");
+			if (in->w && (in->w != W || in->h != H)) return fail(PB_ERR_ARG, "writer is %dx%d but input image is %dx%d", W, H, in->w, in->h);
+			out->expr.reset();
+			// a field write must keep the other field's lines: push pending host contents first
+			if (interlace != 0 && (r = flush_host(out, s))) return r;
+			out->host_dirty = false;
+			if ((r = ensure_dev(out))) return r;
+			if (v210 && in->expr) {
+				Compiler cc{c};
+				if ((r = cc.compile(in->expr))) return r;
+				cc.d.wc = wc;
+				cc.d.interlace = interlace;
+				cc.d.out = out->dev;
+				cc.d.out_pitch = v210_pitch_bytes(W);
+				e = pb::launch_fused(s, cc.d, nullptr);
+				c->stats.fused_launches++;
+				record_launch(c, cc, nullptr, out);
+				fused_launch = true;
+				break;
+			}
+			const void *src;
+			if ((r = real_input(in, &src))) return r;
+			if (v210) e = pb::launch_v210_write(s, src, out->dev, W, H, interlace, wc);
+			else e = pb::launch_rgba8_write(s, src, out->dev, W, H, interlace, g->op == PB_OP_BGRA8_WRITE, wc);
+			break;
+		}
+		case PB_OP_COMBINE: {
+			pb_buf *out, *ins[64];
+			int cnt = 0;
+			char name[16];
+			if ((r = need_buf(p, n, "output", &out))) return r;
+			for (; cnt < 64; ++cnt) {
+				snprintf(name, sizeof name, "l%dIn", cnt);
+				if (!find(p, n, name)) break;
+				if ((r = need_buf(p, n, name, &ins[cnt]))) return r;
+			}
+			if (cnt < 2) return fail(PB_ERR_ARG, "combine needs at least l0In and l1In");
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if (defer) {
+				NodeP nd = new_node(c, N_COMBINE, W, H);
+				for (int i = 0; i < cnt; ++i) {
+					NodeP x;
+					if ((r = input_expr(ins[i], &x))) return r;
+					if (x->w != W || x->h != H) return fail(PB_ERR_ARG, "combine layer %d is %dx%d, expected %dx%d", i, x->w, x->h, W, H);
+					nd->in.push_back(x);
+				}
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
+			if (cnt > pb::kMaxLayers) return fail(PB_ERR_ARG, "eager combine supports at most %d layers", pb::kMaxLayers);
+			const void *src[pb::kMaxLayers];
+			for (int i = 0; i < cnt; ++i)
+				if ((r = real_input(ins[i], &src[i]))) return r;
+			void *o;
+			if ((r = real_output(out, &o))) return r;
+			e = pb::launch_combine(s, src, cnt, o, W, H);
+			break;
+		}
+		case PB_OP_DISSOLVE:
+		case PB_OP_MIX: {
+			pb_buf *in0, *in1, *out;
+			double mix;
+			if ((r = need_buf(p, n, "input0", &in0)) || (r = need_buf(p, n, "input1", &in1)) || (r = need_buf(p, n, "output", &out)) ||
+			    (r = need_num(p, n, "mix", &mix)))
+				return r;
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if (defer) {
+				NodeP nd = new_node(c, N_DISSOLVE, W, H);
+				NodeP a, b;
+				if ((r = input_expr(in0, &a)) || (r = input_expr(in1, &b))) return r;
+				if (a->w != W || a->h != H || b->w != W || b->h != H) return fail(PB_ERR_ARG, "dissolve inputs must be %dx%d", W, H);
+				nd->in = {a, b};
+				nd->mix = (float)mix;
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
+			const void *a, *b;
+			void *o;
+			if ((r = real_input(in0, &a)) || (r = real_input(in1, &b)) || (r = real_output(out, &o))) return r;
+			e = pb::launch_dissolve(s, a, b, (float)mix, o, W, H);
+			break;
+		}
+		case PB_OP_WIPE_MASK: {
+			pb_buf *in0, *in1, *mask, *out;
+			if ((r = need_buf(p, n, "input0", &in0)) || (r = need_buf(p, n, "input1", &in1)) || (r = need_buf(p, n, "maskIn", &mask)) ||
+			    (r = need_buf(p, n, "output", &out)))
+				return r;
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if (defer) {
+				NodeP nd = new_node(c, N_WIPE_MASK, W, H);
+				NodeP a, b, m;
+				if ((r = input_expr(in0, &a)) || (r = input_expr(in1, &b)) || (r = input_expr(mask, &m))) return r;
+				if (a->w != W || a->h != H || b->w != W || b->h != H || m->w != W || m->h != H)
+					return fail(PB_ERR_ARG, "wipe inputs must be %dx%d", W, H);
+				nd->in = {a, b, m};
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
+			const void *a, *b, *m;
+			void *o;
+			if ((r = real_input(in0, &a)) || (r = real_input(in1, &b)) || (r = real_input(mask, &m)) || (r = real_output(out, &o))) return r;
+			e = pb::launch_wipe_mask(s, a, b, m, o, W, H);
+			break;
+		}
+		case PB_OP_WIPE: {
+			pb_buf *in0, *in1, *out;
+			double wipe;
+			if ((r = need_buf(p, n, "input0", &in0)) || (r = need_buf(p, n, "input1", &in1)) || (r = need_buf(p, n, "output", &out)) ||
+			    (r = need_num(p, n, "wipe", &wipe)))
+				return r;
+			if ((r = check_image(out, W, H, "output"))) return r;
+			const void *a, *b;
+			void *o;
+			if ((r = real_input(in0, &a)) || (r = real_input(in1, &b)) || (r = real_output(out, &o))) return r;
+			e = pb::launch_wipe(s, a, b, (float)wipe, o, W, H);
+			break;
+		}
+		case PB_OP_TRANSFORM: {
+			pb_buf *in, *out, *mb;
+			float m9[9];
+			if ((r = need_buf(p, n, "input", &in)) || (r = need_buf(p, n, "output", &out)) || (r = need_buf(p, n, "transformMatrix", &mb)))
+				return r;
+			if ((r = host_floats(mb, 9, m9, "transformMatrix"))) return r;
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if (defer) {
+				NodeP child;
+				if ((r = input_expr(in, &child))) return r;
+				NodeP nd = new_node(c, N_TRANSFORM, W, H);
+				nd->in = {child};
+				memcpy(nd->mat, m9, sizeof nd->mat);
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
+			if (in->w <= 0 || in->h <= 0) return fail(PB_ERR_ARG, "transform input was created without imageDims");
+			const void *src;
+			void *o;
+			if ((r = real_input(in, &src)) || (r = real_output(out, &o))) return r;
+			e = pb::launch_transform(s, src, in->w, in->h, m9, o, W, H);
+			break;
+		}
+		case PB_OP_RESIZE: {
+			pb_buf *in, *out, *fb;
+			double scale, ox, oy;
+			float flip[4];
+			if ((r = need_buf(p, n, "input", &in)) || (r = need_buf(p, n, "output", &out)) || (r = need_buf(p, n, "flip", &fb)) ||
+			    (r = need_num(p, n, "scale", &scale)) || (r = need_num(p, n, "offsetX", &ox)) || (r = need_num(p, n, "offsetY", &oy)))
+				return r;
+			if ((r = host_floats(fb, 4, flip, "flip"))) return r;
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if (in->w <= 0 || in->h <= 0) return fail(PB_ERR_ARG, "resize input was created without imageDims");
+			const void *src;
+			void *o;
+			if ((r = real_input(in, &src)) || (r = real_output(out, &o))) return r;
+			e = pb::launch_resize(s, src, in->w, in->h, (float)scale, (float)ox, (float)oy, flip, o, W, H);
+			break;
+		}
+		case PB_OP_YADIF: {
+			pb_buf *prev, *cur, *next, *out;
+			double parity, tff, skip;
+			if ((r = need_buf(p, n, "prev", &prev)) || (r = need_buf(p, n, "cur", &cur)) || (r = need_buf(p, n, "next", &next)) ||
+			    (r = need_buf(p, n, "output", &out)) || (r = need_num(p, n, "parity", &parity)) || (r = need_num(p, n, "tff", &tff)) ||
+			    (r = need_num(p, n, "skipSpatial", &skip)))
+				return r;
+			if ((r = check_image(out, W, H, "output"))) return r;
+			const void *a, *b, *d;
+			void *o;
+			if ((r = real_input(prev, &a)) || (r = real_input(cur, &b)) || (r = real_input(next, &d)) || (r = real_output(out, &o))) return r;
+			out->w = W;
+			out->h = H;
+			e = pb::launch_yadif(s, a, b, d, (int)parity, tff != 0, skip != 0, o, W, H);
+			break;
+		}
+		default:
+			return fail(PB_ERR_ARG, "unknown op %d", g->op);
+	}
+	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "kernel launch (op %d): %s", g->op, cudaGetErrorString(e));
+	c->stats.kernel_launches++;
+	if (c->recording && !fused_launch)
+		c->recording->complete = false;   // a stand-alone kernel ran: the chain cannot reproduce it
+	return PB_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ------------------------------------------------------------------------------------
+extern "C" {
+
+const char *pb_last_error(void) { return g_err.c_str(); }
+const char *pb_version(void) { return "phaneron_b200 0.1 (sm_100a)"; }
+
+int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out) {
+	if (!out) return fail(PB_ERR_ARG, "out is null");
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(PB_ERR_NO_DEVICE, "no CUDA device (%s); phaneron_b200 has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+	if (gpu_index < 0 || gpu_index >= count) return fail(PB_ERR_ARG, "gpu_index %d out of range (%d devices)", gpu_index, count);
+	CU(cudaSetDevice(gpu_index));
+	auto *c = new pb_ctx;
+	c->dev = gpu_index;
+	c->flags = flags;
+	CU(cudaGetDeviceProperties(&c->prop, gpu_index));
+	for (auto &q : c->q) CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+	CU(cudaEventCreate(&c->ev0));
+	CU(cudaEventCreate(&c->ev1));
+	CU(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+	*out = c;
+	return PB_OK;
+}
+
+int pb_ctx_destroy(pb_ctx *c) {
+	if (!c) return PB_OK;
+	cudaSetDevice(c->dev);
+	cudaDeviceSynchronize();
+	c->pool.destroy();
+	for (auto &q : c->q) cudaStreamDestroy(q);
+	cudaEventDestroy(c->ev0);
+	cudaEventDestroy(c->ev1);
+	cudaEventDestroy(c->ev_x);
+	delete c;
+	return PB_OK;
+}
+
+int pb_ctx_info(pb_ctx *c, char *buf, size_t n) {
+	if (!c || !buf) return fail(PB_ERR_ARG, "null argument");
+	snprintf(buf, n,
+	         "{\"vendor\":\"NVIDIA Corporation\",\"name\":\"phaneron_b200\",\"version\":\"%s\",\"devices\":[{\"type\":\"GPU\","
+	         "\"name\":\"%s\",\"computeCapability\":\"%d.%d\",\"multiProcessorCount\":%d,\"totalGlobalMem\":%zu}]}",
+	         pb_version(), c->prop.name, c->prop.major, c->prop.minor, c->prop.multiProcessorCount, (size_t)c->prop.totalGlobalMem);
+	return PB_OK;
+}
+
+int pb_ctx_stats(pb_ctx *c, pb_stats *out) {
+	if (!c || !out) return fail(PB_ERR_ARG, "null argument");
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	*out = c->stats;
+	out->dev_bytes_live = c->pool.dev_live;
+	out->dev_bytes_pooled = c->pool.dev_pooled;
+	return PB_OK;
+}
+
+int pb_ctx_set_flags(pb_ctx *c, unsigned flags) {
+	if (!c) return fail(PB_ERR_ARG, "null context");
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	c->flags = flags;
+	return PB_OK;
+}
+
+int pb_buf_create(pb_ctx *c, size_t bytes, int dir, int svm, int image_w, int image_h, const char *owner, pb_buf **out) {
+	if (!c || !out) return fail(PB_ERR_ARG, "null argument");
+	if (bytes == 0) return fail(PB_ERR_ARG, "zero-sized buffer");
+	if (image_w < 0 || image_h < 0) return fail(PB_ERR_ARG, "negative image dimensions");
+	if (image_w && (size_t)image_w * image_h * 16 > bytes) return fail(PB_ERR_ARG, "imageDims %dx%d exceed %zu bytes", image_w, image_h, bytes);
+	auto *b = new pb_buf;
+	b->ctx = c;
+	b->bytes = bytes;
+	b->dir = dir;
+	b->svm = svm;
+	b->w = image_w;
+	b->h = image_h;
+	if (owner) b->owner = owner;
+	*out = b;
+	return PB_OK;
+}
+
+int pb_buf_wrap(pb_ctx *c, void *dev_ptr, size_t bytes, int image_w, int image_h, pb_buf **out) {
+	if (!dev_ptr) return fail(PB_ERR_ARG, "null device pointer");
+	int r = pb_buf_create(c, bytes, PB_DIR_READWRITE, PB_SVM_NONE, image_w, image_h, "wrapped", out);
+	if (r) return r;
+	(*out)->dev = dev_ptr;
+	(*out)->dev_external = true;
+	return PB_OK;
+}
+
+int pb_buf_addref(pb_buf *b) {
+	if (!b) return fail(PB_ERR_ARG, "null buffer");
+	b->refs.fetch_add(1);
+	return PB_OK;
+}
+
+int pb_buf_release(pb_buf *b) {
+	if (!b) return fail(PB_ERR_ARG, "null buffer");
+	pb_ctx *c = b->ctx;
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	cudaSetDevice(c->dev);
+	buf_release_locked(b);
+	return PB_OK;
+}
+
+int pb_buf_refs(pb_buf *b) { return b ? b->refs.load() : 0; }
+size_t pb_buf_bytes(pb_buf *b) { return b ? b->bytes : 0; }
+
+void *pb_buf_host_ptr(pb_buf *b) {
+	if (!b) return nullptr;
+	std::lock_guard<std::recursive_mutex> lk(b->ctx->mu);
+	cudaSetDevice(b->ctx->dev);
+	if (ensure_host(b)) return nullptr;
+	return b->host;
+}
+
+void *pb_buf_dev_ptr(pb_buf *b) {
+	if (!b) return nullptr;
+	std::lock_guard<std::recursive_mutex> lk(b->ctx->mu);
+	cudaSetDevice(b->ctx->dev);
+	if (materialise_buf(b)) return nullptr;
+	if (flush_host(b, b->ctx->q[PB_QUEUE_PROCESS])) return nullptr;
+	if (ensure_dev(b)) return nullptr;
+	return b->dev;
+}
+
+int pb_buf_is_deferred(pb_buf *b) { return (b && b->expr) ? 1 : 0; }
+
+int pb_buf_host_access(pb_buf *b, int mode, int queue, const void *src, size_t src_bytes) {
+	if (!b) return fail(PB_ERR_ARG, "null buffer");
+	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
+	pb_ctx *c = b->ctx;
+	cudaStream_t s;
+	{
+		std::lock_guard<std::recursive_mutex> lk(c->mu);
+		cudaSetDevice(c->dev);
+		s = c->q[queue];
+		int r;
+		switch (mode) {
+			case PB_ACCESS_WRITEONLY:
+				b->expr.reset();
+				if ((!src || src_bytes <= 65536) && (r = ensure_host(b))) return r;
+				if (src) {
+					if (src_bytes > b->bytes) return fail(PB_ERR_ARG, "source (%zu bytes) larger than buffer (%zu)", src_bytes, b->bytes);
+					if ((r = ensure_dev(b))) return r;
+					if (src_bytes <= 65536) {
+						// small constants (matrices, flip values) are also read from the host face
+						memcpy(b->host, src, src_bytes);
+						CU(cudaMemcpyAsync(b->dev, b->host, src_bytes, cudaMemcpyHostToDevice, s));
+					} else {
+						// frames: DMA straight from the caller's memory (pinned if it came from pb_host_alloc)
+						CU(cudaMemcpyAsync(b->dev, src, src_bytes, cudaMemcpyHostToDevice, s));
+					}
+					c->stats.h2d_bytes += src_bytes;
+					b->host_dirty = false;
+				} else {
+					b->host_dirty = true;   // host will write through pb_buf_host_ptr(); flushed on next use
+					return PB_OK;
+				}
+				break;
+			case PB_ACCESS_READONLY: {
+				if ((r = ensure_host(b))) return r;
+				if (b->host_dirty && !b->expr) return PB_OK;   // host face is the newest copy
+				const bool was_deferred = (bool)b->expr;
+				if ((r = materialise_buf(b))) return r;
+				if (!b->dev) {   // never written: reads as zeros
+					memset(b->host, 0, b->bytes);
+					return PB_OK;
+				}
+				if (was_deferred || s != c->q[PB_QUEUE_PROCESS]) {   // order the copy after the producing kernels
+					CU(cudaEventRecord(c->ev_x, c->q[PB_QUEUE_PROCESS]));
+					CU(cudaStreamWaitEvent(s, c->ev_x, 0));
+				}
+				CU(cudaMemcpyAsync(b->host, b->dev, b->bytes, cudaMemcpyDeviceToHost, s));
+				c->stats.d2h_bytes += b->bytes;
+				break;
+			}
+			case PB_ACCESS_NONE:
+				if ((r = flush_host(b, s))) return r;
+				break;
+			default:
+				return fail(PB_ERR_ARG, "bad access mode %d", mode);
+		}
+	}
+	CU(cudaStreamSynchronize(s));
+	return PB_OK;
+}
+
+int pb_buf_upload_async(pb_buf *b, int queue, const void *src, size_t bytes) {
+	if (!b || !src) return fail(PB_ERR_ARG, "null argument");
+	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
+	if (bytes > b->bytes) return fail(PB_ERR_ARG, "upload larger than buffer");
+	pb_ctx *c = b->ctx;
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	cudaSetDevice(c->dev);
+	b->expr.reset();
+	b->host_dirty = false;
+	int r = ensure_dev(b);
+	if (r) return r;
+	CU(cudaMemcpyAsync(b->dev, src, bytes, cudaMemcpyHostToDevice, c->q[queue]));
+	c->stats.h2d_bytes += bytes;
+	return PB_OK;
+}
+
+int pb_buf_download_async(pb_buf *b, int queue, void *dst, size_t bytes) {
+	if (!b || !dst) return fail(PB_ERR_ARG, "null argument");
+	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
+	if (bytes > b->bytes) return fail(PB_ERR_ARG, "download larger than buffer");
+	pb_ctx *c = b->ctx;
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	cudaSetDevice(c->dev);
+	int r = materialise_buf(b);
+	if (r) return r;
+	if (!b->dev) return fail(PB_ERR_STATE, "buffer has no device contents");
+	CU(cudaMemcpyAsync(dst, b->dev, bytes, cudaMemcpyDeviceToHost, c->q[queue]));
+	c->stats.d2h_bytes += bytes;
+	return PB_OK;
+}
+
+void *pb_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+		fail(PB_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+		return nullptr;
+	}
+	return p;
+}
+
+void pb_host_free(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
+int pb_prog_create(pb_ctx *c, int op, int width, int height, pb_prog **out) {
+	if (!c || !out) return fail(PB_ERR_ARG, "null argument");
+	if (width <= 0 || height <= 0) return fail(PB_ERR_ARG, "bad program dimensions %dx%d", width, height);
+	switch (op) {
+		case PB_OP_V210_READ: case PB_OP_V210_WRITE: case PB_OP_RGBA8_READ: case PB_OP_RGBA8_WRITE: case PB_OP_BGRA8_READ:
+		case PB_OP_BGRA8_WRITE: case PB_OP_COMBINE: case PB_OP_DISSOLVE: case PB_OP_WIPE_MASK: case PB_OP_TRANSFORM:
+		case PB_OP_YADIF: case PB_OP_MIX: case PB_OP_WIPE: case PB_OP_RESIZE:
+			break;
+		default:
+			return fail(PB_ERR_ARG, "unknown op %d", op);
+	}
+	if ((op == PB_OP_V210_READ || op == PB_OP_V210_WRITE) && (width % 2)) return fail(PB_ERR_ARG, "v210 width must be even");
+	*out = new pb_prog{c, op, width, height};
+	return PB_OK;
+}
+
+int pb_prog_destroy(pb_prog *g) {
+	delete g;
+	return PB_OK;
+}
+
+int pb_run_program(pb_ctx *c, pb_prog *g, const pb_param *params, int num_params, int queue, pb_timings *t) {
+	if (!c || !g || (num_params && !params)) return fail(PB_ERR_ARG, "null argument");
+	if (g->ctx != c) return fail(PB_ERR_ARG, "program belongs to another context");
+	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	CU(cudaSetDevice(c->dev));
+	cudaStream_t s = c->q[queue];
+	if (t) {
+		memset(t, 0, sizeof *t);
+		CU(cudaEventRecord(c->ev0, s));
+	}
+	const uint64_t before = c->stats.kernel_launches;
+	int r = run_locked(c, g, params, num_params, s);
+	if (r) return r;
+	if (t && c->stats.kernel_launches != before) {
+		CU(cudaEventRecord(c->ev1, s));
+		CU(cudaEventSynchronize(c->ev1));
+		float ms = 0.f;
+		CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+		t->kernelExec = (uint32_t)(ms * 1000.0f + 0.5f);
+		t->totalTime = t->kernelExec;
+	}
+	return PB_OK;
+}
+
+int pb_wait_finish(pb_ctx *c, int queue) {
+	if (!c) return fail(PB_ERR_ARG, "null context");
+	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
+	CU(cudaSetDevice(c->dev));
+	CU(cudaStreamSynchronize(c->q[queue]));
+	return PB_OK;
+}
+
+int pb_queue_wait_queue(pb_ctx *c, int queue, int on_queue) {
+	if (!c) return fail(PB_ERR_ARG, "null context");
+	if (queue < 0 || queue > 2 || on_queue < 0 || on_queue > 2) return fail(PB_ERR_ARG, "bad queue");
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	CU(cudaSetDevice(c->dev));
+	CU(cudaEventRecord(c->ev_x, c->q[on_queue]));
+	CU(cudaStreamWaitEvent(c->q[queue], c->ev_x, 0));
+	return PB_OK;
+}
+
+int pb_chain_begin(pb_ctx *c) {
+	if (!c) return fail(PB_ERR_ARG, "null context");
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	if (c->recording) return fail(PB_ERR_STATE, "already recording");
+	c->recording = new pb_chain;
+	c->recording->ctx = c;
+	return PB_OK;
+}
+
+int pb_chain_end(pb_ctx *c, pb_chain **out) {
+	if (!c || !out) return fail(PB_ERR_ARG, "null argument");
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	if (!c->recording) return fail(PB_ERR_STATE, "not recording");
+	*out = c->recording;
+	c->recording = nullptr;
+	return PB_OK;
+}
+
+int pb_chain_info(pb_chain *ch, int *launches, int *complete) {
+	if (!ch) return fail(PB_ERR_ARG, "null chain");
+	if (launches) *launches = (int)ch->items.size();
+	if (complete) *complete = ch->complete ? 1 : 0;
+	return PB_OK;
+}
+
+int pb_chain_replay(pb_chain *ch, int queue) {
+	if (!ch || queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad argument");
+	pb_ctx *c = ch->ctx;
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	CU(cudaSetDevice(c->dev));
+	for (const auto &it : ch->items) {
+		cudaError_t e = pb::launch_fused(c->q[queue], it.d, it.out_rgba);
+		if (e != cudaSuccess) return fail(PB_ERR_CUDA, "chain replay: %s", cudaGetErrorString(e));
+		c->stats.kernel_launches++;
+		c->stats.fused_launches++;
+	}
+	return PB_OK;
+}
+
+int pb_chain_destroy(pb_chain *ch) {
+	if (!ch) return PB_OK;
+	pb_ctx *c = ch->ctx;
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	cudaSetDevice(c->dev);
+	for (auto &it : ch->items) {
+		it.keep.clear();
+		if (it.out_buf) buf_release_locked(it.out_buf);
+	}
+	delete ch;
+	return PB_OK;
+}
+
+struct pb_event {
+	pb_ctx *ctx;
+	cudaEvent_t ev;
+};
+
+int pb_event_create(pb_ctx *c, pb_event **out) {
+	if (!c || !out) return fail(PB_ERR_ARG, "null argument");
+	CU(cudaSetDevice(c->dev));
+	auto *e = new pb_event{c, nullptr};
+	CU(cudaEventCreate(&e->ev));
+	*out = e;
+	return PB_OK;
+}
+int pb_event_record(pb_event *e, int queue) {
+	if (!e || queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad argument");
+	CU(cudaSetDevice(e->ctx->dev));
+	CU(cudaEventRecord(e->ev, e->ctx->q[queue]));
+	return PB_OK;
+}
+int pb_event_sync(pb_event *e) {
+	if (!e) return fail(PB_ERR_ARG, "null event");
+	CU(cudaEventSynchronize(e->ev));
+	return PB_OK;
+}
+int pb_event_elapsed_ms(pb_event *a, pb_event *b, float *ms) {
+	if (!a || !b || !ms) return fail(PB_ERR_ARG, "null argument");
+	CU(cudaEventElapsedTime(ms, a->ev, b->ev));
+	return PB_OK;
+}
+int pb_event_destroy(pb_event *e) {
+	if (e) {
+		cudaEventDestroy(e->ev);
+		delete e;
+	}
+	return PB_OK;
+}
+
+void *pb_ctx_stream(pb_ctx *c, int queue) {
+	if (!c || queue < 0 || queue > 2) return nullptr;
+	return (void *)c->q[queue];
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+"""Oracle-side evaluation of a harness scene: the reference's UNFUSED stage sequence
+(v210 read -> transform -> transition -> combine -> v210 write) with RGBA-f32
+intermediates, every stage the CPU restatement in oracle/."""
+from __future__ import annotations
+
+import numpy as np
+
+import oracle
+
+_XF_KEYS = ("flipH", "flipV", "anchorX", "anchorY", "scaleX", "scaleY", "offsetX", "offsetY", "rotate")
+
+
+def _or(v, d):
+    return v if v else d   # JS `x || d`
+
+
+def xf_matrix(W, H, xf):
+    return oracle.transform_matrix(W, H, bool(xf.get("flipH")), bool(xf.get("flipV")), _or(xf.get("anchorX"), 0.0),
+                                   _or(xf.get("anchorY"), 0.0), _or(xf.get("scaleX"), 1.0), _or(xf.get("scaleY"), 1.0),
+                                   _or(xf.get("offsetX"), 0.0), _or(xf.get("offsetY"), 0.0), _or(xf.get("rotate"), 0.0))
+
+
+class SceneOracle:
+    def __init__(self, scene):
+        self.s = scene
+        self.W, self.H = scene["width"], scene["height"]
+        cr, cw = scene.get("colRead", "709"), scene.get("colWork", "709")
+        self.cm_r = oracle.ycbcr2rgb_matrix(cr)
+        self.lut_r = oracle.gamma2linear_lut(cr)
+        self.gamut = oracle.rgb2rgb_matrix(cr, cw)
+        self.cm_w = oracle.rgb2ycbcr_matrix(cw)
+        self.lut_w = oracle.linear2gamma_lut(cw)
+
+    def source(self, src, sw, sh, xf):
+        rgba = oracle.v210_read(src, sw, sh, self.cm_r, self.lut_r, self.gamut)
+        if xf is None:
+            return rgba
+        return oracle.transform(rgba, xf_matrix(self.W, self.H, xf), self.W, self.H)
+
+    def layer(self, L):
+        a = self.source(L["src"], L["sw"], L["sh"], L.get("xf"))
+        t = L.get("transition")
+        if not t:
+            return a
+        b = self.source(t["src"], t["sw"], t["sh"], t.get("xf"))
+        if t["type"] == "dissolve":
+            return oracle.dissolve(a, b, t["mix"])
+        m = self.source(t["mask"], t["mask_sw"], t["mask_sh"], t.get("mask_xf"))
+        return oracle.wipe_mask(a, b, m)
+
+    def composite(self):
+        layers = [self.layer(L) for L in self.s["layers"]]
+        return layers[0] if len(layers) == 1 else oracle.combine(layers)
+
+    def packed(self, interlace=0, out=None):
+        return oracle.v210_write(self.composite(), self.W, self.H, interlace, self.cm_w, self.lut_w, out=out)

@@ -1,0 +1,197 @@
+"""The fused chain against the oracle's unfused stage sequence, driven through the
+harness that calls the operators like phaneron's mixer/transitioner/combiner/consumer do.
+Packed output: bit-exact bytes.  RGBA composite (materialised): bit-exact floats (0 ulp)."""
+import numpy as np
+import pytest
+
+from phaneron_b200.harness import ChannelHarness
+from phaneron_b200.process.packer import Interlace
+from phaneron_b200.scenes import IDENTITY_XF, layered_scene, make_frame, pip, single_layer_scene
+
+from gpu_util import Env, assert_bits_equal, run
+from scene_oracle import SceneOracle
+
+pytestmark = pytest.mark.gpu
+
+
+async def _run_scene(scene, deferred=True):
+    async with Env(deferred) as env:
+        h = ChannelHarness(env.ctx, scene, env.pj)
+        await h.init()
+        before = env.ctx.stats()
+        out = await h.run_frame()
+        after = env.ctx.stats()
+        return out, {k: after[k] - before[k] for k in after}
+
+
+@pytest.mark.parametrize("inputs", ["ramp", "noise"])
+@pytest.mark.parametrize("variant", ["plain", "mix", "wipe"])
+def test_four_layer_scene_fused_vs_oracle(inputs, variant):
+    """BASELINE config 3 shape (4-layer Mix/Wipe composite, 709 -> 2020) at a size the oracle finishes in seconds"""
+    scene = layered_scene(480, 270, 4, inputs, variant, "709", "2020")
+    out, st = run(_run_scene(scene))
+    assert np.array_equal(out, SceneOracle(scene).packed())
+    # the whole layer graph collapsed into ONE launch and no RGBA frame touched HBM
+    assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0
+
+
+@pytest.mark.parametrize("n_layers", [1, 2, 3, 8])
+def test_layer_counts(n_layers):
+    scene = layered_scene(384, 216, n_layers, "noise", "plain", "709", "709")
+    out, st = run(_run_scene(scene))
+    assert np.array_equal(out, SceneOracle(scene).packed())
+    assert st["kernel_launches"] == 1
+
+
+def test_eager_mode_matches_deferred_and_oracle():
+    scene = layered_scene(384, 216, 3, "noise", "mix", "709", "2020")
+    eager, st_e = run(_run_scene(scene, deferred=False))
+    fused, st_f = run(_run_scene(scene, deferred=True))
+    ref = SceneOracle(scene).packed()
+    assert np.array_equal(eager, ref) and np.array_equal(fused, ref)
+    # eager = the reference's launch structure: 4 reads + 4 transforms + 1 dissolve + 1 combine + 1 write
+    assert st_e["kernel_launches"] == 11 and st_f["kernel_launches"] == 1
+
+
+def test_single_layer_config2_passthrough_combine():
+    """BASELINE config 2: ToRGBA -> Combine (0/1 layers: passthrough, combiner.ts:219-228) -> FromRGBA"""
+    for with_mixer in (False, True):
+        scene = single_layer_scene(1920, 1080, "ramp", with_mixer)
+        out, st = run(_run_scene(scene))
+        assert np.array_equal(out, SceneOracle(scene).packed())
+        assert st["kernel_launches"] == 1
+        if not with_mixer:
+            assert np.array_equal(out, scene["layers"][0]["src"])   # round trip of the fixture
+
+
+def test_rotated_and_scaled_layers():
+    w, h = 480, 270
+    scene = layered_scene(w, h, 3, "noise", "plain", "709", "709")
+    scene["layers"][1]["xf"] = dict(pip(0.6, 0.2, 0.1), rotate=0.04)
+    scene["layers"][2]["xf"] = dict(IDENTITY_XF, scaleX=1.3, scaleY=0.7, offsetX=0.11, flipH=True)
+    out, st = run(_run_scene(scene))
+    assert np.array_equal(out, SceneOracle(scene).packed())
+    assert st["kernel_launches"] == 1
+
+
+def test_sources_of_different_sizes():
+    """a 720p and a ragged 1280-wide source (Q1 tail) transformed into a 480x270 channel"""
+    w, h = 480, 270
+    scene = layered_scene(w, h, 2, "ramp", "plain", "709", "709")
+    scene["layers"][0].update(src=make_frame("ramp", 1280, 72, 0), sw=1280, sh=72)
+    scene["layers"][1].update(src=make_frame("noise", 960, 540, 3), sw=960, sh=540)
+    out, _ = run(_run_scene(scene))
+    assert np.array_equal(out, SceneOracle(scene).packed())
+
+
+def test_ragged_output_width_1280():
+    scene = layered_scene(1280, 72, 2, "ramp", "plain", "709", "709")
+    out, _ = run(_run_scene(scene))
+    assert np.array_equal(out, SceneOracle(scene).packed())
+
+
+def test_interlaced_consumer_two_fields_one_buffer():
+    """macadamConsumer.ts:224-244: two consecutive channel frames fill top then bottom lines"""
+    async def go():
+        scene = layered_scene(480, 270, 2, "noise", "plain", "709", "709")
+        scene["interlaced"] = True
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            dests = await h.fromRGBA.createDests("il")
+            dests[0].fill(0)
+            await dests[0].hostAccess("writeonly")
+            for il in (Interlace.TopField, Interlace.BottomField):
+                ups = await h.upload_all(int(il))
+                frame = await h.compose(ups, int(il))
+                await h.consume(frame, dests, il, download=(il == Interlace.BottomField))
+            so = SceneOracle(scene)
+            ref = np.zeros_like(dests[0].host)
+            so.packed(1, ref)
+            so.packed(3, ref)
+            assert np.array_equal(dests[0].host, ref)
+    run(go())
+
+
+def test_deferred_frame_materialises_on_host_read():
+    """ScreenConsumer / ROUTE style access: hostAccess('readonly') on a frame that only
+    exists as an expression must produce the RGBA floats the unfused path would"""
+    async def go():
+        scene = layered_scene(384, 216, 3, "noise", "wipe", "709", "2020")
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            ups = await h.upload_all(0)
+            frame = await h.compose(ups, 0)
+            assert frame.deferred
+            got = await env.fetch(frame, 384, 216)
+            assert not frame.deferred
+            assert_bits_equal(got, SceneOracle(scene).composite(), "materialised composite")
+            # and it can still feed the writer afterwards
+            dests = await h.consume(frame)
+            assert np.array_equal(dests[0].host, SceneOracle(scene).packed())
+    run(go())
+
+
+def test_chain_replay_reproduces_the_frame():
+    async def go():
+        scene = layered_scene(480, 270, 4, "noise", "mix", "709", "2020")
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            chain, dests = await h.record_chain()
+            assert chain.complete and chain.launches == 1
+            dests[0].fill(0)
+            await dests[0].hostAccess("writeonly")
+            await dests[0].hostAccess("none")
+            chain.replay()
+            await env.ctx.waitFinish(env.ctx.queue.process)
+            await dests[0].hostAccess("readonly")
+            assert np.array_equal(dests[0].host, SceneOracle(scene).packed())
+            chain.destroy()
+    run(go())
+
+
+def test_buffers_are_recycled_not_leaked():
+    async def go():
+        scene = layered_scene(384, 216, 3, "ramp", "mix", "709", "709")
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            await h.run_frame()
+            live0 = env.ctx.stats()["dev_bytes_live"]
+            for _ in range(5):
+                await h.run_frame()
+            st = env.ctx.stats()
+            assert st["dev_bytes_live"] == live0
+    run(go())
+
+
+def test_full_size_2160p_properties():
+    """BASELINE config 3 at full size.  The oracle would take minutes here, so use
+    size-independent properties: (1) an opaque full-frame identity top layer over anything
+    equals that layer alone; (2) a dissolve at mix=1 equals input0, at mix=0 input1;
+    (3) fused == eager byte for byte."""
+    async def go():
+        w, h = 3840, 2160
+        async with Env() as env:
+            base = layered_scene(w, h, 4, "ramp", "plain", "709", "2020")
+            top_only = dict(base, layers=[base["layers"][0]])
+            covered = dict(base, layers=[base["layers"][1], base["layers"][2], base["layers"][0]])
+            async def frame_of(scene):
+                hs = ChannelHarness(env.ctx, scene, env.pj)
+                await hs.init()
+                return await hs.run_frame()
+            a = await frame_of(top_only)
+            b = await frame_of(covered)
+            # identity Transform blends row 0 / column 0 with the transparent border (Q6), so
+            # the top layer is not opaque there; compare everything else
+            words = lambda x: x.view(np.uint32).reshape(h, -1)
+            assert np.array_equal(words(a)[1:, 4:], words(b)[1:, 4:])
+            mix1 = dict(base, layers=[dict(base["layers"][0], transition=dict(type="dissolve", mix=1.0, src=base["layers"][1]["src"], sw=w, sh=h, xf=dict(IDENTITY_XF)))])
+            assert np.array_equal(await frame_of(mix1), a)
+            fused = await frame_of(base)
+            env.ctx.setDeferred(False)
+            eager = await frame_of(base)
+            assert np.array_equal(fused, eager)
+    run(go())
