@@ -7,11 +7,16 @@
 // to ONE kernel launch (pb_fused.cu).
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace pb {
 
 constexpr int kMaxLayers = 8;   // combine_N inputs (combiner.ts builds N = number of layers)
 constexpr int kMaxReadConsts = 8;
+constexpr int kMaxRingLeaves = 8;    // strip kernel: leaves with a shared-memory row ring
+constexpr int kStripPx = 192;        // output pixels per strip (= threads per CTA = 32 v210 groups)
+constexpr int kRingGroups = 66;      // source v210 groups a ring row can hold
+constexpr int kRingRow = kRingGroups * 6;
 
 enum LeafKind : int { LEAF_NONE = 0, LEAF_V210 = 1, LEAF_RGBA_F32 = 2 };
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
@@ -39,6 +44,12 @@ struct Leaf {
 	int has_xf;        // 0: sample texel (x,y) directly; 1: Transform (transform.ts:36-59)
 	int xf_w, xf_h;    // dimensions of the Transform's output image
 	float m[6];        // rows 0 and 1 of the 3x3 transformMatrix
+	// strip kernel only: exact per-column / per-row sampling tables built on the host
+	// ({i0, bits(a)} per output x, {j0, bits(b)} per output y) and the leaf's ring slot
+	const int2 *col_tab;
+	const int2 *row_tab;
+	int ring;          // index of this leaf's row ring in shared memory, -1 if none
+	int pad_;
 };
 
 struct Layer {
@@ -54,6 +65,7 @@ struct FusedDesc {
 	int out_pitch;     // bytes per output line
 	int n_rc;
 	void *out;
+	int n_ring, band_lines;   // strip kernel
 	WriteConsts wc;
 	ReadConsts rc[kMaxReadConsts];
 	Layer layers[kMaxLayers];

@@ -23,6 +23,9 @@ cudaError_t launch_yadif(cudaStream_t s, const void *prev, const void *cur, cons
 // Fused chain: N layers of (leaf | dissolve | wipe) -> combine -> v210 pack, one launch.
 // out_rgba != nullptr writes the composite as RGBA-f32 instead of packing (materialise).
 cudaError_t launch_fused(cudaStream_t s, const FusedDesc &d, void *out_rgba);
+// Marching-strip kernel (pb_strip.cu); the descriptor must have been prepared (tables, rings).
+cudaError_t launch_fused_strip(cudaStream_t s, const FusedDesc &d);
+size_t strip_smem_bytes(const FusedDesc &d);
 // name of the kernel variant launch_fused would pick (for stats / tests)
 const char *fused_variant(const FusedDesc &d);
 

@@ -10,7 +10,9 @@
 // RGBA leaf.  Host reads of a deferred frame materialise it on demand.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -120,6 +122,15 @@ struct pb_ctx {
 	pb_stats stats{};
 	cudaDeviceProp prop{};
 	struct pb_chain *recording = nullptr;
+	// sampling tables of the strip kernel, cached per (transform, source dims, output dims)
+	struct SampleTab {
+		float m[6];
+		int sw, sh, W, H, has_xf;
+		int2 *dcol = nullptr, *drow = nullptr;
+		std::vector<int2> hcol;
+	};
+	std::vector<SampleTab> tabs;
+	bool allow_strip = true;
 };
 
 struct pb_buf {
@@ -144,6 +155,7 @@ struct pb_chain {
 	pb_ctx *ctx = nullptr;
 	struct Item {
 		pb::FusedDesc d;
+		bool strip = false;
 		void *out_rgba;
 		std::vector<std::shared_ptr<void>> keep;   // expression nodes (hold the leaf buffers)
 		pb_buf *out_buf;                           // addref'd destination
@@ -422,10 +434,141 @@ struct Compiler {
 	}
 };
 
-void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf) {
+
+// ---- strip kernel preparation -----------------------------------------------------------------
+// Exact host evaluation of the sampling position of transform.ts:54-57 followed by the
+// OpenCL 1.2 8.2 linear-filter prologue, for one axis of a separable (no rotation / shear)
+// transform.  Same operations, same order, same rounding as pb_device.cuh transform_pos() +
+// sample_linear_clamp(); the host compiler runs with -ffp-contract=off.
+inline int2 axis_entry(int o, int out_n, int src_n, float m_scale, float m_other, float m_off, bool is_x, bool has_xf) {
+	int2 e;
+	if (!has_xf) {   // direct read of texel o: weight 1 on (o, o), nothing on o+1
+		e.x = o;
+		e.y = 0;
+		return e;
+	}
+	const float ic = (float)o / (float)out_n - 0.5f;
+	// dot3(ix, iy, 1, m): t = ix*m[0]; t = fma(iy, m[1], t); t = fma(1, m[2], t), with the cross term exactly zero
+	float t;
+	if (is_x) {
+		t = ic * m_scale;                 // ix * m0
+		t = fmaf(0.0f, m_other, t);       // iy * 0 (m_other == 0 is an eligibility condition; iy is finite)
+	} else {
+		t = 0.0f * m_other;               // ix * 0
+		t = fmaf(ic, m_scale, t);         // iy * m4
+	}
+	t = fmaf(1.0f, m_off, t);
+	const float p = t + 0.5f;
+	const float um = p * (float)src_n - 0.5f;
+	const float fu = floorf(um);
+	const float a = um - fu;
+	int i0;
+	if (!(fu >= -2.0f)) i0 = -2; else if (fu > (float)src_n) i0 = src_n; else i0 = (int)fu;
+	e.x = i0;
+	memcpy(&e.y, &a, 4);
+	return e;
+}
+
+int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, pb_ctx::SampleTab **out) {
+	for (auto &t : c->tabs)
+		if (t.sw == lf.w && t.sh == lf.h && t.W == W && t.H == H && t.has_xf == lf.has_xf &&
+		    (!lf.has_xf || 0 == memcmp(t.m, lf.m, sizeof t.m))) {
+			*out = &t;
+			return PB_OK;
+		}
+	if (c->tabs.size() >= 256) {   // parameters are animating: start over (rare; tables are tiny)
+		CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));
+		for (auto &t : c->tabs) {
+			cudaFree(t.dcol);
+			cudaFree(t.drow);
+		}
+		c->tabs.clear();
+	}
+	pb_ctx::SampleTab t;
+	memcpy(t.m, lf.m, sizeof t.m);
+	t.sw = lf.w; t.sh = lf.h; t.W = W; t.H = H; t.has_xf = lf.has_xf;
+	t.hcol.resize(W);
+	std::vector<int2> hrow(H);
+	for (int x = 0; x < W; ++x) t.hcol[x] = axis_entry(x, W, lf.w, lf.m[0], lf.m[1], lf.m[2], true, lf.has_xf != 0);
+	for (int y = 0; y < H; ++y) hrow[y] = axis_entry(y, H, lf.h, lf.m[4], lf.m[3], lf.m[5], false, lf.has_xf != 0);
+	CU(cudaMalloc(&t.dcol, (size_t)W * sizeof(int2)));
+	CU(cudaMalloc(&t.drow, (size_t)H * sizeof(int2)));
+	CU(cudaMemcpyAsync(t.dcol, t.hcol.data(), (size_t)W * sizeof(int2), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+	CU(cudaMemcpyAsync(t.drow, hrow.data(), (size_t)H * sizeof(int2), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+	CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // hrow is a local; once per new transform only
+	c->tabs.push_back(std::move(t));
+	*out = &c->tabs.back();
+	return PB_OK;
+}
+
+// Decide whether the marching-strip kernel can evaluate this descriptor and, if so, attach the
+// sampling tables and ring slots.  Returns 1 = strip, 0 = use the generic kernel, <0 = error.
+int prepare_strip(pb_ctx *c, pb::FusedDesc &d) {
+	if (!c->allow_strip) return 0;
+	if (d.out_w % 48 != 0 || d.out_h < 2) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
+	int n_ring = 0;
+	for (int l = 0; l < d.n_layers; ++l) {
+		pb::Layer &ly = d.layers[l];
+		pb::Leaf *leaves[3] = {&ly.a, &ly.b, &ly.mask};
+		const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
+		for (int q = 0; q < nleaf; ++q) {
+			pb::Leaf &lf = *leaves[q];
+			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) return 0;
+			if (lf.has_xf) {
+				for (float v : lf.m)
+					if (!(v == v) || v > 1e30f || v < -1e30f) return 0;
+				if (lf.m[1] != 0.0f || lf.m[3] != 0.0f) return 0;   // rotation / shear
+				if (lf.xf_w != d.out_w || lf.xf_h != d.out_h) return 0;
+			} else if (lf.w != d.out_w || lf.h != d.out_h) {
+				return 0;
+			}
+			if (n_ring >= pb::kMaxRingLeaves) return 0;
+			pb_ctx::SampleTab *t;
+			int r = get_tabs(c, lf, d.out_w, d.out_h, &t);
+			if (r) return r;
+			// every strip's source footprint must fit a ring row
+			for (int x0 = 0; x0 < d.out_w; x0 += pb::kStripPx) {
+				const int x1 = std::min(x0 + pb::kStripPx, d.out_w) - 1;
+				const int ia = t->hcol[x0].x, ib = t->hcol[x1].x;
+				int lo = std::min(ia, ib), hi = std::max(ia, ib) + 1;
+				if (hi < 0 || lo >= lf.w) continue;
+				lo = std::max(lo, 0);
+				hi = std::min(hi, lf.w - 1);
+				if (hi / 6 - lo / 6 + 1 > pb::kRingGroups) return 0;
+			}
+			lf.col_tab = t->dcol;
+			lf.row_tab = t->drow;
+			lf.ring = n_ring++;
+		}
+	}
+	d.n_ring = n_ring;
+	const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
+	const int n_strips = (d.out_w + pb::kStripPx - 1) / pb::kStripPx;
+	const int sms = c->prop.multiProcessorCount > 0 ? c->prop.multiProcessorCount : 148;
+	const int bands = std::max(1, (4 * sms) / n_strips);
+	d.band_lines = std::max(16, (n_lines + bands - 1) / bands);
+	return 1;
+}
+
+// launch a compiled descriptor (strip kernel when eligible); *strip_out reports the choice
+int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, bool *strip_out) {
+	bool strip = false;
+	if (!out_rgba) {
+		int r = prepare_strip(c, d);
+		if (r < 0) return r;
+		strip = r == 1;
+	}
+	cudaError_t e = strip ? pb::launch_fused_strip(s, d) : pb::launch_fused(s, d, out_rgba);
+	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (%s): %s", strip ? "strip" : "generic", cudaGetErrorString(e));
+	if (strip_out) *strip_out = strip;
+	return PB_OK;
+}
+
+void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf, bool strip = false) {
 	if (!c->recording) return;
 	pb_chain::Item it;
 	it.d = cc.d;
+	it.strip = strip;
 	it.out_rgba = out_rgba;
 	for (const auto &k : cc.keep) it.keep.push_back(std::static_pointer_cast<void>(k));
 	it.out_buf = out_buf;
@@ -614,9 +757,11 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 				cc.d.interlace = interlace;
 				cc.d.out = out->dev;
 				cc.d.out_pitch = v210_pitch_bytes(W);
-				e = pb::launch_fused(s, cc.d, nullptr);
+				bool strip = false;
+				if ((r = launch_desc(c, s, cc.d, nullptr, &strip))) return r;
 				c->stats.fused_launches++;
-				record_launch(c, cc, nullptr, out);
+				if (strip) c->stats.strip_launches++;
+				record_launch(c, cc, nullptr, out, strip);
 				fused_launch = true;
 				break;
 			}
@@ -809,6 +954,7 @@ int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out) {
 	auto *c = new pb_ctx;
 	c->dev = gpu_index;
 	c->flags = flags;
+	c->allow_strip = !(flags & PB_CTX_NO_STRIP);
 	CU(cudaGetDeviceProperties(&c->prop, gpu_index));
 	for (auto &q : c->q) CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
 	CU(cudaEventCreate(&c->ev0));
@@ -823,6 +969,10 @@ int pb_ctx_destroy(pb_ctx *c) {
 	cudaSetDevice(c->dev);
 	cudaDeviceSynchronize();
 	c->pool.destroy();
+	for (auto &t : c->tabs) {
+		cudaFree(t.dcol);
+		cudaFree(t.drow);
+	}
 	for (auto &q : c->q) cudaStreamDestroy(q);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
@@ -853,6 +1003,7 @@ int pb_ctx_set_flags(pb_ctx *c, unsigned flags) {
 	if (!c) return fail(PB_ERR_ARG, "null context");
 	std::lock_guard<std::recursive_mutex> lk(c->mu);
 	c->flags = flags;
+	c->allow_strip = !(flags & PB_CTX_NO_STRIP);
 	return PB_OK;
 }
 
@@ -1119,10 +1270,11 @@ int pb_chain_replay(pb_chain *ch, int queue) {
 	std::lock_guard<std::recursive_mutex> lk(c->mu);
 	CU(cudaSetDevice(c->dev));
 	for (const auto &it : ch->items) {
-		cudaError_t e = pb::launch_fused(c->q[queue], it.d, it.out_rgba);
+		cudaError_t e = it.strip ? pb::launch_fused_strip(c->q[queue], it.d) : pb::launch_fused(c->q[queue], it.d, it.out_rgba);
 		if (e != cudaSuccess) return fail(PB_ERR_CUDA, "chain replay: %s", cudaGetErrorString(e));
 		c->stats.kernel_launches++;
 		c->stats.fused_launches++;
+		if (it.strip) c->stats.strip_launches++;
 	}
 	return PB_OK;
 }

@@ -168,6 +168,7 @@ class clContext:
         self.overlapping = bool(options.get("overlapping", True))
         # product extension: defer RGBA intermediates and fuse the chain at packed sinks
         self.deferred = bool(options.get("deferred", True))
+        self.stripKernel = bool(options.get("stripKernel", True))   # False: always the generic fused kernel
         self.queue = _Queues()
         self._h = 0
 
@@ -175,8 +176,11 @@ class clContext:
         if self.platformIndex != 0:
             raise PhaneronError("phaneron_b200 exposes one platform (CUDA); platformIndex must be 0")
         h = C.c_void_p()
-        check(_lib.lib().pb_ctx_create(self.deviceIndex, _lib.CTX_DEFER if self.deferred else 0, C.byref(h)))
+        check(_lib.lib().pb_ctx_create(self.deviceIndex, self._flags(), C.byref(h)))
         self._h = h.value
+
+    def _flags(self) -> int:
+        return (_lib.CTX_DEFER if self.deferred else 0) | (0 if self.stripKernel else _lib.CTX_NO_STRIP)
 
     def close(self) -> None:
         if self._h:
@@ -190,7 +194,11 @@ class clContext:
 
     def setDeferred(self, on: bool) -> None:
         self.deferred = bool(on)
-        check(_lib.lib().pb_ctx_set_flags(self._need(), _lib.CTX_DEFER if on else 0))
+        check(_lib.lib().pb_ctx_set_flags(self._need(), self._flags()))
+
+    def setStripKernel(self, on: bool) -> None:
+        self.stripKernel = bool(on)
+        check(_lib.lib().pb_ctx_set_flags(self._need(), self._flags()))
 
     def getPlatformInfo(self) -> Dict[str, Any]:
         buf = C.create_string_buffer(1024)

@@ -195,3 +195,95 @@ def test_full_size_2160p_properties():
             eager = await frame_of(base)
             assert np.array_equal(fused, eager)
     run(go())
+
+
+# ---- the marching-strip kernel vs the generic fused kernel vs the oracle --------------------------
+async def _run_scene_variant(scene, strip):
+    async with Env(True) as env:
+        env.ctx.setStripKernel(strip)
+        h = ChannelHarness(env.ctx, scene, env.pj)
+        await h.init()
+        before = env.ctx.stats()
+        out = await h.run_frame()
+        after = env.ctx.stats()
+        return out, {k: after[k] - before[k] for k in after}
+
+
+def _xf(**kw):
+    return dict(IDENTITY_XF, **kw)
+
+
+STRIP_SCENES = {
+    "north_star_mix": lambda: layered_scene(480, 270, 4, "noise", "mix", "709", "2020"),
+    "north_star_wipe": lambda: layered_scene(480, 270, 4, "noise", "wipe", "709", "2020"),
+    "full_strip_width": lambda: layered_scene(768, 54, 3, "noise", "plain", "709", "709"),
+    "single_direct": lambda: single_layer_scene(384, 100, "noise", False),
+    "flips_and_upscale": lambda: _with_xf(layered_scene(480, 270, 3, "noise", "plain", "709", "709"),
+                                          [_xf(flipH=True), _xf(flipV=True, scaleX=1.5, scaleY=2.25, offsetX=0.1),
+                                           _xf(flipH=True, flipV=True, scaleX=0.75, scaleY=0.6, offsetY=-0.2)]),
+    "odd_fractions": lambda: _with_xf(layered_scene(480, 270, 2, "noise", "plain", "709", "709"),
+                                      [_xf(scaleX=1.0001, scaleY=0.9999, offsetX=0.00013), _xf(scaleX=0.731, scaleY=0.577, offsetX=0.21, offsetY=0.13)]),
+    "mostly_outside": lambda: _with_xf(layered_scene(480, 270, 2, "noise", "plain", "709", "709"),
+                                       [_xf(offsetX=0.97, offsetY=-0.96), _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.7)]),
+}
+
+
+def _with_xf(scene, xfs):
+    for L, xf in zip(scene["layers"], xfs):
+        L["xf"] = xf
+    return scene
+
+
+@pytest.mark.parametrize("name", sorted(STRIP_SCENES))
+def test_strip_kernel_matches_generic_and_oracle(name):
+    scene = STRIP_SCENES[name]()
+    fast, st_fast = run(_run_scene_variant(scene, True))
+    slow, st_slow = run(_run_scene_variant(scene, False))
+    assert st_fast["strip_launches"] == 1 and st_slow["strip_launches"] == 0
+    assert st_fast["kernel_launches"] == 1 and st_slow["kernel_launches"] == 1
+    ref = SceneOracle(scene).packed()
+    assert np.array_equal(slow, ref)
+    assert np.array_equal(fast, ref)
+
+
+def test_strip_kernel_declines_what_it_cannot_do():
+    """rotation, a deep downscale (footprint wider than a ring row) and ragged widths fall back to the generic kernel"""
+    rot = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(rotate=0.01)])
+    deep = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(scaleX=0.2, scaleY=0.2)])
+    ragged = layered_scene(1280, 36, 2, "ramp", "plain")
+    for scene in (rot, deep, ragged):
+        out, st = run(_run_scene_variant(scene, True))
+        assert st["strip_launches"] == 0 and st["fused_launches"] == 1
+        assert np.array_equal(out, SceneOracle(scene).packed())
+
+
+def test_strip_kernel_interlaced_fields():
+    async def go():
+        scene = layered_scene(480, 270, 3, "noise", "mix", "709", "2020")
+        scene["interlaced"] = True
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            dests = await h.fromRGBA.createDests("il")
+            dests[0].fill(0)
+            await dests[0].hostAccess("writeonly")
+            for il in (Interlace.TopField, Interlace.BottomField):
+                ups = await h.upload_all(int(il))
+                frame = await h.compose(ups, int(il))
+                await h.consume(frame, dests, il, download=(il == Interlace.BottomField))
+            assert env.ctx.stats()["strip_launches"] == 2
+            so = SceneOracle(scene)
+            ref = np.zeros_like(dests[0].host)
+            so.packed(1, ref)
+            so.packed(3, ref)
+            assert np.array_equal(dests[0].host, ref)
+    run(go())
+
+
+def test_strip_kernel_full_size_equals_generic_2160p():
+    """BASELINE config 3 at full size: the strip kernel must reproduce the generic kernel byte for byte"""
+    scene = layered_scene(3840, 2160, 4, "noise", "mix", "709", "2020")
+    fast, st = run(_run_scene_variant(scene, True))
+    slow, _ = run(_run_scene_variant(scene, False))
+    assert st["strip_launches"] == 1
+    assert np.array_equal(fast, slow)
