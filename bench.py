@@ -178,7 +178,8 @@ async def run_ours(args, rank, world, local_rank):
             dist.barrier()
 
     lib = _lib.lib()
-    ctx = clContext({"platformIndex": 0, "deviceIndex": local_rank, "overlapping": True})
+    ctx = clContext({"platformIndex": 0, "deviceIndex": local_rank, "overlapping": True,
+                     "marchKernel": args.kernel != "generic", "rawLut": args.kernel == "march_raw"})
     await ctx.initialise()
 
     # ---- scenes: enough distinct input sets that a replay never finds its inputs in L2 ----
@@ -308,6 +309,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inputs", default="noise", choices=["ramp", "noise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", default="march", choices=["march", "march_raw", "generic"],
+                    help="march: fused kernel, gamma tables in shared memory (default); march_raw: same kernel gathering "
+                         "from the raw tables; generic: the fallback fused kernel")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.gpus > 1 and world == 1:

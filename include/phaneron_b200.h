@@ -80,11 +80,13 @@ typedef struct pb_timings {
 typedef struct pb_stats {
 	uint64_t kernel_launches;   /* every CUDA kernel this context launched */
 	uint64_t fused_launches;    /* of which: fused chain launches */
-	uint64_t strip_launches;    /* of which: marching-strip kernel */
+	uint64_t march_launches;    /* of which: the march kernel (pb_march.cu) */
 	uint64_t deferred_nodes;    /* jobs recorded into the frame-expression DAG */
 	uint64_t materialised;      /* deferred RGBA frames that had to be written to HBM */
 	uint64_t h2d_bytes, d2h_bytes;
 	uint64_t dev_bytes_live, dev_bytes_pooled;
+	uint64_t lut_tables;        /* distinct gamma tables seen (by content) */
+	uint64_t lut_tables_d8;     /* of which: held in the lossless one-byte form the march kernel keeps in shared memory */
 } pb_stats;
 
 const char *pb_last_error(void);
@@ -94,8 +96,11 @@ const char *pb_version(void);
    (index.ts:94-102).  flags: bit0 = defer RGBA intermediates and fuse at sinks
    (default behaviour of the product); 0 = eager, one launch per job. */
 #define PB_CTX_DEFER 1u
-/* bit1 = never pick the marching-strip kernel (always the generic fused kernel); for A/B tests */
-#define PB_CTX_NO_STRIP 2u
+/* bit1 = never pick the march kernel (always the generic fused kernel); for A/B tests */
+#define PB_CTX_NO_MARCH 2u
+/* bit2 = march kernel gathers from the raw 256 KiB gamma tables in global memory instead of the
+   one-byte shared-memory form (A/B tests; faster only on very coherent pictures) */
+#define PB_CTX_RAW_LUT 4u
 int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out);
 int pb_ctx_destroy(pb_ctx *ctx);
 /* getPlatformInfo() (index.ts:103-107): JSON text into buf */

@@ -4,7 +4,7 @@
 // frame: leaves are packed source frames (or RGBA-f32 frames that had to be
 // materialised), inner nodes are Transform / Transition / Combine, the root is a
 // packed writer.  The runtime flattens an expression into a FusedDesc and hands it
-// to ONE kernel launch (pb_fused.cu).
+// to ONE kernel launch (pb_march.cu when eligible, else pb_fused.cu).
 #pragma once
 #include <stdint.h>
 #include <vector_types.h>
@@ -13,26 +13,50 @@ namespace pb {
 
 constexpr int kMaxLayers = 8;   // combine_N inputs (combiner.ts builds N = number of layers)
 constexpr int kMaxReadConsts = 8;
-constexpr int kMaxRingLeaves = 8;    // strip kernel: leaves with a shared-memory row ring
-constexpr int kStripPx = 192;        // output pixels per strip (= threads per CTA = 32 v210 groups)
-constexpr int kRingGroups = 66;      // source v210 groups a ring row can hold
-constexpr int kRingRow = kRingGroups * 6;
+constexpr int kMaxLuts = 3;          // march kernel: distinct gamma tables resident in shared memory
+
+// ---- march kernel geometry (pb_march.cu) ---------------------------------------------
+constexpr int kMarchWarps = 16;              // warps per CTA; one persistent CTA per SM
+constexpr int kMarchThreads = kMarchWarps * 32;
+constexpr int kStripGroupsXf = 31;           // output v210 groups per strip when a leaf is bilinear-sampled:
+                                             // 186 px need <= 187 texels = <= 32 source groups at scale 1
+constexpr int kStripGroupsDirect = 32;       // all leaves sampled 1:1
+constexpr int kRowGroups = 64;               // source groups a warp's row buffer can hold
+constexpr int kRowCap = kRowGroups * 6;      // texels per plane
+constexpr int kRowFloats = 3 * kRowCap;      // planar R | G | B
 
 enum LeafKind : int { LEAF_NONE = 0, LEAF_V210 = 1, LEAF_RGBA_F32 = 2 };
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
+
+// Lossless shared-memory form of a 65536-entry gamma table (colourMaths.ts:130-169):
+//   table[i] == bits( base(i) ) + d8[i]      for every i, verified exhaustively when the table is fitted
+//   base(i)   = i < J ? i*kt : s * ex2(G * lg2(i*p + q)) + o      (MUFU.LG2 / MUFU.EX2)
+// The d8 bytes are produced ON the device by the same code that decodes them (pb_lut.cuh).
+struct LutParams {
+	float p, q, G, s, o, kt, Jf;
+	int affine;   // 0: s == 1 and o == 0 (gamma -> linear direction)
+};
 
 // Loader constants (loadSave.ts:41-64): YCbCr->RGB 3x4, gamma->linear LUT, gamut 3x3
 struct ReadConsts {
 	float cm[12];
 	float gamut[9];
-	const float *lut;
-	const uint8_t *lut_res;   // optional smem-residual form (see pb_lut.cuh); may be null
+	const float *lut;     // raw table in global memory (always valid)
+	int lut_slot;         // march kernel: index into FusedDesc::luts, -1 if the table has no compressed form
+	int pad_;
 };
 
 // Saver constants (loadSave.ts:130-150): linear->gamma LUT, RGB->YCbCr 3x4
 struct WriteConsts {
 	float cm[12];
 	const float *lut;
+	int lut_slot;
+	int pad_;
+};
+
+struct LutDesc {
+	const int8_t *d8;   // 65536 bytes in global memory, copied into shared memory by each CTA
+	LutParams lp;
 };
 
 struct Leaf {
@@ -44,12 +68,13 @@ struct Leaf {
 	int has_xf;        // 0: sample texel (x,y) directly; 1: Transform (transform.ts:36-59)
 	int xf_w, xf_h;    // dimensions of the Transform's output image
 	float m[6];        // rows 0 and 1 of the 3x3 transformMatrix
-	// strip kernel only: exact per-column / per-row sampling tables built on the host
-	// ({i0, bits(a)} per output x, {j0, bits(b)} per output y) and the leaf's ring slot
+	// march kernel only: exact per-column / per-row sampling tables built on the host
+	// ({i0, bits(a)} per output x, {j0, bits(b)} per output y) and per-strip source footprints
+	// ({flags, first source group, group count, 0} per strip; flags bit0 = strip touches the image,
+	// bit1 = some tap column of the strip lies outside the image)
 	const int2 *col_tab;
 	const int2 *row_tab;
-	int ring;          // index of this leaf's row ring in shared memory, -1 if none
-	int pad_;
+	const int4 *strip_tab;
 };
 
 struct Layer {
@@ -65,7 +90,12 @@ struct FusedDesc {
 	int out_pitch;     // bytes per output line
 	int n_rc;
 	void *out;
-	int n_ring, band_lines;   // strip kernel
+	// march kernel
+	int strip_groups;  // output groups per strip
+	int n_strips;
+	int n_luts;        // tables to stage in shared memory (0: gather from the raw tables in global memory)
+	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
+	LutDesc luts[kMaxLuts];
 	WriteConsts wc;
 	ReadConsts rc[kMaxReadConsts];
 	Layer layers[kMaxLayers];

@@ -23,9 +23,12 @@ cudaError_t launch_yadif(cudaStream_t s, const void *prev, const void *cur, cons
 // Fused chain: N layers of (leaf | dissolve | wipe) -> combine -> v210 pack, one launch.
 // out_rgba != nullptr writes the composite as RGBA-f32 instead of packing (materialise).
 cudaError_t launch_fused(cudaStream_t s, const FusedDesc &d, void *out_rgba);
-// Marching-strip kernel (pb_strip.cu); the descriptor must have been prepared (tables, rings).
-cudaError_t launch_fused_strip(cudaStream_t s, const FusedDesc &d);
-size_t strip_smem_bytes(const FusedDesc &d);
+// March kernel (pb_march.cu); the descriptor must have been prepared (sampling tables, LUT slots).
+cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms);
+size_t march_smem_bytes(const FusedDesc &d);
+// gamma table -> one-byte-per-entry form (pb_lut.cuh): n_cands candidate models evaluated in one launch
+struct LutFitResult;
+cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *cands_dev, int n_cands, int8_t *d8_out, void *results_dev);
 // name of the kernel variant launch_fused would pick (for stats / tests)
 const char *fused_variant(const FusedDesc &d);
 

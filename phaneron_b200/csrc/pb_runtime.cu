@@ -122,15 +122,34 @@ struct pb_ctx {
 	pb_stats stats{};
 	cudaDeviceProp prop{};
 	struct pb_chain *recording = nullptr;
-	// sampling tables of the strip kernel, cached per (transform, source dims, output dims)
+	// sampling tables of the march kernel, cached per (transform, source dims, output dims, strip width)
 	struct SampleTab {
 		float m[6];
-		int sw, sh, W, H, has_xf;
+		int sw, sh, W, H, has_xf, strip_groups, fits = 1;
+		void *dev = nullptr;
 		int2 *dcol = nullptr, *drow = nullptr;
-		std::vector<int2> hcol;
+		int4 *dstrip = nullptr;
 	};
 	std::vector<SampleTab> tabs;
-	bool allow_strip = true;
+	bool allow_march = true;
+	// gamma tables by content (see lut_table_of)
+	struct LutTable {
+		unsigned long long hash = 0;
+		float *raw = nullptr;      // context-owned copy every ReadConsts/WriteConsts points at
+		int8_t *d8 = nullptr;      // one-byte form, null if no model fits
+		pb::LutParams lp{};
+		int model = -1, dmin = 0, dmax = 0;
+		bool unit_range = false;
+	};
+	struct LutFit {
+		uint64_t version;
+		int table;
+	};
+	std::vector<LutTable> lut_tables;
+	std::vector<LutFit> lut_fits;
+	pb::LutParams lut_cands[4];
+	void *lut_cands_dev = nullptr, *lut_res_dev = nullptr, *lut_scratch = nullptr;
+	uint64_t version_counter = 0;
 };
 
 struct pb_buf {
@@ -142,6 +161,7 @@ struct pb_buf {
 	bool dev_external = false;
 	void *host = nullptr;
 	bool host_dirty = false;   // host face written since the last upload
+	uint64_t version = 0;      // unique id of the device contents (bumped on every upload)
 	NodeP expr;                // non-null: frame exists only as an expression
 	std::string owner;
 };
@@ -155,7 +175,7 @@ struct pb_chain {
 	pb_ctx *ctx = nullptr;
 	struct Item {
 		pb::FusedDesc d;
-		bool strip = false;
+		bool march = false;
 		void *out_rgba;
 		std::vector<std::shared_ptr<void>> keep;   // expression nodes (hold the leaf buffers)
 		pb_buf *out_buf;                           // addref'd destination
@@ -223,6 +243,7 @@ int flush_host(pb_buf *b, cudaStream_t s) {
 	CU(cudaMemcpyAsync(b->dev, b->host, b->bytes, cudaMemcpyHostToDevice, s));
 	b->ctx->stats.h2d_bytes += b->bytes;
 	b->host_dirty = false;
+	b->version = ++b->ctx->version_counter;
 	return PB_OK;
 }
 
@@ -255,6 +276,8 @@ int host_floats(pb_buf *b, int count, float *out, const char *what) {
 	return PB_OK;
 }
 
+int lut_table_of(pb_ctx *c, pb_buf *lut, int *table_out);
+
 int make_read_consts(pb_ctx *c, const pb_param *p, int n, bool ycbcr, pb::ReadConsts *rc, pb_buf **lut_out) {
 	pb_buf *lut, *gamut, *cm = nullptr;
 	int r;
@@ -267,7 +290,10 @@ int make_read_consts(pb_ctx *c, const pb_param *p, int n, bool ycbcr, pb::ReadCo
 	if (lut->bytes < 65536 * 4) return fail(PB_ERR_ARG, "gammaLut must hold 65536 floats");
 	if ((r = flush_host(lut, c->q[PB_QUEUE_PROCESS]))) return r;
 	if (!lut->dev) return fail(PB_ERR_STATE, "gammaLut was never written");
-	rc->lut = (const float *)lut->dev;
+	int table;
+	if ((r = lut_table_of(c, lut, &table))) return r;
+	rc->lut = c->lut_tables[table].raw;   // one pointer per distinct table content
+	rc->lut_slot = -1;
 	*lut_out = lut;
 	return PB_OK;
 }
@@ -282,7 +308,10 @@ int make_write_consts(pb_ctx *c, const pb_param *p, int n, bool ycbcr, pb::Write
 	if (lut->bytes < 65536 * 4) return fail(PB_ERR_ARG, "gammaLut must hold 65536 floats");
 	if ((r = flush_host(lut, c->q[PB_QUEUE_PROCESS]))) return r;
 	if (!lut->dev) return fail(PB_ERR_STATE, "gammaLut was never written");
-	wc->lut = (const float *)lut->dev;
+	int table;
+	if ((r = lut_table_of(c, lut, &table))) return r;
+	wc->lut = c->lut_tables[table].raw;
+	wc->lut_slot = -1;
 	return PB_OK;
 }
 
@@ -435,14 +464,122 @@ struct Compiler {
 };
 
 
-// ---- strip kernel preparation -----------------------------------------------------------------
+// ---- gamma tables: content-deduplicated, with a lossless one-byte form for the march kernel -------
+// Every Loader/Saver uploads its own copy of a 65536-float table (loadSave.ts:69-77, 155-164); five
+// sources mean five identical buffers.  The context keeps ONE device copy per distinct content
+// (keyed by a device-computed hash) plus, when the table is one of the transfer functions of
+// colourMaths.ts:42-128, the d8 form of pb_lut.cuh.  Fitting is a tiny kernel + one blocking
+// read-back, paid once per uploaded table.
+struct TransferSet {
+	double alpha, beta, gamma, delta;
+};
+constexpr TransferSet kTransferSets[] = {
+	{1.099, 0.018, 0.45, 4.5},                   // 601 / 709 / 2020
+	{1.055, 0.0031308, 1.0 / 2.4, 12.92},        // sRGB
+};
+constexpr int kLutCands = 4;
+
+void lut_candidates(pb::LutParams *out) {
+	int n = 0;
+	for (const TransferSet &t : kTransferSets) {
+		pb::LutParams g{};   // gamma2linearLUT (colourMaths.ts:130-149)
+		g.p = (float)(1.0 / (65535.0 * t.alpha));
+		g.q = (float)((t.alpha - 1.0) / t.alpha);
+		g.G = (float)(1.0 / t.gamma);
+		g.s = 1.0f;
+		g.o = 0.0f;
+		g.kt = (float)(1.0 / (65535.0 * t.delta));
+		int J = 0;
+		while (J < 65536 && J / 65535.0 < t.beta * t.delta) ++J;
+		g.Jf = (float)J;
+		g.affine = 0;
+		out[n++] = g;
+		pb::LutParams l{};   // linear2gammaLUT (colourMaths.ts:151-169)
+		l.p = (float)(1.0 / 65535.0);
+		l.q = 0.0f;
+		l.G = (float)t.gamma;
+		l.s = (float)t.alpha;
+		l.o = (float)(-(t.alpha - 1.0));
+		l.kt = (float)(t.delta / 65535.0);
+		J = 0;
+		while (J < 65536 && J / 65535.0 < t.beta) ++J;
+		l.Jf = (float)J;
+		l.affine = 1;
+		out[n++] = l;
+	}
+}
+
+struct FitResultHost {   // mirrors pb::LutFitResult
+	int dmin, dmax;
+	unsigned long long hash;
+	int not_unit, pad;
+};
+
+int lut_table_of(pb_ctx *c, pb_buf *lut, int *table_out) {
+	for (const auto &f : c->lut_fits)
+		if (f.version == lut->version) {
+			*table_out = f.table;
+			return PB_OK;
+		}
+	cudaStream_t s = c->q[PB_QUEUE_PROCESS];
+	if (!c->lut_scratch) {
+		pb::LutParams cands[kLutCands];
+		lut_candidates(cands);
+		memcpy(c->lut_cands, cands, sizeof cands);
+		CU(cudaMalloc(&c->lut_cands_dev, sizeof cands));
+		CU(cudaMemcpyAsync(c->lut_cands_dev, cands, sizeof cands, cudaMemcpyHostToDevice, s));
+		CU(cudaMalloc(&c->lut_res_dev, kLutCands * sizeof(FitResultHost)));
+		CU(cudaMalloc(&c->lut_scratch, (size_t)kLutCands * 65536));
+	}
+	FitResultHost res[kLutCands];
+	for (auto &r : res) r = FitResultHost{INT32_MAX, INT32_MIN, 0ull, 0, 0};
+	CU(cudaMemcpyAsync(c->lut_res_dev, res, sizeof res, cudaMemcpyHostToDevice, s));
+	cudaError_t e = pb::launch_lut_fit(s, (const float *)lut->dev, (const pb::LutParams *)c->lut_cands_dev, kLutCands, (int8_t *)c->lut_scratch, c->lut_res_dev);
+	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "lut fit launch: %s", cudaGetErrorString(e));
+	CU(cudaMemcpyAsync(res, c->lut_res_dev, sizeof res, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	int table = -1;
+	for (size_t i = 0; i < c->lut_tables.size(); ++i)
+		if (c->lut_tables[i].hash == res[0].hash) table = (int)i;
+	if (table < 0) {
+		pb_ctx::LutTable t;
+		t.hash = res[0].hash;
+		t.unit_range = res[0].not_unit == 0;
+		CU(cudaMalloc(&t.raw, 65536 * sizeof(float)));
+		CU(cudaMemcpyAsync(t.raw, lut->dev, 65536 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+		for (int k = 0; k < kLutCands && !t.d8; ++k)
+			if (res[k].dmin >= -128 && res[k].dmax <= 127) {
+				CU(cudaMalloc(&t.d8, 65536));
+				CU(cudaMemcpyAsync(t.d8, (const char *)c->lut_scratch + (size_t)k * 65536, 65536, cudaMemcpyDeviceToDevice, s));
+				t.lp = c->lut_cands[k];
+				t.model = k;
+				t.dmin = res[k].dmin;
+				t.dmax = res[k].dmax;
+			}
+		CU(cudaStreamSynchronize(s));
+		c->lut_tables.push_back(t);
+		table = (int)c->lut_tables.size() - 1;
+	}
+	if (c->lut_fits.size() >= 4096) c->lut_fits.erase(c->lut_fits.begin(), c->lut_fits.begin() + 2048);
+	c->lut_fits.push_back({lut->version, table});
+	*table_out = table;
+	return PB_OK;
+}
+
+int lut_table_by_raw(pb_ctx *c, const float *raw) {
+	for (size_t i = 0; i < c->lut_tables.size(); ++i)
+		if (c->lut_tables[i].raw == raw) return (int)i;
+	return -1;
+}
+
+// ---- march kernel preparation -------------------------------------------------------------------
 // Exact host evaluation of the sampling position of transform.ts:54-57 followed by the
 // OpenCL 1.2 8.2 linear-filter prologue, for one axis of a separable (no rotation / shear)
 // transform.  Same operations, same order, same rounding as pb_device.cuh transform_pos() +
 // sample_linear_clamp(); the host compiler runs with -ffp-contract=off.
 inline int2 axis_entry(int o, int out_n, int src_n, float m_scale, float m_other, float m_off, bool is_x, bool has_xf) {
 	int2 e;
-	if (!has_xf) {   // direct read of texel o: weight 1 on (o, o), nothing on o+1
+	if (!has_xf) {   // direct read of texel o
 		e.x = o;
 		e.y = 0;
 		return e;
@@ -469,106 +606,158 @@ inline int2 axis_entry(int o, int out_n, int src_n, float m_scale, float m_other
 	return e;
 }
 
-int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, pb_ctx::SampleTab **out) {
+// sampling tables of one leaf; *fits = 0 if some strip's source footprint exceeds a row buffer
+int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_ctx::SampleTab **out, int *fits) {
 	for (auto &t : c->tabs)
-		if (t.sw == lf.w && t.sh == lf.h && t.W == W && t.H == H && t.has_xf == lf.has_xf &&
+		if (t.sw == lf.w && t.sh == lf.h && t.W == W && t.H == H && t.has_xf == lf.has_xf && t.strip_groups == strip_groups &&
 		    (!lf.has_xf || 0 == memcmp(t.m, lf.m, sizeof t.m))) {
 			*out = &t;
+			*fits = t.fits;
 			return PB_OK;
 		}
 	if (c->tabs.size() >= 256) {   // parameters are animating: start over (rare; tables are tiny)
 		CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));
-		for (auto &t : c->tabs) {
-			cudaFree(t.dcol);
-			cudaFree(t.drow);
-		}
+		for (auto &t : c->tabs) cudaFree(t.dev);
 		c->tabs.clear();
 	}
 	pb_ctx::SampleTab t;
 	memcpy(t.m, lf.m, sizeof t.m);
-	t.sw = lf.w; t.sh = lf.h; t.W = W; t.H = H; t.has_xf = lf.has_xf;
-	t.hcol.resize(W);
-	std::vector<int2> hrow(H);
-	for (int x = 0; x < W; ++x) t.hcol[x] = axis_entry(x, W, lf.w, lf.m[0], lf.m[1], lf.m[2], true, lf.has_xf != 0);
+	t.sw = lf.w; t.sh = lf.h; t.W = W; t.H = H; t.has_xf = lf.has_xf; t.strip_groups = strip_groups;
+	const int strip_px = strip_groups * 6;
+	const int n_strips = (W + strip_px - 1) / strip_px;
+	// one allocation: int2 col[W] | int2 row[H] | int4 strip[n_strips]
+	const size_t bytes = ((size_t)W + H) * sizeof(int2) + (size_t)n_strips * sizeof(int4);
+	std::vector<char> host(bytes);
+	int2 *hcol = reinterpret_cast<int2 *>(host.data());
+	int2 *hrow = hcol + W;
+	int4 *hstrip = reinterpret_cast<int4 *>(hrow + H);
+	for (int x = 0; x < W; ++x) hcol[x] = axis_entry(x, W, lf.w, lf.m[0], lf.m[1], lf.m[2], true, lf.has_xf != 0);
 	for (int y = 0; y < H; ++y) hrow[y] = axis_entry(y, H, lf.h, lf.m[4], lf.m[3], lf.m[5], false, lf.has_xf != 0);
-	CU(cudaMalloc(&t.dcol, (size_t)W * sizeof(int2)));
-	CU(cudaMalloc(&t.drow, (size_t)H * sizeof(int2)));
-	CU(cudaMemcpyAsync(t.dcol, t.hcol.data(), (size_t)W * sizeof(int2), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
-	CU(cudaMemcpyAsync(t.drow, hrow.data(), (size_t)H * sizeof(int2), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
-	CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // hrow is a local; once per new transform only
+	t.fits = 1;
+	for (int sidx = 0; sidx < n_strips; ++sidx) {
+		const int x0 = sidx * strip_px, x1 = std::min(x0 + strip_px, W) - 1;
+		int lo = INT32_MAX, hi = INT32_MIN;
+		for (int x = x0; x <= x1; ++x) {   // not assumed monotone (flips, degenerate scales)
+			lo = std::min(lo, hcol[x].x);
+			hi = std::max(hi, hcol[x].x + (lf.has_xf ? 1 : 0));
+		}
+		int4 e = make_int4(0, 0, 0, 0);
+		if (!(hi < 0 || lo >= lf.w)) {
+			e.x = 1 | ((lo < 0 || hi >= lf.w) ? 2 : 0);
+			lo = std::max(lo, 0);
+			hi = std::min(hi, lf.w - 1);
+			e.y = lo / 6;
+			e.z = hi / 6 - e.y + 1;
+			if (e.z > pb::kRowGroups) t.fits = 0;
+		}
+		hstrip[sidx] = e;
+	}
+	CU(cudaMalloc(&t.dev, bytes));
+	CU(cudaMemcpyAsync(t.dev, host.data(), bytes, cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+	CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // `host` is a local; once per new transform only
+	t.dcol = reinterpret_cast<int2 *>(t.dev);
+	t.drow = t.dcol + W;
+	t.dstrip = reinterpret_cast<int4 *>(t.drow + H);
 	c->tabs.push_back(std::move(t));
 	*out = &c->tabs.back();
+	*fits = c->tabs.back().fits;
 	return PB_OK;
 }
 
-// Decide whether the marching-strip kernel can evaluate this descriptor and, if so, attach the
-// sampling tables and ring slots.  Returns 1 = strip, 0 = use the generic kernel, <0 = error.
-int prepare_strip(pb_ctx *c, pb::FusedDesc &d) {
-	if (!c->allow_strip) return 0;
-	if (d.out_w % 48 != 0 || d.out_h < 2) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
-	int n_ring = 0;
+// Decide whether the march kernel can evaluate this descriptor and, if so, attach the sampling
+// tables and gamma-table slots.  Returns 1 = march, 0 = use the generic kernel, <0 = error.
+int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
+	if (!c->allow_march) return 0;
+	if (d.out_w % 48 != 0 || d.out_h < 1) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
+	if (d.interlace != 0 && d.out_h < 2) return 0;
+	bool any_xf = false;
+	pb::Leaf *leaves[3 * pb::kMaxLayers];
+	int n_leaves = 0;
 	for (int l = 0; l < d.n_layers; ++l) {
 		pb::Layer &ly = d.layers[l];
-		pb::Leaf *leaves[3] = {&ly.a, &ly.b, &ly.mask};
+		pb::Leaf *ll[3] = {&ly.a, &ly.b, &ly.mask};
 		const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
 		for (int q = 0; q < nleaf; ++q) {
-			pb::Leaf &lf = *leaves[q];
+			pb::Leaf &lf = *ll[q];
 			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) return 0;
 			if (lf.has_xf) {
 				for (float v : lf.m)
 					if (!(v == v) || v > 1e30f || v < -1e30f) return 0;
 				if (lf.m[1] != 0.0f || lf.m[3] != 0.0f) return 0;   // rotation / shear
 				if (lf.xf_w != d.out_w || lf.xf_h != d.out_h) return 0;
+				any_xf = true;
 			} else if (lf.w != d.out_w || lf.h != d.out_h) {
 				return 0;
 			}
-			if (n_ring >= pb::kMaxRingLeaves) return 0;
-			pb_ctx::SampleTab *t;
-			int r = get_tabs(c, lf, d.out_w, d.out_h, &t);
-			if (r) return r;
-			// every strip's source footprint must fit a ring row
-			for (int x0 = 0; x0 < d.out_w; x0 += pb::kStripPx) {
-				const int x1 = std::min(x0 + pb::kStripPx, d.out_w) - 1;
-				const int ia = t->hcol[x0].x, ib = t->hcol[x1].x;
-				int lo = std::min(ia, ib), hi = std::max(ia, ib) + 1;
-				if (hi < 0 || lo >= lf.w) continue;
-				lo = std::max(lo, 0);
-				hi = std::min(hi, lf.w - 1);
-				if (hi / 6 - lo / 6 + 1 > pb::kRingGroups) return 0;
-			}
-			lf.col_tab = t->dcol;
-			lf.row_tab = t->drow;
-			lf.ring = n_ring++;
+			leaves[n_leaves++] = &lf;
 		}
 	}
-	d.n_ring = n_ring;
-	const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
-	const int n_strips = (d.out_w + pb::kStripPx - 1) / pb::kStripPx;
-	const int sms = c->prop.multiProcessorCount > 0 ? c->prop.multiProcessorCount : 148;
-	const int bands = std::max(1, (4 * sms) / n_strips);
-	d.band_lines = std::max(16, (n_lines + bands - 1) / bands);
+	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
+	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
+	for (int i = 0; i < n_leaves; ++i) {
+		pb_ctx::SampleTab *t;
+		int fits = 0;
+		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
+		if (r) return r;
+		if (!fits) return 0;
+		leaves[i]->col_tab = t->dcol;
+		leaves[i]->row_tab = t->drow;
+		leaves[i]->strip_tab = t->dstrip;
+	}
+	// the write side packs three codes into one word while regrouping: they must fit 10 bits
+	const int wt = lut_table_by_raw(c, d.wc.lut);
+	if (wt < 0 || !c->lut_tables[wt].unit_range) return 0;
+	for (int row = 0; row < 3; ++row) {
+		double hi = d.wc.cm[row * 4 + 3];
+		for (int k = 0; k < 3; ++k) hi += std::max(0.0, (double)d.wc.cm[row * 4 + k]);
+		if (!(hi < 1023.25)) return 0;
+	}
+	// gamma tables: all in the one-byte form (shared memory) or all raw (global memory)
+	d.sparse_cm = 1;
+	int slots[pb::kMaxLuts], n_slots = 0;
+	bool all_d8 = !(c->flags & PB_CTX_RAW_LUT);
+	auto slot_of = [&](int table) -> int {
+		if (table < 0 || !c->lut_tables[table].d8) return -1;
+		for (int i = 0; i < n_slots; ++i)
+			if (slots[i] == table) return i;
+		if (n_slots >= pb::kMaxLuts) return -1;
+		slots[n_slots] = table;
+		return n_slots++;
+	};
+	d.wc.lut_slot = slot_of(wt);
+	if (d.wc.lut_slot < 0) all_d8 = false;
+	for (int i = 0; i < d.n_rc; ++i) {
+		if (d.rc[i].cm[1] != 0.0f || d.rc[i].cm[10] != 0.0f) d.sparse_cm = 0;
+		d.rc[i].lut_slot = slot_of(lut_table_by_raw(c, d.rc[i].lut));
+		if (d.rc[i].lut_slot < 0) all_d8 = false;
+	}
+	d.n_luts = all_d8 ? n_slots : 0;
+	for (int i = 0; i < d.n_luts; ++i) {
+		d.luts[i].d8 = c->lut_tables[slots[i]].d8;
+		d.luts[i].lp = c->lut_tables[slots[i]].lp;
+	}
 	return 1;
 }
 
-// launch a compiled descriptor (strip kernel when eligible); *strip_out reports the choice
-int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, bool *strip_out) {
-	bool strip = false;
+// launch a compiled descriptor (march kernel when eligible); *march_out reports the choice
+int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, bool *march_out) {
+	bool march = false;
 	if (!out_rgba) {
-		int r = prepare_strip(c, d);
+		int r = prepare_march(c, d);
 		if (r < 0) return r;
-		strip = r == 1;
+		march = r == 1;
 	}
-	cudaError_t e = strip ? pb::launch_fused_strip(s, d) : pb::launch_fused(s, d, out_rgba);
-	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (%s): %s", strip ? "strip" : "generic", cudaGetErrorString(e));
-	if (strip_out) *strip_out = strip;
+	cudaError_t e = march ? pb::launch_fused_march(s, d, c->prop.multiProcessorCount) : pb::launch_fused(s, d, out_rgba);
+	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (%s): %s", march ? "march" : "generic", cudaGetErrorString(e));
+	if (march_out) *march_out = march;
 	return PB_OK;
 }
 
-void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf, bool strip = false) {
+void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf, bool march = false) {
 	if (!c->recording) return;
 	pb_chain::Item it;
 	it.d = cc.d;
-	it.strip = strip;
+	it.march = march;
 	it.out_rgba = out_rgba;
 	for (const auto &k : cc.keep) it.keep.push_back(std::static_pointer_cast<void>(k));
 	it.out_buf = out_buf;
@@ -651,6 +840,7 @@ int real_input(pb_buf *b, const void **p) {
 int real_output(pb_buf *b, void **p) {
 	b->expr.reset();
 	b->host_dirty = false;
+	b->version = ++b->ctx->version_counter;
 	int r = ensure_dev(b);
 	if (r) return r;
 	*p = b->dev;
@@ -757,11 +947,11 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 				cc.d.interlace = interlace;
 				cc.d.out = out->dev;
 				cc.d.out_pitch = v210_pitch_bytes(W);
-				bool strip = false;
-				if ((r = launch_desc(c, s, cc.d, nullptr, &strip))) return r;
+				bool march = false;
+				if ((r = launch_desc(c, s, cc.d, nullptr, &march))) return r;
 				c->stats.fused_launches++;
-				if (strip) c->stats.strip_launches++;
-				record_launch(c, cc, nullptr, out, strip);
+				if (march) c->stats.march_launches++;
+				record_launch(c, cc, nullptr, out, march);
 				fused_launch = true;
 				break;
 			}
@@ -954,7 +1144,7 @@ int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out) {
 	auto *c = new pb_ctx;
 	c->dev = gpu_index;
 	c->flags = flags;
-	c->allow_strip = !(flags & PB_CTX_NO_STRIP);
+	c->allow_march = !(flags & PB_CTX_NO_MARCH);
 	CU(cudaGetDeviceProperties(&c->prop, gpu_index));
 	for (auto &q : c->q) CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
 	CU(cudaEventCreate(&c->ev0));
@@ -969,10 +1159,14 @@ int pb_ctx_destroy(pb_ctx *c) {
 	cudaSetDevice(c->dev);
 	cudaDeviceSynchronize();
 	c->pool.destroy();
-	for (auto &t : c->tabs) {
-		cudaFree(t.dcol);
-		cudaFree(t.drow);
+	for (auto &t : c->tabs) cudaFree(t.dev);
+	for (auto &t : c->lut_tables) {
+		cudaFree(t.raw);
+		cudaFree(t.d8);
 	}
+	cudaFree(c->lut_cands_dev);
+	cudaFree(c->lut_res_dev);
+	cudaFree(c->lut_scratch);
 	for (auto &q : c->q) cudaStreamDestroy(q);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
@@ -996,6 +1190,9 @@ int pb_ctx_stats(pb_ctx *c, pb_stats *out) {
 	*out = c->stats;
 	out->dev_bytes_live = c->pool.dev_live;
 	out->dev_bytes_pooled = c->pool.dev_pooled;
+	out->lut_tables = c->lut_tables.size();
+	out->lut_tables_d8 = 0;
+	for (const auto &t : c->lut_tables) out->lut_tables_d8 += t.d8 ? 1 : 0;
 	return PB_OK;
 }
 
@@ -1003,7 +1200,7 @@ int pb_ctx_set_flags(pb_ctx *c, unsigned flags) {
 	if (!c) return fail(PB_ERR_ARG, "null context");
 	std::lock_guard<std::recursive_mutex> lk(c->mu);
 	c->flags = flags;
-	c->allow_strip = !(flags & PB_CTX_NO_STRIP);
+	c->allow_march = !(flags & PB_CTX_NO_MARCH);
 	return PB_OK;
 }
 
@@ -1098,6 +1295,7 @@ int pb_buf_host_access(pb_buf *b, int mode, int queue, const void *src, size_t s
 					}
 					c->stats.h2d_bytes += src_bytes;
 					b->host_dirty = false;
+					b->version = ++c->version_counter;
 				} else {
 					b->host_dirty = true;   // host will write through pb_buf_host_ptr(); flushed on next use
 					return PB_OK;
@@ -1144,6 +1342,7 @@ int pb_buf_upload_async(pb_buf *b, int queue, const void *src, size_t bytes) {
 	if (r) return r;
 	CU(cudaMemcpyAsync(b->dev, src, bytes, cudaMemcpyHostToDevice, c->q[queue]));
 	c->stats.h2d_bytes += bytes;
+	b->version = ++c->version_counter;
 	return PB_OK;
 }
 
@@ -1270,11 +1469,11 @@ int pb_chain_replay(pb_chain *ch, int queue) {
 	std::lock_guard<std::recursive_mutex> lk(c->mu);
 	CU(cudaSetDevice(c->dev));
 	for (const auto &it : ch->items) {
-		cudaError_t e = it.strip ? pb::launch_fused_strip(c->q[queue], it.d) : pb::launch_fused(c->q[queue], it.d, it.out_rgba);
+		cudaError_t e = it.march ? pb::launch_fused_march(c->q[queue], it.d, c->prop.multiProcessorCount) : pb::launch_fused(c->q[queue], it.d, it.out_rgba);
 		if (e != cudaSuccess) return fail(PB_ERR_CUDA, "chain replay: %s", cudaGetErrorString(e));
 		c->stats.kernel_launches++;
 		c->stats.fused_launches++;
-		if (it.strip) c->stats.strip_launches++;
+		if (it.march) c->stats.march_launches++;
 	}
 	return PB_OK;
 }

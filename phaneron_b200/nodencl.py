@@ -168,7 +168,8 @@ class clContext:
         self.overlapping = bool(options.get("overlapping", True))
         # product extension: defer RGBA intermediates and fuse the chain at packed sinks
         self.deferred = bool(options.get("deferred", True))
-        self.stripKernel = bool(options.get("stripKernel", True))   # False: always the generic fused kernel
+        self.marchKernel = bool(options.get("marchKernel", True))   # False: always the generic fused kernel
+        self.rawLut = bool(options.get("rawLut", False))            # True: march kernel gathers from the raw gamma tables
         self.queue = _Queues()
         self._h = 0
 
@@ -180,7 +181,8 @@ class clContext:
         self._h = h.value
 
     def _flags(self) -> int:
-        return (_lib.CTX_DEFER if self.deferred else 0) | (0 if self.stripKernel else _lib.CTX_NO_STRIP)
+        return ((_lib.CTX_DEFER if self.deferred else 0) | (0 if self.marchKernel else _lib.CTX_NO_MARCH)
+                | (_lib.CTX_RAW_LUT if self.rawLut else 0))
 
     def close(self) -> None:
         if self._h:
@@ -196,8 +198,10 @@ class clContext:
         self.deferred = bool(on)
         check(_lib.lib().pb_ctx_set_flags(self._need(), self._flags()))
 
-    def setStripKernel(self, on: bool) -> None:
-        self.stripKernel = bool(on)
+    def setMarchKernel(self, on: bool, rawLut: Optional[bool] = None) -> None:
+        self.marchKernel = bool(on)
+        if rawLut is not None:
+            self.rawLut = bool(rawLut)
         check(_lib.lib().pb_ctx_set_flags(self._need(), self._flags()))
 
     def getPlatformInfo(self) -> Dict[str, Any]:

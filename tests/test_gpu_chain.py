@@ -197,27 +197,39 @@ def test_full_size_2160p_properties():
     run(go())
 
 
-# ---- the marching-strip kernel vs the generic fused kernel vs the oracle --------------------------
-async def _run_scene_variant(scene, strip):
+# ---- the march kernel (pb_march.cu) vs the generic fused kernel vs the oracle --------------------------
+async def _run_scene_variant(scene, mode):
+    """mode: 'march' (gamma tables in the one-byte shared-memory form), 'march_raw' (raw tables from
+    global memory), 'generic' (pb_fused.cu)"""
     async with Env(True) as env:
-        env.ctx.setStripKernel(strip)
+        env.ctx.setMarchKernel(mode != "generic", rawLut=(mode == "march_raw"))
         h = ChannelHarness(env.ctx, scene, env.pj)
         await h.init()
         before = env.ctx.stats()
         out = await h.run_frame()
         after = env.ctx.stats()
-        return out, {k: after[k] - before[k] for k in after}
+        st = {k: after[k] - before[k] for k in after}
+        st["lut_tables"], st["lut_tables_d8"] = after["lut_tables"], after["lut_tables_d8"]
+        return out, st
 
 
 def _xf(**kw):
     return dict(IDENTITY_XF, **kw)
 
 
-STRIP_SCENES = {
+def _with_xf(scene, xfs):
+    for L, xf in zip(scene["layers"], xfs):
+        L["xf"] = xf
+    return scene
+
+
+MARCH_SCENES = {
     "north_star_mix": lambda: layered_scene(480, 270, 4, "noise", "mix", "709", "2020"),
     "north_star_wipe": lambda: layered_scene(480, 270, 4, "noise", "wipe", "709", "2020"),
+    "north_star_ramp": lambda: layered_scene(480, 270, 4, "ramp", "mix", "709", "2020"),
     "full_strip_width": lambda: layered_scene(768, 54, 3, "noise", "plain", "709", "709"),
-    "single_direct": lambda: single_layer_scene(384, 100, "noise", False),
+    "two_strips_direct": lambda: single_layer_scene(384, 100, "noise", False),
+    "srgb_working_space": lambda: layered_scene(480, 64, 2, "noise", "plain", "709", "sRGB"),
     "flips_and_upscale": lambda: _with_xf(layered_scene(480, 270, 3, "noise", "plain", "709", "709"),
                                           [_xf(flipH=True), _xf(flipV=True, scaleX=1.5, scaleY=2.25, offsetX=0.1),
                                            _xf(flipH=True, flipV=True, scaleX=0.75, scaleY=0.6, offsetY=-0.2)]),
@@ -228,36 +240,39 @@ STRIP_SCENES = {
 }
 
 
-def _with_xf(scene, xfs):
-    for L, xf in zip(scene["layers"], xfs):
-        L["xf"] = xf
-    return scene
-
-
-@pytest.mark.parametrize("name", sorted(STRIP_SCENES))
-def test_strip_kernel_matches_generic_and_oracle(name):
-    scene = STRIP_SCENES[name]()
-    fast, st_fast = run(_run_scene_variant(scene, True))
-    slow, st_slow = run(_run_scene_variant(scene, False))
-    assert st_fast["strip_launches"] == 1 and st_slow["strip_launches"] == 0
-    assert st_fast["kernel_launches"] == 1 and st_slow["kernel_launches"] == 1
+@pytest.mark.parametrize("name", sorted(MARCH_SCENES))
+def test_march_kernel_matches_generic_and_oracle(name):
+    scene = MARCH_SCENES[name]()
     ref = SceneOracle(scene).packed()
+    slow, st_slow = run(_run_scene_variant(scene, "generic"))
+    assert st_slow["march_launches"] == 0 and st_slow["kernel_launches"] == 1
     assert np.array_equal(slow, ref)
-    assert np.array_equal(fast, ref)
+    for mode in ("march", "march_raw"):
+        fast, st = run(_run_scene_variant(scene, mode))
+        assert st["march_launches"] == 1 and st["kernel_launches"] == 1, (mode, st)
+        assert np.array_equal(fast, ref), f"{mode}: {int((fast != ref).sum())} bytes differ"
 
 
-def test_strip_kernel_declines_what_it_cannot_do():
-    """rotation, a deep downscale (footprint wider than a ring row) and ragged widths fall back to the generic kernel"""
+def test_gamma_tables_are_deduplicated_and_compressed():
+    """five Loaders + one Saver upload six tables; the context keeps two (709 gamma->linear, 2020
+    linear->gamma), both in the lossless one-byte form (pb_lut.cuh)"""
+    scene = layered_scene(480, 270, 4, "noise", "mix", "709", "2020")
+    _, st = run(_run_scene_variant(scene, "march"))
+    assert st["lut_tables"] == 2 and st["lut_tables_d8"] == 2, st
+
+
+def test_march_kernel_declines_what_it_cannot_do():
+    """rotation, a deep downscale (footprint wider than a row buffer) and ragged widths fall back to the generic kernel"""
     rot = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(rotate=0.01)])
     deep = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(scaleX=0.2, scaleY=0.2)])
     ragged = layered_scene(1280, 36, 2, "ramp", "plain")
     for scene in (rot, deep, ragged):
-        out, st = run(_run_scene_variant(scene, True))
-        assert st["strip_launches"] == 0 and st["fused_launches"] == 1
+        out, st = run(_run_scene_variant(scene, "march"))
+        assert st["march_launches"] == 0 and st["fused_launches"] == 1
         assert np.array_equal(out, SceneOracle(scene).packed())
 
 
-def test_strip_kernel_interlaced_fields():
+def test_march_kernel_interlaced_fields():
     async def go():
         scene = layered_scene(480, 270, 3, "noise", "mix", "709", "2020")
         scene["interlaced"] = True
@@ -271,7 +286,7 @@ def test_strip_kernel_interlaced_fields():
                 ups = await h.upload_all(int(il))
                 frame = await h.compose(ups, int(il))
                 await h.consume(frame, dests, il, download=(il == Interlace.BottomField))
-            assert env.ctx.stats()["strip_launches"] == 2
+            assert env.ctx.stats()["march_launches"] == 2
             so = SceneOracle(scene)
             ref = np.zeros_like(dests[0].host)
             so.packed(1, ref)
@@ -280,10 +295,11 @@ def test_strip_kernel_interlaced_fields():
     run(go())
 
 
-def test_strip_kernel_full_size_equals_generic_2160p():
-    """BASELINE config 3 at full size: the strip kernel must reproduce the generic kernel byte for byte"""
+def test_march_kernel_full_size_equals_generic_2160p():
+    """BASELINE config 3 at full size: the march kernel must reproduce the generic kernel byte for byte"""
     scene = layered_scene(3840, 2160, 4, "noise", "mix", "709", "2020")
-    fast, st = run(_run_scene_variant(scene, True))
-    slow, _ = run(_run_scene_variant(scene, False))
-    assert st["strip_launches"] == 1
-    assert np.array_equal(fast, slow)
+    slow, _ = run(_run_scene_variant(scene, "generic"))
+    for mode in ("march", "march_raw"):
+        fast, st = run(_run_scene_variant(scene, mode))
+        assert st["march_launches"] == 1
+        assert np.array_equal(fast, slow), mode
