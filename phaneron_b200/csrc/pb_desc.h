@@ -29,12 +29,15 @@ enum LeafKind : int { LEAF_NONE = 0, LEAF_V210 = 1, LEAF_RGBA_F32 = 2 };
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
 
 // Lossless shared-memory form of a 65536-entry gamma table (colourMaths.ts:130-169):
-//   table[i] == bits( base(i) ) + d8[i]      for every i, verified exhaustively when the table is fitted
+//   (for every i, by construction: the bytes are fitted on the device by the decoding code itself)
 //   base(i)   = i < J ? i*kt : s * ex2(G * lg2(i*p + q)) + o      (MUFU.LG2 / MUFU.EX2)
+//   table[i] == bits( base(i) ) + d8[i] - 128
 // The d8 bytes are produced ON the device by the same code that decodes them (pb_lut.cuh).
+// The toe / power select is arithmetic (FMA pipe, no predicate): with h = sat(i + cJ) = (i >= J),
+//   base(i) = h * pw(i) + sat(i*kt - 16h)        -- exactly pw(i) or exactly i*kt
 struct LutParams {
-	float p, q, G, s, o, kt, Jf;
-	int affine;   // 0: s == 1 and o == 0 (gamma -> linear direction)
+	float p, q, G, s, o, kt, cJ;   // cJ = 1 - J
+	int affine;                    // 0: s == 1 and o == 0 (gamma -> linear direction)
 };
 
 // Loader constants (loadSave.ts:41-64): YCbCr->RGB 3x4, gamma->linear LUT, gamut 3x3
@@ -46,6 +49,15 @@ struct ReadConsts {
 	int pad_;
 };
 
+// march kernel: ReadConsts::cm pre-scaled for v210 fields converted without a shift.  A 10-bit field
+// at bit 10 of a word is read as the float 1024*v (mask | 2^23 exponent trick), so its coefficient is
+// m / 1024 (exact: power of two); [c][0] multiplies plain fields, [c][1] fields scaled by 1024.
+// oY = -2^23 * mY folds the exponent-trick bias of the luma field into the first FMA of the chain:
+// fma(2^23 + s*y, m/s, -2^23*m/s) == RN(y*m) exactly.
+struct ReadK {
+	float mY[3][2], oY[3][2], mCb[3][2], mCr[3][2];
+};
+
 // Saver constants (loadSave.ts:130-150): linear->gamma LUT, RGB->YCbCr 3x4
 struct WriteConsts {
 	float cm[12];
@@ -55,7 +67,7 @@ struct WriteConsts {
 };
 
 struct LutDesc {
-	const int8_t *d8;   // 65536 bytes in global memory, copied into shared memory by each CTA
+	const uint8_t *d8;   // 65536 bytes in global memory, copied into shared memory by each CTA
 	LutParams lp;
 };
 
@@ -95,9 +107,11 @@ struct FusedDesc {
 	int n_strips;
 	int n_luts;        // tables to stage in shared memory (0: gather from the raw tables in global memory)
 	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
-	LutDesc luts[kMaxLuts];
+	LutDesc luts[kMaxLuts];   // slot 0 = rc[0]'s table
+	LutParams wlp;            // = luts[wc.lut_slot].lp, at a fixed offset for the encoder
 	WriteConsts wc;
 	ReadConsts rc[kMaxReadConsts];
+	ReadK rk[kMaxReadConsts];
 	Layer layers[kMaxLayers];
 };
 

@@ -28,7 +28,7 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms);
 size_t march_smem_bytes(const FusedDesc &d);
 // gamma table -> one-byte-per-entry form (pb_lut.cuh): n_cands candidate models evaluated in one launch
 struct LutFitResult;
-cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *cands_dev, int n_cands, int8_t *d8_out, void *results_dev);
+cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *cands_dev, int n_cands, uint8_t *d8_out, void *results_dev);
 // name of the kernel variant launch_fused would pick (for stats / tests)
 const char *fused_variant(const FusedDesc &d);
 

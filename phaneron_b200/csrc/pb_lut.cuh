@@ -6,8 +6,8 @@
 // reference's algorithm on a B200 (tools/lut_bench.cu: 0.8 Tlookup/s from L2 vs 2.0 from this
 // encoding on incoherent indices).  So the fused kernel keeps, per table, ONE BYTE per entry:
 //
-//     table[i] == as_float( as_int( base(i) ) + d8[i] )           for all 65536 i
-//     base(i)   = i < J ? i * kt : s * ex2.approx(G * lg2.approx(i * p + q)) + o
+//     table[i] == as_float( as_int( base(i) ) + d8[i] - 128 )     for all 65536 i
+//     base(i)   = i < J ? i * kt : s * ex2.approx(lg2.approx(i * p + q) * G) + o
 //
 // base() is the analytic transfer function evaluated with the SFU approximations (a handful of
 // ulps off); d8 is the integer distance from it to the exact table value.  d8 is computed on the
@@ -33,18 +33,23 @@ __device__ __forceinline__ float lg2_approx(float x) {
 	return r;
 }
 
-// fi = the table index as an exact float (0 .. 65535)
+// fi = the table index as an exact float (0 .. 65535).  The march kernel evaluates the same
+// expression two indices at a time with packed f32x2 instructions (pb_march.cu lut2); every
+// operation is IEEE round-to-nearest or an SFU approximation, so both forms agree bit for bit.
 __device__ __forceinline__ float lut_base(float fi, const LutParams &lp) {
 	const float x = __fmaf_rn(fi, lp.p, lp.q);
-	float pw = ex2_approx(__fmul_rn(lp.G, lg2_approx(x)));
+	float pw = ex2_approx(__fmul_rn(lg2_approx(x), lp.G));
 	if (lp.affine) pw = __fmaf_rn(pw, lp.s, lp.o);
 	const float toe = __fmul_rn(fi, lp.kt);
-	return fi < lp.Jf ? toe : pw;
+	const float h = __saturatef(__fadd_rn(fi, lp.cJ));               // 0 below the knee, 1 from it on
+	const float toe_sel = __saturatef(__fmaf_rn(h, -16.0f, toe));      // toe below the knee (toe < 1), 0 from it on
+	return __fmaf_rn(h, pw, toe_sel);                                 // exactly one term is non-zero
 }
 
 // exact table value from the byte table (shared or global memory)
-__device__ __forceinline__ float lut_decode(float fi, uint32_t idx, const int8_t *d8, const LutParams &lp) {
-	return __int_as_float(__float_as_int(lut_base(fi, lp)) + (int)d8[idx]);
+// (bytes hold the distance + 128 so that the decode is one unsigned byte load and one 3-input add)
+__device__ __forceinline__ float lut_decode(float fi, uint32_t idx, const uint8_t *d8, const LutParams &lp) {
+	return __int_as_float(__float_as_int(lut_base(fi, lp)) + (int)d8[idx] - 128);
 }
 
 struct LutFitResult {
@@ -54,13 +59,13 @@ struct LutFitResult {
 };
 
 // one candidate parameter set per blockIdx.y
-__global__ void lut_fit_kernel(const float *table, const LutParams *cands, int8_t *d8_out, LutFitResult *res) {
+__global__ void lut_fit_kernel(const float *table, const LutParams *cands, uint8_t *d8_out, LutFitResult *res) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= 65536) return;
 	const LutParams lp = cands[blockIdx.y];
 	const uint32_t tb = __float_as_uint(table[i]);
 	const int d = (int)tb - __float_as_int(lut_base((float)i, lp));
-	d8_out[(size_t)blockIdx.y * 65536 + i] = (int8_t)max(-128, min(127, d));
+	d8_out[(size_t)blockIdx.y * 65536 + i] = (uint8_t)(max(-128, min(127, d)) + 128);
 	atomicMin(&res[blockIdx.y].dmin, d);
 	atomicMax(&res[blockIdx.y].dmax, d);
 	if (blockIdx.y == 0) {

@@ -136,7 +136,7 @@ struct pb_ctx {
 	struct LutTable {
 		unsigned long long hash = 0;
 		float *raw = nullptr;      // context-owned copy every ReadConsts/WriteConsts points at
-		int8_t *d8 = nullptr;      // one-byte form, null if no model fits
+		uint8_t *d8 = nullptr;      // one-byte form, null if no model fits
 		pb::LutParams lp{};
 		int model = -1, dmin = 0, dmax = 0;
 		bool unit_range = false;
@@ -491,7 +491,7 @@ void lut_candidates(pb::LutParams *out) {
 		g.kt = (float)(1.0 / (65535.0 * t.delta));
 		int J = 0;
 		while (J < 65536 && J / 65535.0 < t.beta * t.delta) ++J;
-		g.Jf = (float)J;
+		g.cJ = (float)(1 - J);
 		g.affine = 0;
 		out[n++] = g;
 		pb::LutParams l{};   // linear2gammaLUT (colourMaths.ts:151-169)
@@ -503,7 +503,7 @@ void lut_candidates(pb::LutParams *out) {
 		l.kt = (float)(t.delta / 65535.0);
 		J = 0;
 		while (J < 65536 && J / 65535.0 < t.beta) ++J;
-		l.Jf = (float)J;
+		l.cJ = (float)(1 - J);
 		l.affine = 1;
 		out[n++] = l;
 	}
@@ -534,7 +534,7 @@ int lut_table_of(pb_ctx *c, pb_buf *lut, int *table_out) {
 	FitResultHost res[kLutCands];
 	for (auto &r : res) r = FitResultHost{INT32_MAX, INT32_MIN, 0ull, 0, 0};
 	CU(cudaMemcpyAsync(c->lut_res_dev, res, sizeof res, cudaMemcpyHostToDevice, s));
-	cudaError_t e = pb::launch_lut_fit(s, (const float *)lut->dev, (const pb::LutParams *)c->lut_cands_dev, kLutCands, (int8_t *)c->lut_scratch, c->lut_res_dev);
+	cudaError_t e = pb::launch_lut_fit(s, (const float *)lut->dev, (const pb::LutParams *)c->lut_cands_dev, kLutCands, (uint8_t *)c->lut_scratch, c->lut_res_dev);
 	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "lut fit launch: %s", cudaGetErrorString(e));
 	CU(cudaMemcpyAsync(res, c->lut_res_dev, sizeof res, cudaMemcpyDeviceToHost, s));
 	CU(cudaStreamSynchronize(s));
@@ -707,10 +707,14 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	// the write side packs three codes into one word while regrouping: they must fit 10 bits
 	const int wt = lut_table_by_raw(c, d.wc.lut);
 	if (wt < 0 || !c->lut_tables[wt].unit_range) return 0;
+	// (and, being inside [0, 1023], need no saturation: the encoder drops the clamp of convert_ushort_sat_rte)
 	for (int row = 0; row < 3; ++row) {
-		double hi = d.wc.cm[row * 4 + 3];
-		for (int k = 0; k < 3; ++k) hi += std::max(0.0, (double)d.wc.cm[row * 4 + k]);
-		if (!(hi < 1023.25)) return 0;
+		double hi = d.wc.cm[row * 4 + 3], lo = hi;
+		for (int k = 0; k < 3; ++k) {
+			hi += std::max(0.0, (double)d.wc.cm[row * 4 + k]);
+			lo += std::min(0.0, (double)d.wc.cm[row * 4 + k]);
+		}
+		if (!(hi < 1023.25 && lo > -0.25)) return 0;
 	}
 	// gamma tables: all in the one-byte form (shared memory) or all raw (global memory)
 	d.sparse_cm = 1;
@@ -724,18 +728,27 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		slots[n_slots] = table;
 		return n_slots++;
 	};
-	d.wc.lut_slot = slot_of(wt);
-	if (d.wc.lut_slot < 0) all_d8 = false;
-	for (int i = 0; i < d.n_rc; ++i) {
+	for (int i = 0; i < d.n_rc; ++i) {   // rc[0]'s table takes slot 0
 		if (d.rc[i].cm[1] != 0.0f || d.rc[i].cm[10] != 0.0f) d.sparse_cm = 0;
 		d.rc[i].lut_slot = slot_of(lut_table_by_raw(c, d.rc[i].lut));
 		if (d.rc[i].lut_slot < 0) all_d8 = false;
+		for (int ch = 0; ch < 3; ++ch)
+			for (int sc = 0; sc < 2; ++sc) {
+				const float k = sc ? 1.0f / 1024.0f : 1.0f;   // exact scalings
+				d.rk[i].mY[ch][sc] = d.rc[i].cm[ch * 4 + 0] * k;
+				d.rk[i].oY[ch][sc] = -8388608.0f * d.rk[i].mY[ch][sc];
+				d.rk[i].mCb[ch][sc] = d.rc[i].cm[ch * 4 + 1] * k;
+				d.rk[i].mCr[ch][sc] = d.rc[i].cm[ch * 4 + 2] * k;
+			}
 	}
+	d.wc.lut_slot = slot_of(wt);
+	if (d.wc.lut_slot < 0) all_d8 = false;
 	d.n_luts = all_d8 ? n_slots : 0;
 	for (int i = 0; i < d.n_luts; ++i) {
 		d.luts[i].d8 = c->lut_tables[slots[i]].d8;
 		d.luts[i].lp = c->lut_tables[slots[i]].lp;
 	}
+	if (d.n_luts) d.wlp = d.luts[d.wc.lut_slot].lp;
 	return 1;
 }
 
