@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libphaneron_b200.so")
+LIB_PATH = os.environ.get("PB_LIB") or os.path.join(HERE, "libphaneron_b200.so")   # PB_LIB: kernel-variant experiments
 
 PB_OK = 0
 QUEUE_LOAD, QUEUE_PROCESS, QUEUE_UNLOAD = 0, 1, 2

@@ -21,6 +21,9 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
     "-Xptxas", "-v",
 ]
+for _k in ("PB_MARCH_WARPS", "PB_MARCH_ROUNDS"):   # kernel-variant experiments
+    if os.environ.get(_k):
+        NVCC_FLAGS += [f"-D{_k}={int(os.environ[_k])}"]
 
 
 def _nvcc() -> str:

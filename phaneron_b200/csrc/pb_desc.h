@@ -16,14 +16,22 @@ constexpr int kMaxReadConsts = 8;
 constexpr int kMaxLuts = 3;          // march kernel: distinct gamma tables resident in shared memory
 
 // ---- march kernel geometry (pb_march.cu) ---------------------------------------------
-constexpr int kMarchWarps = 16;              // warps per CTA; one persistent CTA per SM
+#ifndef PB_MARCH_WARPS
+#define PB_MARCH_WARPS 16
+#endif
+constexpr int kMarchWarps = PB_MARCH_WARPS;  // warps per CTA; one persistent CTA per SM
 constexpr int kMarchThreads = kMarchWarps * 32;
-constexpr int kStripGroupsXf = 31;           // output v210 groups per strip when a leaf is bilinear-sampled:
-                                             // 186 px need <= 187 texels = <= 32 source groups at scale 1
-constexpr int kStripGroupsDirect = 32;       // all leaves sampled 1:1
-constexpr int kRowGroups = 64;               // source groups a warp's row buffer can hold
-constexpr int kRowCap = kRowGroups * 6;      // texels per plane
-constexpr int kRowFloats = 3 * kRowCap;      // planar R | G | B
+#ifndef PB_MARCH_ROUNDS
+#define PB_MARCH_ROUNDS 3
+#endif
+constexpr int kRounds = PB_MARCH_ROUNDS;     // output pixels per lane: a strip is <= 32 * kRounds px
+// Output v210 groups per strip when a leaf is bilinear-sampled: 16*kRounds/3 - 1, so that at scale 1
+// the n+1 texels n pixels need span <= 16*kRounds/3 source groups for any alignment.  With kRounds = 3
+// that is 16 groups per row: the two source rows of a leaf convert in ONE 32-lane pass.
+constexpr int kStripGroupsXf = 16 * kRounds / 3 - 1;
+constexpr int kStripGroupsDirect = 16 * kRounds / 3;   // all leaves sampled 1:1
+constexpr int kRowGroups = 32 * kRounds / 3;           // source groups a warp's row buffer holds (2 rows x 16 when they fit, else 1 row)
+constexpr int kRowFloats = kRowGroups * 18;            // planar R | G | B per row slot
 
 enum LeafKind : int { LEAF_NONE = 0, LEAF_V210 = 1, LEAF_RGBA_F32 = 2 };
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
@@ -49,13 +57,12 @@ struct ReadConsts {
 	int pad_;
 };
 
-// march kernel: ReadConsts::cm pre-scaled for v210 fields converted without a shift.  A 10-bit field
-// at bit 10 of a word is read as the float 1024*v (mask | 2^23 exponent trick), so its coefficient is
-// m / 1024 (exact: power of two); [c][0] multiplies plain fields, [c][1] fields scaled by 1024.
-// oY = -2^23 * mY folds the exponent-trick bias of the luma field into the first FMA of the chain:
-// fma(2^23 + s*y, m/s, -2^23*m/s) == RN(y*m) exactly.
+// march kernel: ReadConsts::cm rearranged.  oY = -2^23 * mY folds the bias of the exponent-trick luma
+// float into the first FMA of the chain: fma(2^23 + y, m, -2^23 * m) == RN(y * m) exactly.  A 10-bit
+// chroma field at bit 10 of a word is read as the float 1024*c, so its coefficient is m / 1024 (exact:
+// power of two); [c][0] multiplies plain fields, [c][1] fields scaled by 1024.
 struct ReadK {
-	float mY[3][2], oY[3][2], mCb[3][2], mCr[3][2];
+	float mY[3], oY[3], mCb[3][2], mCr[3][2];
 };
 
 // Saver constants (loadSave.ts:130-150): linear->gamma LUT, RGB->YCbCr 3x4
@@ -87,6 +94,9 @@ struct Leaf {
 	const int2 *col_tab;
 	const int2 *row_tab;
 	const int4 *strip_tab;
+	// strips [s0, s1] and output lines [y0, y1] outside of which every tap of this leaf is a border
+	// texel: the kernel skips the leaf there without touching memory
+	int s0, s1, y0, y1;
 };
 
 struct Layer {
@@ -106,6 +116,8 @@ struct FusedDesc {
 	int strip_groups;  // output groups per strip
 	int n_strips;
 	int n_luts;        // tables to stage in shared memory (0: gather from the raw tables in global memory)
+	int dbg;           // experiment switches (PB_DBG environment variable), 0 in production
+	uint32_t e_magic;  // 0x4B000000, handed to the kernel as data so that (w & mask) | e stays one LOP3
 	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
 	LutDesc luts[kMaxLuts];   // slot 0 = rc[0]'s table
 	LutParams wlp;            // = luts[wc.lut_slot].lp, at a fixed offset for the encoder

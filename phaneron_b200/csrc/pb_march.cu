@@ -9,23 +9,25 @@
 // Shape of the kernel:
 //   * one persistent CTA per SM, kMarchWarps warps; the gamma tables live in shared memory in the
 //     lossless one-byte-per-entry form of pb_lut.cuh (128 KiB for a read + a write table);
-//   * a work item is one output line of one strip (31 or 32 v210 groups = 186 / 192 px); items are
-//     dealt round-robin to all warps of the grid, so a warp never waits on another warp: no
-//     __syncthreads after the table load, only __syncwarp;
-//   * per leaf and source row the warp converts the strip's source footprint ONCE (lane = v210
-//     group: one 128-bit load, 6 texels) into its private planar row buffer, then every lane
-//     takes its taps for 6 output pixels (lane = pixel, stride-1 conflict-free LDS) with the exact
-//     {i0, a} / {j0, b} tables the host derived from the reference's float formula;
-//   * the canonical FMA chain of the oracle (w00*t00 -> +w10*t10 -> +w01*t01 -> +w11*t11) is
-//     evaluated row by row, so one row buffer per warp suffices;
-//   * the 6-pixel / 4-word v210 regroup goes through the same buffer: 32 lanes x 6 rounds of
+//   * a work item is one output line of one strip (15 or 16 v210 groups = 90 / 96 px, 3 pixels per
+//     lane); items are dealt round-robin to all warps of the grid, so a warp never waits on another
+//     warp: no __syncthreads after the table load, only __syncwarp.  Narrow strips keep the per-lane
+//     pixel state small (registers, not occupancy, were the limit of wider strips: profiles/);
+//   * per leaf the warp converts the strip's source footprint ONCE (lane = v210 group: one 128-bit
+//     load, 6 texels) into its private planar row buffer.  At scale >= ~1 a row needs <= 16 groups,
+//     so lanes 0-15 convert row j0 and lanes 16-31 row j0+1 in ONE full-width pass and the 4-tap
+//     bilinear chain runs at once; smaller scales (<= 32 groups per row) take one pass per row and
+//     continue the oracle's canonical chain (w00*t00 -> +w10*t10 -> +w01*t01 -> +w11*t11) across them;
+//   * every lane then takes its taps for 3 output pixels (lane = pixel, stride-1 conflict-free
+//     LDS) with the exact {i0, a} / {j0, b} tables the host derived from the reference's float formula;
+//   * the 6-pixel / 4-word v210 regroup goes through the same buffer: 32 lanes x 3 rounds of
 //     codes in, lane = group out, one coalesced 16-byte store per lane.
 // Instruction economy (the kernel is issue / FMA-pipe / SFU bound, not HBM bound -- DESIGN.md 4.3):
 //   * the two pixels of a 4:2:2 chroma pair are converted together with packed fp32x2
 //     instructions (fma.rn.f32x2: same lane rate as FFMA, half the issue slots);
-//   * 10-bit fields become floats with one LOP3 (mask | 2^23 exponent) and no shift where the
-//     field sits at bit 10: it is read as 1024*v and meets a coefficient pre-divided by 1024;
-//   * the luma bias of that trick is folded into the first FMA of the matrix row (ReadK::oY);
+//   * 10-bit fields become floats with one LOP3 (mask | 2^23 exponent); a chroma field at bit 10
+//     needs no shift: it is read as 1024*c and meets a coefficient pre-divided by 1024;
+//   * the 2^23 bias of the luma floats is folded into the first FMA of the matrix row (ReadK::oY);
 //   * the table index, the table address and the exact float index all come from ONE add of a
 //     per-table magic constant 2^23 + (shared-memory address of the table);
 //   * the toe / power select of the transfer function is arithmetic (saturating FMAs), keeping
@@ -45,7 +47,6 @@ namespace pb {
 
 namespace {
 
-constexpr int kRounds = 6;   // 192 px / 32 lanes
 constexpr float kTwo23 = 8388608.0f;
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
@@ -93,17 +94,17 @@ __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const 
 }
 
 // Two horizontally adjacent pixels sharing one chroma pair -> linear RGB in the working gamut
-// (v210.ts:65-77).  ya/yb/cb/cr are the raw exponent-trick floats 2^23 + s*v; SYA.. say whether
-// s is 1 (0) or 1024 (1) for that field.
-template <int kLutMode, bool kSparse, int SYA, int SYB, int SCB, int SCR>
+// (v210.ts:65-77).  ya/yb are the exponent-trick floats 2^23 + y; cb/cr are 2^23 + s*c with s = 1
+// (SCB/SCR = 0) or 1024 (= 1: a field at bit 10 taken without a shift, met by a coefficient / 1024).
+template <int kLutMode, bool kSparse, int SCB, int SCR>
 __device__ __forceinline__ void convert_pair(uint32_t ya, uint32_t yb, uint32_t cb, uint32_t cr, const ReadConsts &rc, const ReadK &rk,
                                              const LutK<kLutMode> &lut, const LutParams &lp, float2 &R, float2 &G, float2 &B) {
 	const float2 Y = f2(__uint_as_float(ya), __uint_as_float(yb));
 	const float2 C = __fadd2_rn(f2(__uint_as_float(cb), __uint_as_float(cr)), f2s(-kTwo23));   // exact (scaled) chroma codes
 	// dot(yuva, colMatrix row): mul, fma, fma, fma(1, m3, t) -- the last is RN(t + m3), fused with the saturate
-	float2 tr = __ffma2_rn(Y, f2(rk.mY[0][SYA], rk.mY[0][SYB]), f2(rk.oY[0][SYA], rk.oY[0][SYB]));
-	float2 tg = __ffma2_rn(Y, f2(rk.mY[1][SYA], rk.mY[1][SYB]), f2(rk.oY[1][SYA], rk.oY[1][SYB]));
-	float2 tb = __ffma2_rn(Y, f2(rk.mY[2][SYA], rk.mY[2][SYB]), f2(rk.oY[2][SYA], rk.oY[2][SYB]));
+	float2 tr = __ffma2_rn(Y, f2s(rk.mY[0]), f2s(rk.oY[0]));   // == RN(y * m0): the 2^23 bias of Y is folded into oY
+	float2 tg = __ffma2_rn(Y, f2s(rk.mY[1]), f2s(rk.oY[1]));
+	float2 tb = __ffma2_rn(Y, f2s(rk.mY[2]), f2s(rk.oY[2]));
 	if (!kSparse) tr = f2(fma_(C.x, rk.mCb[0][SCB], tr.x), fma_(C.x, rk.mCb[0][SCB], tr.y));   // cm[1] == 0: fma(cb, 0, t) == t
 	tr = f2(fma_(C.y, rk.mCr[0][SCR], tr.x), fma_(C.y, rk.mCr[0][SCR], tr.y));
 	tg = f2(fma_(C.x, rk.mCb[1][SCB], tg.x), fma_(C.x, rk.mCb[1][SCB], tg.y));
@@ -119,30 +120,42 @@ __device__ __forceinline__ void convert_pair(uint32_t ya, uint32_t yb, uint32_t 
 	B = __ffma2_rn(b, f2s(rc.gamut[8]), __ffma2_rn(g, f2s(rc.gamut[7]), __fmul2_rn(r, f2s(rc.gamut[6]))));
 }
 
-// one v210 group (6 texels, v210.ts:58-63) -> the warp's planar row buffer at texel column 6g
+// (w & mask) | e in one LOP3: `e` (0x4B000000, FusedDesc::e_magic) arrives in a register so that
+// ptxas does not split the operation around two immediates
+__device__ __forceinline__ uint32_t mask_or(uint32_t w, uint32_t mask, uint32_t e) {
+	uint32_t o;
+	asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(o) : "r"(w), "r"(mask), "r"(e));
+	return o;
+}
+
+// one v210 group (6 texels, v210.ts:58-63) -> planar row slot `row` (plane stride `cap` texels) at texel column 6g
 template <int kLutMode, bool kSparse>
-__device__ __forceinline__ void convert_group(const uint4 &w, int g, const ReadConsts &rc, const ReadK &rk, const LutK<kLutMode> &lut,
-                                              const LutParams &lp, float *buf) {
-	float2 *pr = reinterpret_cast<float2 *>(buf + 0 * kRowCap + g * 6);
-	float2 *pg = reinterpret_cast<float2 *>(buf + 1 * kRowCap + g * 6);
-	float2 *pb_ = reinterpret_cast<float2 *>(buf + 2 * kRowCap + g * 6);
-	constexpr uint32_t E = 0x4B000000u, M0 = 0x3ffu, M10 = 0xffc00u;
+__device__ __forceinline__ void convert_group(const uint4 &w, int g, uint32_t E, const ReadConsts &rc, const ReadK &rk,
+                                              const LutK<kLutMode> &lut, const LutParams &lp, float *row, int cap) {
+	float2 *pr = reinterpret_cast<float2 *>(row + g * 6);
+	float2 *pg = reinterpret_cast<float2 *>(row + cap + g * 6);
+	float2 *pb_ = reinterpret_cast<float2 *>(row + 2 * cap + g * 6);
+	constexpr uint32_t M0 = 0x3ffu, M10 = 0xffc00u;
 	float2 R, G, B;
 	// word 0: Cr0 | Y0 | Cb0     word 1: Y2 | Cb1 | Y1     word 2: Cb2 | Y3 | Cr1     word 3: Y5 | Cr2 | Y4
-	convert_pair<kLutMode, kSparse, 1, 0, 0, 0>((w.x & M10) | E, (w.y & M0) | E, (w.x & M0) | E, ((w.x >> 20) & M0) | E, rc, rk, lut, lp, R, G, B);
+	convert_pair<kLutMode, kSparse, 0, 0>(mask_or(w.x >> 10, M0, E), mask_or(w.y, M0, E), mask_or(w.x, M0, E), mask_or(w.x >> 20, M0, E), rc, rk, lut, lp,
+	                                      R, G, B);
 	pr[0] = R; pg[0] = G; pb_[0] = B;
-	convert_pair<kLutMode, kSparse, 0, 1, 1, 0>(((w.y >> 20) & M0) | E, (w.z & M10) | E, (w.y & M10) | E, (w.z & M0) | E, rc, rk, lut, lp, R, G, B);
+	convert_pair<kLutMode, kSparse, 1, 0>(mask_or(w.y >> 20, M0, E), mask_or(w.z >> 10, M0, E), mask_or(w.y, M10, E), mask_or(w.z, M0, E), rc, rk, lut, lp,
+	                                      R, G, B);
 	pr[1] = R; pg[1] = G; pb_[1] = B;
-	convert_pair<kLutMode, kSparse, 0, 0, 0, 1>((w.w & M0) | E, ((w.w >> 20) & M0) | E, ((w.z >> 20) & M0) | E, (w.w & M10) | E, rc, rk, lut, lp, R, G, B);
+	convert_pair<kLutMode, kSparse, 0, 1>(mask_or(w.w, M0, E), mask_or(w.w >> 20, M0, E), mask_or(w.z >> 20, M0, E), mask_or(w.w, M10, E), rc, rk, lut, lp,
+	                                      R, G, B);
 	pr[2] = R; pg[2] = G; pb_[2] = B;
 }
 
-// value of one leaf at the 6 pixels of this lane -> p[r] = (r, g, b, alpha)
+// value of one leaf at the 3 pixels of this lane -> p[r] = (r, g, b, alpha)
 template <int kLutMode, bool kSparse, bool kSingleRc>
 __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, float *buf, int lane, int strip, int y,
                                           int x_first, int x_last, float4 (&p)[kRounds]) {
 #pragma unroll
 	for (int r = 0; r < kRounds; ++r) p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (strip < lf.s0 || strip > lf.s1 || y < lf.y0 || y > lf.y1) return;   // nothing but border texels here
 	const int4 si = __ldg(lf.strip_tab + strip);
 	const int2 rt = __ldg(lf.row_tab + y);
 	if (!(si.x & 1)) return;   // the strip does not touch this leaf's image: border colour everywhere
@@ -152,13 +165,34 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	const bool has_xf = lf.has_xf != 0;
 	const bool ok0 = (unsigned)j0 < (unsigned)lf.h, ok1 = has_xf && (unsigned)(j0 + 1) < (unsigned)lf.h;
 	if (!ok0 && !ok1) return;   // both rows are border rows
+	const bool paired = ng <= 16;   // both rows fit one 32-lane pass
 
-	// issue every HBM load of this leaf up front: <= 2 groups per lane per row (kRowGroups = 64)
-	const uint4 *src0 = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j0 * lf.pitch) + g_lo + lane;
-	const uint4 *src1 = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(src0) + lf.pitch);
+	// issue every HBM load of this leaf up front
+	const char *row0 = reinterpret_cast<const char *>(lf.ptr) + (size_t)j0 * lf.pitch + (size_t)g_lo * 16;
 	const uint4 z4 = make_uint4(0, 0, 0, 0);
-	const uint4 a0 = (ok0 && lane < ng) ? ld_stream(src0) : z4, a1 = (ok0 && lane + 32 < ng) ? ld_stream(src0 + 32) : z4;
-	const uint4 b0 = (ok1 && lane < ng) ? ld_stream(src1) : z4, b1 = (ok1 && lane + 32 < ng) ? ld_stream(src1 + 32) : z4;
+	uint4 wa = z4, wb = z4;
+	if (paired) {   // lanes 0-15: row j0, lanes 16-31: row j0 + 1
+		const int hi = lane >> 4, g = lane & 15;
+		if (g < ng && (hi ? ok1 : ok0)) wa = ld_stream(reinterpret_cast<const uint4 *>(row0 + (hi ? lf.pitch : 0)) + g);
+	} else {
+		if (lane < ng && ok0) wa = ld_stream(reinterpret_cast<const uint4 *>(row0) + lane);
+		if (lane < ng && ok1) wb = ld_stream(reinterpret_cast<const uint4 *>(row0 + lf.pitch) + lane);
+	}
+	// sampling columns of this lane's pixels (exact host tables): buffer column of tap 0 and the weight a
+	int c0[kRounds];
+	float ca[kRounds];
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		const int x = min(x_first + r * 32 + lane, x_last);   // clamp for the ragged last strip / the unused lanes of round 2
+		if (has_xf) {
+			const int2 ct = __ldg(lf.col_tab + x);
+			c0[r] = ct.x - origin;
+			ca[r] = __int_as_float(ct.y);
+		} else {
+			c0[r] = x - origin;
+			ca[r] = 0.0f;
+		}
+	}
 
 	const float b = __int_as_float(rt.y), rb = sub(1.0f, b);
 	const int rci = kSingleRc ? 0 : lf.rc;
@@ -169,62 +203,98 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	LutK<kLutMode> lut;
 	lut.raw = rc.lut;
 	lut.magic = kLutMode ? kTwo23 + (float)(lut_saddr + (kSingleRc ? 0 : slot) * 65536) : kTwo23;
+	const uint32_t E = d.e_magic;
 
-#pragma unroll 1
-	for (int rr = 0; rr < 2; ++rr) {
-		if (!(rr ? ok1 : ok0)) continue;   // border row: all its taps are (0,0,0,0)
-#pragma unroll 1
-		for (int it = 0; it < 2; ++it) {
-			const int g = lane + it * 32;
-			if (g < ng) {
-				const uint4 w = rr ? (it ? b1 : b0) : (it ? a1 : a0);
-				convert_group<kLutMode, kSparse>(w, g, rc, rk, lut, lp, buf);
-			}
+	if (paired) {
+		constexpr int cap = 96, slot_floats = 3 * cap;   // two row slots of 16 groups
+		{
+			const int hi = lane >> 4, g = lane & 15;
+			if (g < ng && (hi ? ok1 : ok0)) convert_group<kLutMode, kSparse>(wa, g, E, rc, rk, lut, lp, buf + hi * slot_floats, cap);
 		}
 		__syncwarp();
 		if (!has_xf) {   // 1:1 read of texel (x, y): exact passthrough, alpha = 1 (leaf_value in pb_device.cuh)
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const float *t = buf + (min(x_first + r * 32 + lane, x_last) - origin);
-				p[r] = make_float4(t[0], t[kRowCap], t[2 * kRowCap], 1.0f);
+				const float *t = buf + c0[r];
+				p[r] = make_float4(t[0], t[cap], t[2 * cap], 1.0f);
+			}
+		} else if (!edge && ok0 && ok1) {   // interior: all four taps are texels
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const float *t0 = buf + c0[r], *t1 = t0 + slot_floats;
+				const float ra = sub(1.0f, ca[r]);
+				const float w00 = mul(ra, rb), w10 = mul(ca[r], rb), w01 = mul(ra, b), w11 = mul(ca[r], b);
+				p[r].x = fma_(w11, t1[1], fma_(w01, t1[0], fma_(w10, t0[1], mul(w00, t0[0]))));
+				p[r].y = fma_(w11, t1[cap + 1], fma_(w01, t1[cap], fma_(w10, t0[cap + 1], mul(w00, t0[cap]))));
+				p[r].z = fma_(w11, t1[2 * cap + 1], fma_(w01, t1[2 * cap], fma_(w10, t0[2 * cap + 1], mul(w00, t0[2 * cap]))));
+				p[r].w = add(w11, add(w01, add(w10, w00)));   // alpha taps are all 1: fma(w, 1, al) = RN(w + al)
+			}
+		} else {   // some taps are border texels (0,0,0,0): fma(w, 0, x) = x
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const int i0 = c0[r] + origin;
+				const bool fc0 = (unsigned)i0 < (unsigned)lf.w, fc1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
+				const bool f00 = fc0 && ok0, f10 = fc1 && ok0, f01 = fc0 && ok1, f11 = fc1 && ok1;
+				const float *t0 = buf + min(max(c0[r], 0), last), *t1 = buf + min(max(c0[r] + 1, 0), last);
+				const float ra = sub(1.0f, ca[r]);
+				const float w00 = mul(ra, rb), w10 = mul(ca[r], rb), w01 = mul(ra, b), w11 = mul(ca[r], b);
+#define PB_TAP(flag, ptr, off) ((flag) ? (ptr)[off] : 0.0f)
+				p[r].x = fma_(w11, PB_TAP(f11, t1, slot_floats), fma_(w01, PB_TAP(f01, t0, slot_floats), fma_(w10, PB_TAP(f10, t1, 0), mul(w00, PB_TAP(f00, t0, 0)))));
+				p[r].y = fma_(w11, PB_TAP(f11, t1, slot_floats + cap),
+				              fma_(w01, PB_TAP(f01, t0, slot_floats + cap), fma_(w10, PB_TAP(f10, t1, cap), mul(w00, PB_TAP(f00, t0, cap)))));
+				p[r].z = fma_(w11, PB_TAP(f11, t1, slot_floats + 2 * cap),
+				              fma_(w01, PB_TAP(f01, t0, slot_floats + 2 * cap), fma_(w10, PB_TAP(f10, t1, 2 * cap), mul(w00, PB_TAP(f00, t0, 2 * cap)))));
+#undef PB_TAP
+				float al = f00 ? w00 : 0.0f;
+				al = f10 ? add(w10, al) : al;
+				al = f01 ? add(w01, al) : al;
+				al = f11 ? add(w11, al) : al;
+				p[r].w = al;
+			}
+		}
+		__syncwarp();
+		return;
+	}
+
+	// wide footprint (more than 16 groups per row): one pass per row, the canonical chain continues across them
+	constexpr int cap = kRowGroups * 6;
+#pragma unroll 1
+	for (int rr = 0; rr < 2; ++rr) {
+		if (!(rr ? ok1 : ok0)) continue;   // border row: all its taps are (0,0,0,0)
+		if (lane < ng) convert_group<kLutMode, kSparse>(rr ? wb : wa, lane, E, rc, rk, lut, lp, buf, cap);
+#pragma unroll 1
+		for (int g = lane + 32; g < ng; g += 32) {   // only strips wider than 96 px get here
+			const uint4 w = ld_stream(reinterpret_cast<const uint4 *>(row0 + (rr ? lf.pitch : 0)) + g);
+			convert_group<kLutMode, kSparse>(w, g, E, rc, rk, lut, lp, buf, cap);
+		}
+		__syncwarp();
+		const float wr = rr == 0 ? rb : b;
+		if (!edge) {
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const float *t = buf + c0[r];
+				const float w0 = mul(sub(1.0f, ca[r]), wr), w1 = mul(ca[r], wr);   // w00|w01 , w10|w11
+				p[r].x = fma_(w1, t[1], fma_(w0, t[0], p[r].x));
+				p[r].y = fma_(w1, t[cap + 1], fma_(w0, t[cap], p[r].y));
+				p[r].z = fma_(w1, t[2 * cap + 1], fma_(w0, t[2 * cap], p[r].z));
+				p[r].w = add(w1, add(w0, p[r].w));
 			}
 		} else {
-			const float wr = rr == 0 ? rb : b;
-			const int2 *ctab = lf.col_tab + x_first + lane;
-			const int xmax = x_last - x_first - lane;   // clamp for the ragged last strip
-			if (!edge) {
 #pragma unroll
-				for (int r = 0; r < kRounds; ++r) {
-					const int2 ct = __ldg(ctab + min(r * 32, xmax));
-					const float *t = buf + (ct.x - origin);
-					const float ca = __int_as_float(ct.y);
-					const float w0 = mul(sub(1.0f, ca), wr), w1 = mul(ca, wr);   // w00|w01 , w10|w11
-					p[r].x = fma_(w1, t[1], fma_(w0, t[0], p[r].x));
-					p[r].y = fma_(w1, t[kRowCap + 1], fma_(w0, t[kRowCap], p[r].y));
-					p[r].z = fma_(w1, t[2 * kRowCap + 1], fma_(w0, t[2 * kRowCap], p[r].z));
-					// alpha taps are 1 inside the image: fma(w, 1, al) = RN(w + al)
-					p[r].w = add(w1, add(w0, p[r].w));
-				}
-			} else {
-#pragma unroll
-				for (int r = 0; r < kRounds; ++r) {
-					const int2 ct = __ldg(ctab + min(r * 32, xmax));
-					const int i0 = ct.x, c0 = i0 - origin;
-					const float ca = __int_as_float(ct.y);
-					const bool f0 = (unsigned)i0 < (unsigned)lf.w, f1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
-					const float *t0 = buf + min(max(c0, 0), last), *t1 = buf + min(max(c0 + 1, 0), last);
-					const float w0 = mul(sub(1.0f, ca), wr), w1 = mul(ca, wr);
-					const float t0r = f0 ? t0[0] : 0.0f, t0g = f0 ? t0[kRowCap] : 0.0f, t0b = f0 ? t0[2 * kRowCap] : 0.0f;
-					const float t1r = f1 ? t1[0] : 0.0f, t1g = f1 ? t1[kRowCap] : 0.0f, t1b = f1 ? t1[2 * kRowCap] : 0.0f;
-					p[r].x = fma_(w1, t1r, fma_(w0, t0r, p[r].x));
-					p[r].y = fma_(w1, t1g, fma_(w0, t0g, p[r].y));
-					p[r].z = fma_(w1, t1b, fma_(w0, t0b, p[r].z));
-					// border taps have alpha 0: fma(w, 0, al) = al
-					float al = p[r].w;
-					al = f0 ? add(w0, al) : al;
-					al = f1 ? add(w1, al) : al;
-					p[r].w = al;
-				}
+			for (int r = 0; r < kRounds; ++r) {
+				const int i0 = c0[r] + origin;
+				const bool f0 = (unsigned)i0 < (unsigned)lf.w, f1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
+				const float *t0 = buf + min(max(c0[r], 0), last), *t1 = buf + min(max(c0[r] + 1, 0), last);
+				const float w0 = mul(sub(1.0f, ca[r]), wr), w1 = mul(ca[r], wr);
+				const float t0r = f0 ? t0[0] : 0.0f, t0g = f0 ? t0[cap] : 0.0f, t0b = f0 ? t0[2 * cap] : 0.0f;
+				const float t1r = f1 ? t1[0] : 0.0f, t1g = f1 ? t1[cap] : 0.0f, t1b = f1 ? t1[2 * cap] : 0.0f;
+				p[r].x = fma_(w1, t1r, fma_(w0, t0r, p[r].x));
+				p[r].y = fma_(w1, t1g, fma_(w0, t0g, p[r].y));
+				p[r].z = fma_(w1, t1b, fma_(w0, t0b, p[r].z));
+				float al = p[r].w;
+				al = f0 ? add(w0, al) : al;
+				al = f1 ? add(w1, al) : al;
+				p[r].w = al;
 			}
 		}
 		__syncwarp();
@@ -321,12 +391,12 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			}
 		}
 
-		// ---- encode (v210.ts:145-156), two rounds at a time, and regroup 6 pixels -> 4 words through the row buffer ----
+		// ---- encode (v210.ts:145-156) and regroup 6 pixels -> 4 words through the row buffer ----
 		// The host has checked that every code lies in [0, 1023] for table values in [0, 1], so
 		// convert_ushort_sat_rte reduces to the RNE add and the three codes share one word.
 		uint32_t *stage = reinterpret_cast<uint32_t *>(buf);
 #pragma unroll
-		for (int r = 0; r < kRounds; r += 2) {
+		for (int r = 0; r + 1 < kRounds; r += 2) {   // two rounds at a time
 			const float2 gr = lut2<kLutMode>(f2(__saturatef(acc[r].x), __saturatef(acc[r + 1].x)), wlut, wlp);
 			const float2 gg = lut2<kLutMode>(f2(__saturatef(acc[r].y), __saturatef(acc[r + 1].y)), wlut, wlp);
 			const float2 gb = lut2<kLutMode>(f2(__saturatef(acc[r].z), __saturatef(acc[r + 1].z)), wlut, wlp);
@@ -341,6 +411,18 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			}
 			stage[r * 32 + lane] = code0;
 			stage[(r + 1) * 32 + lane] = code1;
+		}
+		if (kRounds & 1) {   // the odd round out: (r, g) as one pair, b alone
+			constexpr int r = kRounds - 1;
+			const float2 hrg = lut2<kLutMode>(f2(__saturatef(acc[r].x), __saturatef(acc[r].y)), wlut, wlp);
+			const float2 hb = lut2<kLutMode>(f2s(__saturatef(acc[r].z)), wlut, wlp);
+			uint32_t code = 0;
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				const float u = add(add(fma_(hb.x, d.wc.cm[c * 4 + 2], fma_(hrg.y, d.wc.cm[c * 4 + 1], mul(hrg.x, d.wc.cm[c * 4 + 0]))), d.wc.cm[c * 4 + 3]), kTwo23);
+				code |= (__float_as_uint(u) & 0x3ffu) << (10 * c);
+			}
+			stage[r * 32 + lane] = code;
 		}
 		__syncwarp();
 		if (x_first + lane * 6 <= x_last) {

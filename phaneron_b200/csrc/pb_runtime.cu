@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -126,6 +127,7 @@ struct pb_ctx {
 	struct SampleTab {
 		float m[6];
 		int sw, sh, W, H, has_xf, strip_groups, fits = 1;
+		int s0 = 0, s1 = -1, y0 = 0, y1 = -1;   // active strips / lines
 		void *dev = nullptr;
 		int2 *dcol = nullptr, *drow = nullptr;
 		int4 *dstrip = nullptr;
@@ -651,6 +653,18 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 			if (e.z > pb::kRowGroups) t.fits = 0;
 		}
 		hstrip[sidx] = e;
+		if (e.x & 1) {
+			if (t.s1 < t.s0) t.s0 = sidx;
+			t.s1 = sidx;
+		}
+	}
+	for (int y = 0; y < H; ++y) {
+		const int j0 = hrow[y].x;
+		const bool ok = (j0 >= 0 && j0 < lf.h) || (lf.has_xf && j0 + 1 >= 0 && j0 + 1 < lf.h);
+		if (ok) {
+			if (t.y1 < t.y0) t.y0 = y;
+			t.y1 = y;
+		}
 	}
 	CU(cudaMalloc(&t.dev, bytes));
 	CU(cudaMemcpyAsync(t.dev, host.data(), bytes, cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
@@ -692,6 +706,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			leaves[n_leaves++] = &lf;
 		}
 	}
+	if (const char *dbg = getenv("PB_DBG")) d.dbg = atoi(dbg);
+	d.e_magic = 0x4B000000u;
 	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
 	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
 	for (int i = 0; i < n_leaves; ++i) {
@@ -703,6 +719,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		leaves[i]->col_tab = t->dcol;
 		leaves[i]->row_tab = t->drow;
 		leaves[i]->strip_tab = t->dstrip;
+		leaves[i]->s0 = t->s0; leaves[i]->s1 = t->s1; leaves[i]->y0 = t->y0; leaves[i]->y1 = t->y1;
 	}
 	// the write side packs three codes into one word while regrouping: they must fit 10 bits
 	const int wt = lut_table_by_raw(c, d.wc.lut);
@@ -732,14 +749,15 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		if (d.rc[i].cm[1] != 0.0f || d.rc[i].cm[10] != 0.0f) d.sparse_cm = 0;
 		d.rc[i].lut_slot = slot_of(lut_table_by_raw(c, d.rc[i].lut));
 		if (d.rc[i].lut_slot < 0) all_d8 = false;
-		for (int ch = 0; ch < 3; ++ch)
+		for (int ch = 0; ch < 3; ++ch) {
+			d.rk[i].mY[ch] = d.rc[i].cm[ch * 4 + 0];
+			d.rk[i].oY[ch] = -8388608.0f * d.rk[i].mY[ch];
 			for (int sc = 0; sc < 2; ++sc) {
 				const float k = sc ? 1.0f / 1024.0f : 1.0f;   // exact scalings
-				d.rk[i].mY[ch][sc] = d.rc[i].cm[ch * 4 + 0] * k;
-				d.rk[i].oY[ch][sc] = -8388608.0f * d.rk[i].mY[ch][sc];
 				d.rk[i].mCb[ch][sc] = d.rc[i].cm[ch * 4 + 1] * k;
 				d.rk[i].mCr[ch][sc] = d.rc[i].cm[ch * 4 + 2] * k;
 			}
+		}
 	}
 	d.wc.lut_slot = slot_of(wt);
 	if (d.wc.lut_slot < 0) all_d8 = false;
