@@ -154,6 +154,17 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel, inputs):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same scene (profiles/r01_march_ncu_summary.json); None if not captured"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_march_ncu_summary.json")) as f:
+            j = json.load(f)
+        return j.get(f"{kernel}_{inputs}", {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def workload_name(inputs):
     return (f"{WIDTH}x{HEIGHT} v210, {LAYERS}-layer composite (L1 identity, L2-L4 MIXER FILL 0.5 PiP, top layer dissolve mix=0.5 "
             f"with a 5th source), {COL_READ}->{COL_WORK}, inputs={inputs}")
@@ -198,13 +209,18 @@ async def run_ours(args, rank, world, local_rank):
         harnesses.append(h)
         chains.append(chain)
         keep.append(dests)
+    st_k = ctx.stats()
+    kernel_name = ("k_fused_march (pb_march.cu), gamma tables as 1-byte deltas in shared memory" if st_k["march_launches"] and args.kernel == "march"
+                   else "k_fused_march, raw gamma tables from global memory" if st_k["march_launches"] else "k_fused_generic (pb_fused.cu)")
     alg_bytes = harnesses[0].algorithmic_bytes()
     launches_per_frame = chains[0].launches
     await ctx.waitFinish(ctx.queue.process)
 
+    fps_n = args.frames_per_step
+
     def replay_step(step_index):
-        base = step_index * FRAMES_PER_STEP
-        for f in range(FRAMES_PER_STEP):
+        base = step_index * fps_n
+        for f in range(fps_n):
             chains[(base + f) % n_sets].replay()
 
     # ---- device-resident leg ----------------------------------------------------------------
@@ -234,7 +250,7 @@ async def run_ours(args, rank, world, local_rank):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    frames = args.steps * FRAMES_PER_STEP
+    frames = args.steps * fps_n
     fps_rank = frames / (ms * 1e-3)
     launches = st1["kernel_launches"] - st0["kernel_launches"]
 
@@ -250,13 +266,19 @@ async def run_ours(args, rank, world, local_rank):
     s0 = ctx.stats()
     te0 = time.perf_counter()
     checksum = 0
-    for i in range(e2e_steps * E2E_FRAMES_PER_STEP):
-        ups = await he.upload_all(1000 + i)              # H2D of every source frame, from pinned host memory
-        frame = await he.compose(ups, 1000 + i)          # operators + job queue (records the expression)
-        dests = await he.consume(frame, download=True)   # fused launch + D2H of the packed result
+    # Frames are pipelined the way phaneron's redioactive pipes run them: while frame i is composed, packed and
+    # read back, frame i+1's sources are already being copied in (every call is async work, see nodencl.py).
+    n_e2e = e2e_steps * E2E_FRAMES_PER_STEP
+    ups = await he.upload_all(1000)                          # H2D of every source frame, from pinned host memory
+    for i in range(n_e2e):
+        nxt = asyncio.ensure_future(he.upload_all(1001 + i)) if i + 1 < n_e2e else None
+        frame = await he.compose(ups, 1000 + i)              # operators + job queue (records the expression)
+        dests = await he.consume(frame, download=True)       # fused launch + D2H of the packed result
         checksum ^= int(dests[0].host[:64].view(np.uint64).sum())
         for d in dests:
             d.release()
+        if nxt is not None:
+            ups = await nxt
     te1 = time.perf_counter()
     s1 = ctx.stats()
     e2e_dt = te1 - te0
@@ -275,12 +297,12 @@ async def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": fps_rank * world, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.inputs), "frames_per_step": FRAMES_PER_STEP, "input_sets": n_sets,
+            "config": {"workload": workload_name(args.inputs), "frames_per_step": fps_n, "kernel": kernel_name, "input_sets": n_sets,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating sets x {set_bytes} B = {n_sets * set_bytes} B > 126 MiB",
                        "channels": world, "parallelism": f"{world} independent channel(s), one per GPU",
                        "launches_per_frame": launches_per_frame, "occlusion_culling": False},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": f"of {peak_kind}", "frac_of_nominal_8TBps": achieved / 8000.0,
+                         "traffic": ncu_traffic(args.kernel, args.inputs), "peak_kind": f"of {peak_kind}", "frac_of_nominal_8TBps": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": alg_bytes // launches_per_frame, "launch_us": launch_ms * 1e3},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // e2e_steps,
                     "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // e2e_steps, "frames_per_step": E2E_FRAMES_PER_STEP,
@@ -290,7 +312,7 @@ async def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = 20
+            n = 150   # ~1 s of wall clock on 16 cores = ~15-20 core-seconds of CPU work
             fps, dt = cpu_reference_fps(n, 1, args.inputs, threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "sample": f"{n} x {WIDTH}x{REF_SAMPLE_LINES} bands ({REF_SAMPLE_LINES}/{HEIGHT} frame each) of the same scene, "
@@ -309,6 +331,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inputs", default="noise", choices=["ramp", "noise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP, help="frames per device-resident step (profiling runs use a few)")
     ap.add_argument("--kernel", default="march", choices=["march", "march_raw", "generic"],
                     help="march: fused kernel, gamma tables in shared memory (default); march_raw: same kernel gathering "
                          "from the raw tables; generic: the fallback fused kernel")

@@ -9,10 +9,12 @@
  *   - all arithmetic IEEE-754 binary32, round-to-nearest-even, no implicit
  *     contraction (this file is compiled with -ffp-contract=off and every
  *     fused operation is an explicit fmaf());
- *   - OpenCL dot(a,b) = left-to-right FMA chain, the expansion clang/libclc
- *     (POCL) and NVIDIA's OpenCL compiler produce for
- *     a.x*b.x + a.y*b.y + a.z*b.z (+ a.w*b.w) with contraction on:
- *         t = a.x*b.x; t = fma(a.y,b.y,t); t = fma(a.z,b.z,t); [t = fma(a.w,b.w,t)]
+ *   - OpenCL dot(a,b) = the expansion LLVM produces for
+ *     a.x*b.x + a.y*b.y + a.z*b.z (+ a.w*b.w) with contraction on (the OpenCL default),
+ *     read off the PTX NVIDIA's OpenCL compiler emits for the reference's own kernels on the
+ *     B200 (profiles/r01_reference_opencl_ptx_excerpt.txt): the first sum fuses as
+ *     fma(a.x, b.x, a.y*b.y), so the .y product is the one plain multiply:
+ *         t = a.y*b.y; t = fma(a.x,b.x,t); t = fma(a.z,b.z,t); [t = fma(a.w,b.w,t)]
  *   - fma() in kernel source is a single correctly rounded fma;
  *   - float division is correctly rounded;
  *   - convert_T_sat_rte: NaN -> 0, clamp, round half to even;
@@ -282,15 +284,15 @@ void orc_transform_matrix(int width, int height, int flip_h, int flip_v, double 
 /* OpenCL built-ins under the canonical semantics                            */
 /* ------------------------------------------------------------------------- */
 static inline float dot4(const float a[4], const float b[4]) {
-	float t = a[0] * b[0];
-	t = fmaf(a[1], b[1], t);
+	float t = a[1] * b[1];   /* a.x*b.x + a.y*b.y contracts to fma(a.x, b.x, a.y*b.y): the .y product is the plain multiply */
+	t = fmaf(a[0], b[0], t);
 	t = fmaf(a[2], b[2], t);
 	t = fmaf(a[3], b[3], t);
 	return t;
 }
 static inline float dot3(const float a[3], const float b[3]) {
-	float t = a[0] * b[0];
-	t = fmaf(a[1], b[1], t);
+	float t = a[1] * b[1];
+	t = fmaf(a[0], b[0], t);
 	t = fmaf(a[2], b[2], t);
 	return t;
 }

@@ -1,0 +1,229 @@
+"""TEST INFRASTRUCTURE: the reference's own OpenCL kernels, run on the NVIDIA OpenCL driver of the GPU box.
+
+`oracle/_ref/kernels/*.cl` are the kernel strings of /root/reference/src/process/*.ts, extracted verbatim by
+extract_kernels.py (git-ignored, shipped to the GPU box); `oracle/_ref/libocl_ref.so` is ocl_runner.c.
+Each function below launches a kernel with the NDRange and argument list its reference wrapper uses
+(file:line cited), so its output IS the reference's output on this device.  tests/test_gpu_reference_opencl.py
+compares the CPU oracle and the CUDA path against it.  Nothing under phaneron_b200/ imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(os.path.dirname(HERE), "_ref")
+LIB = os.path.join(REF_DIR, "libocl_ref.so")
+KERNELS = os.path.join(REF_DIR, "kernels")
+
+_lib = None
+_kernels = {}
+
+
+def build() -> str:
+    """gcc ocl_runner.c -> oracle/_ref/libocl_ref.so, and (when /root/reference is present) refresh the kernel strings"""
+    os.makedirs(REF_DIR, exist_ok=True)
+    src = os.path.join(HERE, "ocl_runner.c")
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.run([cc, "-O2", "-std=c99", "-fPIC", "-shared", "-o", LIB, src, "-ldl"], check=True)
+    if os.path.isdir("/root/reference/src/process"):
+        subprocess.run(["python", os.path.join(HERE, "extract_kernels.py"), "/root/reference"], check=True, stdout=subprocess.DEVNULL)
+    return LIB
+
+
+def available() -> bool:
+    """True when the runner is built, the kernel strings are present and an NVIDIA OpenCL device answers"""
+    global _lib
+    if _lib is not None:
+        return True
+    if not (os.path.exists(LIB) and os.path.isdir(KERNELS)):
+        return False
+    l = C.CDLL(LIB)
+    l.ocl_log.restype = C.c_char_p
+    l.ocl_device_name.restype = C.c_char_p
+    l.ocl_kernel.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    l.ocl_buffer.argtypes = [C.c_size_t, C.c_void_p]
+    l.ocl_image.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    l.ocl_read_buffer.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+    l.ocl_read_image.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int]
+    l.ocl_arg_u32.argtypes = [C.c_int, C.c_int, C.c_uint32]
+    l.ocl_arg_f32.argtypes = [C.c_int, C.c_int, C.c_float]
+    l.ocl_run.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t]
+    if l.ocl_init() != 0:
+        return False
+    _lib = l
+    return True
+
+
+def why_unavailable() -> str:
+    if not os.path.exists(LIB):
+        return f"{LIB} not built"
+    if not os.path.isdir(KERNELS):
+        return f"{KERNELS} missing (run oracle/ref_ocl/extract_kernels.py where /root/reference exists)"
+    l = C.CDLL(LIB)
+    l.ocl_log.restype = C.c_char_p
+    l.ocl_init()
+    return l.ocl_log().decode()
+
+
+def device_name() -> str:
+    return _lib.ocl_device_name().decode()
+
+
+def _ck(rc):
+    if rc < 0:
+        raise RuntimeError(_lib.ocl_log().decode())
+    return rc
+
+
+def _kernel(file: str, entry: str, options: str = "") -> int:
+    key = (file, entry, options)
+    if key not in _kernels:
+        with open(os.path.join(KERNELS, file)) as f:
+            src = f.read()
+        _kernels[key] = _ck(_lib.ocl_kernel(src.encode(), entry.encode(), options.encode()))
+    return _kernels[key]
+
+
+def program_text(file: str, entry: str, options: str = "") -> str:
+    """what the driver compiled the kernel to (PTX text on NVIDIA): the ground truth for dot()/fma contraction"""
+    k = _kernel(file, entry, options)
+    _lib.ocl_program_binary.restype = C.c_long
+    _lib.ocl_program_binary.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+    buf = C.create_string_buffer(1 << 20)
+    n = _lib.ocl_program_binary(k, buf, len(buf))
+    if n < 0:
+        raise RuntimeError(_lib.ocl_log().decode())
+    return buf.raw[:n].decode(errors="replace")
+
+
+def _buf(arr: Optional[np.ndarray] = None, nbytes: int = 0) -> int:
+    if arr is not None:
+        a = np.ascontiguousarray(arr)
+        return _ck(_lib.ocl_buffer(a.nbytes, a.ctypes.data))
+    return _ck(_lib.ocl_buffer(nbytes, None))
+
+
+def _img(w: int, h: int, arr: Optional[np.ndarray] = None) -> int:
+    if arr is not None:
+        a = np.ascontiguousarray(arr, np.float32)
+        assert a.size == w * h * 4
+        return _ck(_lib.ocl_image(w, h, a.ctypes.data))
+    return _ck(_lib.ocl_image(w, h, None))
+
+
+def _read_img(m: int, w: int, h: int) -> np.ndarray:
+    out = np.empty((h, w, 4), np.float32)
+    _ck(_lib.ocl_read_image(m, out.ctypes.data, w, h))
+    return out
+
+
+def _free(*mems):
+    for m in mems:
+        _lib.ocl_release(m)
+
+
+def _pad(a, n):
+    flat = np.asarray(a, np.float32).reshape(-1)
+    out = np.zeros(n, np.float32)
+    out[: flat.size] = flat
+    return out
+
+
+def _pitch(width: int) -> int:   # v210.ts:198-204, pixels
+    return ((width + 47) // 48) * 48
+
+
+def v210_read(src: np.ndarray, width: int, height: int, col_matrix, gamma_lut, gamut, options: str = "") -> np.ndarray:
+    """v210.ts:25-111 with Reader's NDRange (v210.ts:293-294): one work-group per line"""
+    k = _kernel("v210.cl", "read", options)
+    wpg = _pitch(width) // 48
+    i, o = _buf(src), _buf(nbytes=width * height * 16)
+    cm, lut, gm = _buf(_pad(col_matrix, 12)), _buf(np.asarray(gamma_lut, np.float32)), _buf(_pad(gamut, 16))   # Q4: 3 float4 are read
+    for n, m in enumerate((i, o)):
+        _ck(_lib.ocl_arg_mem(k, n, m))
+    _ck(_lib.ocl_arg_u32(k, 2, width))
+    for n, m in zip((3, 4, 5), (cm, lut, gm)):
+        _ck(_lib.ocl_arg_mem(k, n, m))
+    _ck(_lib.ocl_run(k, 1, wpg * height, 1, wpg))
+    out = np.empty((height, width, 4), np.float32)
+    _ck(_lib.ocl_read_buffer(o, out.ctypes.data, out.nbytes))
+    _free(i, o, cm, lut, gm)
+    return out
+
+
+def v210_write(rgba: np.ndarray, width: int, height: int, interlace: int, col_matrix, gamma_lut, out: Optional[np.ndarray] = None,
+               options: str = "") -> np.ndarray:
+    """v210.ts:113-195 with Writer's NDRange (v210.ts:322-323)"""
+    k = _kernel("v210.cl", "write", options)
+    wpg = _pitch(width) // 48
+    nbytes = wpg * 128 * height
+    if out is None:
+        out = np.zeros(nbytes, np.uint8)
+    i, o = _buf(np.asarray(rgba, np.float32)), _buf(out)
+    cm, lut = _buf(_pad(col_matrix, 12)), _buf(np.asarray(gamma_lut, np.float32))
+    _ck(_lib.ocl_arg_mem(k, 0, i))
+    _ck(_lib.ocl_arg_mem(k, 1, o))
+    _ck(_lib.ocl_arg_u32(k, 2, width))
+    _ck(_lib.ocl_arg_u32(k, 3, interlace))
+    _ck(_lib.ocl_arg_mem(k, 4, cm))
+    _ck(_lib.ocl_arg_mem(k, 5, lut))
+    _ck(_lib.ocl_run(k, 1, wpg * height // (2 if interlace else 1), 1, wpg))
+    _ck(_lib.ocl_read_buffer(o, out.ctypes.data, nbytes))
+    _free(i, o, cm, lut)
+    return out
+
+
+def _image_op(file: str, entry: str, images: List[np.ndarray], w: int, h: int, scalar: Optional[float] = None) -> np.ndarray:
+    """ProcessImpl NDRange = [width, height] (imageProcess.ts:48-50); inputs, [float], output"""
+    k = _kernel(file, entry)
+    mems = [_img(im.shape[1], im.shape[0], im) for im in images]
+    o = _img(w, h)
+    n = 0
+    for m in mems:
+        _ck(_lib.ocl_arg_mem(k, n, m))
+        n += 1
+    if scalar is not None:
+        _ck(_lib.ocl_arg_f32(k, n, scalar))
+        n += 1
+    _ck(_lib.ocl_arg_mem(k, n, o))
+    _ck(_lib.ocl_run(k, 2, w, h, 0))
+    out = _read_img(o, w, h)
+    _free(o, *mems)
+    return out
+
+
+def combine(layers: List[np.ndarray]) -> np.ndarray:
+    """combine.ts:24-68"""
+    h, w, _ = layers[0].shape
+    return _image_op(f"combine_{len(layers)}.cl", f"combine_{len(layers)}", layers, w, h)
+
+
+def dissolve(in0: np.ndarray, in1: np.ndarray, mix: float) -> np.ndarray:
+    """transition.ts:60-65"""
+    h, w, _ = in0.shape
+    return _image_op("transition_dissolve.cl", "transition_dissolve", [in0, in1], w, h, scalar=mix)
+
+
+def wipe_mask(in0: np.ndarray, in1: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """transition.ts:66-73"""
+    h, w, _ = in0.shape
+    return _image_op("transition_wipe.cl", "transition_wipe", [in0, in1, mask], w, h)
+
+
+def transform(src: np.ndarray, mat9, w: int, h: int) -> np.ndarray:
+    """transform.ts:36-59: (input image, transformMatrix buffer, output image)"""
+    k = _kernel("transform.cl", "transform")
+    i, o, m = _img(src.shape[1], src.shape[0], src), _img(w, h), _buf(_pad(mat9, 12))
+    _ck(_lib.ocl_arg_mem(k, 0, i))
+    _ck(_lib.ocl_arg_mem(k, 1, m))
+    _ck(_lib.ocl_arg_mem(k, 2, o))
+    _ck(_lib.ocl_run(k, 2, w, h, 0))
+    out = _read_img(o, w, h)
+    _free(i, o, m)
+    return out

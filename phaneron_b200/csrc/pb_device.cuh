@@ -2,8 +2,8 @@
 //
 // Float semantics are the "canonical" ones documented in DESIGN.md: every operation
 // is an explicit round-to-nearest intrinsic (__fmul_rn/__fadd_rn/__fmaf_rn/__fdiv_rn),
-// so nvcc's -fmad contraction can never change a result; OpenCL dot() is the
-// left-to-right FMA chain; convert_*_sat_rte is clamp + RNE (NaN -> 0).
+// so nvcc's -fmad contraction can never change a result; OpenCL dot() is LLVM's contracted
+// chain (see dot3/dot4); convert_*_sat_rte is clamp + RNE (NaN -> 0).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,14 +18,16 @@ __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b);
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
+// OpenCL dot() as LLVM contracts it (read off the PTX NVIDIA's OpenCL compiler emits for the reference's
+// kernels): a.x*b.x + a.y*b.y fuses to fma(a.x, b.x, a.y*b.y), the rest chain on.
 __device__ __forceinline__ float dot3(float a0, float a1, float a2, const float *b) {
-	float t = mul(a0, b[0]);
-	t = fma_(a1, b[1], t);
+	float t = mul(a1, b[1]);
+	t = fma_(a0, b[0], t);
 	return fma_(a2, b[2], t);
 }
 __device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3, const float *b) {
-	float t = mul(a0, b[0]);
-	t = fma_(a1, b[1], t);
+	float t = mul(a1, b[1]);
+	t = fma_(a0, b[0], t);
 	t = fma_(a2, b[2], t);
 	return fma_(a3, b[3], t);
 }

@@ -99,25 +99,29 @@ __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const 
 template <int kLutMode, bool kSparse, int SCB, int SCR>
 __device__ __forceinline__ void convert_pair(uint32_t ya, uint32_t yb, uint32_t cb, uint32_t cr, const ReadConsts &rc, const ReadK &rk,
                                              const LutK<kLutMode> &lut, const LutParams &lp, float2 &R, float2 &G, float2 &B) {
-	const float2 Y = f2(__uint_as_float(ya), __uint_as_float(yb));
-	const float2 C = __fadd2_rn(f2(__uint_as_float(cb), __uint_as_float(cr)), f2s(-kTwo23));   // exact (scaled) chroma codes
-	// dot(yuva, colMatrix row): mul, fma, fma, fma(1, m3, t) -- the last is RN(t + m3), fused with the saturate
-	float2 tr = __ffma2_rn(Y, f2s(rk.mY[0]), f2s(rk.oY[0]));   // == RN(y * m0): the 2^23 bias of Y is folded into oY
-	float2 tg = __ffma2_rn(Y, f2s(rk.mY[1]), f2s(rk.oY[1]));
-	float2 tb = __ffma2_rn(Y, f2s(rk.mY[2]), f2s(rk.oY[2]));
-	if (!kSparse) tr = f2(fma_(C.x, rk.mCb[0][SCB], tr.x), fma_(C.x, rk.mCb[0][SCB], tr.y));   // cm[1] == 0: fma(cb, 0, t) == t
+	// dot(yuva, colMatrix row) as LLVM contracts it: t = cb*m1; t = fma(y, m0, t); t = fma(cr, m2, t); t = fma(1, m3, t).
+	// The cb product is shared by the two pixels; the last step is RN(t + m3), fused with the saturate below.
+	const float2 Yb = f2(__uint_as_float(ya), __uint_as_float(yb));                                // 2^23 + y
+	const float2 C = __fadd2_rn(f2(__uint_as_float(cb), __uint_as_float(cr)), f2s(-kTwo23));       // exact (scaled) chroma codes
+	float2 tr, tg, tb;
+	if (kSparse) {   // cm[1] == 0: cb*0 = 0 and fma(y, m0, 0) = RN(y*m0) = fma(2^23 + y, m0, -2^23*m0)
+		tr = __ffma2_rn(Yb, f2s(rk.mY[0]), f2s(rk.oY[0]));
+	} else {
+		tr = __ffma2_rn(__fadd2_rn(Yb, f2s(-kTwo23)), f2s(rk.mY[0]), f2s(mul(C.x, rk.mCb[0][SCB])));
+	}
+	const float2 Y = __fadd2_rn(Yb, f2s(-kTwo23));
+	tg = __ffma2_rn(Y, f2s(rk.mY[1]), f2s(mul(C.x, rk.mCb[1][SCB])));
+	tb = __ffma2_rn(Y, f2s(rk.mY[2]), f2s(mul(C.x, rk.mCb[2][SCB])));
 	tr = f2(fma_(C.y, rk.mCr[0][SCR], tr.x), fma_(C.y, rk.mCr[0][SCR], tr.y));
-	tg = f2(fma_(C.x, rk.mCb[1][SCB], tg.x), fma_(C.x, rk.mCb[1][SCB], tg.y));
 	tg = f2(fma_(C.y, rk.mCr[1][SCR], tg.x), fma_(C.y, rk.mCr[1][SCR], tg.y));
-	tb = f2(fma_(C.x, rk.mCb[2][SCB], tb.x), fma_(C.x, rk.mCb[2][SCB], tb.y));
-	if (!kSparse) tb = f2(fma_(C.y, rk.mCr[2][SCR], tb.x), fma_(C.y, rk.mCr[2][SCR], tb.y));
+	if (!kSparse) tb = f2(fma_(C.y, rk.mCr[2][SCR], tb.x), fma_(C.y, rk.mCr[2][SCR], tb.y));   // cm[10] == 0: fma(cr, 0, t) == t
 	const float2 r = lut2<kLutMode>(f2(__saturatef(add(tr.x, rc.cm[3])), __saturatef(add(tr.y, rc.cm[3]))), lut, lp);
 	const float2 g = lut2<kLutMode>(f2(__saturatef(add(tg.x, rc.cm[7])), __saturatef(add(tg.y, rc.cm[7]))), lut, lp);
 	const float2 b = lut2<kLutMode>(f2(__saturatef(add(tb.x, rc.cm[11])), __saturatef(add(tb.y, rc.cm[11]))), lut, lp);
-	// gamut 3x3: mul, fma, fma per row
-	R = __ffma2_rn(b, f2s(rc.gamut[2]), __ffma2_rn(g, f2s(rc.gamut[1]), __fmul2_rn(r, f2s(rc.gamut[0]))));
-	G = __ffma2_rn(b, f2s(rc.gamut[5]), __ffma2_rn(g, f2s(rc.gamut[4]), __fmul2_rn(r, f2s(rc.gamut[3]))));
-	B = __ffma2_rn(b, f2s(rc.gamut[8]), __ffma2_rn(g, f2s(rc.gamut[7]), __fmul2_rn(r, f2s(rc.gamut[6]))));
+	// gamut 3x3, dot(rgb, row): t = g*m1; t = fma(r, m0, t); t = fma(b, m2, t)
+	R = __ffma2_rn(b, f2s(rc.gamut[2]), __ffma2_rn(r, f2s(rc.gamut[0]), __fmul2_rn(g, f2s(rc.gamut[1]))));
+	G = __ffma2_rn(b, f2s(rc.gamut[5]), __ffma2_rn(r, f2s(rc.gamut[3]), __fmul2_rn(g, f2s(rc.gamut[4]))));
+	B = __ffma2_rn(b, f2s(rc.gamut[8]), __ffma2_rn(r, f2s(rc.gamut[6]), __fmul2_rn(g, f2s(rc.gamut[7]))));
 }
 
 // (w & mask) | e in one LOP3: `e` (0x4B000000, FusedDesc::e_magic) arrives in a register so that
@@ -402,8 +406,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			const float2 gb = lut2<kLutMode>(f2(__saturatef(acc[r].z), __saturatef(acc[r + 1].z)), wlut, wlp);
 			uint32_t code0 = 0, code1 = 0;
 #pragma unroll
-			for (int c = 0; c < 3; ++c) {   // dot(rgba, colMatrix row): mul, fma, fma, fma(1, m3, t) = RN(t + m3)
-				float2 v = __ffma2_rn(gb, f2s(d.wc.cm[c * 4 + 2]), __ffma2_rn(gg, f2s(d.wc.cm[c * 4 + 1]), __fmul2_rn(gr, f2s(d.wc.cm[c * 4 + 0]))));
+			for (int c = 0; c < 3; ++c) {   // dot(rgba, colMatrix row): t = g*m1; fma(r, m0, t); fma(b, m2, t); fma(1, m3, t) = RN(t + m3)
+				float2 v = __ffma2_rn(gb, f2s(d.wc.cm[c * 4 + 2]), __ffma2_rn(gr, f2s(d.wc.cm[c * 4 + 0]), __fmul2_rn(gg, f2s(d.wc.cm[c * 4 + 1]))));
 				v = __fadd2_rn(v, f2s(d.wc.cm[c * 4 + 3]));
 				v = __fadd2_rn(v, f2s(kTwo23));
 				code0 |= (__float_as_uint(v.x) & 0x3ffu) << (10 * c);
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			uint32_t code = 0;
 #pragma unroll
 			for (int c = 0; c < 3; ++c) {
-				const float u = add(add(fma_(hb.x, d.wc.cm[c * 4 + 2], fma_(hrg.y, d.wc.cm[c * 4 + 1], mul(hrg.x, d.wc.cm[c * 4 + 0]))), d.wc.cm[c * 4 + 3]), kTwo23);
+				const float u = add(add(fma_(hb.x, d.wc.cm[c * 4 + 2], fma_(hrg.x, d.wc.cm[c * 4 + 0], mul(hrg.y, d.wc.cm[c * 4 + 1]))), d.wc.cm[c * 4 + 3]), kTwo23);
 				code |= (__float_as_uint(u) & 0x3ffu) << (10 * c);
 			}
 			stage[r * 32 + lane] = code;

@@ -16,6 +16,7 @@ names 'read'/'write' for every packer, so identity has to come from the source).
 """
 from __future__ import annotations
 
+import asyncio
 import ctypes as C
 import json
 import time
@@ -66,6 +67,9 @@ class OpenCLProgram:
                 _lib.lib().pb_prog_destroy(self._h)
         except Exception:
             pass
+
+
+_ASYNC_COPY_BYTES = 1 << 20
 
 
 class OpenCLBuffer:
@@ -157,7 +161,15 @@ class OpenCLBuffer:
             arr = src.host if isinstance(src, OpenCLBuffer) else np.frombuffer(src, np.uint8) if not isinstance(src, np.ndarray) else src
             arr = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             ptr, n = arr.ctypes.data, arr.size
-        check(_lib.lib().pb_buf_host_access(self._h, _lib.ACCESS[mode], int(queue or 0), ptr, n))
+        h, m, q = self._h, _lib.ACCESS[mode], int(queue or 0)
+        if (n if src is not None else self.numBytes) >= _ASYNC_COPY_BYTES and mode != "none":
+            # nodencl runs every call as async work on the libuv pool: frame-sized copies go to a
+            # worker thread (ctypes drops the GIL), so `await Promise.all([...])`-style callers overlap H2D, D2H
+            # and kernel launches exactly as they do under Node
+            rc = await asyncio.get_running_loop().run_in_executor(None, _lib.lib().pb_buf_host_access, h, m, q, ptr, n)
+            check(rc)
+        else:
+            check(_lib.lib().pb_buf_host_access(h, m, q, ptr, n))
 
 
 class clContext:
