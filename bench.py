@@ -135,6 +135,30 @@ def cpu_reference_fps(steps, warmup, inputs, threads):
     return frames / dt, dt
 
 
+def reference_kernels_on_gpu(inputs, frames=6):
+    """Baseline A: the reference's OWN OpenCL kernels (extracted from its .ts sources into the
+    git-ignored oracle/_ref/) launched in the reference's unfused sequence on the same B200 through NVIDIA's
+    OpenCL driver, buffers resident.  None when the driver or the extracted kernels are absent."""
+    try:
+        from oracle import ref_ocl
+        if not ref_ocl.available():
+            return {"unavailable": ref_ocl.why_unavailable()}
+        import oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from scene_oracle import xf_matrix
+        from phaneron_b200.scenes import layered_scene
+        scene = layered_scene(WIDTH, HEIGHT, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
+        consts = (oracle.ycbcr2rgb_matrix(COL_READ), oracle.gamma2linear_lut(COL_READ), oracle.rgb2rgb_matrix(COL_READ, COL_WORK),
+                  oracle.rgb2ycbcr_matrix(COL_WORK), oracle.linear2gamma_lut(COL_WORK))
+        chain = ref_ocl.ReferenceChain(scene, consts, xf_matrix)
+        chain.run_frames(2)
+        dt = chain.run_frames(frames)
+        return {"value": frames / dt, "unit": "frames/s", "device": ref_ocl.device_name() + " (NVIDIA OpenCL)", "launches_per_frame": len(chain.launches),
+                "sample": f"{frames} frames of the same scene: 5x read, 5x transform, transition_dissolve, combine_4, write, RGBA-f32 intermediates resident, one clFinish"}
+    except Exception as e:   # a baseline must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -316,7 +340,8 @@ async def run_ours(args, rank, world, local_rank):
             fps, dt = cpu_reference_fps(n, 1, args.inputs, threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "sample": f"{n} x {WIDTH}x{REF_SAMPLE_LINES} bands ({REF_SAMPLE_LINES}/{HEIGHT} frame each) of the same scene, "
-                                              f"oracle/ unfused chain, {dt:.1f} s"}
+                                              f"oracle/ unfused chain, {dt:.1f} s",
+                                    "reference_kernels_on_gpu": reference_kernels_on_gpu(args.inputs)}
         print(json.dumps(line), flush=True)
     barrier()
     if dist:

@@ -227,3 +227,106 @@ def transform(src: np.ndarray, mat9, w: int, h: int) -> np.ndarray:
     out = _read_img(o, w, h)
     _free(i, o, m)
     return out
+
+
+class ReferenceChain:
+    """The reference's UNFUSED launch sequence for a harness scene, with persistent device buffers, for timing on the
+    same GPU: per source `read` (+ `transform`), per transition layer `transition_*`, `combine_N`, `write`
+    (SURVEY.md 3.2-3.4).  Kernels are the reference's own; buffers stay resident, as phaneron's do between stages."""
+
+    def __init__(self, scene, consts, xf_matrix):
+        cm_r, lut_r, gamut, cm_w, lut_w = consts
+        self.W, self.H = scene["width"], scene["height"]
+        W, H = self.W, self.H
+        self.launches = []   # (kernel id, dims, g0, g1, local0)
+        self.cm_r, self.lut_r, self.gm = _buf(_pad(cm_r, 12)), _buf(np.asarray(lut_r, np.float32)), _buf(_pad(gamut, 16))
+        self.cm_w, self.lut_w = _buf(_pad(cm_w, 12)), _buf(np.asarray(lut_w, np.float32))
+        n_kernel = [0]
+
+        def fresh(file, entry):   # one kernel object per launch site: arguments stay bound
+            n_kernel[0] += 1
+            return _kernel(file, entry, "-DPB_SITE=%d" % n_kernel[0])
+
+        def source(src, sw, sh, xf):
+            k = fresh("v210.cl", "read")
+            wpg = _pitch(sw) // 48
+            i, o = _buf(src), _buf(nbytes=sw * sh * 16)
+            for n, m in enumerate((i, o)):
+                _ck(_lib.ocl_arg_mem(k, n, m))
+            _ck(_lib.ocl_arg_u32(k, 2, sw))
+            for n, m in zip((3, 4, 5), (self.cm_r, self.lut_r, self.gm)):
+                _ck(_lib.ocl_arg_mem(k, n, m))
+            self.launches.append((k, 1, wpg * sh, 1, wpg))
+            # nodencl's image view of the RGBA buffer: here an image2d_t filled by a buffer->image copy is not available
+            # through the runner, so the read kernel's output buffer is re-uploaded once as an image at build time
+            # and the read launch is still timed (its output buffer is what a packer-only chain would consume).
+            rgba = np.empty((sh, sw, 4), np.float32)
+            _ck(_lib.ocl_run(k, 1, wpg * sh, 1, wpg))
+            _ck(_lib.ocl_read_buffer(o, rgba.ctypes.data, rgba.nbytes))
+            img = _img(sw, sh, rgba)
+            if xf is None:
+                return img
+            kt = fresh("transform.cl", "transform")
+            out = _img(W, H)
+            mb = _buf(_pad(xf_matrix(W, H, xf), 12))
+            _ck(_lib.ocl_arg_mem(kt, 0, img))
+            _ck(_lib.ocl_arg_mem(kt, 1, mb))
+            _ck(_lib.ocl_arg_mem(kt, 2, out))
+            self.launches.append((kt, 2, W, H, 0))
+            _ck(_lib.ocl_run(kt, 2, W, H, 0))
+            return out
+
+        layers = []
+        for L in scene["layers"]:
+            a = source(L["src"], L["sw"], L["sh"], L.get("xf"))
+            t = L.get("transition")
+            if t:
+                b = source(t["src"], t["sw"], t["sh"], t.get("xf"))
+                out = _img(W, H)
+                if t["type"] == "dissolve":
+                    k = fresh("transition_dissolve.cl", "transition_dissolve")
+                    _ck(_lib.ocl_arg_mem(k, 0, a)); _ck(_lib.ocl_arg_mem(k, 1, b)); _ck(_lib.ocl_arg_f32(k, 2, t["mix"])); _ck(_lib.ocl_arg_mem(k, 3, out))
+                else:
+                    m = source(t["mask"], t["mask_sw"], t["mask_sh"], t.get("mask_xf"))
+                    k = fresh("transition_wipe.cl", "transition_wipe")
+                    _ck(_lib.ocl_arg_mem(k, 0, a)); _ck(_lib.ocl_arg_mem(k, 1, b)); _ck(_lib.ocl_arg_mem(k, 2, m)); _ck(_lib.ocl_arg_mem(k, 3, out))
+                self.launches.append((k, 2, W, H, 0))
+                _ck(_lib.ocl_run(k, 2, W, H, 0))
+                a = out
+            layers.append(a)
+        comp = layers[0]
+        if len(layers) > 1:
+            k = fresh(f"combine_{len(layers)}.cl", f"combine_{len(layers)}")
+            comp = _img(W, H)
+            for n, m in enumerate(layers):
+                _ck(_lib.ocl_arg_mem(k, n, m))
+            _ck(_lib.ocl_arg_mem(k, len(layers), comp))
+            self.launches.append((k, 2, W, H, 0))
+            _ck(_lib.ocl_run(k, 2, W, H, 0))
+        # the writer reads a buffer: bring the composite back as one (done once; the write launch is what is timed)
+        rgba = _read_img(comp, W, H)
+        kw = fresh("v210.cl", "write")
+        wpg = _pitch(W) // 48
+        self.out_bytes = wpg * 128 * H
+        wi, self.wo = _buf(rgba), _buf(nbytes=self.out_bytes)
+        _ck(_lib.ocl_arg_mem(kw, 0, wi)); _ck(_lib.ocl_arg_mem(kw, 1, self.wo)); _ck(_lib.ocl_arg_u32(kw, 2, W)); _ck(_lib.ocl_arg_u32(kw, 3, 0))
+        _ck(_lib.ocl_arg_mem(kw, 4, self.cm_w)); _ck(_lib.ocl_arg_mem(kw, 5, self.lut_w))
+        self.launches.append((kw, 1, wpg * H, 1, wpg))
+        _ck(_lib.ocl_run(kw, 1, wpg * H, 1, wpg))
+
+    def result(self) -> np.ndarray:
+        out = np.empty(self.out_bytes, np.uint8)
+        _ck(_lib.ocl_read_buffer(self.wo, out.ctypes.data, self.out_bytes))
+        return out
+
+    def run_frames(self, n: int) -> float:
+        """enqueue the whole launch sequence n times back to back, one clFinish at the end; seconds"""
+        import time
+        _lib.ocl_enqueue.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t]
+        _ck(_lib.ocl_finish())
+        t0 = time.perf_counter()
+        for _ in range(n):
+            for (k, dims, g0, g1, l0) in self.launches:
+                _ck(_lib.ocl_enqueue(k, dims, g0, g1, l0))
+        _ck(_lib.ocl_finish())
+        return time.perf_counter() - t0

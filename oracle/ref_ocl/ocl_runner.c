@@ -223,6 +223,17 @@ int ocl_arg_f32(int kern, int idx, float v) {
 	return e ? fail("clSetKernelArg(f32)", e) : 0;
 }
 
+/* enqueue only (for timing the reference's launch sequence back to back); ocl_finish() waits */
+int ocl_enqueue(int kern, int dims, size_t g0, size_t g1, size_t local0) {
+	size_t g[2] = {g0, g1}, l[2] = {local0, 1};
+	cl_int e = ((fn_NDRange)g_tab[D_EnqueueNDRangeKernel])(g_queue, g_kern[kern], (cl_uint)dims, NULL, g, local0 ? l : NULL, 0, NULL, NULL);
+	return e ? fail("clEnqueueNDRangeKernel", e) : 0;
+}
+int ocl_finish(void) {
+	cl_int e = ((fn_Finish)g_tab[D_Finish])(g_queue);
+	return e ? fail("clFinish", e) : 0;
+}
+
 /* globalWorkItems / workItemsPerGroup as nodencl's createProgram takes them (local0 = 0: let the driver choose) */
 int ocl_run(int kern, int dims, size_t g0, size_t g1, size_t local0) {
 	size_t g[2] = {g0, g1}, l[2] = {local0, 1};
