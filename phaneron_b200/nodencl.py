@@ -239,6 +239,16 @@ class clContext:
                                        (owner or "").encode(), C.byref(out)))
         return OpenCLBuffer(self, out.value, int(numBytes), owner or "", imageDims)
 
+    def wrapDeviceMemory(self, devicePointer: int, numBytes: int, imageDims: Optional[Dict[str, int]] = None,
+                         owner: str = "wrapped") -> OpenCLBuffer:
+        """an OpenCLBuffer over device memory the caller owns (pb_buf_wrap): how a ROUTE frame received over NCCL
+        enters a channel as a layer source (route.py); the memory must outlive the buffer"""
+        w = int(imageDims["width"]) if imageDims else 0
+        h = int(imageDims["height"]) if imageDims else 0
+        out = C.c_void_p()
+        check(_lib.lib().pb_buf_wrap(self._need(), C.c_void_p(devicePointer), int(numBytes), w, h, C.byref(out)))
+        return OpenCLBuffer(self, out.value, int(numBytes), owner, imageDims)
+
     async def createProgram(self, kernel: KernelSpec, options: Dict[str, Any]) -> OpenCLProgram:
         if not isinstance(kernel, KernelSpec):
             raise PhaneronError("createProgram expects a KernelSpec where the reference passes OpenCL source")
