@@ -17,7 +17,7 @@ constexpr int kMaxLuts = 3;          // march kernel: distinct gamma tables resi
 
 // ---- march kernel geometry (pb_march.cu) ---------------------------------------------
 #ifndef PB_MARCH_WARPS
-#define PB_MARCH_WARPS 16
+#define PB_MARCH_WARPS 20
 #endif
 constexpr int kMarchWarps = PB_MARCH_WARPS;  // warps per CTA; one persistent CTA per SM
 constexpr int kMarchThreads = kMarchWarps * 32;
@@ -42,7 +42,7 @@ enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2
 //   table[i] == bits( base(i) ) + d8[i] - 128
 // The d8 bytes are produced ON the device by the same code that decodes them (pb_lut.cuh).
 // The toe / power select is arithmetic (FMA pipe, no predicate): with h = sat(i + cJ) = (i >= J),
-//   base(i) = h * pw(i) + sat(i*kt - 16h)        -- exactly pw(i) or exactly i*kt
+//   base(i) = i*kt + h * (pw(i) - i*kt)          -- exactly i*kt below the knee, pw(i) to a few ulp above it
 struct LutParams {
 	float p, q, G, s, o, kt, cJ;   // cJ = 1 - J
 	int affine;                    // 0: s == 1 and o == 0 (gamma -> linear direction)

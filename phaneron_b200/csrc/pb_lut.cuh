@@ -41,9 +41,10 @@ __device__ __forceinline__ float lut_base(float fi, const LutParams &lp) {
 	float pw = ex2_approx(__fmul_rn(lg2_approx(x), lp.G));
 	if (lp.affine) pw = __fmaf_rn(pw, lp.s, lp.o);
 	const float toe = __fmul_rn(fi, lp.kt);
-	const float h = __saturatef(__fadd_rn(fi, lp.cJ));               // 0 below the knee, 1 from it on
-	const float toe_sel = __saturatef(__fmaf_rn(h, -16.0f, toe));      // toe below the knee (toe < 1), 0 from it on
-	return __fmaf_rn(h, pw, toe_sel);                                 // exactly one term is non-zero
+	const float h = __saturatef(__fadd_rn(fi, lp.cJ));   // 0 below the knee, 1 from it on
+	// below the knee exactly the toe; above it RN(RN(pw - toe) + toe), a few ulp from pw -- any deterministic
+	// function of the index will do here, the byte table holds the distance to the exact value
+	return __fmaf_rn(h, __fsub_rn(pw, toe), toe);
 }
 
 // exact table value from the byte table (shared or global memory)

@@ -48,6 +48,9 @@ namespace pb {
 namespace {
 
 constexpr float kTwo23 = 8388608.0f;
+// Keeps the three pixel pairs of a v210 group from being interleaved: fewer table lookups in flight at once means
+// fewer live registers, and registers (not ILP) bound the number of resident warps (profiles/r01_kbench_warps_fence.txt).
+#define PB_PAIR_FENCE() asm volatile("" ::: "memory")
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
@@ -86,10 +89,9 @@ __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const 
 	const float2 y = __fmul2_rn(f2(lg2_approx(x.x), lg2_approx(x.y)), f2s(lp.G));
 	float2 pw = f2(ex2_approx(y.x), ex2_approx(y.y));
 	if (lp.affine) pw = __ffma2_rn(pw, f2s(lp.s), f2s(lp.o));
-	const float2 toe = __fmul2_rn(fi, f2s(lp.kt));
+	const float2 toe = mul2_unfusable(fi, f2s(lp.kt));   // feeds a packed add below
 	const float h0 = __saturatef(add(fi.x, lp.cJ)), h1 = __saturatef(add(fi.y, lp.cJ));
-	const float t0 = __saturatef(fma_(h0, -16.0f, toe.x)), t1 = __saturatef(fma_(h1, -16.0f, toe.y));
-	const float2 base = __ffma2_rn(f2(h0, h1), pw, f2(t0, t1));
+	const float2 base = __ffma2_rn(f2(h0, h1), __fadd2_rn(pw, f2(-toe.x, -toe.y)), toe);
 	return f2(__int_as_float(__float_as_int(base.x) + (int)d0 - 128), __int_as_float(__float_as_int(base.y) + (int)d1 - 128));
 }
 
@@ -145,9 +147,11 @@ __device__ __forceinline__ void convert_group(const uint4 &w, int g, uint32_t E,
 	convert_pair<kLutMode, kSparse, 0, 0>(mask_or(w.x >> 10, M0, E), mask_or(w.y, M0, E), mask_or(w.x, M0, E), mask_or(w.x >> 20, M0, E), rc, rk, lut, lp,
 	                                      R, G, B);
 	pr[0] = R; pg[0] = G; pb_[0] = B;
+	PB_PAIR_FENCE();
 	convert_pair<kLutMode, kSparse, 1, 0>(mask_or(w.y >> 20, M0, E), mask_or(w.z >> 10, M0, E), mask_or(w.y, M10, E), mask_or(w.z, M0, E), rc, rk, lut, lp,
 	                                      R, G, B);
 	pr[1] = R; pg[1] = G; pb_[1] = B;
+	PB_PAIR_FENCE();
 	convert_pair<kLutMode, kSparse, 0, 1>(mask_or(w.w, M0, E), mask_or(w.w >> 20, M0, E), mask_or(w.z >> 20, M0, E), mask_or(w.w, M10, E), rc, rk, lut, lp,
 	                                      R, G, B);
 	pr[2] = R; pg[2] = G; pb_[2] = B;
@@ -346,6 +350,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			const Layer &ly = d.layers[l];
 			float4 p[kRounds], t[kRounds];
 			float m[kRounds];
+			(void)t; (void)m;
 			// evaluation order keeps at most {t, p} live: dissolve = b then a; wipe = mask, a, b
 			const int nleaf = ly.kind == LAYER_DIRECT ? 1 : (ly.kind == LAYER_DISSOLVE ? 2 : 3);
 #pragma unroll 1
