@@ -193,11 +193,11 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	for (int r = 0; r < kRounds; ++r) {
 		const int x = min(x_first + r * 32 + lane, x_last);   // clamp for the ragged last strip / the unused lanes of round 2
 		if (has_xf) {
-			const int2 ct = __ldg(lf.col_tab + x);
-			c0[r] = ct.x - origin;
+			const int2 ct = __ldg(lf.col_tab + x);   // consumed after the conversion: the L2 latency hides behind it
+			c0[r] = ct.x;
 			ca[r] = __int_as_float(ct.y);
 		} else {
-			c0[r] = x - origin;
+			c0[r] = x;
 			ca[r] = 0.0f;
 		}
 	}
@@ -212,6 +212,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	lut.raw = rc.lut;
 	lut.magic = kLutMode ? kTwo23 + (float)(lut_saddr + (kSingleRc ? 0 : slot) * 65536) : kTwo23;
 	const uint32_t E = d.e_magic;
+	const float *bufo = buf - origin;   // row buffer addressed by source column
 
 	if (paired) {
 		constexpr int cap = 96, slot_floats = 3 * cap;   // two row slots of 16 groups
@@ -223,13 +224,13 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		if (!has_xf) {   // 1:1 read of texel (x, y): exact passthrough, alpha = 1 (leaf_value in pb_device.cuh)
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const float *t = buf + c0[r];
+				const float *t = bufo + c0[r];
 				p[r] = make_float4(t[0], t[cap], t[2 * cap], 1.0f);
 			}
 		} else if (!edge && ok0 && ok1) {   // interior: all four taps are texels
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const float *t0 = buf + c0[r], *t1 = t0 + slot_floats;
+				const float *t0 = bufo + c0[r], *t1 = t0 + slot_floats;
 				const float ra = sub(1.0f, ca[r]);
 				const float w00 = mul(ra, rb), w10 = mul(ca[r], rb), w01 = mul(ra, b), w11 = mul(ca[r], b);
 				p[r].x = fma_(w11, t1[1], fma_(w01, t1[0], fma_(w10, t0[1], mul(w00, t0[0]))));
@@ -240,10 +241,10 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		} else {   // some taps are border texels (0,0,0,0): fma(w, 0, x) = x
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const int i0 = c0[r] + origin;
+				const int i0 = c0[r];
 				const bool fc0 = (unsigned)i0 < (unsigned)lf.w, fc1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
 				const bool f00 = fc0 && ok0, f10 = fc1 && ok0, f01 = fc0 && ok1, f11 = fc1 && ok1;
-				const float *t0 = buf + min(max(c0[r], 0), last), *t1 = buf + min(max(c0[r] + 1, 0), last);
+				const float *t0 = buf + min(max(i0 - origin, 0), last), *t1 = buf + min(max(i0 - origin + 1, 0), last);
 				const float ra = sub(1.0f, ca[r]);
 				const float w00 = mul(ra, rb), w10 = mul(ca[r], rb), w01 = mul(ra, b), w11 = mul(ca[r], b);
 #define PB_TAP(flag, ptr, off) ((flag) ? (ptr)[off] : 0.0f)
@@ -280,7 +281,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		if (!edge) {
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const float *t = buf + c0[r];
+				const float *t = bufo + c0[r];
 				const float w0 = mul(sub(1.0f, ca[r]), wr), w1 = mul(ca[r], wr);   // w00|w01 , w10|w11
 				p[r].x = fma_(w1, t[1], fma_(w0, t[0], p[r].x));
 				p[r].y = fma_(w1, t[cap + 1], fma_(w0, t[cap], p[r].y));
@@ -290,9 +291,9 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		} else {
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const int i0 = c0[r] + origin;
+				const int i0 = c0[r];
 				const bool f0 = (unsigned)i0 < (unsigned)lf.w, f1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
-				const float *t0 = buf + min(max(c0[r], 0), last), *t1 = buf + min(max(c0[r] + 1, 0), last);
+				const float *t0 = buf + min(max(i0 - origin, 0), last), *t1 = buf + min(max(i0 - origin + 1, 0), last);
 				const float w0 = mul(sub(1.0f, ca[r]), wr), w1 = mul(ca[r], wr);
 				const float t0r = f0 ? t0[0] : 0.0f, t0g = f0 ? t0[cap] : 0.0f, t0b = f0 ? t0[2 * cap] : 0.0f;
 				const float t1r = f1 ? t1[0] : 0.0f, t1g = f1 ? t1[cap] : 0.0f, t1b = f1 ? t1[2 * cap] : 0.0f;
@@ -318,12 +319,27 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	float *buf = reinterpret_cast<float *>(smem_raw + (kLutMode ? (size_t)d.n_luts * 65536 : 0)) + warp * kRowFloats;
 
 	if (kLutMode) {
-		for (int t = 0; t < d.n_luts; ++t) {
-			const uint4 *src = reinterpret_cast<const uint4 *>(d.luts[t].d8);
-			uint4 *dst = reinterpret_cast<uint4 *>(lut_s + (size_t)t * 65536);
-			for (int i = threadIdx.x; i < 65536 / 16; i += kMarchThreads) dst[i] = __ldg(src + i);
+		// The byte tables arrive by TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by one thread and
+		// tracked by an mbarrier: 64 KiB per table without a register round trip or a per-thread loop.
+		__shared__ __align__(8) unsigned long long lut_bar;
+		const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&lut_bar);
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(d.n_luts * 65536) : "memory");
+			for (int t = 0; t < d.n_luts; ++t)
+				for (int c = 0; c < 4; ++c)   // 16 KiB per copy
+					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+					                 lut_saddr + t * 65536 + c * 16384),
+					             "l"(d.luts[t].d8 + c * 16384), "r"(16384), "r"(bar)
+					             : "memory");
+		}
+		uint32_t done = 0;
+		while (!done)
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
 	}
 
 	const int step = d.interlace == 0 ? 1 : 2;
@@ -468,7 +484,7 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		{
 			std::lock_guard<std::mutex> lk(mu);
 			if (!configured.count({(const void *)kernel, dev})) {
-				cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+				cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);   // 1 KiB left for static shared memory (the mbarrier)
 				if (e != cudaSuccess) return e;
 				configured.insert({(const void *)kernel, dev});
 			}
