@@ -229,6 +229,55 @@ def transform(src: np.ndarray, mat9, w: int, h: int) -> np.ndarray:
     return out
 
 
+def yadif(prev: np.ndarray, cur: np.ndarray, nxt: np.ndarray, parity: int, tff: bool, skip_spatial: bool) -> np.ndarray:
+    """yadifCl.ts:105-167 with YadifCL's parameter list (yadifCl.ts:178-188)"""
+    h, w, _ = cur.shape
+    k = _kernel("yadif.cl", "yadif")
+    mems = [_img(w, h, im) for im in (prev, cur, nxt)]
+    o = _img(w, h)
+    for n, m in enumerate(mems):
+        _ck(_lib.ocl_arg_mem(k, n, m))
+    _ck(_lib.ocl_arg_u32(k, 3, int(parity)))
+    _ck(_lib.ocl_arg_u32(k, 4, 1 if tff else 0))
+    _ck(_lib.ocl_arg_u32(k, 5, 1 if skip_spatial else 0))
+    _ck(_lib.ocl_arg_mem(k, 6, o))
+    _ck(_lib.ocl_run(k, 2, w, h, 0))
+    out = _read_img(o, w, h)
+    _free(o, *mems)
+    return out
+
+
+def rgba8_read(src: np.ndarray, width: int, height: int, gamma_lut, gamut) -> np.ndarray:
+    """rgba8.ts:25-67 with Reader's NDRange (rgba8.ts:171-173): 64 pixels per work-item, one group per line"""
+    assert width % 64 == 0, "Q13: the reference's work-group size is width/64 without a ceil"
+    k = _kernel("rgba8.cl", "read")
+    wpg = width // 64
+    i, o = _buf(np.asarray(src, np.uint8)), _buf(nbytes=width * height * 16)
+    lut, gm = _buf(np.asarray(gamma_lut, np.float32)), _buf(_pad(gamut, 16))
+    _ck(_lib.ocl_arg_mem(k, 0, i)); _ck(_lib.ocl_arg_mem(k, 1, o)); _ck(_lib.ocl_arg_u32(k, 2, width))
+    _ck(_lib.ocl_arg_mem(k, 3, lut)); _ck(_lib.ocl_arg_mem(k, 4, gm))
+    _ck(_lib.ocl_run(k, 1, wpg * height, 1, wpg))
+    out = np.empty((height, width, 4), np.float32)
+    _ck(_lib.ocl_read_buffer(o, out.ctypes.data, out.nbytes))
+    _free(i, o, lut, gm)
+    return out
+
+
+def rgba8_write(rgba: np.ndarray, width: int, height: int, interlace: int, gamma_lut) -> np.ndarray:
+    """rgba8.ts:69-103 with Writer's NDRange (rgba8.ts:195-197)"""
+    assert width % 64 == 0
+    k = _kernel("rgba8.cl", "write")
+    wpg = width // 64
+    out = np.zeros(width * height * 4, np.uint8)
+    i, o, lut = _buf(np.asarray(rgba, np.float32)), _buf(out), _buf(np.asarray(gamma_lut, np.float32))
+    _ck(_lib.ocl_arg_mem(k, 0, i)); _ck(_lib.ocl_arg_mem(k, 1, o)); _ck(_lib.ocl_arg_u32(k, 2, width)); _ck(_lib.ocl_arg_u32(k, 3, interlace))
+    _ck(_lib.ocl_arg_mem(k, 4, lut))
+    _ck(_lib.ocl_run(k, 1, wpg * height // (2 if interlace else 1), 1, wpg))
+    _ck(_lib.ocl_read_buffer(o, out.ctypes.data, out.nbytes))
+    _free(i, o, lut)
+    return out
+
+
 class ReferenceChain:
     """The reference's UNFUSED launch sequence for a harness scene, with persistent device buffers, for timing on the
     same GPU: per source `read` (+ `transform`), per transition layer `transition_*`, `combine_N`, `write`

@@ -107,3 +107,23 @@ def test_fused_cuda_dissolve_and_combine_bit_exact_vs_reference_kernel_chain():
     rd = lambda s: ref_ocl.v210_read(s, w, h, cm_r, lut_r, gamut)
     comp = ref_ocl.combine([rd(c), ref_ocl.dissolve(rd(a), rd(b), 0.3)])
     assert np.array_equal(ours, ref_ocl.v210_write(comp, w, h, 0, cm_w, lut_w))
+
+
+@pytest.mark.parametrize("parity,tff,skip", [(0, True, False), (1, True, False), (1, False, True), (0, False, False)])
+def test_oracle_yadif_bit_exact_vs_reference_kernel(parity, tff, skip):
+    """yadifCl.ts:105-167 on the driver vs the restatement: compares, selects and adds only, so every bit must agree"""
+    rng = np.random.default_rng(13)
+    prev, cur, nxt = (rng.random((72, 128, 4), dtype=np.float32) for _ in range(3))
+    ref = ref_ocl.yadif(prev, cur, nxt, parity, tff, skip)
+    assert np.array_equal(_bits(ref), _bits(oracle.yadif(prev, cur, nxt, parity, tff, skip)))
+
+
+def test_oracle_rgba8_bit_exact_vs_reference_kernels():
+    """rgba8.ts:25-103 (ScreenConsumer / FFmpegProducer path): sRGB tables, alpha through the LUT on read, forced 255 on write"""
+    w, h = 640, 90
+    rng = np.random.default_rng(14)
+    src = rng.integers(0, 256, w * h * 4, dtype=np.uint8)
+    lut_r, gamut, lut_w = oracle.gamma2linear_lut("sRGB"), oracle.rgb2rgb_matrix("sRGB", "709"), oracle.linear2gamma_lut("sRGB")
+    ref = ref_ocl.rgba8_read(src, w, h, lut_r, gamut)
+    assert np.array_equal(_bits(ref), _bits(oracle.rgba8_read(src, w, h, lut_r, gamut)))
+    assert np.array_equal(ref_ocl.rgba8_write(ref, w, h, 0, lut_w), oracle.rgba8_write(ref, w, h, 0, lut_w))
