@@ -57,7 +57,11 @@ typedef enum pb_op {
 	PB_OP_YADIF = 14,       /* yadifCl.ts:105-167 */
 	PB_OP_MIX = 15,         /* mix.ts:30-45 */
 	PB_OP_WIPE = 16,        /* wipe.ts:30-47 */
-	PB_OP_RESIZE = 17       /* resize.ts:35-59 */
+	PB_OP_RESIZE = 17,      /* resize.ts:35-59 */
+	PB_OP_YUV422P10_READ = 20,   /* yuv422p10.ts:25-124  (params inputY, inputU, inputV, output, ...) */
+	PB_OP_YUV422P10_WRITE = 21,  /* yuv422p10.ts:126-219 (params input, outputY, outputU, outputV, ...) */
+	PB_OP_YUV422P8_READ = 22,    /* yuv422p8.ts:25-124  */
+	PB_OP_YUV422P8_WRITE = 23    /* yuv422p8.ts:126-219 */
 } pb_op;
 
 /* One kernel argument, bound BY KERNEL PARAMETER NAME as nodencl's runProgram

@@ -223,3 +223,38 @@ def rgba8_write(rgba, width, height, interlace, gamma_lut, bgra=False, out=None)
         out = np.zeros(width * height * 4, np.uint8)
     lib().orc_rgba8_write(_f(rgba), out, width, height, interlace, _f(gamma_lut), int(bgra))
     return out
+
+
+# ---- yuv422p10le / yuv422p8 (yuv422p10.ts, yuv422p8.ts) -------------------------------------------------------
+def yuv422p_pitch(width: int) -> int:
+    return int(lib().orc_yuv422p_pitch(width))
+
+
+def yuv422p_plane_bytes(bits: int, width: int, height: int):
+    luma = yuv422p_pitch(width) * (1 if bits == 8 else 2) * height
+    return [luma, luma // 2, luma // 2]
+
+
+def yuv422p_fill(bits: int, width: int, height: int) -> np.ndarray:
+    buf = np.zeros(sum(yuv422p_plane_bytes(bits, width, height)), np.uint8)
+    lib().orc_yuv422p_fill(bits, buf.ctypes.data_as(C.c_void_p), width, height)
+    return buf
+
+
+def yuv422p_read(bits: int, y, u, v, width: int, height: int, col_matrix, gamma_lut, gamut) -> np.ndarray:
+    out = np.empty((height, width, 4), np.float32)
+    y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+    lib().orc_yuv422p_read(bits, y.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p),
+                           out.ctypes.data_as(C.c_void_p), width, height, _f(col_matrix).ctypes.data_as(C.c_void_p),
+                           _f(gamma_lut).ctypes.data_as(C.c_void_p), _f(gamut).ctypes.data_as(C.c_void_p))
+    return out
+
+
+def yuv422p_write(bits: int, rgba, width: int, height: int, interlace: int, col_matrix, gamma_lut, outs=None):
+    nb = yuv422p_plane_bytes(bits, width, height)
+    if outs is None:
+        outs = [np.zeros(n, np.uint8) for n in nb]
+    rgba = _f(rgba)
+    lib().orc_yuv422p_write(bits, rgba.ctypes.data_as(C.c_void_p), *(o.ctypes.data_as(C.c_void_p) for o in outs), width, height, interlace,
+                            _f(col_matrix).ctypes.data_as(C.c_void_p), _f(gamma_lut).ctypes.data_as(C.c_void_p))
+    return outs

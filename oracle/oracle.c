@@ -729,3 +729,133 @@ void orc_rgba8_write(const float *input, uint8_t *output, uint32_t width, uint32
 		}
 	}
 }
+
+/* ------------------------------------------------------------------------- */
+/* yuv422p10le / yuv422p8: src/process/yuv422p10.ts, src/process/yuv422p8.ts  */
+/* The two files differ only in the sample type (ushort / uchar), the tail    */
+/* fill values and the host-side range constants; `bits` selects.            */
+/* ------------------------------------------------------------------------- */
+uint32_t orc_yuv422p_pitch(uint32_t width) { return width + 7 - ((width - 1) % 8); } /* yuv422p10.ts:222, pixels */
+
+static inline uint32_t ld_s(const uint8_t *plane, size_t i, int bits) {
+	return bits == 8 ? plane[i] : (uint32_t)plane[2 * i] | (uint32_t)plane[2 * i + 1] << 8;
+}
+static inline void st_s(uint8_t *plane, size_t i, uint32_t v, int bits) {
+	if (bits == 8) {
+		plane[i] = (uint8_t)v; /* Q11: convert_ushort_sat_rte() assigned to a uchar field wraps (yuv422p8.ts:153,163-165) */
+	} else {
+		plane[2 * i] = (uint8_t)v;
+		plane[2 * i + 1] = (uint8_t)(v >> 8);
+	}
+}
+
+/* fillBuf: yuv422p10.ts:225-255 / yuv422p8.ts:225-253 (one buffer: Y plane | U plane | V plane) */
+void orc_yuv422p_fill(int bits, uint8_t *buf, uint32_t width, uint32_t height) {
+	const uint32_t pitch = orc_yuv422p_pitch(width);
+	const uint32_t black = bits == 8 ? 16 : 64, grey = bits == 8 ? 128 : 512, wrap = bits == 8 ? 234 : 938;
+	uint8_t *py = buf, *pu = buf + (size_t)pitch * height * (bits == 8 ? 1 : 2), *pv = pu + (size_t)(pitch / 2) * height * (bits == 8 ? 1 : 2);
+	for (size_t i = 0; i < (size_t)pitch * height; ++i) st_s(py, i, black, bits);
+	for (size_t i = 0; i < (size_t)(pitch / 2) * height; ++i) {
+		st_s(pu, i, grey, bits);
+		st_s(pv, i, grey, bits);
+	}
+	uint32_t Y = black;
+	for (uint32_t y = 0; y < height; ++y) {
+		for (uint32_t x = 0; x < width; x += 2) {
+			st_s(py, (size_t)y * pitch + x, Y, bits);
+			st_s(py, (size_t)y * pitch + x + 1, Y + 1, bits);
+			st_s(pu, (size_t)y * (pitch / 2) + x / 2, grey, bits);
+			st_s(pv, (size_t)y * (pitch / 2) + x / 2, grey, bits);
+			Y = (wrap == Y) ? black : Y + 2;
+		}
+	}
+}
+
+/* read kernel: yuv422p10.ts:25-124.  One work-group per line, 64 pixels per work-item, blocks of 8. */
+void orc_yuv422p_read(int bits, const uint8_t *inY, const uint8_t *inU, const uint8_t *inV, float *output, uint32_t width,
+                      uint32_t height, const float *cm, const float *lut, const float *gamut) {
+	const uint32_t itemsPerLine = (orc_yuv422p_pitch(width) + 63) / 64; /* Math.ceil(getPitch/64), yuv422p10.ts:308 */
+	const uint32_t pitchReads = (width + 7) / 8;
+	PAR_FOR
+	for (int64_t gid = 0; gid < (int64_t)height; ++gid) {
+		for (uint32_t lid = 0; lid < itemsPerLine; ++lid) {
+			const int last = lid == itemsPerLine - 1;
+			const uint32_t numPixels = (last && (0 != width % 64)) ? width % 64 : 64;
+			const uint32_t numLoops = numPixels / 8, remain = numPixels % 8;
+			size_t inOff = 8 * (size_t)lid + (size_t)pitchReads * gid;
+			size_t outOff = (size_t)width * gid + (size_t)lid * 64;
+			for (uint32_t i = 0; i <= numLoops; ++i) {
+				const uint32_t n = i < numLoops ? 8 : remain; /* the tail block converts `remain` pixels the same way (:90-123) */
+				for (uint32_t p = 0; p < n; ++p) {
+					const uint32_t yuv[3] = {ld_s(inY, inOff * 8 + p, bits), ld_s(inU, inOff * 4 + p / 2, bits), ld_s(inV, inOff * 4 + p / 2, bits)};
+					read_px(yuv, 1.0f, cm, lut, gamut, output + (outOff + p) * 4);
+				}
+				inOff++;
+				outOff += 8;
+			}
+		}
+	}
+}
+
+/* write kernel: yuv422p10.ts:126-219 */
+void orc_yuv422p_write(int bits, const float *input, uint8_t *outY, uint8_t *outU, uint8_t *outV, uint32_t width, uint32_t height,
+                       uint32_t interlace, const float *cm, const float *lut) {
+	const uint32_t itemsPerLine = (orc_yuv422p_pitch(width) + 63) / 64;
+	const uint32_t pitchReads = (width + 7) / 8;
+	const uint32_t groups = (0 == interlace) ? height : height / 2;
+	PAR_FOR
+	for (int64_t gid = 0; gid < (int64_t)groups; ++gid) {
+		for (uint32_t lid = 0; lid < itemsPerLine; ++lid) {
+			const int last = lid == itemsPerLine - 1;
+			const uint32_t numPixels = (last && (0 != width % 64)) ? width % 64 : 64;
+			const uint32_t numLoops = numPixels / 8, remain = numPixels % 8;
+			const uint32_t line = (uint32_t)gid * ((0 == interlace) ? 1 : 2) + ((3 == interlace) ? 1 : 0);
+			size_t inOff = (size_t)width * line + (size_t)lid * 64;
+			size_t outOff = (size_t)pitchReads * line + (size_t)lid * 8;
+			for (uint32_t i = 0; i < numLoops; ++i) {
+				uint32_t yuv[8][3];
+				for (uint32_t p = 0; p < 8; ++p) {
+					const float *l = input + (inOff + p) * 4;
+					const float rgba[4] = {lut[sat_rte(l[0] * 65535.0f, 65535.0f)], lut[sat_rte(l[1] * 65535.0f, 65535.0f)],
+					                       lut[sat_rte(l[2] * 65535.0f, 65535.0f)], 1.0f};
+					yuv[p][0] = sat_rte(dot4(rgba, cm + 0), 65535.0f);
+					yuv[p][1] = sat_rte(dot4(rgba, cm + 4), 65535.0f);
+					yuv[p][2] = sat_rte(dot4(rgba, cm + 8), 65535.0f);
+				}
+				for (uint32_t p = 0; p < 8; ++p) st_s(outY, outOff * 8 + p, yuv[p][0], bits);
+				for (uint32_t c = 0; c < 4; ++c) { /* chroma from even pixels only (:170-171) */
+					st_s(outU, outOff * 4 + c, yuv[2 * c][1], bits);
+					st_s(outV, outOff * 4 + c, yuv[2 * c][2], bits);
+				}
+				inOff += 8;
+				outOff++;
+			}
+			if (remain > 0) { /* :180-218 */
+				uint32_t y[8], u[4], v[4], yuv[6][3] = {{0}};
+				for (int k = 0; k < 8; ++k) y[k] = bits == 8 ? 16 : 64;
+				for (int k = 0; k < 4; ++k) u[k] = v[k] = bits == 8 ? 128 : 512;
+				for (uint32_t p = 0; p < remain && p < 6; ++p) {
+					const float *l = input + (inOff + p) * 4;
+					const float rgba[4] = {lut[sat_rte(l[0] * 65535.0f, 65535.0f)], lut[sat_rte(l[1] * 65535.0f, 65535.0f)],
+					                       lut[sat_rte(l[2] * 65535.0f, 65535.0f)], 1.0f};
+					yuv[p][0] = sat_rte(roundf(dot4(rgba, cm + 0)), 65535.0f); /* round(): half away from zero */
+					yuv[p][1] = sat_rte(roundf(dot4(rgba, cm + 4)), 65535.0f);
+					yuv[p][2] = sat_rte(roundf(dot4(rgba, cm + 8)), 65535.0f);
+				}
+				y[0] = yuv[0][0]; y[1] = yuv[1][0]; u[0] = yuv[0][1]; v[0] = yuv[0][2];
+				if (remain > 2) {
+					y[2] = yuv[2][0]; y[3] = yuv[3][0]; u[1] = yuv[2][1]; v[1] = yuv[2][2];
+					if (remain > 4) {
+						y[4] = yuv[4][0]; y[5] = yuv[5][0];
+						u[1] = yuv[4][1]; v[1] = yuv[4][2]; /* Q12: .s1 where .s2 is meant (yuv422p10.ts:210-211) */
+					}
+				}
+				for (uint32_t p = 0; p < 8; ++p) st_s(outY, outOff * 8 + p, y[p], bits);
+				for (uint32_t c = 0; c < 4; ++c) {
+					st_s(outU, outOff * 4 + c, u[c], bits);
+					st_s(outV, outOff * 4 + c, v[c], bits);
+				}
+			}
+		}
+	}
+}

@@ -70,6 +70,16 @@ void orc_rgba8_read(const uint8_t *input, float *output, uint32_t width, uint32_
 void orc_rgba8_write(const float *input, uint8_t *output, uint32_t width, uint32_t height,
                      uint32_t interlace, const float *gamma_lut, int bgra);
 
+/* yuv422p10le / yuv422p8: bits = 10 or 8; planes are byte pointers (little-endian samples) */
+uint32_t orc_yuv422p_pitch(uint32_t width); /* pixels */
+void orc_yuv422p_fill(int bits, uint8_t *buf, uint32_t width, uint32_t height);
+void orc_yuv422p_read(int bits, const uint8_t *inY, const uint8_t *inU, const uint8_t *inV, float *output,
+                      uint32_t width, uint32_t height, const float *col_matrix12, const float *gamma_lut,
+                      const float *gamut9);
+void orc_yuv422p_write(int bits, const float *input, uint8_t *outY, uint8_t *outU, uint8_t *outV,
+                       uint32_t width, uint32_t height, uint32_t interlace, const float *col_matrix12,
+                       const float *gamma_lut);
+
 #ifdef __cplusplus
 }
 #endif

@@ -278,6 +278,54 @@ def rgba8_write(rgba: np.ndarray, width: int, height: int, interlace: int, gamma
     return out
 
 
+def _yuv422p_geom(bits: int, width: int, height: int):
+    pitch = width + 7 - ((width - 1) % 8)                      # yuv422p10.ts:222
+    luma = pitch * (2 if bits == 10 else 1) * height
+    return -(-pitch // 64), [luma, luma // 2, luma // 2]       # Math.ceil(getPitch / 64) work-items per line (:308)
+
+
+def yuv422p_read(bits: int, y, u, v, width: int, height: int, col_matrix, gamma_lut, gamut) -> np.ndarray:
+    """yuv422p10.ts:25-124 / yuv422p8.ts:25-124 with Reader's NDRange"""
+    k = _kernel(f"yuv422p{bits}.cl", "read")
+    wpg, _ = _yuv422p_geom(bits, width, height)
+    mems = [_buf(np.asarray(a, np.uint8)) for a in (y, u, v)]
+    o = _buf(nbytes=width * height * 16)
+    cm, lut, gm = _buf(_pad(col_matrix, 12)), _buf(np.asarray(gamma_lut, np.float32)), _buf(_pad(gamut, 16))
+    for n, m in enumerate(mems + [o]):
+        _ck(_lib.ocl_arg_mem(k, n, m))
+    _ck(_lib.ocl_arg_u32(k, 4, width))
+    for n, m in zip((5, 6, 7), (cm, lut, gm)):
+        _ck(_lib.ocl_arg_mem(k, n, m))
+    _ck(_lib.ocl_run(k, 1, wpg * height, 1, wpg))
+    out = np.empty((height, width, 4), np.float32)
+    _ck(_lib.ocl_read_buffer(o, out.ctypes.data, out.nbytes))
+    _free(o, cm, lut, gm, *mems)
+    return out
+
+
+def yuv422p_write(bits: int, rgba, width: int, height: int, interlace: int, col_matrix, gamma_lut, outs=None):
+    """yuv422p10.ts:126-219 / yuv422p8.ts:126-219 with Writer's NDRange"""
+    k = _kernel(f"yuv422p{bits}.cl", "write")
+    wpg, nb = _yuv422p_geom(bits, width, height)
+    if outs is None:
+        outs = [np.zeros(n, np.uint8) for n in nb]
+    i = _buf(np.asarray(rgba, np.float32))
+    mems = [_buf(o) for o in outs]
+    cm, lut = _buf(_pad(col_matrix, 12)), _buf(np.asarray(gamma_lut, np.float32))
+    _ck(_lib.ocl_arg_mem(k, 0, i))
+    for n, m in enumerate(mems):
+        _ck(_lib.ocl_arg_mem(k, 1 + n, m))
+    _ck(_lib.ocl_arg_u32(k, 4, width))
+    _ck(_lib.ocl_arg_u32(k, 5, interlace))
+    _ck(_lib.ocl_arg_mem(k, 6, cm))
+    _ck(_lib.ocl_arg_mem(k, 7, lut))
+    _ck(_lib.ocl_run(k, 1, wpg * height // (2 if interlace else 1), 1, wpg))
+    for o, m in zip(outs, mems):
+        _ck(_lib.ocl_read_buffer(m, o.ctypes.data, o.nbytes))
+    _free(i, cm, lut, *mems)
+    return outs
+
+
 class ReferenceChain:
     """The reference's UNFUSED launch sequence for a harness scene, with persistent device buffers, for timing on the
     same GPU: per source `read` (+ `transform`), per transition layer `transition_*`, `combine_N`, `write`

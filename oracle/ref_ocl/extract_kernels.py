@@ -91,6 +91,8 @@ def main():
         "transform.cl": literal_after(rd("transform.ts"), "const transformKernel ="),
         "yadif.cl": literal_after(rd("yadifCl.ts"), "const yadifKernel ="),
         "rgba8.cl": literal_after(rd("rgba8.ts"), "const rgba8Kernel ="),
+        "yuv422p10.cl": literal_after(rd("yuv422p10.ts"), "const yuv422p10leKernel ="),
+        "yuv422p8.cl": literal_after(rd("yuv422p8.ts"), "const yuv422p8Kernel ="),
         "transition_dissolve.cl": gen_transition(rd("transition.ts"), "dissolve"),
         "transition_wipe.cl": gen_transition(rd("transition.ts"), "wipe"),
     }

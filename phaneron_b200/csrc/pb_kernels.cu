@@ -113,6 +113,91 @@ __global__ void __launch_bounds__(kThreads) k_rgba8_write(const float4 *__restri
 	out[(size_t)line * width + x] = o;
 }
 
+// ---- yuv422p10le / yuv422p8: yuv422p10.ts:25-219, yuv422p8.ts:25-219 ----------------------
+// Three planes, line pitch = width rounded up to 8 samples (chroma: half).  The read kernel has no
+// tail quirk (the partial last block converts like the others), so it is one thread per pixel.
+template <int BITS>
+__device__ __forceinline__ uint32_t ld_sample(const void *plane, size_t i) {
+	return BITS == 8 ? (uint32_t) reinterpret_cast<const uint8_t *>(plane)[i] : (uint32_t) reinterpret_cast<const uint16_t *>(plane)[i];
+}
+template <int BITS>
+__device__ __forceinline__ void st_sample(void *plane, size_t i, uint32_t v) {
+	if (BITS == 8) reinterpret_cast<uint8_t *>(plane)[i] = (uint8_t)v;   // Q11: the 16-bit conversion result wraps into a uchar
+	else reinterpret_cast<uint16_t *>(plane)[i] = (uint16_t)v;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kThreads) k_yuv422p_read(const void *__restrict__ Y, const void *__restrict__ U, const void *__restrict__ V,
+                                                           float4 *__restrict__ out, int width, int height, const __grid_constant__ ReadConsts rc) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)width * height) return;
+	const int line = (int)(tid / width), x = (int)(tid - (size_t)line * width);
+	const int pitch = (width + 7) / 8 * 8;
+	Ycc c;
+	c.y = ld_sample<BITS>(Y, (size_t)line * pitch + x);
+	c.cb = ld_sample<BITS>(U, (size_t)line * (pitch / 2) + x / 2);
+	c.cr = ld_sample<BITS>(V, (size_t)line * (pitch / 2) + x / 2);
+	const float3 rgb = ycc_to_linear(c, 1.0f, rc);
+	out[tid] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+}
+
+// one thread per block of 8 pixels (one ushort8 / uchar8 of luma, 4 + 4 chroma samples)
+template <int BITS>
+__global__ void __launch_bounds__(kThreads) k_yuv422p_write(const float4 *__restrict__ in, void *__restrict__ Y, void *__restrict__ U,
+                                                            void *__restrict__ V, int width, int lines, int interlace,
+                                                            const __grid_constant__ WriteConsts wc) {
+	const int blocks = (width + 7) / 8;
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)blocks * lines) return;
+	const int gl = (int)(tid / blocks), bx = (int)(tid - (size_t)gl * blocks);
+	const int line = gl * (interlace == 0 ? 1 : 2) + (interlace == 3 ? 1 : 0);
+	const int x0 = bx * 8, n = min(8, width - x0);
+	const size_t yo = ((size_t)line * blocks + bx) * 8, co = ((size_t)line * blocks + bx) * 4;
+	uint32_t y[8], u[4], v[4];
+	if (n == 8) {   // yuv422p10.ts:155-178
+#pragma unroll
+		for (int p = 0; p < 8; ++p) {
+			const float4 l = __ldg(in + (size_t)line * width + x0 + p);
+			const Ycc c = linear_to_ycc(l.x, l.y, l.z, wc);
+			y[p] = c.y;
+			if (!(p & 1)) { u[p / 2] = c.cb; v[p / 2] = c.cr; }   // chroma from even pixels only
+		}
+	} else {   // the partial last block of a line, yuv422p10.ts:180-218
+#pragma unroll
+		for (int k = 0; k < 8; ++k) y[k] = BITS == 8 ? 16 : 64;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) u[k] = v[k] = BITS == 8 ? 128 : 512;
+		uint32_t ty[6], tu[6], tv[6];
+#pragma unroll
+		for (int p = 0; p < 6; ++p) {
+			ty[p] = tu[p] = tv[p] = 0;
+			if (p < n) {
+				const float4 l = __ldg(in + (size_t)line * width + x0 + p);
+				const float gr = __ldg(wc.lut + sat_rte_u16(mul(l.x, 65535.0f))), gg = __ldg(wc.lut + sat_rte_u16(mul(l.y, 65535.0f))),
+				            gb = __ldg(wc.lut + sat_rte_u16(mul(l.z, 65535.0f)));
+				ty[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 0)));   // round(): half away from zero
+				tu[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 4)));
+				tv[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 8)));
+			}
+		}
+		y[0] = ty[0]; y[1] = ty[1]; u[0] = tu[0]; v[0] = tv[0];
+		if (n > 2) {
+			y[2] = ty[2]; y[3] = ty[3]; u[1] = tu[2]; v[1] = tv[2];
+			if (n > 4) {
+				y[4] = ty[4]; y[5] = ty[5];
+				u[1] = tu[4]; v[1] = tv[4];   // Q12: .s1 where .s2 is meant (yuv422p10.ts:210-211)
+			}
+		}
+	}
+#pragma unroll
+	for (int p = 0; p < 8; ++p) st_sample<BITS>(Y, yo + p, y[p]);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		st_sample<BITS>(U, co + k, u[k]);
+		st_sample<BITS>(V, co + k, v[k]);
+	}
+}
+
 // ---- combine_N: combine.ts:24-68 --------------------------------------------------------
 struct CombineArgs {
 	const float4 *in[kMaxLayers];
@@ -294,6 +379,21 @@ cudaError_t launch_rgba8_read(cudaStream_t s, const void *in, void *out, int w, 
 cudaError_t launch_rgba8_write(cudaStream_t s, const void *in, void *out, int w, int h, int interlace, int bgra, const WriteConsts &wc) {
 	const int lines = interlace == 0 ? h : h / 2;
 	k_rgba8_write<<<blocks_for((size_t)w * lines), kThreads, 0, s>>>((const float4 *)in, (uchar4 *)out, w, lines, interlace, bgra, wc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_yuv422p_read(cudaStream_t s, int bits, const void *y, const void *u, const void *v, void *out, int w, int h, const ReadConsts &rc) {
+	const size_t n = (size_t)w * h;
+	if (bits == 8) k_yuv422p_read<8><<<blocks_for(n), kThreads, 0, s>>>(y, u, v, (float4 *)out, w, h, rc);
+	else k_yuv422p_read<10><<<blocks_for(n), kThreads, 0, s>>>(y, u, v, (float4 *)out, w, h, rc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_yuv422p_write(cudaStream_t s, int bits, const void *in, void *y, void *u, void *v, int w, int h, int interlace, const WriteConsts &wc) {
+	const int lines = interlace == 0 ? h : h / 2;
+	const size_t n = (size_t)((w + 7) / 8) * lines;
+	if (bits == 8) k_yuv422p_write<8><<<blocks_for(n), kThreads, 0, s>>>((const float4 *)in, y, u, v, w, lines, interlace, wc);
+	else k_yuv422p_write<10><<<blocks_for(n), kThreads, 0, s>>>((const float4 *)in, y, u, v, w, lines, interlace, wc);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }

@@ -992,6 +992,56 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 			else e = pb::launch_rgba8_write(s, src, out->dev, W, H, interlace, g->op == PB_OP_BGRA8_WRITE, wc);
 			break;
 		}
+		case PB_OP_YUV422P10_READ:
+		case PB_OP_YUV422P8_READ: {
+			const int bits = g->op == PB_OP_YUV422P8_READ ? 8 : 10;
+			pb_buf *iy, *iu, *iv, *out, *lut;
+			pb::ReadConsts rc;
+			if ((r = need_buf(p, n, "inputY", &iy)) || (r = need_buf(p, n, "inputU", &iu)) || (r = need_buf(p, n, "inputV", &iv)) ||
+			    (r = need_buf(p, n, "output", &out)))
+				return r;
+			if ((r = make_read_consts(c, p, n, true, &rc, &lut))) return r;
+			const size_t luma = (size_t)((W + 7) / 8 * 8) * (bits == 8 ? 1 : 2) * H;
+			if (iy->bytes < luma || iu->bytes < luma / 2 || iv->bytes < luma / 2) return fail(PB_ERR_ARG, "yuv422p input plane too small");
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if ((r = flush_host(iy, s)) || (r = flush_host(iu, s)) || (r = flush_host(iv, s))) return r;
+			if (!iy->dev || !iu->dev || !iv->dev) return fail(PB_ERR_STATE, "yuv422p input has no contents");
+			void *o;
+			if ((r = real_output(out, &o))) return r;
+			out->w = W;
+			out->h = H;
+			e = pb::launch_yuv422p_read(s, bits, iy->dev, iu->dev, iv->dev, o, W, H, rc);
+			break;
+		}
+		case PB_OP_YUV422P10_WRITE:
+		case PB_OP_YUV422P8_WRITE: {
+			const int bits = g->op == PB_OP_YUV422P8_WRITE ? 8 : 10;
+			pb_buf *in, *oy, *ou, *ov;
+			pb::WriteConsts wc;
+			double il = 0;
+			if ((r = need_buf(p, n, "input", &in)) || (r = need_buf(p, n, "outputY", &oy)) || (r = need_buf(p, n, "outputU", &ou)) ||
+			    (r = need_buf(p, n, "outputV", &ov)))
+				return r;
+			if ((r = make_write_consts(c, p, n, true, &wc))) return r;
+			if (find(p, n, "interlace") && (r = need_num(p, n, "interlace", &il))) return r;
+			const int interlace = (int)il;
+			if (interlace != 0 && interlace != 1 && interlace != 3) return fail(PB_ERR_ARG, "interlace must be 0, 1 or 3");
+			const size_t luma = (size_t)((W + 7) / 8 * 8) * (bits == 8 ? 1 : 2) * H;
+			if (oy->bytes < luma || ou->bytes < luma / 2 || ov->bytes < luma / 2) return fail(PB_ERR_ARG, "yuv422p output plane too small");
+			if (in->w && (in->w != W || in->h != H)) return fail(PB_ERR_ARG, "writer is %dx%d but input image is %dx%d", W, H, in->w, in->h);
+			pb_buf *outs[3] = {oy, ou, ov};
+			for (pb_buf *o : outs) {
+				o->expr.reset();
+				if (interlace != 0 && (r = flush_host(o, s))) return r;   // a field write keeps the other field's lines
+				o->host_dirty = false;
+				if ((r = ensure_dev(o))) return r;
+				o->version = ++c->version_counter;
+			}
+			const void *src;
+			if ((r = real_input(in, &src))) return r;
+			e = pb::launch_yuv422p_write(s, bits, src, oy->dev, ou->dev, ov->dev, W, H, interlace, wc);
+			break;
+		}
 		case PB_OP_COMBINE: {
 			pb_buf *out, *ins[64];
 			int cnt = 0;
@@ -1412,6 +1462,7 @@ int pb_prog_create(pb_ctx *c, int op, int width, int height, pb_prog **out) {
 		case PB_OP_V210_READ: case PB_OP_V210_WRITE: case PB_OP_RGBA8_READ: case PB_OP_RGBA8_WRITE: case PB_OP_BGRA8_READ:
 		case PB_OP_BGRA8_WRITE: case PB_OP_COMBINE: case PB_OP_DISSOLVE: case PB_OP_WIPE_MASK: case PB_OP_TRANSFORM:
 		case PB_OP_YADIF: case PB_OP_MIX: case PB_OP_WIPE: case PB_OP_RESIZE:
+		case PB_OP_YUV422P10_READ: case PB_OP_YUV422P10_WRITE: case PB_OP_YUV422P8_READ: case PB_OP_YUV422P8_WRITE:
 			break;
 		default:
 			return fail(PB_ERR_ARG, "unknown op %d", op);

@@ -195,3 +195,16 @@ def test_rgba8_roundtrip_fixture():
     dst = oracle.rgba8_write(rgba, w, h, 0, lut_w)
     assert np.array_equal(src, dst)
     assert rgba[0, 0, 3] == 1.0
+
+
+@pytest.mark.parametrize("bits,w,h", [(10, 1920, 1080), (8, 718, 1080), (8, 1920, 64), (10, 718, 64)])
+def test_yuv422p_fixture_round_trips(bits, w, h):
+    """the pass criterion of src/process/test/yuv422p10Test.ts / yuv422p8Test.ts (`compare() === 0`; 718 wide for the tails)"""
+    rng = (10, 64, 940, 896) if bits == 10 else (8, 16, 235, 224)
+    src = oracle.yuv422p_fill(bits, w, h)
+    nb = oracle.yuv422p_plane_bytes(bits, w, h)
+    y, u, v = src[: nb[0]], src[nb[0]: nb[0] + nb[1]], src[nb[0] + nb[1]:]
+    rgba = oracle.yuv422p_read(bits, y, u, v, w, h, oracle.ycbcr2rgb_matrix("709", *rng), oracle.gamma2linear_lut("709"),
+                               oracle.rgb2rgb_matrix("709", "709"))
+    outs = oracle.yuv422p_write(bits, rgba, w, h, 0, oracle.rgb2ycbcr_matrix("709", *rng), oracle.linear2gamma_lut("709"))
+    assert np.array_equal(np.concatenate(outs), src)
