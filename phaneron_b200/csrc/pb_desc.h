@@ -105,6 +105,23 @@ struct Layer {
 	Leaf a, b, mask;
 };
 
+// march kernel: the layer graph flattened by the host into a list of leaf evaluations, each followed by an action
+enum MarchAct : int {
+	ACT_OVER = 0,        // direct layer: acc = fma(acc, 1 - p.a, p)                          (combine.ts:49-59)
+	ACT_DIS_B = 1,       // dissolve, second input first: t = p * (1 - mix)                   (transition.ts:60-65)
+	ACT_DIS_A_OVER = 2,  // dissolve, first input: p = fma(p, mix, t); then over
+	ACT_WIPE_M = 3,      // wipe, mask first: m = p.r                                         (transition.ts:66-73)
+	ACT_WIPE_A = 4,      // wipe, first input: t = p * (1 - m)
+	ACT_WIPE_B_OVER = 5  // wipe, second input: p = fma(p, m, t); then over
+};
+struct MarchOp {
+	int layer, which;    // the leaf: (&layers[layer].a)[which]
+	int act;             // MarchAct
+	float mix;
+};
+constexpr int kMaxOps = 3 * kMaxLayers;
+constexpr int kMaxStrips = 128;
+
 struct FusedDesc {
 	int n_layers;
 	int out_w, out_h;
@@ -125,6 +142,10 @@ struct FusedDesc {
 	ReadConsts rc[kMaxReadConsts];
 	ReadK rk[kMaxReadConsts];
 	Layer layers[kMaxLayers];
+	// march kernel
+	int n_ops;
+	MarchOp ops[kMaxOps];
+	uint32_t strip_ops[kMaxStrips];   // per strip: bit i set if op i can touch the strip (all ops of a transition layer together)
 };
 
 }  // namespace pb

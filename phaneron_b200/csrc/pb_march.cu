@@ -315,7 +315,11 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(lut_s);
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	// read %tid.x once through a volatile asm: the compiler otherwise re-reads the special register (S2R, ~20 cycles)
+	// wherever lane / warp are needed again (profiles/r01_march_ncu_lines.txt)
+	uint32_t tid_x;
+	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
+	const int lane = tid_x & 31, warp = tid_x >> 5;
 	float *buf = reinterpret_cast<float *>(smem_raw + (kLutMode ? (size_t)d.n_luts * 65536 : 0)) + warp * kRowFloats;
 
 	if (kLutMode) {
@@ -360,59 +364,61 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		const int x_first = strip * strip_px;
 		const int x_last = min(x_first + strip_px, d.out_w) - 1;
 
+		// The host flattened the layer graph into ops (a leaf evaluation + an action) and marked, per strip, the ops
+		// that can touch it: leaves that lie elsewhere cost nothing here.  acc starts at 0 and every layer, the bottom
+		// one included, is composited with `over`: fma(0, k, p) == p.
 		float3 acc[kRounds];
+		float4 p[kRounds], t[kRounds];
+		float m[kRounds];
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) {
+			acc[r] = make_float3(0.f, 0.f, 0.f);
+			t[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+			m[r] = 0.f;
+		}
+		uint32_t todo = d.strip_ops[strip];
 #pragma unroll 1
-		for (int l = 0; l < d.n_layers; ++l) {
-			const Layer &ly = d.layers[l];
-			float4 p[kRounds], t[kRounds];
-			float m[kRounds];
-			(void)t; (void)m;
-			// evaluation order keeps at most {t, p} live: dissolve = b then a; wipe = mask, a, b
-			const int nleaf = ly.kind == LAYER_DIRECT ? 1 : (ly.kind == LAYER_DISSOLVE ? 2 : 3);
-#pragma unroll 1
-			for (int q = 0; q < nleaf; ++q) {
-				const Leaf &lf = ly.kind == LAYER_DIRECT ? ly.a
-				                 : ly.kind == LAYER_DISSOLVE ? (q == 0 ? ly.b : ly.a)
-				                                             : (q == 0 ? ly.mask : (q == 1 ? ly.a : ly.b));
-				eval_leaf<kLutMode, kSparse, kSingleRc>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
-				if (ly.kind == LAYER_DISSOLVE) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
-					if (q == 0) {
-						const float rmix = sub(1.0f, ly.mix);
+		while (todo) {
+			const int oi = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const MarchOp &op = d.ops[oi];
+			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
+			eval_leaf<kLutMode, kSparse, kSingleRc>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
+			const int act = op.act;
+			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
+				const float rmix = sub(1.0f, op.mix);
 #pragma unroll
-						for (int r = 0; r < kRounds; ++r) t[r] = make_float4(mul(p[r].x, rmix), mul(p[r].y, rmix), mul(p[r].z, rmix), mul(p[r].w, rmix));
-					} else {
-#pragma unroll
-						for (int r = 0; r < kRounds; ++r)
-							p[r] = make_float4(fma_(p[r].x, ly.mix, t[r].x), fma_(p[r].y, ly.mix, t[r].y), fma_(p[r].z, ly.mix, t[r].z),
-							                   fma_(p[r].w, ly.mix, t[r].w));
-					}
-				} else if (ly.kind == LAYER_WIPE_MASK) {   // transition.ts:66-73: fma(in1, m, in0 * (1 - m)), m = mask.r
-					if (q == 0) {
-#pragma unroll
-						for (int r = 0; r < kRounds; ++r) m[r] = p[r].x;
-					} else if (q == 1) {
-#pragma unroll
-						for (int r = 0; r < kRounds; ++r) {
-							const float rm = sub(1.0f, m[r]);
-							t[r] = make_float4(mul(p[r].x, rm), mul(p[r].y, rm), mul(p[r].z, rm), mul(p[r].w, rm));
-						}
-					} else {
-#pragma unroll
-						for (int r = 0; r < kRounds; ++r)
-							p[r] = make_float4(fma_(p[r].x, m[r], t[r].x), fma_(p[r].y, m[r], t[r].y), fma_(p[r].z, m[r], t[r].z),
-							                   fma_(p[r].w, m[r], t[r].w));
-					}
-				}
+				for (int r = 0; r < kRounds; ++r) t[r] = make_float4(mul(p[r].x, rmix), mul(p[r].y, rmix), mul(p[r].z, rmix), mul(p[r].w, rmix));
+				continue;
 			}
-			if (l == 0) {
+			if (act == ACT_WIPE_M) {   // transition.ts:66-73: fma(in1, m, in0 * (1 - m)), m = mask.r
 #pragma unroll
-				for (int r = 0; r < kRounds; ++r) acc[r] = make_float3(p[r].x, p[r].y, p[r].z);
-			} else {   // combine.ts:49-59: fma(prev, 1 - l.a, l)
+				for (int r = 0; r < kRounds; ++r) m[r] = p[r].x;
+				continue;
+			}
+			if (act == ACT_WIPE_A) {
 #pragma unroll
 				for (int r = 0; r < kRounds; ++r) {
-					const float kk = sub(1.0f, p[r].w);
-					acc[r] = make_float3(fma_(acc[r].x, kk, p[r].x), fma_(acc[r].y, kk, p[r].y), fma_(acc[r].z, kk, p[r].z));
+					const float rm = sub(1.0f, m[r]);
+					t[r] = make_float4(mul(p[r].x, rm), mul(p[r].y, rm), mul(p[r].z, rm), mul(p[r].w, rm));
 				}
+				continue;
+			}
+			if (act == ACT_DIS_A_OVER) {
+				const float mix = op.mix;
+#pragma unroll
+				for (int r = 0; r < kRounds; ++r)
+					p[r] = make_float4(fma_(p[r].x, mix, t[r].x), fma_(p[r].y, mix, t[r].y), fma_(p[r].z, mix, t[r].z), fma_(p[r].w, mix, t[r].w));
+			} else if (act == ACT_WIPE_B_OVER) {
+#pragma unroll
+				for (int r = 0; r < kRounds; ++r)
+					p[r] = make_float4(fma_(p[r].x, m[r], t[r].x), fma_(p[r].y, m[r], t[r].y), fma_(p[r].z, m[r], t[r].z), fma_(p[r].w, m[r], t[r].w));
+			}
+			// combine.ts:49-59: fma(prev, 1 - l.a, l)
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const float kk = sub(1.0f, p[r].w);
+				acc[r] = make_float3(fma_(acc[r].x, kk, p[r].x), fma_(acc[r].y, kk, p[r].y), fma_(acc[r].z, kk, p[r].z));
 			}
 		}
 

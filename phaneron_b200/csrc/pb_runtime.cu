@@ -710,6 +710,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.e_magic = 0x4B000000u;
 	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
 	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
+	if (d.n_strips > pb::kMaxStrips) return 0;
 	for (int i = 0; i < n_leaves; ++i) {
 		pb_ctx::SampleTab *t;
 		int fits = 0;
@@ -720,6 +721,39 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		leaves[i]->row_tab = t->drow;
 		leaves[i]->strip_tab = t->dstrip;
 		leaves[i]->s0 = t->s0; leaves[i]->s1 = t->s1; leaves[i]->y0 = t->y0; leaves[i]->y1 = t->y1;
+	}
+	// flatten the layer graph: evaluation order keeps at most {t, p} live (dissolve = b then a; wipe = mask, a, b)
+	d.n_ops = 0;
+	int layer_first_op[pb::kMaxLayers], layer_n_ops[pb::kMaxLayers];
+	for (int l = 0; l < d.n_layers; ++l) {
+		const pb::Layer &ly = d.layers[l];
+		layer_first_op[l] = d.n_ops;
+		auto push = [&](int which, int act) { d.ops[d.n_ops++] = pb::MarchOp{l, which, act, ly.mix}; };
+		if (ly.kind == pb::LAYER_DIRECT) {
+			push(0, pb::ACT_OVER);
+		} else if (ly.kind == pb::LAYER_DISSOLVE) {
+			push(1, pb::ACT_DIS_B);
+			push(0, pb::ACT_DIS_A_OVER);
+		} else {
+			push(2, pb::ACT_WIPE_M);
+			push(0, pb::ACT_WIPE_A);
+			push(1, pb::ACT_WIPE_B_OVER);
+		}
+		layer_n_ops[l] = d.n_ops - layer_first_op[l];
+	}
+	for (int sidx = 0; sidx < d.n_strips; ++sidx) {
+		uint32_t mask = 0;
+		for (int l = 0; l < d.n_layers; ++l) {
+			const pb::Layer &ly = d.layers[l];
+			const pb::Leaf *ll[3] = {&ly.a, &ly.b, &ly.mask};
+			const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
+			bool any = false;
+			for (int q = 0; q < nleaf; ++q) any = any || (sidx >= ll[q]->s0 && sidx <= ll[q]->s1);
+			// a transition whose leaves are all elsewhere yields (0,0,0,0): `over` leaves acc untouched, skip the layer;
+			// otherwise all of its ops run (a leaf that is elsewhere evaluates to the border colour by itself)
+			if (any) mask |= ((1u << layer_n_ops[l]) - 1u) << layer_first_op[l];
+		}
+		d.strip_ops[sidx] = mask;
 	}
 	// the write side packs three codes into one word while regrouping: they must fit 10 bits
 	const int wt = lut_table_by_raw(c, d.wc.lut);
