@@ -146,6 +146,7 @@ struct FusedDesc {
 	int n_ops;
 	MarchOp ops[kMaxOps];
 	uint32_t strip_ops[kMaxStrips];   // per strip: bit i set if op i can touch the strip (all ops of a transition layer together)
+	const uint32_t *line_ops;         // per output line, same meaning (device memory, out_h entries)
 };
 
 }  // namespace pb

@@ -161,18 +161,20 @@ __device__ __forceinline__ void convert_group(const uint4 &w, int g, uint32_t E,
 template <int kLutMode, bool kSparse, bool kSingleRc>
 __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, float *buf, int lane, int strip, int y,
                                           int x_first, int x_last, float4 (&p)[kRounds]) {
-#pragma unroll
-	for (int r = 0; r < kRounds; ++r) p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-	if (strip < lf.s0 || strip > lf.s1 || y < lf.y0 || y > lf.y1) return;   // nothing but border texels here
+	// (strips / lines where the whole layer is border colour never get here: FusedDesc::strip_ops & line_ops)
 	const int4 si = __ldg(lf.strip_tab + strip);
 	const int2 rt = __ldg(lf.row_tab + y);
-	if (!(si.x & 1)) return;   // the strip does not touch this leaf's image: border colour everywhere
+	auto border = [&]() {
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+	};
+	if (!(si.x & 1)) return border();   // the strip does not touch this leaf's image: border colour everywhere
 	const bool edge = (si.x & 2) != 0;
 	const int g_lo = si.y, ng = si.z, origin = g_lo * 6, last = ng * 6 - 1;
 	const int j0 = rt.x;
 	const bool has_xf = lf.has_xf != 0;
 	const bool ok0 = (unsigned)j0 < (unsigned)lf.h, ok1 = has_xf && (unsigned)(j0 + 1) < (unsigned)lf.h;
-	if (!ok0 && !ok1) return;   // both rows are border rows
+	if (!ok0 && !ok1) return border();   // both rows are border rows
 	const bool paired = ng <= 16;   // both rows fit one 32-lane pass
 
 	// issue every HBM load of this leaf up front
@@ -267,6 +269,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 
 	// wide footprint (more than 16 groups per row): one pass per row, the canonical chain continues across them
 	constexpr int cap = kRowGroups * 6;
+	border();
 #pragma unroll 1
 	for (int rr = 0; rr < 2; ++rr) {
 		if (!(rr ? ok1 : ok0)) continue;   // border row: all its taps are (0,0,0,0)
@@ -357,9 +360,15 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	wlut.magic = kLutMode ? kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536) : kTwo23;
 	const LutParams &wlp = d.wlp;
 
+	// item -> (line k, strip) is kept incrementally: no integer division per item
+	const int stride = gridDim.x * kMarchWarps, stride_k = stride / d.n_strips, stride_s = stride - stride_k * d.n_strips;
+	int k = (blockIdx.x * kMarchWarps + warp) / d.n_strips, strip = (blockIdx.x * kMarchWarps + warp) - k * d.n_strips;
 #pragma unroll 1
-	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += gridDim.x * kMarchWarps) {
-		const int k = item / d.n_strips, strip = item - k * d.n_strips;
+	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride, k += stride_k, strip += stride_s) {
+		if (strip >= d.n_strips) {
+			strip -= d.n_strips;
+			++k;
+		}
 		const int y = first_line + k * step;
 		const int x_first = strip * strip_px;
 		const int x_last = min(x_first + strip_px, d.out_w) - 1;
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			t[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 			m[r] = 0.f;
 		}
-		uint32_t todo = d.strip_ops[strip];
+		uint32_t todo = d.strip_ops[strip] & __ldg(d.line_ops + y);
 #pragma unroll 1
 		while (todo) {
 			const int oi = __ffs(todo) - 1;

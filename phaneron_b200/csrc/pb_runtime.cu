@@ -152,6 +152,11 @@ struct pb_ctx {
 	pb::LutParams lut_cands[4];
 	void *lut_cands_dev = nullptr, *lut_res_dev = nullptr, *lut_scratch = nullptr;
 	uint64_t version_counter = 0;
+	struct LineOps {   // per-line op masks of the march kernel
+		std::vector<int> key;
+		uint32_t *dev = nullptr;
+	};
+	std::vector<LineOps> line_ops;
 };
 
 struct pb_buf {
@@ -755,6 +760,46 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		}
 		d.strip_ops[sidx] = mask;
 	}
+	{   // the same per output line; cached per (layer structure, leaf line ranges, height)
+		std::vector<int> key = {d.out_h, d.n_layers};
+		for (int l = 0; l < d.n_layers; ++l) {
+			const pb::Layer &ly = d.layers[l];
+			key.push_back(ly.kind);
+			const pb::Leaf *ll[3] = {&ly.a, &ly.b, &ly.mask};
+			for (int q = 0; q < 3; ++q) { key.push_back(ll[q]->y0); key.push_back(ll[q]->y1); }
+		}
+		pb_ctx::LineOps *found = nullptr;
+		for (auto &lo : c->line_ops)
+			if (lo.key == key) found = &lo;
+		if (!found) {
+			if (c->line_ops.size() >= 64) {
+				CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));
+				for (auto &lo : c->line_ops) cudaFree(lo.dev);
+				c->line_ops.clear();
+			}
+			std::vector<uint32_t> host((size_t)d.out_h);
+			for (int y = 0; y < d.out_h; ++y) {
+				uint32_t mask = 0;
+				for (int l = 0; l < d.n_layers; ++l) {
+					const pb::Layer &ly = d.layers[l];
+					const pb::Leaf *ll[3] = {&ly.a, &ly.b, &ly.mask};
+					const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
+					bool any = false;
+					for (int q = 0; q < nleaf; ++q) any = any || (y >= ll[q]->y0 && y <= ll[q]->y1);
+					if (any) mask |= ((1u << layer_n_ops[l]) - 1u) << layer_first_op[l];
+				}
+				host[y] = mask;
+			}
+			pb_ctx::LineOps lo;
+			lo.key = key;
+			CU(cudaMalloc(&lo.dev, host.size() * sizeof(uint32_t)));
+			CU(cudaMemcpyAsync(lo.dev, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+			CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // `host` is a local
+			c->line_ops.push_back(std::move(lo));
+			found = &c->line_ops.back();
+		}
+		d.line_ops = found->dev;
+	}
 	// the write side packs three codes into one word while regrouping: they must fit 10 bits
 	const int wt = lut_table_by_raw(c, d.wc.lut);
 	if (wt < 0 || !c->lut_tables[wt].unit_range) return 0;
@@ -1279,6 +1324,7 @@ int pb_ctx_destroy(pb_ctx *c) {
 		cudaFree(t.raw);
 		cudaFree(t.d8);
 	}
+	for (auto &lo : c->line_ops) cudaFree(lo.dev);
 	cudaFree(c->lut_cands_dev);
 	cudaFree(c->lut_res_dev);
 	cudaFree(c->lut_scratch);
