@@ -65,6 +65,28 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
 	return v;
 }
 
+// A float* into the warp's row buffer, held as a 32-bit shared-window address.  A generic pointer makes the compiler
+// re-derive the shared window base (S2UR SR_CgaCtaId ...) at every use site -- 3 % of the instructions and 8 % of
+// the stall samples of the kernel (profiles/r01_march_ncu_lines.txt); an opaque 32-bit address costs one register.
+struct SPtr {
+	uint32_t a;
+	__device__ __forceinline__ SPtr operator+(int i) const { return SPtr{a + 4u * (uint32_t)i}; }
+	__device__ __forceinline__ float operator[](int i) const {
+		float v;
+		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a + 4u * (uint32_t)i));
+		return v;
+	}
+	__device__ __forceinline__ void st2(int i, float2 v) const {
+		asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + 4u * (uint32_t)i), "f"(v.x), "f"(v.y) : "memory");
+	}
+	__device__ __forceinline__ uint32_t ldu(int i) const {
+		uint32_t v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + 4u * (uint32_t)i));
+		return v;
+	}
+	__device__ __forceinline__ void stu(int i, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 4u * (uint32_t)i), "r"(v) : "memory"); }
+};
+
 // one gamma table as the kernel sees it
 template <int kLutMode>
 struct LutK {
@@ -137,29 +159,27 @@ __device__ __forceinline__ uint32_t mask_or(uint32_t w, uint32_t mask, uint32_t 
 // one v210 group (6 texels, v210.ts:58-63) -> planar row slot `row` (plane stride `cap` texels) at texel column 6g
 template <int kLutMode, bool kSparse>
 __device__ __forceinline__ void convert_group(const uint4 &w, int g, uint32_t E, const ReadConsts &rc, const ReadK &rk,
-                                              const LutK<kLutMode> &lut, const LutParams &lp, float *row, int cap) {
-	float2 *pr = reinterpret_cast<float2 *>(row + g * 6);
-	float2 *pg = reinterpret_cast<float2 *>(row + cap + g * 6);
-	float2 *pb_ = reinterpret_cast<float2 *>(row + 2 * cap + g * 6);
+                                              const LutK<kLutMode> &lut, const LutParams &lp, SPtr row, int cap) {
+	const SPtr pr = row + g * 6, pg = row + (cap + g * 6), pb_ = row + (2 * cap + g * 6);
 	constexpr uint32_t M0 = 0x3ffu, M10 = 0xffc00u;
 	float2 R, G, B;
 	// word 0: Cr0 | Y0 | Cb0     word 1: Y2 | Cb1 | Y1     word 2: Cb2 | Y3 | Cr1     word 3: Y5 | Cr2 | Y4
 	convert_pair<kLutMode, kSparse, 0, 0>(mask_or(w.x >> 10, M0, E), mask_or(w.y, M0, E), mask_or(w.x, M0, E), mask_or(w.x >> 20, M0, E), rc, rk, lut, lp,
 	                                      R, G, B);
-	pr[0] = R; pg[0] = G; pb_[0] = B;
+	pr.st2(0, R); pg.st2(0, G); pb_.st2(0, B);
 	PB_PAIR_FENCE();
 	convert_pair<kLutMode, kSparse, 1, 0>(mask_or(w.y >> 20, M0, E), mask_or(w.z >> 10, M0, E), mask_or(w.y, M10, E), mask_or(w.z, M0, E), rc, rk, lut, lp,
 	                                      R, G, B);
-	pr[1] = R; pg[1] = G; pb_[1] = B;
+	pr.st2(2, R); pg.st2(2, G); pb_.st2(2, B);
 	PB_PAIR_FENCE();
 	convert_pair<kLutMode, kSparse, 0, 1>(mask_or(w.w, M0, E), mask_or(w.w >> 20, M0, E), mask_or(w.z >> 20, M0, E), mask_or(w.w, M10, E), rc, rk, lut, lp,
 	                                      R, G, B);
-	pr[2] = R; pg[2] = G; pb_[2] = B;
+	pr.st2(4, R); pg.st2(4, G); pb_.st2(4, B);
 }
 
 // value of one leaf at the 3 pixels of this lane -> p[r] = (r, g, b, alpha)
 template <int kLutMode, bool kSparse, bool kSingleRc>
-__device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, float *buf, int lane, int strip, int y,
+__device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, SPtr buf, int lane, int strip, int y,
                                           int x_first, int x_last, float4 (&p)[kRounds]) {
 	// (strips / lines where the whole layer is border colour never get here: FusedDesc::strip_ops & line_ops)
 	const int4 si = __ldg(lf.strip_tab + strip);
@@ -214,7 +234,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	lut.raw = rc.lut;
 	lut.magic = kLutMode ? kTwo23 + (float)(lut_saddr + (kSingleRc ? 0 : slot) * 65536) : kTwo23;
 	const uint32_t E = d.e_magic;
-	const float *bufo = buf - origin;   // row buffer addressed by source column
+	const SPtr bufo = buf + (-origin);   // row buffer addressed by source column
 
 	if (paired) {
 		constexpr int cap = 96, slot_floats = 3 * cap;   // two row slots of 16 groups
@@ -226,13 +246,13 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		if (!has_xf) {   // 1:1 read of texel (x, y): exact passthrough, alpha = 1 (leaf_value in pb_device.cuh)
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const float *t = bufo + c0[r];
+				const SPtr t = bufo + c0[r];
 				p[r] = make_float4(t[0], t[cap], t[2 * cap], 1.0f);
 			}
 		} else if (!edge && ok0 && ok1) {   // interior: all four taps are texels
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const float *t0 = bufo + c0[r], *t1 = t0 + slot_floats;
+				const SPtr t0 = bufo + c0[r], t1 = t0 + slot_floats;
 				const float ra = sub(1.0f, ca[r]);
 				const float w00 = mul(ra, rb), w10 = mul(ca[r], rb), w01 = mul(ra, b), w11 = mul(ca[r], b);
 				p[r].x = fma_(w11, t1[1], fma_(w01, t1[0], fma_(w10, t0[1], mul(w00, t0[0]))));
@@ -246,7 +266,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 				const int i0 = c0[r];
 				const bool fc0 = (unsigned)i0 < (unsigned)lf.w, fc1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
 				const bool f00 = fc0 && ok0, f10 = fc1 && ok0, f01 = fc0 && ok1, f11 = fc1 && ok1;
-				const float *t0 = buf + min(max(i0 - origin, 0), last), *t1 = buf + min(max(i0 - origin + 1, 0), last);
+				const SPtr t0 = buf + min(max(i0 - origin, 0), last), t1 = buf + min(max(i0 - origin + 1, 0), last);
 				const float ra = sub(1.0f, ca[r]);
 				const float w00 = mul(ra, rb), w10 = mul(ca[r], rb), w01 = mul(ra, b), w11 = mul(ca[r], b);
 #define PB_TAP(flag, ptr, off) ((flag) ? (ptr)[off] : 0.0f)
@@ -284,7 +304,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		if (!edge) {
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const float *t = bufo + c0[r];
+				const SPtr t = bufo + c0[r];
 				const float w0 = mul(sub(1.0f, ca[r]), wr), w1 = mul(ca[r], wr);   // w00|w01 , w10|w11
 				p[r].x = fma_(w1, t[1], fma_(w0, t[0], p[r].x));
 				p[r].y = fma_(w1, t[cap + 1], fma_(w0, t[cap], p[r].y));
@@ -296,7 +316,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 			for (int r = 0; r < kRounds; ++r) {
 				const int i0 = c0[r];
 				const bool f0 = (unsigned)i0 < (unsigned)lf.w, f1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
-				const float *t0 = buf + min(max(i0 - origin, 0), last), *t1 = buf + min(max(i0 - origin + 1, 0), last);
+				const SPtr t0 = buf + min(max(i0 - origin, 0), last), t1 = buf + min(max(i0 - origin + 1, 0), last);
 				const float w0 = mul(sub(1.0f, ca[r]), wr), w1 = mul(ca[r], wr);
 				const float t0r = f0 ? t0[0] : 0.0f, t0g = f0 ? t0[cap] : 0.0f, t0b = f0 ? t0[2 * cap] : 0.0f;
 				const float t1r = f1 ? t1[0] : 0.0f, t1g = f1 ? t1[cap] : 0.0f, t1b = f1 ? t1[2 * cap] : 0.0f;
@@ -323,7 +343,11 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	uint32_t tid_x;
 	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
 	const int lane = tid_x & 31, warp = tid_x >> 5;
-	float *buf = reinterpret_cast<float *>(smem_raw + (kLutMode ? (size_t)d.n_luts * 65536 : 0)) + warp * kRowFloats;
+	SPtr buf;   // this warp's row buffer
+	{
+		const uint32_t addr = lut_saddr + (kLutMode ? (uint32_t)d.n_luts * 65536u : 0u) + (uint32_t)warp * (kRowFloats * 4u);
+		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));   // opaque: keep it in a register, do not re-derive it
+	}
 
 	if (kLutMode) {
 		// The byte tables arrive by TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by one thread and
@@ -434,7 +458,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		// ---- encode (v210.ts:145-156) and regroup 6 pixels -> 4 words through the row buffer ----
 		// The host has checked that every code lies in [0, 1023] for table values in [0, 1], so
 		// convert_ushort_sat_rte reduces to the RNE add and the three codes share one word.
-		uint32_t *stage = reinterpret_cast<uint32_t *>(buf);
+		const SPtr stage = buf;
 #pragma unroll
 		for (int r = 0; r + 1 < kRounds; r += 2) {   // two rounds at a time
 			const float2 gr = lut2<kLutMode>(f2(__saturatef(acc[r].x), __saturatef(acc[r + 1].x)), wlut, wlp);
@@ -449,8 +473,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 				code0 |= (__float_as_uint(v.x) & 0x3ffu) << (10 * c);
 				code1 |= (__float_as_uint(v.y) & 0x3ffu) << (10 * c);
 			}
-			stage[r * 32 + lane] = code0;
-			stage[(r + 1) * 32 + lane] = code1;
+			stage.stu(r * 32 + lane, code0);
+			stage.stu((r + 1) * 32 + lane, code1);
 		}
 		if (kRounds & 1) {   // the odd round out: (r, g) as one pair, b alone
 			constexpr int r = kRounds - 1;
@@ -462,12 +486,12 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 				const float u = add(add(fma_(hb.x, d.wc.cm[c * 4 + 2], fma_(hrg.x, d.wc.cm[c * 4 + 0], mul(hrg.y, d.wc.cm[c * 4 + 1]))), d.wc.cm[c * 4 + 3]), kTwo23);
 				code |= (__float_as_uint(u) & 0x3ffu) << (10 * c);
 			}
-			stage[r * 32 + lane] = code;
+			stage.stu(r * 32 + lane, code);
 		}
 		__syncwarp();
 		if (x_first + lane * 6 <= x_last) {
-			const uint32_t p0 = stage[lane * 6 + 0], p1 = stage[lane * 6 + 1], p2 = stage[lane * 6 + 2], p3 = stage[lane * 6 + 3],
-			               p4 = stage[lane * 6 + 4], p5 = stage[lane * 6 + 5];
+			const SPtr sp = stage + lane * 6;
+			const uint32_t p0 = sp.ldu(0), p1 = sp.ldu(1), p2 = sp.ldu(2), p3 = sp.ldu(3), p4 = sp.ldu(4), p5 = sp.ldu(5);
 			uint4 w;   // v210.ts:158-163: chroma from even pixels only
 			w.x = (p0 & 0x3ff00000u) | (p0 & 0x3ffu) << 10 | ((p0 >> 10) & 0x3ffu);
 			w.y = (p2 & 0x3ffu) << 20 | (p2 & 0xffc00u) | (p1 & 0x3ffu);
