@@ -214,7 +214,8 @@ async def run_ours(args, rank, world, local_rank):
 
     lib = _lib.lib()
     ctx = clContext({"platformIndex": 0, "deviceIndex": local_rank, "overlapping": True,
-                     "marchKernel": args.kernel != "generic", "rawLut": args.kernel == "march_raw"})
+                     "marchKernel": args.kernel != "generic", "rawLut": args.kernel == "march_raw",
+                     "occlusionCulling": not args.no_culling, "footprint": True})
     await ctx.initialise()
 
     # ---- scenes: enough distinct input sets that a replay never finds its inputs in L2 ----
@@ -223,6 +224,7 @@ async def run_ours(args, rank, world, local_rank):
     set_bytes = (n_in + 1) * frame_bytes
     n_sets = max(3, -(-2 * L2_BYTES // set_bytes) + 1)
     harnesses, chains, keep = [], [], []
+    chains_nocull = []   # the same frames with occlusion culling off (reported beside the default)
     for s in range(n_sets):
         scene = layered_scene(WIDTH, HEIGHT, LAYERS, args.inputs, VARIANT, COL_READ, COL_WORK, frame_set=s + rank * n_sets)
         h = ChannelHarness(ctx, scene, chanID=f"ch{rank}s{s}")
@@ -233,7 +235,20 @@ async def run_ours(args, rank, world, local_rank):
         harnesses.append(h)
         chains.append(chain)
         keep.append(dests)
+        if not args.no_culling and args.kernel != "generic":
+            ctx.setOcclusionCulling(False)
+            chain2, dests2 = await h.record_chain()
+            ctx.setOcclusionCulling(True)
+            chains_nocull.append(chain2)
+            keep.append(dests2)
     st_k = ctx.stats()
+    src_bytes_read = st_k["march_src_bytes"]   # distinct packed source bytes of the last march launch recorded
+    if chains_nocull:   # the last launch recorded was a no-culling one: account a culled launch again
+        chain3, dests3 = await harnesses[-1].record_chain()
+        src_bytes_read = ctx.stats()["march_src_bytes"]
+        keep.append(dests3)
+    ctx.footprint = False   # accounting costs a host pass per launch: not inside any timed region
+    ctx.setOcclusionCulling(not args.no_culling)
     kernel_name = ("k_fused_march (pb_march.cu), gamma tables as 1-byte deltas in shared memory" if st_k["march_launches"] and args.kernel == "march"
                    else "k_fused_march, raw gamma tables from global memory" if st_k["march_launches"] else "k_fused_generic (pb_fused.cu)")
     alg_bytes = harnesses[0].algorithmic_bytes()
@@ -242,10 +257,25 @@ async def run_ours(args, rank, world, local_rank):
 
     fps_n = args.frames_per_step
 
-    def replay_step(step_index):
+    def replay_step(step_index, which=None):
         base = step_index * fps_n
+        cs = which or chains
         for f in range(fps_n):
-            chains[(base + f) % n_sets].replay()
+            cs[(base + f) % n_sets].replay()
+
+    # ---- the same frames without occlusion culling (untimed by the contract; reported in config) ----
+    nocull_fps = None
+    if chains_nocull:
+        for w in range(args.warmup):
+            replay_step(w, chains_nocull)
+        await ctx.waitFinish(ctx.queue.process)
+        e0, e1 = ctx.createEvent(), ctx.createEvent()
+        e0.record()
+        for k in range(args.steps):
+            replay_step(k, chains_nocull)
+        e1.record()
+        e1.synchronize()
+        nocull_fps = args.steps * fps_n / (e0.elapsed_ms(e1) * 1e-3)
 
     # ---- device-resident leg ----------------------------------------------------------------
     for w in range(args.warmup):
@@ -316,7 +346,13 @@ async def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_kind = measured_peak()
         launch_ms = ms / (frames * launches_per_frame)
-        achieved = alg_bytes / launches_per_frame / (launch_ms * 1e-3) / 1e9
+        # algorithmic bytes = (distinct packed inputs + 1 output) x frame bytes.  With occlusion culling the
+        # kernel does not read source rows that lie under opaque layers: the roofline figure counts only the bytes the
+        # launch has to move (what it reads after culling + the output frame), never more than the 8(d) figure.
+        moved = alg_bytes // launches_per_frame
+        if st_k["march_launches"] and src_bytes_read:
+            moved = min(moved, int(src_bytes_read) + frame_bytes)
+        achieved = moved / (launch_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": fps_rank * world, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -324,10 +360,15 @@ async def run_ours(args, rank, world, local_rank):
             "config": {"workload": workload_name(args.inputs), "frames_per_step": fps_n, "kernel": kernel_name, "input_sets": n_sets,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating sets x {set_bytes} B = {n_sets * set_bytes} B > 126 MiB",
                        "channels": world, "parallelism": f"{world} independent channel(s), one per GPU",
-                       "launches_per_frame": launches_per_frame, "occlusion_culling": False},
+                       "launches_per_frame": launches_per_frame,
+                       "occlusion_culling": bool(st_k["march_launches"]) and not args.no_culling,
+                       "occlusion_culling_note": "exact: ops under a layer whose alpha is 1.0f bit for bit over a whole strip line are skipped "
+                                                 "(combine.ts multiplies them by 1 - 1 = 0); output bytes identical, tests/test_gpu_chain.py",
+                       "frames_per_s_without_culling": nocull_fps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.kernel, args.inputs), "peak_kind": f"of {peak_kind}", "frac_of_nominal_8TBps": achieved / 8000.0,
-                         "algorithmic_bytes_per_launch": alg_bytes // launches_per_frame, "launch_us": launch_ms * 1e3},
+                         "algorithmic_bytes_per_launch": alg_bytes // launches_per_frame, "bytes_moved_per_launch": moved,
+                         "launch_us": launch_ms * 1e3},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // e2e_steps,
                     "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // e2e_steps, "frames_per_step": E2E_FRAMES_PER_STEP,
                     "steps": e2e_steps, "checksum": checksum & 0xFFFFFFFF},
@@ -356,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inputs", default="noise", choices=["ramp", "noise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-culling", action="store_true", help="evaluate layers hidden under opaque ones too (A/B)")
     ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP, help="frames per device-resident step (profiling runs use a few)")
     ap.add_argument("--kernel", default="march", choices=["march", "march_raw", "generic"],
                     help="march: fused kernel, gamma tables in shared memory (default); march_raw: same kernel gathering "

@@ -91,6 +91,7 @@ typedef struct pb_stats {
 	uint64_t dev_bytes_live, dev_bytes_pooled;
 	uint64_t lut_tables;        /* distinct gamma tables seen (by content) */
 	uint64_t lut_tables_d8;     /* of which: held in the lossless one-byte form the march kernel keeps in shared memory */
+	uint64_t march_src_bytes;   /* PB_CTX_FOOTPRINT: distinct packed source bytes read by the last march launch */
 } pb_stats;
 
 const char *pb_last_error(void);
@@ -105,6 +106,13 @@ const char *pb_version(void);
 /* bit2 = march kernel gathers from the raw 256 KiB gamma tables in global memory instead of the
    one-byte shared-memory form (A/B tests; faster only on very coherent pictures) */
 #define PB_CTX_RAW_LUT 4u
+/* bit3 = no occlusion culling in the march kernel.  By default, ops of layers that lie under a layer whose alpha is
+   exactly 1.0f over a whole strip line are skipped: combine.ts:49-59 multiplies them by 1 - 1 = 0, so the output
+   bytes are identical either way (tests/test_gpu_chain.py); the flag exists for A/B measurements. */
+#define PB_CTX_NO_CULL 8u
+/* bit4 = account, per march launch, the distinct packed source bytes the launch reads (pb_stats.march_src_bytes);
+   costs a host pass over the op masks, so it is off by default (bench.py uses it for the roofline figure) */
+#define PB_CTX_FOOTPRINT 16u
 int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out);
 int pb_ctx_destroy(pb_ctx *ctx);
 /* getPlatformInfo() (index.ts:103-107): JSON text into buf */

@@ -19,6 +19,8 @@ ACCESS = {"none": 0, "readonly": 1, "writeonly": 2}
 CTX_DEFER = 1
 CTX_NO_MARCH = 2
 CTX_RAW_LUT = 4
+CTX_NO_CULL = 8
+CTX_FOOTPRINT = 16
 
 OPS = {
     "v210_read": 1, "v210_write": 2, "rgba8_read": 3, "rgba8_write": 4, "bgra8_read": 5, "bgra8_write": 6,
@@ -51,7 +53,7 @@ class Timings(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "kernel_launches", "fused_launches", "march_launches", "deferred_nodes", "materialised", "h2d_bytes", "d2h_bytes",
-        "dev_bytes_live", "dev_bytes_pooled", "lut_tables", "lut_tables_d8")]
+        "dev_bytes_live", "dev_bytes_pooled", "lut_tables", "lut_tables_d8", "march_src_bytes")]
 
 
 class PhaneronError(RuntimeError):

@@ -119,7 +119,7 @@ struct MarchOp {
 	int act;             // MarchAct
 	float mix;
 };
-constexpr int kMaxOps = 3 * kMaxLayers;
+constexpr int kMaxOps = 3 * kMaxLayers;   // 24: op masks share a word with 8 layer-opacity bits
 constexpr int kMaxStrips = 128;
 
 struct FusedDesc {
@@ -145,8 +145,13 @@ struct FusedDesc {
 	// march kernel
 	int n_ops;
 	MarchOp ops[kMaxOps];
-	uint32_t strip_ops[kMaxStrips];   // per strip: bit i set if op i can touch the strip (all ops of a transition layer together)
+	// per strip: bit i (< 24) set if op i can touch the strip (all ops of a transition layer together); bit 24 + l set
+	// if layer l is exactly opaque (alpha == 1.0f) on every column of the strip
+	uint32_t strip_ops[kMaxStrips];
 	const uint32_t *line_ops;         // per output line, same meaning (device memory, out_h entries)
+	// Exact occlusion culling: where (strip_ops & line_ops) >> 24 names an opaque layer L, `over` discards everything
+	// below it (fma(prev, 1 - 1, l) == l), so ops before layer_first_op[L] are dropped for that strip line.
+	int layer_first_op[kMaxLayers];
 };
 
 }  // namespace pb

@@ -409,7 +409,10 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			t[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 			m[r] = 0.f;
 		}
-		uint32_t todo = d.strip_ops[strip] & __ldg(d.line_ops + y);
+		const uint32_t both = d.strip_ops[strip] & __ldg(d.line_ops + y);
+		uint32_t todo = both & 0xFFFFFFu;
+		// exact occlusion culling: the topmost layer that is opaque over this whole strip line hides all ops below it
+		if (both >> 24) todo &= ~0u << d.layer_first_op[(31 - __clz(both)) - 24];
 #pragma unroll 1
 		while (todo) {
 			const int oi = __ffs(todo) - 1;

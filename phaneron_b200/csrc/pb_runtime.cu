@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -131,8 +132,17 @@ struct pb_ctx {
 		void *dev = nullptr;
 		int2 *dcol = nullptr, *drow = nullptr;
 		int4 *dstrip = nullptr;
+		// where the leaf is exactly opaque (alpha == 1.0f bit for bit): whole strips x lines; see leaf_opacity()
+		struct Opq {
+			int id;
+			std::vector<uint8_t> strip_full, row_full;
+			std::vector<int> row_j0, strip_ng;   // first source row each output line reads, source groups per strip (footprint accounting)
+			int rows_per_line = 1, src_h = 0;
+		};
+		std::shared_ptr<const Opq> opq;
 	};
 	std::vector<SampleTab> tabs;
+	int next_tab_id = 0;
 	bool allow_march = true;
 	// gamma tables by content (see lut_table_of)
 	struct LutTable {
@@ -613,6 +623,80 @@ inline int2 axis_entry(int o, int out_n, int src_n, float m_scale, float m_other
 	return e;
 }
 
+// Exact occlusion culling.  combine.ts:49-59 composites `fma(prev, 1 - l.a, l)`: where a layer's
+// alpha is EXACTLY 1.0f, k = 0 and fma(prev, 0, l) == l for every finite prev, so nothing below that layer can
+// reach the output and the march kernel need not evaluate it there.  The alpha of a v210 leaf seen through a
+// Transform is the float sum of its in-image tap weights, w11 + (w01 + (w10 + w00)) with w00 = (1-a)(1-b) ...
+// (pb_march.cu eval_leaf, same chain in pb_device.cuh and the oracle); whether that sum rounds to exactly 1
+// depends on the fractional weights a (per column) and b (per line).  This routine evaluates the very same
+// float chain for every distinct (a, b) pair of the leaf and keeps a separable set columns x lines on which
+// all pairs give 1.0f; strips made of such columns and lines made of such rows are "full".
+std::shared_ptr<const pb_ctx::SampleTab::Opq> leaf_opacity(int id, const pb::Leaf &lf, int W, int H, int strip_px, int n_strips,
+                                                           const int2 *hcol, const int2 *hrow, const int4 *hstrip) {
+	auto o = std::make_shared<pb_ctx::SampleTab::Opq>();
+	o->id = id;
+	o->rows_per_line = lf.has_xf ? 2 : 1;
+	o->src_h = lf.h;
+	o->strip_ng.resize(n_strips);
+	for (int sidx = 0; sidx < n_strips; ++sidx) o->strip_ng[sidx] = (hstrip[sidx].x & 1) ? hstrip[sidx].z : 0;
+	o->strip_full.assign(n_strips, 0);
+	o->row_full.assign(H, 0);
+	o->row_j0.resize(H);
+	for (int y = 0; y < H; ++y) o->row_j0[y] = hrow[y].x;
+	if (!lf.has_xf) {   // 1:1 read: alpha = 1 everywhere (the leaf has the output's dimensions)
+		o->strip_full.assign(n_strips, 1);
+		o->row_full.assign(H, 1);
+		return o;
+	}
+	// candidates: all four taps inside the image
+	std::vector<uint8_t> col_ok(W), row_ok(H);
+	std::map<uint32_t, int> a_ids, b_ids;
+	std::vector<int> col_a(W, -1), row_b(H, -1);
+	for (int x = 0; x < W; ++x) {
+		col_ok[x] = hcol[x].x >= 0 && hcol[x].x + 1 < lf.w;
+		if (col_ok[x]) col_a[x] = a_ids.emplace((uint32_t)hcol[x].y, (int)a_ids.size()).first->second;
+	}
+	for (int y = 0; y < H; ++y) {
+		row_ok[y] = hrow[y].x >= 0 && hrow[y].x + 1 < lf.h;
+		if (row_ok[y]) row_b[y] = b_ids.emplace((uint32_t)hrow[y].y, (int)b_ids.size()).first->second;
+	}
+	const size_t na = a_ids.size(), nb = b_ids.size();
+	if (na == 0 || nb == 0 || na * nb > (size_t)(1u << 21)) return o;   // nothing opaque / too many weight pairs to certify
+	std::vector<float> av(na), bv(nb);
+	for (auto &kv : a_ids) memcpy(&av[kv.second], &kv.first, 4);
+	for (auto &kv : b_ids) memcpy(&bv[kv.second], &kv.first, 4);
+	// cost of giving a value up: an a value takes its strips with it (for every line), a b value only its lines
+	std::vector<int> a_strips(na, 0), b_rows(nb, 0);
+	{
+		std::vector<int> last(na, -1);
+		for (int x = 0; x < W; ++x)
+			if (col_a[x] >= 0 && last[col_a[x]] != x / strip_px) { last[col_a[x]] = x / strip_px; a_strips[col_a[x]]++; }
+		for (int y = 0; y < H; ++y)
+			if (row_b[y] >= 0) b_rows[row_b[y]]++;
+	}
+	std::vector<uint8_t> a_keep(na, 1), b_keep(nb, 1);
+	for (size_t i = 0; i < na; ++i) {
+		const float a = av[i], ra = 1.0f - a;
+		for (size_t j = 0; j < nb; ++j) {
+			if (!b_keep[j]) continue;
+			const float b = bv[j], rb = 1.0f - b;
+			const float w00 = ra * rb, w10 = a * rb, w01 = ra * b, w11 = a * b;
+			const float alpha = w11 + (w01 + (w10 + w00));
+			if (alpha == 1.0f) continue;
+			if ((long long)a_strips[i] * H < (long long)b_rows[j] * n_strips) { a_keep[i] = 0; break; }
+			b_keep[j] = 0;
+		}
+	}
+	for (int y = 0; y < H; ++y) o->row_full[y] = row_b[y] >= 0 && b_keep[row_b[y]];
+	for (int sidx = 0; sidx < n_strips; ++sidx) {
+		const int x0 = sidx * strip_px, x1 = std::min(x0 + strip_px, W) - 1;
+		bool full = true;
+		for (int x = x0; x <= x1 && full; ++x) full = col_a[x] >= 0 && a_keep[col_a[x]];
+		o->strip_full[sidx] = full;
+	}
+	return o;
+}
+
 // sampling tables of one leaf; *fits = 0 if some strip's source footprint exceeds a row buffer
 int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_ctx::SampleTab **out, int *fits) {
 	for (auto &t : c->tabs)
@@ -671,6 +755,7 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 			t.y1 = y;
 		}
 	}
+	t.opq = leaf_opacity(c->next_tab_id++, lf, W, H, strip_px, n_strips, hcol, hrow, hstrip);
 	CU(cudaMalloc(&t.dev, bytes));
 	CU(cudaMemcpyAsync(t.dev, host.data(), bytes, cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
 	CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // `host` is a local; once per new transform only
@@ -716,12 +801,14 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
 	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
 	if (d.n_strips > pb::kMaxStrips) return 0;
+	std::shared_ptr<const pb_ctx::SampleTab::Opq> opq[3 * pb::kMaxLayers];
 	for (int i = 0; i < n_leaves; ++i) {
 		pb_ctx::SampleTab *t;
 		int fits = 0;
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
 		if (r) return r;
 		if (!fits) return 0;
+		opq[i] = t->opq;
 		leaves[i]->col_tab = t->dcol;
 		leaves[i]->row_tab = t->drow;
 		leaves[i]->strip_tab = t->dstrip;
@@ -745,7 +832,37 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			push(1, pb::ACT_WIPE_B_OVER);
 		}
 		layer_n_ops[l] = d.n_ops - layer_first_op[l];
+		d.layer_first_op[l] = layer_first_op[l];
 	}
+	// exact occlusion culling: which layers are opaque (alpha == 1.0f) over whole strips / whole lines.
+	// Needs finite values below (NaN * 0 != 0): every read table must lie in [0, 1].
+	bool cull = !(c->flags & PB_CTX_NO_CULL);
+	for (int i = 0; i < d.n_rc && cull; ++i) {
+		const int t = lut_table_by_raw(c, d.rc[i].lut);
+		cull = t >= 0 && c->lut_tables[t].unit_range;
+	}
+	const pb_ctx::SampleTab::Opq *lopq[pb::kMaxLayers][2] = {};   // per layer: the leaves that must all be full
+	{
+		int li = 0;
+		for (int l = 0; l < d.n_layers; ++l) {
+			const pb::Layer &ly = d.layers[l];
+			const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
+			if (cull && ly.kind == pb::LAYER_DIRECT) {
+				lopq[l][0] = opq[li].get();
+			} else if (cull && ly.kind == pb::LAYER_DISSOLVE) {
+				// transition.ts:60-65 on two alphas of 1: fma(1, mix, 1 * (1 - mix)) = RN(mix + RN(1 - mix))
+				const float rmix = 1.0f - ly.mix;
+				if (ly.mix + rmix == 1.0f) { lopq[l][0] = opq[li].get(); lopq[l][1] = opq[li + 1].get(); }
+			}   // wipe: alpha depends on the mask picture
+			li += nleaf;
+		}
+	}
+	auto layer_full = [&](int l, bool strips, int idx) {
+		if (!lopq[l][0]) return false;
+		for (int q = 0; q < 2; ++q)
+			if (lopq[l][q] && !(strips ? lopq[l][q]->strip_full[idx] : lopq[l][q]->row_full[idx])) return false;
+		return true;
+	};
 	for (int sidx = 0; sidx < d.n_strips; ++sidx) {
 		uint32_t mask = 0;
 		for (int l = 0; l < d.n_layers; ++l) {
@@ -757,6 +874,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			// a transition whose leaves are all elsewhere yields (0,0,0,0): `over` leaves acc untouched, skip the layer;
 			// otherwise all of its ops run (a leaf that is elsewhere evaluates to the border colour by itself)
 			if (any) mask |= ((1u << layer_n_ops[l]) - 1u) << layer_first_op[l];
+			if (layer_full(l, true, sidx)) mask |= 1u << (24 + l);
 		}
 		d.strip_ops[sidx] = mask;
 	}
@@ -767,6 +885,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			key.push_back(ly.kind);
 			const pb::Leaf *ll[3] = {&ly.a, &ly.b, &ly.mask};
 			for (int q = 0; q < 3; ++q) { key.push_back(ll[q]->y0); key.push_back(ll[q]->y1); }
+			for (int q = 0; q < 2; ++q) key.push_back(lopq[l][q] ? lopq[l][q]->id : -1);
 		}
 		pb_ctx::LineOps *found = nullptr;
 		for (auto &lo : c->line_ops)
@@ -787,6 +906,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 					bool any = false;
 					for (int q = 0; q < nleaf; ++q) any = any || (y >= ll[q]->y0 && y <= ll[q]->y1);
 					if (any) mask |= ((1u << layer_n_ops[l]) - 1u) << layer_first_op[l];
+					if (layer_full(l, false, y)) mask |= 1u << (24 + l);
 				}
 				host[y] = mask;
 			}
@@ -846,6 +966,39 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		d.luts[i].lp = c->lut_tables[slots[i]].lp;
 	}
 	if (d.n_luts) d.wlp = d.luts[d.wc.lut_slot].lp;
+	if (c->flags & PB_CTX_FOOTPRINT) {
+		// distinct packed source bytes this launch reads (after bounding-box masks and occlusion culling): per
+		// leaf and strip, the distinct source rows of the lines on which the leaf's op survives
+		std::vector<uint32_t> lines((size_t)d.out_h);
+		CU(cudaMemcpy(lines.data(), d.line_ops, lines.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		const int step = d.interlace == 0 ? 1 : 2, first = d.interlace == 3 ? 1 : 0;
+		uint64_t bytes = 0;
+		std::vector<int> seen;
+		for (int oi = 0; oi < d.n_ops; ++oi) {
+			int li = 0;   // index of the op's leaf in leaves[] / opq[]
+			for (int l = 0; l < d.ops[oi].layer; ++l) li += layer_n_ops[l];
+			li += d.ops[oi].which;
+			const auto &o = *opq[li];
+			for (int sidx = 0; sidx < d.n_strips; ++sidx) {
+				if (!o.strip_ng[sidx]) continue;
+				seen.assign((size_t)o.src_h, 0);
+				for (int y = first; y < d.out_h; y += step) {
+					const uint32_t both = d.strip_ops[sidx] & lines[y];
+					uint32_t todo = both & 0xFFFFFFu;
+					if (both >> 24) todo &= ~0u << d.layer_first_op[(31 - __builtin_clz(both)) - 24];
+					if (!((todo >> oi) & 1u)) continue;
+					for (int r = 0; r < o.rows_per_line; ++r) {
+						const int j = o.row_j0[y] + r;
+						if (j >= 0 && j < o.src_h) seen[j] = 1;
+					}
+				}
+				uint64_t rows = 0;
+				for (int v : seen) rows += v;
+				bytes += rows * (uint64_t)o.strip_ng[sidx] * 16u;
+			}
+		}
+		c->stats.march_src_bytes = bytes;
+	}
 	return 1;
 }
 

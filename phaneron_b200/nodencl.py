@@ -182,6 +182,8 @@ class clContext:
         self.deferred = bool(options.get("deferred", True))
         self.marchKernel = bool(options.get("marchKernel", True))   # False: always the generic fused kernel
         self.rawLut = bool(options.get("rawLut", False))            # True: march kernel gathers from the raw gamma tables
+        self.occlusionCulling = bool(options.get("occlusionCulling", True))   # False: evaluate layers hidden under opaque ones too
+        self.footprint = bool(options.get("footprint", False))      # True: stats()['march_src_bytes'] per march launch
         self.queue = _Queues()
         self._h = 0
 
@@ -194,7 +196,8 @@ class clContext:
 
     def _flags(self) -> int:
         return ((_lib.CTX_DEFER if self.deferred else 0) | (0 if self.marchKernel else _lib.CTX_NO_MARCH)
-                | (_lib.CTX_RAW_LUT if self.rawLut else 0))
+                | (_lib.CTX_RAW_LUT if self.rawLut else 0) | (0 if self.occlusionCulling else _lib.CTX_NO_CULL)
+                | (_lib.CTX_FOOTPRINT if self.footprint else 0))
 
     def close(self) -> None:
         if self._h:
@@ -214,6 +217,10 @@ class clContext:
         self.marchKernel = bool(on)
         if rawLut is not None:
             self.rawLut = bool(rawLut)
+        check(_lib.lib().pb_ctx_set_flags(self._need(), self._flags()))
+
+    def setOcclusionCulling(self, on: bool) -> None:
+        self.occlusionCulling = bool(on)
         check(_lib.lib().pb_ctx_set_flags(self._need(), self._flags()))
 
     def getPlatformInfo(self) -> Dict[str, Any]:

@@ -203,6 +203,8 @@ async def _run_scene_variant(scene, mode):
     global memory), 'generic' (pb_fused.cu)"""
     async with Env(True) as env:
         env.ctx.setMarchKernel(mode != "generic", rawLut=(mode == "march_raw"))
+        env.ctx.footprint = True
+        env.ctx.setOcclusionCulling(mode != "march_nocull")
         h = ChannelHarness(env.ctx, scene, env.pj)
         await h.init()
         before = env.ctx.stats()
@@ -210,6 +212,7 @@ async def _run_scene_variant(scene, mode):
         after = env.ctx.stats()
         st = {k: after[k] - before[k] for k in after}
         st["lut_tables"], st["lut_tables_d8"] = after["lut_tables"], after["lut_tables_d8"]
+        st["march_src_bytes"] = after["march_src_bytes"]
         return out, st
 
 
@@ -251,6 +254,54 @@ def test_march_kernel_matches_generic_and_oracle(name):
         fast, st = run(_run_scene_variant(scene, mode))
         assert st["march_launches"] == 1 and st["kernel_launches"] == 1, (mode, st)
         assert np.array_equal(fast, ref), f"{mode}: {int((fast != ref).sum())} bytes differ"
+
+
+# ---- exact occlusion culling (pb_runtime.cu leaf_opacity) -------------------------------
+def _stack(w, h, xfs, variant="plain", inputs="noise"):
+    return _with_xf(layered_scene(w, h, len(xfs), inputs, variant, "709", "2020"), xfs)
+
+
+CULL_SCENES = {
+    # name: (scene factory, culling must reduce the bytes read)
+    "north_star_mix": (lambda: layered_scene(960, 540, 4, "noise", "mix", "709", "2020"), True),
+    "north_star_wipe": (lambda: layered_scene(960, 540, 4, "noise", "wipe", "709", "2020"), True),   # L2, L3 still hide L1
+    "full_frame_on_top": (lambda: _stack(960, 270, [_xf(), _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.2), _xf()]), True),
+    "direct_on_top": (lambda: _with_xf(layered_scene(960, 270, 3, "noise", "plain", "709", "709"), [_xf(), _xf(scaleX=0.5, scaleY=0.5), None]), True),
+    "pip_over_pip_over_pip": (lambda: _stack(960, 540, [_xf(), _xf(scaleX=0.75, scaleY=0.75, offsetX=-0.1, offsetY=-0.1),
+                                                        _xf(scaleX=0.625, scaleY=0.625, offsetX=-0.2, offsetY=-0.15),
+                                                        _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.3, offsetY=-0.3)]), True),
+    "flipped_pip": (lambda: _stack(960, 540, [_xf(), _xf(flipH=True, flipV=True, scaleX=0.5, scaleY=0.5, offsetX=-0.3, offsetY=-0.2)]), True),
+    "upscaled_top": (lambda: _stack(960, 270, [_xf(), _xf(scaleX=2.0, scaleY=2.0)]), True),
+    "odd_scale_pip": (lambda: _stack(960, 540, [_xf(), _xf(scaleX=0.731, scaleY=0.577, offsetX=-0.21, offsetY=-0.13)]), False),
+    "ramp_inputs": (lambda: layered_scene(960, 540, 4, "ramp", "mix", "709", "2020"), True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CULL_SCENES))
+def test_occlusion_culling_is_exact(name):
+    """hidden layers are skipped where an upper layer's alpha is exactly 1.0f: same bytes out, fewer bytes in"""
+    make, must_cull = CULL_SCENES[name]
+    scene = make()
+    ref = SceneOracle(scene).packed()
+    plain, st0 = run(_run_scene_variant(scene, "march_nocull"))
+    culled, st1 = run(_run_scene_variant(scene, "march"))
+    assert st0["march_launches"] == 1 and st1["march_launches"] == 1
+    assert np.array_equal(plain, ref)
+    assert np.array_equal(culled, ref), f"{int((culled != ref).sum())} bytes differ with culling on"
+    assert st1["march_src_bytes"] <= st0["march_src_bytes"]
+    if must_cull:
+        assert st1["march_src_bytes"] < st0["march_src_bytes"], (st0["march_src_bytes"], st1["march_src_bytes"])
+
+
+def test_dissolve_layer_is_opaque_only_when_its_alpha_rounds_to_one():
+    """top layer in a dissolve: alpha = RN(mix + RN(1 - mix)); culled under it only when that is exactly 1"""
+    for mix in (0.5, 0.3, 1.0 / 3.0, 0.9999999):
+        scene = layered_scene(960, 270, 3, "noise", "mix", "709", "2020")
+        scene["layers"][-1]["transition"]["mix"] = mix
+        ref = SceneOracle(scene).packed()
+        culled, st = run(_run_scene_variant(scene, "march"))
+        assert st["march_launches"] == 1
+        assert np.array_equal(culled, ref), mix
 
 
 def test_gamma_tables_are_deduplicated_and_compressed():
