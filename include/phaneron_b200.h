@@ -61,7 +61,11 @@ typedef enum pb_op {
 	PB_OP_YUV422P10_READ = 20,   /* yuv422p10.ts:25-124  (params inputY, inputU, inputV, output, ...) */
 	PB_OP_YUV422P10_WRITE = 21,  /* yuv422p10.ts:126-219 (params input, outputY, outputU, outputV, ...) */
 	PB_OP_YUV422P8_READ = 22,    /* yuv422p8.ts:25-124  */
-	PB_OP_YUV422P8_WRITE = 23    /* yuv422p8.ts:126-219 */
+	PB_OP_YUV422P8_WRITE = 23,   /* yuv422p8.ts:126-219 */
+	PB_OP_YUV420P_READ = 24,     /* yuv420p.ts:25-140  (params inputY, inputU, inputV, output, ...) */
+	PB_OP_YUV420P_WRITE = 25,    /* yuv420p.ts:142-238 (params input, outputY, outputU, outputV, ...) */
+	PB_OP_NV12_READ = 26,        /* nv12.ts:24-132  (params inputY, inputC, output, ...) */
+	PB_OP_NV12_WRITE = 27        /* nv12.ts:134-240 (params input, outputY, outputC, ...) */
 } pb_op;
 
 /* One kernel argument, bound BY KERNEL PARAMETER NAME as nodencl's runProgram

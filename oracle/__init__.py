@@ -258,3 +258,36 @@ def yuv422p_write(bits: int, rgba, width: int, height: int, interlace: int, col_
     lib().orc_yuv422p_write(bits, rgba.ctypes.data_as(C.c_void_p), *(o.ctypes.data_as(C.c_void_p) for o in outs), width, height, interlace,
                             _f(col_matrix).ctypes.data_as(C.c_void_p), _f(gamma_lut).ctypes.data_as(C.c_void_p))
     return outs
+
+
+# ---- yuv420p / nv12 (yuv420p.ts, nv12.ts) ------------------------------------------------------------------------
+def yuv420_plane_bytes(nv12: bool, width: int, height: int):
+    """Reader.numBytes: [luma, luma/4, luma/4] (yuv420p.ts:332-333) or [luma, luma/2] (nv12.ts:328-329)"""
+    luma = yuv422p_pitch(width) * height
+    return [luma, luma // 2] if nv12 else [luma, luma // 4, luma // 4]
+
+
+def yuv420_fill(nv12: bool, width: int, height: int) -> np.ndarray:
+    buf = np.zeros(sum(yuv420_plane_bytes(nv12, width, height)), np.uint8)
+    lib().orc_yuv420_fill(int(nv12), buf.ctypes.data_as(C.c_void_p), width, height)
+    return buf
+
+
+def yuv420_read(nv12: bool, planes, width: int, height: int, col_matrix, gamma_lut, gamut) -> np.ndarray:
+    out = np.empty((height, width, 4), np.float32)
+    planes = [np.ascontiguousarray(a, np.uint8) for a in planes]
+    ptrs = [a.ctypes.data_as(C.c_void_p) for a in planes] + ([C.c_void_p(0)] if nv12 else [])
+    lib().orc_yuv420_read(int(nv12), *ptrs, out.ctypes.data_as(C.c_void_p), width, height, _f(col_matrix).ctypes.data_as(C.c_void_p),
+                          _f(gamma_lut).ctypes.data_as(C.c_void_p), _f(gamut).ctypes.data_as(C.c_void_p))
+    return out
+
+
+def yuv420_write(nv12: bool, rgba, width: int, height: int, interlace: int, col_matrix, gamma_lut, outs=None):
+    nb = yuv420_plane_bytes(nv12, width, height)
+    if outs is None:
+        outs = [np.zeros(n, np.uint8) for n in nb]
+    rgba = _f(rgba)
+    ptrs = [o.ctypes.data_as(C.c_void_p) for o in outs] + ([C.c_void_p(0)] if nv12 else [])
+    lib().orc_yuv420_write(int(nv12), rgba.ctypes.data_as(C.c_void_p), *ptrs, width, height, interlace,
+                           _f(col_matrix).ctypes.data_as(C.c_void_p), _f(gamma_lut).ctypes.data_as(C.c_void_p))
+    return outs

@@ -859,3 +859,191 @@ void orc_yuv422p_write(int bits, const float *input, uint8_t *outY, uint8_t *out
 		}
 	}
 }
+
+/* ------------------------------------------------------------------------- */
+/* yuv420p / nv12: src/process/yuv420p.ts, src/process/nv12.ts                */
+/* 8-bit 4:2:0.  The two files differ only in the chroma layout: two planes  */
+/* of pitch/2 bytes per line pair (yuv420p) or one plane of interleaved U,V  */
+/* pairs, pitch bytes per line pair (nv12); `nv12` selects.  A work-group is */
+/* one PAIR of lines; the chroma of a pair is read for both lines and        */
+/* written from the first line of the pair that the launch processes.        */
+/* ------------------------------------------------------------------------- */
+void orc_yuv420_plane_bytes(int nv12, uint32_t width, uint32_t height, uint32_t out[3]) {
+	const uint32_t luma = orc_yuv422p_pitch(width) * height; /* yuv420p.ts:240-241,332-333; nv12.ts:322-323 */
+	out[0] = luma;
+	out[1] = nv12 ? luma / 2 : luma / 4;
+	out[2] = nv12 ? 0 : luma / 4;
+}
+
+/* fillBuf: yuv420p.ts:243-280 / nv12.ts:246-281 (one buffer: Y plane | U plane | V plane, or Y plane | C plane) */
+void orc_yuv420_fill(int nv12, uint8_t *buf, uint32_t width, uint32_t height) {
+	const uint32_t lumaPitch = orc_yuv422p_pitch(width);
+	const uint32_t chromaPitch = nv12 ? lumaPitch : lumaPitch / 2;
+	size_t lOff = 0, uOff = (size_t)lumaPitch * height;
+	size_t vOff = uOff + (size_t)chromaPitch * ((height + 1) / 2); /* yuv420p only */
+	const size_t total = nv12 ? uOff + (size_t)chromaPitch * (height / 2) : uOff + 2 * (size_t)(lumaPitch * height / 4);
+	memset(buf, 16, uOff);
+	memset(buf + uOff, 128, total - uOff);
+	uint32_t Y0 = 16, Y1 = 234;
+	for (uint32_t y = 0; y < height; y += 2) {
+		size_t xl = 0, xc = 0;
+		for (uint32_t x = 0; x < width; x += 2) {
+			buf[lOff + xl] = (uint8_t)Y0;
+			buf[lOff + xl + 1] = (uint8_t)(Y0 + 1);
+			buf[lumaPitch + lOff + xl] = (uint8_t)(Y1 + 1);
+			buf[lumaPitch + lOff + xl + 1] = (uint8_t)Y1;
+			xl += 2;
+			if (nv12) {
+				buf[uOff + xc] = 128;
+				buf[uOff + xc + 1] = 128;
+				xc += 2;
+			} else {
+				buf[uOff + xc] = 128;
+				buf[vOff + xc] = 128;
+				xc++;
+			}
+			Y0 = (234 == Y0) ? 16 : Y0 + 2;
+			Y1 = (16 == Y1) ? 234 : Y1 - 2;
+		}
+		lOff += (size_t)lumaPitch * 2;
+		uOff += chromaPitch;
+		vOff += chromaPitch;
+	}
+}
+
+/* chroma sample pair of pixel pair `c` (0..3) in 8-pixel block `blk` of line pair `gid` */
+static inline void ld_chroma420(int nv12, const uint8_t *inU, const uint8_t *inV, size_t blk, uint32_t c, uint32_t *u, uint32_t *v) {
+	if (nv12) { /* uchar8 c: (.s0,.s1) (.s2,.s3) ... = (U,V) pairs, nv12.ts:65-72 */
+		*u = inU[blk * 8 + 2 * c];
+		*v = inU[blk * 8 + 2 * c + 1];
+	} else { /* uchar4 u, v: yuv420p.ts:67-78 */
+		*u = inU[blk * 4 + c];
+		*v = inV[blk * 4 + c];
+	}
+}
+
+/* read kernel: yuv420p.ts:25-140 / nv12.ts:24-132.  One work-group per line pair, 64 pixels per work-item, blocks of 8. */
+void orc_yuv420_read(int nv12, const uint8_t *inY, const uint8_t *inU, const uint8_t *inV, float *output, uint32_t width,
+                     uint32_t height, const float *cm, const float *lut, const float *gamut) {
+	const uint32_t itemsPerLine = (orc_yuv422p_pitch(width) + 63) / 64; /* yuv420p.ts:334 */
+	const uint32_t pitchReads = (width + 7) / 8;
+	PAR_FOR
+	for (int64_t gid = 0; gid < (int64_t)(height / 2); ++gid) { /* globalWorkItems = items * height / 2 (:336) */
+		for (uint32_t lid = 0; lid < itemsPerLine; ++lid) {
+			const int last = lid == itemsPerLine - 1;
+			const uint32_t numPixels = (last && (0 != width % 64)) ? width % 64 : 64;
+			const uint32_t numLoops = numPixels / 8, remain = numPixels % 8;
+			size_t inOffY[2], outOff[2];
+			inOffY[0] = 8 * (size_t)lid + (size_t)pitchReads * gid * 2;
+			inOffY[1] = inOffY[0] + pitchReads;
+			size_t inOffUV = 8 * (size_t)lid + (size_t)pitchReads * gid;
+			outOff[0] = 64 * (size_t)lid + (size_t)width * gid * 2;
+			outOff[1] = outOff[0] + width;
+			for (uint32_t i = 0; i <= numLoops; ++i) {
+				const uint32_t n = i < numLoops ? 8 : remain; /* the tail block converts `remain` pixels the same way */
+				if (n == 0) break;
+				for (uint32_t l = 0; l < 2; ++l) {
+					for (uint32_t p = 0; p < n; ++p) {
+						uint32_t yuv[3];
+						yuv[0] = inY[inOffY[l] * 8 + p];
+						ld_chroma420(nv12, inU, inV, inOffUV, p / 2, &yuv[1], &yuv[2]);
+						read_px(yuv, 1.0f, cm, lut, gamut, output + (outOff[l] + p) * 4);
+					}
+					inOffY[l]++;
+					outOff[l] += 8;
+				}
+				inOffUV++;
+			}
+		}
+	}
+}
+
+/* write kernel: yuv420p.ts:142-238 / nv12.ts:134-240.  Always height/2 work-groups (yuv420p.ts:358); a field launch
+ * (interlace 1 / 3) writes one luma line per group and the group's chroma from that line, so after both fields the
+ * chroma plane holds the bottom field's values. */
+void orc_yuv420_write(int nv12, const float *input, uint8_t *outY, uint8_t *outU, uint8_t *outV, uint32_t width, uint32_t height,
+                      uint32_t interlace, const float *cm, const float *lut) {
+	const uint32_t itemsPerLine = (orc_yuv422p_pitch(width) + 63) / 64;
+	const uint32_t pitchReads = (width + 7) / 8;
+	PAR_FOR
+	for (int64_t gid = 0; gid < (int64_t)(height / 2); ++gid) {
+		for (uint32_t lid = 0; lid < itemsPerLine; ++lid) {
+			const int last = lid == itemsPerLine - 1;
+			const uint32_t numPixels = (last && (0 != width % 64)) ? width % 64 : 64;
+			const uint32_t numLoops = numPixels / 8, remain = numPixels % 8;
+			const uint32_t line = (uint32_t)gid * 2 + ((3 == interlace) ? 1 : 0);
+			const uint32_t numLines = (0 == interlace) ? 2 : 1;
+			size_t inOff[2], outOffY[2];
+			inOff[0] = 64 * (size_t)lid + (size_t)width * line;
+			inOff[1] = inOff[0] + width;
+			outOffY[0] = 8 * (size_t)lid + (size_t)pitchReads * line;
+			outOffY[1] = outOffY[0] + pitchReads;
+			size_t outOffUV = 8 * (size_t)lid + (size_t)pitchReads * gid;
+			for (uint32_t l = 0; l < numLines; ++l) {
+				for (uint32_t i = 0; i < numLoops; ++i) {
+					uint32_t yuv[8][3];
+					for (uint32_t p = 0; p < 8; ++p) {
+						const float *px = input + (inOff[l] + p) * 4;
+						const float rgba[4] = {lut[sat_rte(px[0] * 65535.0f, 65535.0f)], lut[sat_rte(px[1] * 65535.0f, 65535.0f)],
+						                       lut[sat_rte(px[2] * 65535.0f, 65535.0f)], 1.0f};
+						/* uchar3 yuv[p]: the ushort conversion result wraps into a uchar (yuv420p.ts:186-188) */
+						yuv[p][0] = (uint8_t)sat_rte(dot4(rgba, cm + 0), 65535.0f);
+						yuv[p][1] = (uint8_t)sat_rte(dot4(rgba, cm + 4), 65535.0f);
+						yuv[p][2] = (uint8_t)sat_rte(dot4(rgba, cm + 8), 65535.0f);
+					}
+					inOff[l] += 8;
+					for (uint32_t p = 0; p < 8; ++p) outY[outOffY[l] * 8 + p] = (uint8_t)yuv[p][0];
+					outOffY[l]++;
+					if (l == 0) { /* chroma from even pixels of the first line only (:192-200) */
+						for (uint32_t c = 0; c < 4; ++c) {
+							if (nv12) {
+								outU[outOffUV * 8 + 2 * c] = (uint8_t)yuv[2 * c][1];
+								outU[outOffUV * 8 + 2 * c + 1] = (uint8_t)yuv[2 * c][2];
+							} else {
+								outU[outOffUV * 4 + c] = (uint8_t)yuv[2 * c][1];
+								outV[outOffUV * 4 + c] = (uint8_t)yuv[2 * c][2];
+							}
+						}
+						outOffUV++;
+					}
+				}
+			}
+			if (remain > 0) { /* yuv420p.ts:204-236 / nv12.ts:199-238 */
+				for (uint32_t l = 0; l < numLines; ++l) {
+					uint8_t y[8], u[4], v[4];
+					uint32_t yuv[6][3] = {{0}};
+					memset(y, 16, 8);
+					memset(u, 128, 4);
+					memset(v, 128, 4);
+					for (uint32_t p = 0; p < remain && p < 6; ++p) {
+						const float *px = input + (inOff[l] + p) * 4;
+						const float rgba[4] = {lut[sat_rte(px[0] * 65535.0f, 65535.0f)], lut[sat_rte(px[1] * 65535.0f, 65535.0f)],
+						                       lut[sat_rte(px[2] * 65535.0f, 65535.0f)], 1.0f};
+						yuv[p][0] = (uint8_t)sat_rte(roundf(dot4(rgba, cm + 0)), 65535.0f); /* round(): half away from zero */
+						yuv[p][1] = (uint8_t)sat_rte(roundf(dot4(rgba, cm + 4)), 65535.0f);
+						yuv[p][2] = (uint8_t)sat_rte(roundf(dot4(rgba, cm + 8)), 65535.0f);
+					}
+					y[0] = (uint8_t)yuv[0][0]; y[1] = (uint8_t)yuv[1][0]; u[0] = (uint8_t)yuv[0][1]; v[0] = (uint8_t)yuv[0][2];
+					if (remain > 2) {
+						y[2] = (uint8_t)yuv[2][0]; y[3] = (uint8_t)yuv[3][0]; u[1] = (uint8_t)yuv[2][1]; v[1] = (uint8_t)yuv[2][2];
+						if (remain > 4) {
+							y[4] = (uint8_t)yuv[4][0]; y[5] = (uint8_t)yuv[5][0]; u[2] = (uint8_t)yuv[4][1]; v[2] = (uint8_t)yuv[4][2];
+						}
+					}
+					memcpy(outY + outOffY[l] * 8, y, 8);
+					if (l == 0) {
+						if (nv12) {
+							for (uint32_t c = 0; c < 4; ++c) {
+								outU[outOffUV * 8 + 2 * c] = u[c];
+								outU[outOffUV * 8 + 2 * c + 1] = v[c];
+							}
+						} else {
+							memcpy(outU + outOffUV * 4, u, 4);
+							memcpy(outV + outOffUV * 4, v, 4);
+						}
+					}
+				}
+			}
+		}
+	}
+}

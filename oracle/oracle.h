@@ -80,6 +80,16 @@ void orc_yuv422p_write(int bits, const float *input, uint8_t *outY, uint8_t *out
                        uint32_t width, uint32_t height, uint32_t interlace, const float *col_matrix12,
                        const float *gamma_lut);
 
+/* yuv420p / nv12: 8-bit 4:2:0; nv12 = 1: inU is the interleaved chroma plane, inV / outV unused */
+void orc_yuv420_plane_bytes(int nv12, uint32_t width, uint32_t height, uint32_t out[3]);
+void orc_yuv420_fill(int nv12, uint8_t *buf, uint32_t width, uint32_t height);
+void orc_yuv420_read(int nv12, const uint8_t *inY, const uint8_t *inU, const uint8_t *inV, float *output,
+                     uint32_t width, uint32_t height, const float *col_matrix12, const float *gamma_lut,
+                     const float *gamut9);
+void orc_yuv420_write(int nv12, const float *input, uint8_t *outY, uint8_t *outU, uint8_t *outV,
+                      uint32_t width, uint32_t height, uint32_t interlace, const float *col_matrix12,
+                      const float *gamma_lut);
+
 #ifdef __cplusplus
 }
 #endif

@@ -326,6 +326,56 @@ def yuv422p_write(bits: int, rgba, width: int, height: int, interlace: int, col_
     return outs
 
 
+def _yuv420_geom(nv12: bool, width: int, height: int):
+    pitch = width + 7 - ((width - 1) % 8)                      # yuv420p.ts:240
+    luma = pitch * height
+    return -(-pitch // 64), ([luma, luma // 2] if nv12 else [luma, luma // 4, luma // 4])
+
+
+def yuv420_read(nv12: bool, planes, width: int, height: int, col_matrix, gamma_lut, gamut) -> np.ndarray:
+    """yuv420p.ts:25-140 / nv12.ts:24-132 with Reader's NDRange (one work-group per line pair)"""
+    k = _kernel("nv12.cl" if nv12 else "yuv420p.cl", "read")
+    wpg, _ = _yuv420_geom(nv12, width, height)
+    mems = [_buf(np.asarray(a, np.uint8)) for a in planes]
+    o = _buf(nbytes=width * height * 16)
+    cm, lut, gm = _buf(_pad(col_matrix, 12)), _buf(np.asarray(gamma_lut, np.float32)), _buf(_pad(gamut, 16))
+    a = 0
+    for m in mems + [o]:
+        _ck(_lib.ocl_arg_mem(k, a, m)); a += 1
+    _ck(_lib.ocl_arg_u32(k, a, width)); a += 1
+    for m in (cm, lut, gm):
+        _ck(_lib.ocl_arg_mem(k, a, m)); a += 1
+    _ck(_lib.ocl_run(k, 1, wpg * height // 2, 1, wpg))
+    out = np.empty((height, width, 4), np.float32)
+    _ck(_lib.ocl_read_buffer(o, out.ctypes.data, out.nbytes))
+    _free(o, cm, lut, gm, *mems)
+    return out
+
+
+def yuv420_write(nv12: bool, rgba, width: int, height: int, interlace: int, col_matrix, gamma_lut, outs=None):
+    """yuv420p.ts:142-238 / nv12.ts:134-240 with Writer's NDRange (height / 2 work-groups, fields included)"""
+    k = _kernel("nv12.cl" if nv12 else "yuv420p.cl", "write")
+    wpg, nb = _yuv420_geom(nv12, width, height)
+    if outs is None:
+        outs = [np.zeros(n, np.uint8) for n in nb]
+    i = _buf(np.asarray(rgba, np.float32))
+    mems = [_buf(o) for o in outs]
+    cm, lut = _buf(_pad(col_matrix, 12)), _buf(np.asarray(gamma_lut, np.float32))
+    _ck(_lib.ocl_arg_mem(k, 0, i))
+    a = 1
+    for m in mems:
+        _ck(_lib.ocl_arg_mem(k, a, m)); a += 1
+    _ck(_lib.ocl_arg_u32(k, a, width)); a += 1
+    _ck(_lib.ocl_arg_u32(k, a, interlace)); a += 1
+    _ck(_lib.ocl_arg_mem(k, a, cm)); a += 1
+    _ck(_lib.ocl_arg_mem(k, a, lut))
+    _ck(_lib.ocl_run(k, 1, wpg * height // 2, 1, wpg))
+    for o, m in zip(outs, mems):
+        _ck(_lib.ocl_read_buffer(m, o.ctypes.data, o.nbytes))
+    _free(i, cm, lut, *mems)
+    return outs
+
+
 class ReferenceChain:
     """The reference's UNFUSED launch sequence for a harness scene, with persistent device buffers, for timing on the
     same GPU: per source `read` (+ `transform`), per transition layer `transition_*`, `combine_N`, `write`

@@ -93,6 +93,8 @@ def main():
         "rgba8.cl": literal_after(rd("rgba8.ts"), "const rgba8Kernel ="),
         "yuv422p10.cl": literal_after(rd("yuv422p10.ts"), "const yuv422p10leKernel ="),
         "yuv422p8.cl": literal_after(rd("yuv422p8.ts"), "const yuv422p8Kernel ="),
+        "yuv420p.cl": literal_after(rd("yuv420p.ts"), "const yuv420pKernel ="),
+        "nv12.cl": literal_after(rd("nv12.ts"), "const nv12Kernel ="),
         "transition_dissolve.cl": gen_transition(rd("transition.ts"), "dissolve"),
         "transition_wipe.cl": gen_transition(rd("transition.ts"), "wipe"),
     }

@@ -26,6 +26,7 @@ OPS = {
     "v210_read": 1, "v210_write": 2, "rgba8_read": 3, "rgba8_write": 4, "bgra8_read": 5, "bgra8_write": 6,
     "combine": 10, "dissolve": 11, "wipe_mask": 12, "transform": 13, "yadif": 14, "mix": 15, "wipe": 16,
     "resize": 17, "yuv422p10_read": 20, "yuv422p10_write": 21, "yuv422p8_read": 22, "yuv422p8_write": 23,
+    "yuv420p_read": 24, "yuv420p_write": 25, "nv12_read": 26, "nv12_write": 27,
 }
 
 # every symbol include/phaneron_b200.h declares (tests check the .so exports all of them)

@@ -198,6 +198,98 @@ __global__ void __launch_bounds__(kThreads) k_yuv422p_write(const float4 *__rest
 	}
 }
 
+// ---- yuv420p / nv12: yuv420p.ts:25-238, nv12.ts:24-240 --------------------------------------
+// 8-bit 4:2:0: a luma plane (pitch = width rounded up to 8) and the chroma of every line PAIR, as two planes of
+// pitch/2 bytes (yuv420p) or one plane of interleaved (U, V) pairs, pitch bytes (nv12).  The read kernel has no tail
+// quirk (one thread per pixel; both lines of a pair take the pair's chroma).
+template <bool NV12>
+__global__ void __launch_bounds__(kThreads) k_yuv420_read(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint8_t *__restrict__ V,
+                                                          float4 *__restrict__ out, int width, int height, const __grid_constant__ ReadConsts rc) {
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)width * height) return;   // height is even here (the reference launches height / 2 work-groups)
+	const int line = (int)(tid / width), x = (int)(tid - (size_t)line * width);
+	const int pitch = (width + 7) / 8 * 8;
+	Ycc c;
+	c.y = Y[(size_t)line * pitch + x];
+	if (NV12) {
+		const uint8_t *cp = U + (size_t)(line / 2) * pitch + (x / 2) * 2;
+		c.cb = cp[0];
+		c.cr = cp[1];
+	} else {
+		c.cb = U[(size_t)(line / 2) * (pitch / 2) + x / 2];
+		c.cr = V[(size_t)(line / 2) * (pitch / 2) + x / 2];
+	}
+	const float3 rgb = ycc_to_linear(c, 1.0f, rc);
+	out[tid] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+}
+
+// One thread per block of 8 pixels of one line pair: the luma of one line (a field launch, interlace 1 / 3) or of both
+// (progressive), and the pair's chroma taken from the even pixels of the first line processed (yuv420p.ts:160-200).
+template <bool NV12>
+__global__ void __launch_bounds__(kThreads) k_yuv420_write(const float4 *__restrict__ in, uint8_t *__restrict__ Y, uint8_t *__restrict__ U,
+                                                           uint8_t *__restrict__ V, int width, int pairs, int interlace,
+                                                           const __grid_constant__ WriteConsts wc) {
+	const int blocks = (width + 7) / 8;
+	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	if (tid >= (size_t)blocks * pairs) return;
+	const int gid = (int)(tid / blocks), bx = (int)(tid - (size_t)gid * blocks);
+	const int line0 = gid * 2 + (interlace == 3 ? 1 : 0), n_lines = interlace == 0 ? 2 : 1;
+	const int x0 = bx * 8, n = min(8, width - x0);
+	for (int l = 0; l < n_lines; ++l) {
+		const int line = line0 + l;
+		uint32_t y[8], u[4], v[4];
+		if (n == 8) {
+#pragma unroll
+			for (int p = 0; p < 8; ++p) {
+				const float4 px = __ldg(in + (size_t)line * width + x0 + p);
+				const Ycc c = linear_to_ycc(px.x, px.y, px.z, wc);
+				y[p] = c.y;
+				if (!(p & 1)) { u[p / 2] = c.cb; v[p / 2] = c.cr; }
+			}
+		} else {   // the partial last block of a line: round() before the conversion, unwritten samples 16 / 128 (yuv420p.ts:204-236)
+#pragma unroll
+			for (int k = 0; k < 8; ++k) y[k] = 16;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) u[k] = v[k] = 128;
+			uint32_t ty[6], tu[6], tv[6];
+#pragma unroll
+			for (int p = 0; p < 6; ++p) {
+				ty[p] = tu[p] = tv[p] = 0;
+				if (p < n) {
+					const float4 px = __ldg(in + (size_t)line * width + x0 + p);
+					const float gr = __ldg(wc.lut + sat_rte_u16(mul(px.x, 65535.0f))), gg = __ldg(wc.lut + sat_rte_u16(mul(px.y, 65535.0f))),
+					            gb = __ldg(wc.lut + sat_rte_u16(mul(px.z, 65535.0f)));
+					ty[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 0)));
+					tu[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 4)));
+					tv[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 8)));
+				}
+			}
+			y[0] = ty[0]; y[1] = ty[1]; u[0] = tu[0]; v[0] = tv[0];
+			if (n > 2) {
+				y[2] = ty[2]; y[3] = ty[3]; u[1] = tu[2]; v[1] = tv[2];
+				if (n > 4) { y[4] = ty[4]; y[5] = ty[5]; u[2] = tu[4]; v[2] = tv[4]; }
+			}
+		}
+		// uchar stores: the 16-bit conversion results wrap (Q11, as in yuv422p8)
+		uint2 yw;
+		yw.x = (y[0] & 255u) | (y[1] & 255u) << 8 | (y[2] & 255u) << 16 | (y[3] & 255u) << 24;
+		yw.y = (y[4] & 255u) | (y[5] & 255u) << 8 | (y[6] & 255u) << 16 | (y[7] & 255u) << 24;
+		*reinterpret_cast<uint2 *>(Y + ((size_t)line * blocks + bx) * 8) = yw;
+		if (l == 0) {
+			if (NV12) {
+				uint2 cw;
+				cw.x = (u[0] & 255u) | (v[0] & 255u) << 8 | (u[1] & 255u) << 16 | (v[1] & 255u) << 24;
+				cw.y = (u[2] & 255u) | (v[2] & 255u) << 8 | (u[3] & 255u) << 16 | (v[3] & 255u) << 24;
+				*reinterpret_cast<uint2 *>(U + ((size_t)gid * blocks + bx) * 8) = cw;
+			} else {
+				const size_t co = ((size_t)gid * blocks + bx) * 4;
+				*reinterpret_cast<uint32_t *>(U + co) = (u[0] & 255u) | (u[1] & 255u) << 8 | (u[2] & 255u) << 16 | (u[3] & 255u) << 24;
+				*reinterpret_cast<uint32_t *>(V + co) = (v[0] & 255u) | (v[1] & 255u) << 8 | (v[2] & 255u) << 16 | (v[3] & 255u) << 24;
+			}
+		}
+	}
+}
+
 // ---- combine_N: combine.ts:24-68 --------------------------------------------------------
 struct CombineArgs {
 	const float4 *in[kMaxLayers];
@@ -394,6 +486,21 @@ cudaError_t launch_yuv422p_write(cudaStream_t s, int bits, const void *in, void 
 	const size_t n = (size_t)((w + 7) / 8) * lines;
 	if (bits == 8) k_yuv422p_write<8><<<blocks_for(n), kThreads, 0, s>>>((const float4 *)in, y, u, v, w, lines, interlace, wc);
 	else k_yuv422p_write<10><<<blocks_for(n), kThreads, 0, s>>>((const float4 *)in, y, u, v, w, lines, interlace, wc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_yuv420_read(cudaStream_t s, int nv12, const void *y, const void *u, const void *v, void *out, int w, int h, const ReadConsts &rc) {
+	const size_t n = (size_t)w * (h & ~1);
+	if (nv12) k_yuv420_read<true><<<blocks_for(n), kThreads, 0, s>>>((const uint8_t *)y, (const uint8_t *)u, nullptr, (float4 *)out, w, h & ~1, rc);
+	else k_yuv420_read<false><<<blocks_for(n), kThreads, 0, s>>>((const uint8_t *)y, (const uint8_t *)u, (const uint8_t *)v, (float4 *)out, w, h & ~1, rc);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_yuv420_write(cudaStream_t s, int nv12, const void *in, void *y, void *u, void *v, int w, int h, int interlace, const WriteConsts &wc) {
+	const int pairs = h / 2;
+	const size_t n = (size_t)((w + 7) / 8) * pairs;
+	if (nv12) k_yuv420_write<true><<<blocks_for(n), kThreads, 0, s>>>((const float4 *)in, (uint8_t *)y, (uint8_t *)u, nullptr, w, pairs, interlace, wc);
+	else k_yuv420_write<false><<<blocks_for(n), kThreads, 0, s>>>((const float4 *)in, (uint8_t *)y, (uint8_t *)u, (uint8_t *)v, w, pairs, interlace, wc);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }

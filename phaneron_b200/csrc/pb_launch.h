@@ -13,6 +13,9 @@ cudaError_t launch_rgba8_write(cudaStream_t s, const void *in, void *out, int w,
 // planar 4:2:2, bits = 8 or 10 (yuv422p8.ts / yuv422p10.ts)
 cudaError_t launch_yuv422p_read(cudaStream_t s, int bits, const void *y, const void *u, const void *v, void *out, int w, int h, const ReadConsts &rc);
 cudaError_t launch_yuv422p_write(cudaStream_t s, int bits, const void *in, void *y, void *u, void *v, int w, int h, int interlace, const WriteConsts &wc);
+// 8-bit 4:2:0: yuv420p.ts (three planes) / nv12.ts (nv12 = 1: u is the interleaved chroma plane, v unused)
+cudaError_t launch_yuv420_read(cudaStream_t s, int nv12, const void *y, const void *u, const void *v, void *out, int w, int h, const ReadConsts &rc);
+cudaError_t launch_yuv420_write(cudaStream_t s, int nv12, const void *in, void *y, void *u, void *v, int w, int h, int interlace, const WriteConsts &wc);
 cudaError_t launch_combine(cudaStream_t s, const void *const *in, int n, void *out, int w, int h);
 cudaError_t launch_dissolve(cudaStream_t s, const void *in0, const void *in1, float mix, void *out, int w, int h);
 cudaError_t launch_wipe_mask(cudaStream_t s, const void *in0, const void *in1, const void *mask, void *out, int w, int h);

@@ -1274,6 +1274,59 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 			e = pb::launch_yuv422p_write(s, bits, src, oy->dev, ou->dev, ov->dev, W, H, interlace, wc);
 			break;
 		}
+		case PB_OP_YUV420P_READ:
+		case PB_OP_NV12_READ: {
+			const bool nv12 = g->op == PB_OP_NV12_READ;
+			pb_buf *iy, *iu, *iv = nullptr, *out, *lut;
+			pb::ReadConsts rc;
+			if ((r = need_buf(p, n, "inputY", &iy)) || (r = need_buf(p, n, nv12 ? "inputC" : "inputU", &iu)) ||
+			    (!nv12 && (r = need_buf(p, n, "inputV", &iv))) || (r = need_buf(p, n, "output", &out)))
+				return r;
+			if (H & 1) return fail(PB_ERR_ARG, "4:2:0 packers need an even height, found %d", H);   // the reference launches height / 2 work-groups
+			if ((r = make_read_consts(c, p, n, true, &rc, &lut))) return r;
+			const size_t luma = (size_t)((W + 7) / 8 * 8) * H;
+			if (iy->bytes < luma || iu->bytes < (nv12 ? luma / 2 : luma / 4) || (iv && iv->bytes < luma / 4)) return fail(PB_ERR_ARG, "4:2:0 input plane too small");
+			if ((r = check_image(out, W, H, "output"))) return r;
+			if ((r = flush_host(iy, s)) || (r = flush_host(iu, s)) || (iv && (r = flush_host(iv, s)))) return r;
+			if (!iy->dev || !iu->dev || (iv && !iv->dev)) return fail(PB_ERR_STATE, "4:2:0 input has no contents");
+			void *o;
+			if ((r = real_output(out, &o))) return r;
+			out->w = W;
+			out->h = H;
+			e = pb::launch_yuv420_read(s, nv12, iy->dev, iu->dev, iv ? iv->dev : nullptr, o, W, H, rc);
+			break;
+		}
+		case PB_OP_YUV420P_WRITE:
+		case PB_OP_NV12_WRITE: {
+			const bool nv12 = g->op == PB_OP_NV12_WRITE;
+			pb_buf *in, *oy, *ou, *ov = nullptr;
+			pb::WriteConsts wc;
+			double il = 0;
+			if ((r = need_buf(p, n, "input", &in)) || (r = need_buf(p, n, "outputY", &oy)) || (r = need_buf(p, n, nv12 ? "outputC" : "outputU", &ou)) ||
+			    (!nv12 && (r = need_buf(p, n, "outputV", &ov))))
+				return r;
+			if (H & 1) return fail(PB_ERR_ARG, "4:2:0 packers need an even height, found %d", H);
+			if ((r = make_write_consts(c, p, n, true, &wc))) return r;
+			if (find(p, n, "interlace") && (r = need_num(p, n, "interlace", &il))) return r;
+			const int interlace = (int)il;
+			if (interlace != 0 && interlace != 1 && interlace != 3) return fail(PB_ERR_ARG, "interlace must be 0, 1 or 3");
+			const size_t luma = (size_t)((W + 7) / 8 * 8) * H;
+			if (oy->bytes < luma || ou->bytes < (nv12 ? luma / 2 : luma / 4) || (ov && ov->bytes < luma / 4)) return fail(PB_ERR_ARG, "4:2:0 output plane too small");
+			if (in->w && (in->w != W || in->h != H)) return fail(PB_ERR_ARG, "writer is %dx%d but input image is %dx%d", W, H, in->w, in->h);
+			pb_buf *outs[3] = {oy, ou, ov};
+			for (pb_buf *o : outs) {
+				if (!o) continue;
+				o->expr.reset();
+				if (interlace != 0 && (r = flush_host(o, s))) return r;   // a field write keeps the other field's luma lines
+				o->host_dirty = false;
+				if ((r = ensure_dev(o))) return r;
+				o->version = ++c->version_counter;
+			}
+			const void *src;
+			if ((r = real_input(in, &src))) return r;
+			e = pb::launch_yuv420_write(s, nv12, src, oy->dev, ou->dev, ov ? ov->dev : nullptr, W, H, interlace, wc);
+			break;
+		}
 		case PB_OP_COMBINE: {
 			pb_buf *out, *ins[64];
 			int cnt = 0;
@@ -1696,6 +1749,7 @@ int pb_prog_create(pb_ctx *c, int op, int width, int height, pb_prog **out) {
 		case PB_OP_BGRA8_WRITE: case PB_OP_COMBINE: case PB_OP_DISSOLVE: case PB_OP_WIPE_MASK: case PB_OP_TRANSFORM:
 		case PB_OP_YADIF: case PB_OP_MIX: case PB_OP_WIPE: case PB_OP_RESIZE:
 		case PB_OP_YUV422P10_READ: case PB_OP_YUV422P10_WRITE: case PB_OP_YUV422P8_READ: case PB_OP_YUV422P8_WRITE:
+		case PB_OP_YUV420P_READ: case PB_OP_YUV420P_WRITE: case PB_OP_NV12_READ: case PB_OP_NV12_WRITE:
 			break;
 		default:
 			return fail(PB_ERR_ARG, "unknown op %d", op);

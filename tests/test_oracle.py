@@ -208,3 +208,52 @@ def test_yuv422p_fixture_round_trips(bits, w, h):
                                oracle.rgb2rgb_matrix("709", "709"))
     outs = oracle.yuv422p_write(bits, rgba, w, h, 0, oracle.rgb2ycbcr_matrix("709", *rng), oracle.linear2gamma_lut("709"))
     assert np.array_equal(np.concatenate(outs), src)
+
+
+@pytest.mark.parametrize("nv12,w,h", [(False, 1920, 1080), (True, 1920, 1080), (False, 718, 64), (True, 718, 64), (False, 64, 4)])
+def test_yuv420_fixture_round_trips(nv12, w, h):
+    """the pass criterion of src/process/test/yuv420pTest.ts:109 / nv12Test.ts:101 (`compare() === 0`), plus 718 wide for the tails"""
+    rng = (8, 16, 235, 224)
+    src = oracle.yuv420_fill(nv12, w, h)
+    planes, o = [], 0
+    for n in oracle.yuv420_plane_bytes(nv12, w, h):
+        planes.append(src[o: o + n])
+        o += n
+    assert o == src.size
+    rgba = oracle.yuv420_read(nv12, planes, w, h, oracle.ycbcr2rgb_matrix("709", *rng), oracle.gamma2linear_lut("709"),
+                              oracle.rgb2rgb_matrix("709", "709"))
+    assert rgba[..., 3].min() == 1.0
+    outs = oracle.yuv420_write(nv12, rgba, w, h, 0, oracle.rgb2ycbcr_matrix("709", *rng), oracle.linear2gamma_lut("709"))
+    assert np.array_equal(np.concatenate(outs), src)
+
+
+def test_yuv420_fixture_layout():
+    """yuv420p.ts:243-280: first line of a pair ramps up (Y0, Y0 + 1), the second down (Y1 + 1, Y1); chroma 128"""
+    w, h = 16, 4
+    src = oracle.yuv420_fill(False, w, h)
+    Y = src[: 16 * 4].reshape(4, 16)
+    assert list(Y[0, :6]) == [16, 17, 18, 19, 20, 21]
+    assert list(Y[1, :6]) == [235, 234, 233, 232, 231, 230]
+    assert list(Y[2, :4]) == [32, 33, 34, 35]          # Y0 carried across the pair: 16 + 2 * 8
+    assert list(Y[3, :4]) == [219, 218, 217, 216]
+    assert set(src[64:]) == {128}
+    nv = oracle.yuv420_fill(True, w, h)
+    assert np.array_equal(nv[:64], src[:64]) and set(nv[64:]) == {128} and nv.size == 64 + 32
+
+
+def test_yuv420_field_writes_share_the_chroma_plane():
+    """a field launch writes one luma line per pair and the pair's chroma from that line (yuv420p.ts:153-200): after
+    top then bottom field the luma equals the progressive result, the chroma is the bottom field's"""
+    w, h = 64, 8
+    rng = np.random.default_rng(5)
+    rgba = rng.random((h, w, 4), dtype=np.float32)
+    cm, lut = oracle.rgb2ycbcr_matrix("709", 8, 16, 235, 224), oracle.linear2gamma_lut("709")
+    prog = oracle.yuv420_write(False, rgba, w, h, 0, cm, lut)
+    outs = [np.zeros_like(p) for p in prog]
+    oracle.yuv420_write(False, rgba, w, h, 1, cm, lut, outs)
+    top_chroma = outs[1].copy()
+    assert np.array_equal(top_chroma, prog[1])          # progressive chroma comes from the first (top) line too
+    oracle.yuv420_write(False, rgba, w, h, 3, cm, lut, outs)
+    assert np.array_equal(outs[0], prog[0])
+    swapped = rgba.reshape(h // 2, 2, w, 4)[:, ::-1].reshape(h, w, 4).copy()   # bottom lines moved to the top slots
+    assert np.array_equal(outs[1], oracle.yuv420_write(False, swapped, w, h, 0, cm, lut)[1])
