@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -143,6 +144,9 @@ struct pb_ctx {
 	};
 	std::vector<SampleTab> tabs;
 	int next_tab_id = 0;
+	// blocking-sync events for waits on the copy queues: a host thread waiting for a frame-sized DMA sleeps instead of
+	// spinning, and waits for ITS copy only, not for whatever other producers have queued behind it
+	std::vector<cudaEvent_t> copy_events;
 	bool allow_march = true;
 	// gamma tables by content (see lut_table_of)
 	struct LutTable {
@@ -1531,6 +1535,7 @@ int pb_ctx_destroy(pb_ctx *c) {
 		cudaFree(t.d8);
 	}
 	for (auto &lo : c->line_ops) cudaFree(lo.dev);
+	for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
 	cudaFree(c->lut_cands_dev);
 	cudaFree(c->lut_res_dev);
 	cudaFree(c->lut_scratch);
@@ -1635,13 +1640,52 @@ void *pb_buf_dev_ptr(pb_buf *b) {
 
 int pb_buf_is_deferred(pb_buf *b) { return (b && b->expr) ? 1 : 0; }
 
+namespace {
+cudaEvent_t take_copy_event(pb_ctx *c) {   // call with c->mu held
+	if (!c->copy_events.empty()) {
+		cudaEvent_t e = c->copy_events.back();
+		c->copy_events.pop_back();
+		return e;
+	}
+	cudaEvent_t e = nullptr;
+	cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync);
+	return e;
+}
+int wait_copy_event(pb_ctx *c, cudaEvent_t ev) {   // call WITHOUT c->mu
+	const cudaError_t err = cudaEventSynchronize(ev);
+	{
+		std::lock_guard<std::recursive_mutex> lk(c->mu);
+		c->copy_events.push_back(ev);
+	}
+	if (err != cudaSuccess) return fail(PB_ERR_CUDA, "waiting for a copy: %s", cudaGetErrorString(err));
+	return PB_OK;
+}
+}  // namespace
+
 int pb_buf_host_access(pb_buf *b, int mode, int queue, const void *src, size_t src_bytes) {
 	if (!b) return fail(PB_ERR_ARG, "null buffer");
 	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
 	pb_ctx *c = b->ctx;
 	cudaStream_t s;
+	cudaEvent_t ev = nullptr;
+	static const bool trace = getenv("PB_TRACE") != nullptr;   // host-side timing of frame-sized copies, for tools/e2e_probe.py
+	const auto t_in = std::chrono::steady_clock::now();
+	auto t_locked = t_in, t_queued = t_in;
+	struct Trace {
+		const bool on;
+		const int mode, queue;
+		const size_t bytes;
+		const std::chrono::steady_clock::time_point &a, &b, &c;
+		~Trace() {
+			if (!on || bytes < (1u << 20)) return;
+			const auto d = std::chrono::steady_clock::now();
+			auto us = [](auto x, auto y) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(y - x).count(); };
+			fprintf(stderr, "[pb trace] hostAccess mode %d queue %d %zu B: lock %ld us, enqueue %ld us, wait %ld us\n", mode, queue, bytes, us(a, b), us(b, c), us(c, d));
+		}
+	} tr{trace, mode, queue, src ? src_bytes : b->bytes, t_in, t_locked, t_queued};
 	{
 		std::lock_guard<std::recursive_mutex> lk(c->mu);
+		t_locked = std::chrono::steady_clock::now();
 		cudaSetDevice(c->dev);
 		s = c->q[queue];
 		int r;
@@ -1686,12 +1730,19 @@ int pb_buf_host_access(pb_buf *b, int mode, int queue, const void *src, size_t s
 				break;
 			}
 			case PB_ACCESS_NONE:
+				if (!b->host_dirty) return PB_OK;   // nothing to hand back: do not wait for other producers' copies on this queue
 				if ((r = flush_host(b, s))) return r;
 				break;
 			default:
 				return fail(PB_ERR_ARG, "bad access mode %d", mode);
 		}
+		if (queue != PB_QUEUE_PROCESS) {
+			ev = take_copy_event(c);
+			if (ev) CU(cudaEventRecord(ev, s));
+		}
+		t_queued = std::chrono::steady_clock::now();
 	}
+	if (ev) return wait_copy_event(c, ev);
 	CU(cudaStreamSynchronize(s));
 	return PB_OK;
 }
@@ -1793,6 +1844,15 @@ int pb_wait_finish(pb_ctx *c, int queue) {
 	if (!c) return fail(PB_ERR_ARG, "null context");
 	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
 	CU(cudaSetDevice(c->dev));
+	if (queue != PB_QUEUE_PROCESS) {   // copy queues: sleep on an event (see pb_ctx::copy_events)
+		cudaEvent_t ev;
+		{
+			std::lock_guard<std::recursive_mutex> lk(c->mu);
+			ev = take_copy_event(c);
+			if (ev) CU(cudaEventRecord(ev, c->q[queue]));
+		}
+		if (ev) return wait_copy_event(c, ev);
+	}
 	CU(cudaStreamSynchronize(c->q[queue]));
 	return PB_OK;
 }

@@ -13,6 +13,7 @@ Scene description (plain dicts, shared with the oracle-side evaluator in tests/)
 """
 from __future__ import annotations
 
+import asyncio
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -121,10 +122,17 @@ class ChannelHarness:
         return out
 
     async def upload_all(self, timestamp: int) -> List[Dict[str, List[OpenCLBuffer]]]:
-        ups = []
+        # every layer's producer runs its own pipe (producer/*.ts): the uploads of one frame time are concurrent
+        jobs, where = [], []
         for li, ent in enumerate(self.layers):
             fr = self._frames(li)
-            ups.append({k: await ent[k].upload(fr[k], timestamp) for k in fr})
+            for k in fr:
+                jobs.append(ent[k].upload(fr[k], timestamp))
+                where.append((li, k))
+        done = await asyncio.gather(*jobs)
+        ups: List[Dict[str, List[OpenCLBuffer]]] = [{} for _ in self.layers]
+        for (li, k), bufs in zip(where, done):
+            ups[li][k] = bufs
         return ups
 
     async def compose(self, ups: List[Dict[str, List[OpenCLBuffer]]], timestamp: int) -> OpenCLBuffer:

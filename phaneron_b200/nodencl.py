@@ -284,7 +284,13 @@ class clContext:
         return RunTimings(t.dataToKernel, t.kernelExec, t.totalTime)
 
     async def waitFinish(self, queue: int = _lib.QUEUE_PROCESS) -> None:
-        check(_lib.lib().pb_wait_finish(self._need(), int(queue or 0)))
+        q = int(queue or 0)
+        if q == _lib.QUEUE_PROCESS:
+            check(_lib.lib().pb_wait_finish(self._need(), q))
+            return
+        # the copy queues are waited on from a worker thread, like nodencl's waitFinish on the libuv pool: a producer
+        # waiting for its upload (macadamProducer.ts:186) must not stall the loop that is composing the previous frame
+        check(await asyncio.get_running_loop().run_in_executor(None, _lib.lib().pb_wait_finish, self._need(), q))
 
 
 class Chain:
