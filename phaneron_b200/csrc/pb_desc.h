@@ -33,7 +33,18 @@ constexpr int kStripGroupsDirect = 16 * kRounds / 3;   // all leaves sampled 1:1
 constexpr int kRowGroups = 32 * kRounds / 3;           // source groups a warp's row buffer holds (2 rows x 16 when they fit, else 1 row)
 constexpr int kRowFloats = kRowGroups * 18;            // planar R | G | B per row slot
 
-enum LeafKind : int { LEAF_NONE = 0, LEAF_V210 = 1, LEAF_RGBA_F32 = 2 };
+// packed source formats a fused kernel can read directly (the reference's Reader PackImpls) + materialised RGBA-f32 frames
+enum LeafKind : int {
+	LEAF_NONE = 0,
+	LEAF_V210 = 1,        // v210.ts
+	LEAF_RGBA_F32 = 2,
+	LEAF_RGBA8 = 3,       // rgba8.ts (alpha carried, through the LUT)
+	LEAF_BGRA8 = 4,       // bgra8.ts
+	LEAF_YUV422P10 = 5,   // yuv422p10.ts: ptr = Y, ptr_u, ptr_v
+	LEAF_YUV422P8 = 6,    // yuv422p8.ts
+	LEAF_YUV420P = 7,     // yuv420p.ts
+	LEAF_NV12 = 8         // nv12.ts: ptr = Y, ptr_u = interleaved chroma
+};
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
 
 // Lossless shared-memory form of a 65536-entry gamma table (colourMaths.ts:130-169):
@@ -80,6 +91,7 @@ struct LutDesc {
 
 struct Leaf {
 	const void *ptr;
+	const void *ptr_u, *ptr_v;   // planar kinds: chroma planes
 	int kind;          // LeafKind
 	int w, h;          // source dimensions in pixels
 	int pitch;         // bytes per line (v210) / unused for RGBA (w*16)

@@ -134,6 +134,51 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
 	             : "memory");
 }
 
+// ---- texels of the other packed formats (same arithmetic as the stand-alone read kernels in pb_kernels.cu) ----
+// rgba8.ts:40-62 / bgra8.ts: 8-bit codes -> LUT index code * 65535 / 255; alpha goes through the LUT too (rgba8.ts:61)
+__device__ __forceinline__ float4 rgba8_to_linear(uchar4 v, bool bgra, const ReadConsts &rc) {
+	const float c0 = u2f(bgra ? v.z : v.x), c1 = u2f(v.y), c2 = u2f(bgra ? v.x : v.z), c3 = u2f(v.w);
+	const float r = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c0, 65535.0f), 255.0f)));
+	const float g = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c1, 65535.0f), 255.0f)));
+	const float b = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c2, 65535.0f), 255.0f)));
+	float4 o;
+	o.x = dot3(r, g, b, rc.gamut + 0);
+	o.y = dot3(r, g, b, rc.gamut + 3);
+	o.z = dot3(r, g, b, rc.gamut + 6);
+	o.w = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c3, 65535.0f), 255.0f)));
+	return o;
+}
+
+// texel (i, j) of an rgba8 / bgra8 / planar 4:2:2 / 4:2:0 leaf, inside the image
+__device__ __forceinline__ float4 packed_texel(const Leaf &lf, const ReadConsts &rc, int i, int j) {
+	if (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8)
+		return rgba8_to_linear(__ldg(reinterpret_cast<const uchar4 *>(lf.ptr) + (size_t)j * lf.w + i), lf.kind == LEAF_BGRA8, rc);
+	const int pitch = (lf.w + 7) / 8 * 8;   // samples per luma line (yuv422p10.ts:222, yuv420p.ts:240)
+	Ycc c;
+	if (lf.kind == LEAF_YUV422P10) {
+		c.y = __ldg(reinterpret_cast<const uint16_t *>(lf.ptr) + (size_t)j * pitch + i);
+		c.cb = __ldg(reinterpret_cast<const uint16_t *>(lf.ptr_u) + (size_t)j * (pitch / 2) + i / 2);
+		c.cr = __ldg(reinterpret_cast<const uint16_t *>(lf.ptr_v) + (size_t)j * (pitch / 2) + i / 2);
+	} else {
+		const uint8_t *Y = reinterpret_cast<const uint8_t *>(lf.ptr), *U = reinterpret_cast<const uint8_t *>(lf.ptr_u),
+		              *V = reinterpret_cast<const uint8_t *>(lf.ptr_v);
+		c.y = __ldg(Y + (size_t)j * pitch + i);
+		if (lf.kind == LEAF_YUV422P8) {
+			c.cb = __ldg(U + (size_t)j * (pitch / 2) + i / 2);
+			c.cr = __ldg(V + (size_t)j * (pitch / 2) + i / 2);
+		} else if (lf.kind == LEAF_YUV420P) {   // one chroma line per line pair
+			c.cb = __ldg(U + (size_t)(j / 2) * (pitch / 2) + i / 2);
+			c.cr = __ldg(V + (size_t)(j / 2) * (pitch / 2) + i / 2);
+		} else {   // LEAF_NV12: interleaved (U, V) pairs
+			const uint8_t *cp = U + (size_t)(j / 2) * pitch + (i / 2) * 2;
+			c.cb = __ldg(cp);
+			c.cr = __ldg(cp + 1);
+		}
+	}
+	const float3 rgb = ycc_to_linear(c, 1.0f, rc);
+	return make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+}
+
 // ---- leaves -------------------------------------------------------------------------
 // One texel of a leaf as RGBA-f32; texels outside the image are the CLK_ADDRESS_CLAMP
 // border colour (0,0,0,0).
@@ -142,6 +187,7 @@ __device__ __forceinline__ float4 leaf_texel(const Leaf &lf, const ReadConsts *r
 	if (lf.kind == LEAF_RGBA_F32) {
 		return __ldg(reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + i);
 	}
+	if (lf.kind != LEAF_V210) return packed_texel(lf, rcs[lf.rc], i, j);
 	const int g = i / 6, p = i - g * 6;
 	const uint4 w = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);
 	const Ycc c = v210_px(w, p);

@@ -207,7 +207,7 @@ struct pb_chain {
 
 namespace {
 
-enum NodeKind { N_LEAF_V210, N_LEAF_RGBA, N_TRANSFORM, N_DISSOLVE, N_WIPE_MASK, N_COMBINE };
+enum NodeKind { N_LEAF_V210, N_LEAF_RGBA, N_TRANSFORM, N_DISSOLVE, N_WIPE_MASK, N_COMBINE, N_LEAF_PACKED };
 
 struct Node {
 	NodeKind kind;
@@ -215,8 +215,10 @@ struct Node {
 	int w = 0, h = 0;            // dimensions of the image this node produces
 	std::vector<NodeP> in;
 	pb_buf *src = nullptr;       // leaves: referenced source buffer
-	pb_buf *lut_buf = nullptr;   // v210 leaves: referenced gamma LUT buffer
-	pb::ReadConsts rc{};         // v210 leaves
+	pb_buf *src_u = nullptr, *src_v = nullptr;   // N_LEAF_PACKED, planar formats: chroma planes
+	int leaf_kind = 0;           // N_LEAF_PACKED: pb::LeafKind (rgba8, bgra8, yuv422p10/8, yuv420p, nv12)
+	pb_buf *lut_buf = nullptr;   // packed leaves: referenced gamma LUT buffer
+	pb::ReadConsts rc{};         // packed leaves
 	float mat[6] = {0};          // transform
 	float mix = 0.f;             // dissolve
 	void *mat_dev = nullptr;     // RGBA-f32 copy if this node had to be materialised
@@ -229,6 +231,8 @@ Node::~Node() {
 	std::lock_guard<std::recursive_mutex> lk(ctx->mu);
 	if (mat_dev) ctx->pool.dev_put((size_t)w * h * 16, mat_dev);
 	if (src) buf_release_locked(src);
+	if (src_u) buf_release_locked(src_u);
+	if (src_v) buf_release_locked(src_v);
 	if (lut_buf) buf_release_locked(lut_buf);
 }
 
@@ -398,6 +402,18 @@ struct Compiler {
 			lf->w = n->w;
 			lf->h = n->h;
 			lf->pitch = n->w * 16;
+			return PB_OK;
+		}
+		if (n->kind == N_LEAF_PACKED) {   // rgba8 / bgra8 / planar 4:2:2 / 4:2:0 sources, read in place by the fused kernel
+			int idx;
+			if (rc_index(n->rc, &idx)) return 1;
+			lf->kind = n->leaf_kind;
+			lf->ptr = n->src->dev;
+			lf->ptr_u = n->src_u ? n->src_u->dev : nullptr;
+			lf->ptr_v = n->src_v ? n->src_v->dev : nullptr;
+			lf->w = n->w;
+			lf->h = n->h;
+			lf->rc = idx;
 			return PB_OK;
 		}
 		return 1;
@@ -1182,6 +1198,19 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 			if ((r = check_image(out, W, H, "output"))) return r;
 			if ((r = flush_host(in, s))) return r;
 			if (!in->dev) return fail(PB_ERR_STATE, "rgba8 input has no contents");
+			if (defer) {
+				NodeP nd = new_node(c, N_LEAF_PACKED, W, H);
+				nd->leaf_kind = g->op == PB_OP_BGRA8_READ ? pb::LEAF_BGRA8 : pb::LEAF_RGBA8;
+				nd->src = in;
+				in->refs.fetch_add(1);
+				nd->lut_buf = lut;
+				lut->refs.fetch_add(1);
+				nd->rc = rc;
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
 			void *o;
 			if ((r = real_output(out, &o))) return r;
 			e = pb::launch_rgba8_read(s, in->dev, o, W, H, g->op == PB_OP_BGRA8_READ, rc);
@@ -1242,6 +1271,19 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 			if ((r = check_image(out, W, H, "output"))) return r;
 			if ((r = flush_host(iy, s)) || (r = flush_host(iu, s)) || (r = flush_host(iv, s))) return r;
 			if (!iy->dev || !iu->dev || !iv->dev) return fail(PB_ERR_STATE, "yuv422p input has no contents");
+			if (defer) {
+				NodeP nd = new_node(c, N_LEAF_PACKED, W, H);
+				nd->leaf_kind = bits == 8 ? pb::LEAF_YUV422P8 : pb::LEAF_YUV422P10;
+				nd->src = iy; nd->src_u = iu; nd->src_v = iv;
+				iy->refs.fetch_add(1); iu->refs.fetch_add(1); iv->refs.fetch_add(1);
+				nd->lut_buf = lut;
+				lut->refs.fetch_add(1);
+				nd->rc = rc;
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
 			void *o;
 			if ((r = real_output(out, &o))) return r;
 			out->w = W;
@@ -1293,6 +1335,20 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 			if ((r = check_image(out, W, H, "output"))) return r;
 			if ((r = flush_host(iy, s)) || (r = flush_host(iu, s)) || (iv && (r = flush_host(iv, s)))) return r;
 			if (!iy->dev || !iu->dev || (iv && !iv->dev)) return fail(PB_ERR_STATE, "4:2:0 input has no contents");
+			if (defer) {
+				NodeP nd = new_node(c, N_LEAF_PACKED, W, H);
+				nd->leaf_kind = nv12 ? pb::LEAF_NV12 : pb::LEAF_YUV420P;
+				nd->src = iy; nd->src_u = iu; nd->src_v = iv;
+				iy->refs.fetch_add(1); iu->refs.fetch_add(1);
+				if (iv) iv->refs.fetch_add(1);
+				nd->lut_buf = lut;
+				lut->refs.fetch_add(1);
+				nd->rc = rc;
+				out->w = W;
+				out->h = H;
+				set_deferred(out, nd);
+				return PB_OK;
+			}
 			void *o;
 			if ((r = real_output(out, &o))) return r;
 			out->w = W;

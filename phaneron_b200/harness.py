@@ -32,12 +32,26 @@ _XF_DEFAULT = dict(flipH=False, flipV=False, anchorX=0.0, anchorY=0.0, scaleX=1.
                    offsetX=0.0, offsetY=0.0)
 
 
+def make_reader(fmt: str, w: int, h: int):
+    """the Reader PackImpl of a source format (the formats MacadamProducer / FFmpegProducer hand to ToRGBA)"""
+    from .process import nv12, rgba8, yuv420p, yuv422p8, yuv422p10
+    if fmt == "v210":
+        return v210.Reader(w, h)
+    if fmt in ("rgba8", "bgra8"):
+        return rgba8.Reader(w, h, fmt == "bgra8")
+    mods = {"yuv422p10": yuv422p10, "yuv422p8": yuv422p8, "yuv420p": yuv420p, "nv12": nv12}
+    if fmt not in mods:
+        raise ValueError(f"unknown source format '{fmt}'")
+    return mods[fmt].Reader(w, h)
+
+
 class _Source:
     """producer side of one input: ToRGBA (+ the Mixer's Transform)"""
 
-    def __init__(self, h: "ChannelHarness", sid: str, sw: int, sh: int, xf: Optional[Dict[str, Any]]):
+    def __init__(self, h: "ChannelHarness", sid: str, sw: int, sh: int, xf: Optional[Dict[str, Any]], fmt: str = "v210",
+                 colRead: Optional[str] = None):
         self.h, self.sid, self.sw, self.sh, self.xf = h, sid, sw, sh, xf
-        self.toRGBA = ToRGBA(h.ctx, h.colRead, h.colWork, v210.Reader(sw, sh), h.clJobs)
+        self.toRGBA = ToRGBA(h.ctx, colRead or h.colRead, h.colWork, make_reader(fmt, sw, sh), h.clJobs)
         self.transform: Optional[ImageProcess] = None
         if xf is not None:
             self.transform = ImageProcess(h.ctx, Transform(h.ctx, h.width, h.height), h.clJobs)
@@ -92,7 +106,8 @@ class ChannelHarness:
 
     async def init(self) -> None:
         for li, L in enumerate(self.scene["layers"]):
-            ent: Dict[str, Any] = {"a": _Source(self, f"{self.chanID}-L{li}a", L["sw"], L["sh"], L.get("xf"))}
+            ent: Dict[str, Any] = {"a": _Source(self, f"{self.chanID}-L{li}a", L["sw"], L["sh"], L.get("xf"), L.get("fmt", "v210"),
+                                                L.get("colRead"))}
             t = L.get("transition")
             if t:
                 ent["type"] = t["type"]

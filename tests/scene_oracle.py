@@ -31,14 +31,30 @@ class SceneOracle:
         self.cm_w = oracle.rgb2ycbcr_matrix(cw)
         self.lut_w = oracle.linear2gamma_lut(cw)
 
-    def source(self, src, sw, sh, xf):
-        rgba = oracle.v210_read(src, sw, sh, self.cm_r, self.lut_r, self.gamut)
+    def read(self, src, sw, sh, fmt="v210", colRead=None):
+        """the Reader kernel of the layer's source format with the constants its Loader would upload (loadSave.ts:41-64)"""
+        if fmt == "v210" and colRead is None:
+            return oracle.v210_read(src, sw, sh, self.cm_r, self.lut_r, self.gamut)
+        cr = colRead or self.s.get("colRead", "709")
+        lut, gamut = oracle.gamma2linear_lut(cr), oracle.rgb2rgb_matrix(cr, self.s.get("colWork", "709"))
+        if fmt == "v210":
+            return oracle.v210_read(src, sw, sh, oracle.ycbcr2rgb_matrix(cr), lut, gamut)
+        if fmt in ("rgba8", "bgra8"):
+            return oracle.rgba8_read(src, sw, sh, lut, gamut, bgra=(fmt == "bgra8"))
+        if fmt in ("yuv422p10", "yuv422p8"):
+            bits = 10 if fmt == "yuv422p10" else 8
+            cm = oracle.ycbcr2rgb_matrix(cr, *((10, 64, 940, 896) if bits == 10 else (8, 16, 235, 224)))
+            return oracle.yuv422p_read(bits, *src, sw, sh, cm, lut, gamut)
+        return oracle.yuv420_read(fmt == "nv12", src, sw, sh, oracle.ycbcr2rgb_matrix(cr, 8, 16, 235, 224), lut, gamut)
+
+    def source(self, src, sw, sh, xf, fmt="v210", colRead=None):
+        rgba = self.read(src, sw, sh, fmt, colRead)
         if xf is None:
             return rgba
         return oracle.transform(rgba, xf_matrix(self.W, self.H, xf), self.W, self.H)
 
     def layer(self, L):
-        a = self.source(L["src"], L["sw"], L["sh"], L.get("xf"))
+        a = self.source(L["src"], L["sw"], L["sh"], L.get("xf"), L.get("fmt", "v210"), L.get("colRead"))
         t = L.get("transition")
         if not t:
             return a

@@ -4,6 +4,8 @@ Packed output: bit-exact bytes.  RGBA composite (materialised): bit-exact floats
 import numpy as np
 import pytest
 
+import oracle
+
 from phaneron_b200.harness import ChannelHarness
 from phaneron_b200.process.packer import Interlace
 from phaneron_b200.scenes import IDENTITY_XF, layered_scene, make_frame, pip, single_layer_scene
@@ -354,3 +356,58 @@ def test_march_kernel_full_size_equals_generic_2160p():
         fast, st = run(_run_scene_variant(scene, mode))
         assert st["march_launches"] == 1
         assert np.array_equal(fast, slow), mode
+
+
+# ---- other packed source formats read in place by the fused kernel ("behind the same fused front end") ----
+def _rand_source(fmt, w, h, seed):
+    rng = np.random.default_rng(seed)
+    if fmt in ("rgba8", "bgra8"):
+        return rng.integers(0, 256, w * h * 4, dtype=np.uint8)           # alpha included: Combine becomes non-trivial
+    if fmt in ("yuv422p10", "yuv422p8"):
+        bits = 10 if fmt == "yuv422p10" else 8
+        nb = oracle.yuv422p_plane_bytes(bits, w, h)
+        if bits == 10:
+            return [rng.integers(0, 1024, n // 2, dtype=np.uint16).astype("<u2").view(np.uint8) for n in nb]
+        return [rng.integers(0, 256, n, dtype=np.uint8) for n in nb]
+    return [rng.integers(0, 256, n, dtype=np.uint8) for n in oracle.yuv420_plane_bytes(fmt == "nv12", w, h)]
+
+
+def _mixed_format_scene(w, h, specs):
+    """specs: [(fmt, colRead, xf)]; sources have the channel's dimensions"""
+    layers = []
+    for i, (fmt, col, xf) in enumerate(specs):
+        src = make_frame("noise", w, h, 40 + i) if fmt == "v210" else _rand_source(fmt, w, h, 60 + i)
+        layers.append(dict(src=src, sw=w, sh=h, xf=xf, transition=None, fmt=fmt, colRead=col))
+    return dict(width=w, height=h, colRead="709", colWork="2020", interlaced=False, layers=layers)
+
+
+MIXED_SCENES = {
+    "ffmpeg_formats_stack": lambda: _mixed_format_scene(960, 540, [
+        ("yuv420p", "709", _xf()), ("rgba8", "sRGB", _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.05, offsetY=-0.05)),
+        ("yuv422p10", "709", _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.45, offsetY=-0.1)),
+        ("nv12", "601_525", _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.25, offsetY=-0.45))]),
+    "bgra8_over_v210": lambda: _mixed_format_scene(960, 270, [("v210", None, _xf()), ("bgra8", "sRGB", _xf(scaleX=0.75, scaleY=0.75, rotate=0.02))]),
+    "yuv422p8_direct": lambda: _mixed_format_scene(768, 64, [("yuv422p8", "709", None)]),
+    "rgba8_alpha_stack_direct": lambda: _mixed_format_scene(448, 36, [("yuv422p8", "709", None), ("rgba8", "sRGB", None), ("bgra8", "sRGB", None)]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MIXED_SCENES))
+def test_packed_source_formats_fuse_into_one_launch(name):
+    """rgba8 / bgra8 / yuv422p10 / yuv422p8 / yuv420p / nv12 sources are leaves of the fused kernel: the frame is one
+    launch (no RGBA-f32 intermediate), bit-exact against the unfused oracle chain"""
+    scene = MIXED_SCENES[name]()
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0, st
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+
+
+def test_packed_sources_eager_equals_deferred():
+    scene = MIXED_SCENES["ffmpeg_formats_stack"]()
+    async def go(deferred):
+        async with Env(deferred) as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            return await h.run_frame()
+    assert np.array_equal(run(go(True)), run(go(False)))
