@@ -134,6 +134,17 @@ struct MarchOp {
 constexpr int kMaxOps = 3 * kMaxLayers;   // 24: op masks share a word with 8 layer-opacity bits
 constexpr int kMaxStrips = 128;
 
+// what a fused launch writes: the Writer PackImpl of the consumer (packer.ts), or the composite as RGBA-f32
+enum SinkKind : int {
+	SINK_V210 = 0,       // v210.ts:113-195 (the march kernel's only sink)
+	SINK_RGBA8 = 1,      // rgba8.ts:69-103   (ScreenConsumer)
+	SINK_BGRA8 = 2,      // bgra8.ts:69-103
+	SINK_YUV422P10 = 3,  // yuv422p10.ts:126-219: out = Y, out_u, out_v
+	SINK_YUV422P8 = 4,   // yuv422p8.ts:126-219 (FFmpegConsumer)
+	SINK_YUV420P = 5,    // yuv420p.ts:142-238
+	SINK_NV12 = 6        // nv12.ts:134-240: out = Y, out_u = interleaved chroma
+};
+
 struct FusedDesc {
 	int n_layers;
 	int out_w, out_h;
@@ -141,6 +152,9 @@ struct FusedDesc {
 	int out_pitch;     // bytes per output line
 	int n_rc;
 	void *out;
+	void *out_u, *out_v;   // planar sinks
+	int sink;              // SinkKind
+	int pad_sink_;
 	// march kernel
 	int strip_groups;  // output groups per strip
 	int n_strips;

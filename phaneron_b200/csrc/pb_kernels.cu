@@ -3,6 +3,7 @@
 // in HBM (host read-back, ROUTE hand-off, yadif history, rotated transforms).  The fused
 // chain lives in pb_fused.cu.
 #include "pb_device.cuh"
+#include "pb_writers.cuh"
 #include "pb_launch.h"
 
 namespace pb {
@@ -99,18 +100,7 @@ __global__ void __launch_bounds__(kThreads) k_rgba8_write(const float4 *__restri
 	if (tid >= (size_t)width * lines) return;
 	const int gl = (int)(tid / width), x = (int)(tid - (size_t)gl * width);
 	const int line = gl * (interlace == 0 ? 1 : 2) + (interlace == 3 ? 1 : 0);
-	const float4 v = __ldg(in + (size_t)line * width + x);
-	const float r = __ldg(wc.lut + sat_rte_u16(mul(v.x, 65535.0f)));
-	const float g = __ldg(wc.lut + sat_rte_u16(mul(v.y, 65535.0f)));
-	const float b = __ldg(wc.lut + sat_rte_u16(mul(v.z, 65535.0f)));
-	uchar4 o;
-	const unsigned char r8 = (unsigned char)sat_rte_u8(mul(r, 255.0f)), g8 = (unsigned char)sat_rte_u8(mul(g, 255.0f)),
-	                    b8 = (unsigned char)sat_rte_u8(mul(b, 255.0f));
-	o.x = bgra ? b8 : r8;
-	o.y = g8;
-	o.z = bgra ? r8 : b8;
-	o.w = 255;
-	out[(size_t)line * width + x] = o;
+	rgba8_write_px([&](int px, int ly) { return __ldg(in + (size_t)ly * width + px); }, out, width, line, x, bgra, wc);
 }
 
 // ---- yuv422p10le / yuv422p8: yuv422p10.ts:25-219, yuv422p8.ts:25-219 ----------------------
@@ -119,11 +109,6 @@ __global__ void __launch_bounds__(kThreads) k_rgba8_write(const float4 *__restri
 template <int BITS>
 __device__ __forceinline__ uint32_t ld_sample(const void *plane, size_t i) {
 	return BITS == 8 ? (uint32_t) reinterpret_cast<const uint8_t *>(plane)[i] : (uint32_t) reinterpret_cast<const uint16_t *>(plane)[i];
-}
-template <int BITS>
-__device__ __forceinline__ void st_sample(void *plane, size_t i, uint32_t v) {
-	if (BITS == 8) reinterpret_cast<uint8_t *>(plane)[i] = (uint8_t)v;   // Q11: the 16-bit conversion result wraps into a uchar
-	else reinterpret_cast<uint16_t *>(plane)[i] = (uint16_t)v;
 }
 
 template <int BITS>
@@ -151,51 +136,7 @@ __global__ void __launch_bounds__(kThreads) k_yuv422p_write(const float4 *__rest
 	if (tid >= (size_t)blocks * lines) return;
 	const int gl = (int)(tid / blocks), bx = (int)(tid - (size_t)gl * blocks);
 	const int line = gl * (interlace == 0 ? 1 : 2) + (interlace == 3 ? 1 : 0);
-	const int x0 = bx * 8, n = min(8, width - x0);
-	const size_t yo = ((size_t)line * blocks + bx) * 8, co = ((size_t)line * blocks + bx) * 4;
-	uint32_t y[8], u[4], v[4];
-	if (n == 8) {   // yuv422p10.ts:155-178
-#pragma unroll
-		for (int p = 0; p < 8; ++p) {
-			const float4 l = __ldg(in + (size_t)line * width + x0 + p);
-			const Ycc c = linear_to_ycc(l.x, l.y, l.z, wc);
-			y[p] = c.y;
-			if (!(p & 1)) { u[p / 2] = c.cb; v[p / 2] = c.cr; }   // chroma from even pixels only
-		}
-	} else {   // the partial last block of a line, yuv422p10.ts:180-218
-#pragma unroll
-		for (int k = 0; k < 8; ++k) y[k] = BITS == 8 ? 16 : 64;
-#pragma unroll
-		for (int k = 0; k < 4; ++k) u[k] = v[k] = BITS == 8 ? 128 : 512;
-		uint32_t ty[6], tu[6], tv[6];
-#pragma unroll
-		for (int p = 0; p < 6; ++p) {
-			ty[p] = tu[p] = tv[p] = 0;
-			if (p < n) {
-				const float4 l = __ldg(in + (size_t)line * width + x0 + p);
-				const float gr = __ldg(wc.lut + sat_rte_u16(mul(l.x, 65535.0f))), gg = __ldg(wc.lut + sat_rte_u16(mul(l.y, 65535.0f))),
-				            gb = __ldg(wc.lut + sat_rte_u16(mul(l.z, 65535.0f)));
-				ty[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 0)));   // round(): half away from zero
-				tu[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 4)));
-				tv[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 8)));
-			}
-		}
-		y[0] = ty[0]; y[1] = ty[1]; u[0] = tu[0]; v[0] = tv[0];
-		if (n > 2) {
-			y[2] = ty[2]; y[3] = ty[3]; u[1] = tu[2]; v[1] = tv[2];
-			if (n > 4) {
-				y[4] = ty[4]; y[5] = ty[5];
-				u[1] = tu[4]; v[1] = tv[4];   // Q12: .s1 where .s2 is meant (yuv422p10.ts:210-211)
-			}
-		}
-	}
-#pragma unroll
-	for (int p = 0; p < 8; ++p) st_sample<BITS>(Y, yo + p, y[p]);
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		st_sample<BITS>(U, co + k, u[k]);
-		st_sample<BITS>(V, co + k, v[k]);
-	}
+	yuv422p_write_block<BITS>([&](int px, int ly) { return __ldg(in + (size_t)ly * width + px); }, Y, U, V, width, line, bx, wc);
 }
 
 // ---- yuv420p / nv12: yuv420p.ts:25-238, nv12.ts:24-240 --------------------------------------
@@ -223,8 +164,7 @@ __global__ void __launch_bounds__(kThreads) k_yuv420_read(const uint8_t *__restr
 	out[tid] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
 }
 
-// One thread per block of 8 pixels of one line pair: the luma of one line (a field launch, interlace 1 / 3) or of both
-// (progressive), and the pair's chroma taken from the even pixels of the first line processed (yuv420p.ts:160-200).
+// One thread per block of 8 pixels of one line pair (pb_writers.cuh yuv420_write_block)
 template <bool NV12>
 __global__ void __launch_bounds__(kThreads) k_yuv420_write(const float4 *__restrict__ in, uint8_t *__restrict__ Y, uint8_t *__restrict__ U,
                                                            uint8_t *__restrict__ V, int width, int pairs, int interlace,
@@ -233,61 +173,7 @@ __global__ void __launch_bounds__(kThreads) k_yuv420_write(const float4 *__restr
 	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
 	if (tid >= (size_t)blocks * pairs) return;
 	const int gid = (int)(tid / blocks), bx = (int)(tid - (size_t)gid * blocks);
-	const int line0 = gid * 2 + (interlace == 3 ? 1 : 0), n_lines = interlace == 0 ? 2 : 1;
-	const int x0 = bx * 8, n = min(8, width - x0);
-	for (int l = 0; l < n_lines; ++l) {
-		const int line = line0 + l;
-		uint32_t y[8], u[4], v[4];
-		if (n == 8) {
-#pragma unroll
-			for (int p = 0; p < 8; ++p) {
-				const float4 px = __ldg(in + (size_t)line * width + x0 + p);
-				const Ycc c = linear_to_ycc(px.x, px.y, px.z, wc);
-				y[p] = c.y;
-				if (!(p & 1)) { u[p / 2] = c.cb; v[p / 2] = c.cr; }
-			}
-		} else {   // the partial last block of a line: round() before the conversion, unwritten samples 16 / 128 (yuv420p.ts:204-236)
-#pragma unroll
-			for (int k = 0; k < 8; ++k) y[k] = 16;
-#pragma unroll
-			for (int k = 0; k < 4; ++k) u[k] = v[k] = 128;
-			uint32_t ty[6], tu[6], tv[6];
-#pragma unroll
-			for (int p = 0; p < 6; ++p) {
-				ty[p] = tu[p] = tv[p] = 0;
-				if (p < n) {
-					const float4 px = __ldg(in + (size_t)line * width + x0 + p);
-					const float gr = __ldg(wc.lut + sat_rte_u16(mul(px.x, 65535.0f))), gg = __ldg(wc.lut + sat_rte_u16(mul(px.y, 65535.0f))),
-					            gb = __ldg(wc.lut + sat_rte_u16(mul(px.z, 65535.0f)));
-					ty[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 0)));
-					tu[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 4)));
-					tv[p] = sat_rte_u16(roundf(dot4(gr, gg, gb, 1.0f, wc.cm + 8)));
-				}
-			}
-			y[0] = ty[0]; y[1] = ty[1]; u[0] = tu[0]; v[0] = tv[0];
-			if (n > 2) {
-				y[2] = ty[2]; y[3] = ty[3]; u[1] = tu[2]; v[1] = tv[2];
-				if (n > 4) { y[4] = ty[4]; y[5] = ty[5]; u[2] = tu[4]; v[2] = tv[4]; }
-			}
-		}
-		// uchar stores: the 16-bit conversion results wrap (Q11, as in yuv422p8)
-		uint2 yw;
-		yw.x = (y[0] & 255u) | (y[1] & 255u) << 8 | (y[2] & 255u) << 16 | (y[3] & 255u) << 24;
-		yw.y = (y[4] & 255u) | (y[5] & 255u) << 8 | (y[6] & 255u) << 16 | (y[7] & 255u) << 24;
-		*reinterpret_cast<uint2 *>(Y + ((size_t)line * blocks + bx) * 8) = yw;
-		if (l == 0) {
-			if (NV12) {
-				uint2 cw;
-				cw.x = (u[0] & 255u) | (v[0] & 255u) << 8 | (u[1] & 255u) << 16 | (v[1] & 255u) << 24;
-				cw.y = (u[2] & 255u) | (v[2] & 255u) << 8 | (u[3] & 255u) << 16 | (v[3] & 255u) << 24;
-				*reinterpret_cast<uint2 *>(U + ((size_t)gid * blocks + bx) * 8) = cw;
-			} else {
-				const size_t co = ((size_t)gid * blocks + bx) * 4;
-				*reinterpret_cast<uint32_t *>(U + co) = (u[0] & 255u) | (u[1] & 255u) << 8 | (u[2] & 255u) << 16 | (u[3] & 255u) << 24;
-				*reinterpret_cast<uint32_t *>(V + co) = (v[0] & 255u) | (v[1] & 255u) << 8 | (v[2] & 255u) << 16 | (v[3] & 255u) << 24;
-			}
-		}
-	}
+	yuv420_write_block<NV12>([&](int px, int ly) { return __ldg(in + (size_t)ly * width + px); }, Y, U, V, width, gid, bx, interlace, wc);
 }
 
 // ---- combine_N: combine.ts:24-68 --------------------------------------------------------

@@ -792,6 +792,7 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 // tables and gamma-table slots.  Returns 1 = march, 0 = use the generic kernel, <0 = error.
 int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (!c->allow_march) return 0;
+	if (d.sink != pb::SINK_V210) return 0;   // the march kernel packs v210 only
 	if (d.out_w % 48 != 0 || d.out_h < 1) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
 	if (d.interlace != 0 && d.out_h < 2) return 0;
 	bool any_xf = false;
@@ -1036,7 +1037,41 @@ int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, boo
 	return PB_OK;
 }
 
-void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf, bool march = false) {
+void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf, bool march = false);
+// further destination planes of the launch just recorded: a replayable chain keeps them alive too
+void record_extra_output(pb_ctx *c, pb_buf *b) {
+	if (!c->recording || c->recording->items.empty()) return;
+	b->refs.fetch_add(1);
+	c->recording->items.back().keep.push_back(std::shared_ptr<void>(b, [](void *p) {
+		pb_buf *bb = static_cast<pb_buf *>(p);
+		std::lock_guard<std::recursive_mutex> lk(bb->ctx->mu);
+		buf_release_locked(bb);
+	}));
+}
+
+// A Writer other than v210 whose input is still an expression: evaluate the layer graph inside the writer (one launch,
+// no RGBA-f32 frame).  `outs` are the destination planes (addref'd by a recorded chain through outs[0] only: the
+// recorder keeps the expression nodes; planes stay alive because the caller's job holds them until the request ends).
+int launch_fused_sink(pb_ctx *c, cudaStream_t s, pb_buf *in, int sink, pb_buf *const *outs, int n_outs, int interlace, const pb::WriteConsts &wc,
+                      int W, int H) {
+	Compiler cc{c};
+	int r = cc.compile(in->expr);
+	if (r) return r;
+	if (cc.d.out_w != W || cc.d.out_h != H) return fail(PB_ERR_ARG, "writer is %dx%d but input image is %dx%d", W, H, cc.d.out_w, cc.d.out_h);
+	cc.d.wc = wc;
+	cc.d.interlace = interlace;
+	cc.d.sink = sink;
+	cc.d.out = outs[0]->dev;
+	cc.d.out_u = n_outs > 1 ? outs[1]->dev : nullptr;
+	cc.d.out_v = n_outs > 2 ? outs[2]->dev : nullptr;
+	if ((r = launch_desc(c, s, cc.d, nullptr, nullptr))) return r;
+	c->stats.fused_launches++;
+	record_launch(c, cc, nullptr, outs[0]);
+	for (int i = 1; i < n_outs; ++i) record_extra_output(c, outs[i]);
+	return PB_OK;
+}
+
+void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_buf, bool march) {
 	if (!c->recording) return;
 	pb_chain::Item it;
 	it.d = cc.d;
@@ -1251,6 +1286,12 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 				fused_launch = true;
 				break;
 			}
+			if (!v210 && in->expr) {   // ScreenConsumer path: the layer graph is evaluated inside the rgba8 / bgra8 writer
+				pb_buf *outs[1] = {out};
+				if ((r = launch_fused_sink(c, s, in, g->op == PB_OP_BGRA8_WRITE ? pb::SINK_BGRA8 : pb::SINK_RGBA8, outs, 1, interlace, wc, W, H))) return r;
+				fused_launch = true;
+				break;
+			}
 			const void *src;
 			if ((r = real_input(in, &src))) return r;
 			if (v210) e = pb::launch_v210_write(s, src, out->dev, W, H, interlace, wc);
@@ -1314,6 +1355,11 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 				o->host_dirty = false;
 				if ((r = ensure_dev(o))) return r;
 				o->version = ++c->version_counter;
+			}
+			if (in->expr) {   // FFmpegConsumer path (yuv422p8): the layer graph is evaluated inside the planar writer
+				if ((r = launch_fused_sink(c, s, in, bits == 8 ? pb::SINK_YUV422P8 : pb::SINK_YUV422P10, outs, 3, interlace, wc, W, H))) return r;
+				fused_launch = true;
+				break;
 			}
 			const void *src;
 			if ((r = real_input(in, &src))) return r;
@@ -1381,6 +1427,11 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 				o->host_dirty = false;
 				if ((r = ensure_dev(o))) return r;
 				o->version = ++c->version_counter;
+			}
+			if (in->expr) {
+				if ((r = launch_fused_sink(c, s, in, nv12 ? pb::SINK_NV12 : pb::SINK_YUV420P, outs, nv12 ? 2 : 3, interlace, wc, W, H))) return r;
+				fused_launch = true;
+				break;
 			}
 			const void *src;
 			if ((r = real_input(in, &src))) return r;

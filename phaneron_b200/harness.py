@@ -45,6 +45,19 @@ def make_reader(fmt: str, w: int, h: int):
     return mods[fmt].Reader(w, h)
 
 
+def make_writer(fmt: str, w: int, h: int, interlaced: bool):
+    """the Writer PackImpl of a consumer format (MacadamConsumer v210, FFmpegConsumer yuv422p8, ScreenConsumer rgba8 ...)"""
+    from .process import nv12, rgba8, yuv420p, yuv422p8, yuv422p10
+    if fmt == "v210":
+        return v210.Writer(w, h, interlaced)
+    if fmt in ("rgba8", "bgra8"):
+        return rgba8.Writer(w, h, interlaced, fmt == "bgra8")
+    mods = {"yuv422p10": yuv422p10, "yuv422p8": yuv422p8, "yuv420p": yuv420p, "nv12": nv12}
+    if fmt not in mods:
+        raise ValueError(f"unknown consumer format '{fmt}'")
+    return mods[fmt].Writer(w, h, interlaced)
+
+
 class _Source:
     """producer side of one input: ToRGBA (+ the Mixer's Transform)"""
 
@@ -123,7 +136,8 @@ class ChannelHarness:
         if len(self.layers) >= 2:
             self.combiner = ImageProcess(self.ctx, Combine(len(self.layers), self.width, self.height), self.clJobs)
             await self.combiner.init()
-        self.fromRGBA = FromRGBA(self.ctx, self.colWork, v210.Writer(self.width, self.height, self.interlaced), self.clJobs)
+        self.fromRGBA = FromRGBA(self.ctx, self.scene.get("colWrite", self.colWork),
+                                 make_writer(self.scene.get("outFmt", "v210"), self.width, self.height, self.interlaced), self.clJobs)
         await self.fromRGBA.init()
 
     def _frames(self, li: int) -> Dict[str, np.ndarray]:
@@ -210,7 +224,7 @@ class ChannelHarness:
         ups = await self.upload_all(ts)
         frame = await self.compose(ups, ts)
         dests = await self.consume(frame, download=download)
-        out = dests[0].host.copy() if download else None
+        out = (dests[0].host.copy() if len(dests) == 1 else np.concatenate([d.host for d in dests])) if download else None
         for d in dests:
             d.release()
         return out

@@ -69,4 +69,18 @@ class SceneOracle:
         return layers[0] if len(layers) == 1 else oracle.combine(layers)
 
     def packed(self, interlace=0, out=None):
-        return oracle.v210_write(self.composite(), self.W, self.H, interlace, self.cm_w, self.lut_w, out=out)
+        fmt = self.s.get("outFmt", "v210")
+        if fmt == "v210":
+            return oracle.v210_write(self.composite(), self.W, self.H, interlace, self.cm_w, self.lut_w, out=out)
+        # the other Writer PackImpls, with the constants their Saver uploads (loadSave.ts:130-150); planes concatenated
+        assert out is None
+        cw = self.s.get("colWrite", self.s.get("colWork", "709"))
+        lut = oracle.linear2gamma_lut(cw)
+        rgba = self.composite()
+        if fmt in ("rgba8", "bgra8"):
+            return oracle.rgba8_write(rgba, self.W, self.H, interlace, lut, bgra=(fmt == "bgra8"))
+        if fmt in ("yuv422p10", "yuv422p8"):
+            bits = 10 if fmt == "yuv422p10" else 8
+            cm = oracle.rgb2ycbcr_matrix(cw, *((10, 64, 940, 896) if bits == 10 else (8, 16, 235, 224)))
+            return np.concatenate(oracle.yuv422p_write(bits, rgba, self.W, self.H, interlace, cm, lut))
+        return np.concatenate(oracle.yuv420_write(fmt == "nv12", rgba, self.W, self.H, interlace, oracle.rgb2ycbcr_matrix(cw, 8, 16, 235, 224), lut))

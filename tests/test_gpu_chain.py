@@ -411,3 +411,30 @@ def test_packed_sources_eager_equals_deferred():
             await h.init()
             return await h.run_frame()
     assert np.array_equal(run(go(True)), run(go(False)))
+
+
+# ---- the other consumer formats as fused sinks ("behind the same fused back end") ----
+@pytest.mark.parametrize("out_fmt,w,h", [("yuv422p8", 960, 270), ("yuv422p8", 726, 64), ("yuv422p10", 960, 128), ("yuv422p10", 714, 32),
+                                         ("rgba8", 960, 135), ("bgra8", 384, 36), ("yuv420p", 960, 270), ("yuv420p", 708, 20),
+                                         ("nv12", 960, 128), ("nv12", 726, 32)])
+def test_consumer_formats_are_fused_sinks(out_fmt, w, h):
+    """FFmpegConsumer (yuv422p8) / ScreenConsumer (rgba8) / the other Writer PackImpls: the layer graph is evaluated inside
+    the writer -- one launch, no RGBA-f32 composite in HBM -- bit-exact against the unfused oracle chain (tails included)"""
+    scene = layered_scene(w, h, 3, "noise", "mix", "709", "2020")
+    scene["outFmt"] = out_fmt
+    if out_fmt in ("rgba8", "bgra8"):
+        scene["colWrite"] = "sRGB"
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0, st
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+
+
+def test_mixed_sources_into_a_planar_sink_one_launch():
+    scene = MIXED_SCENES["ffmpeg_formats_stack"]()
+    scene["outFmt"] = "yuv422p8"
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert st["kernel_launches"] == 1 and st["materialised"] == 0, st
+    assert np.array_equal(out, ref)
