@@ -97,7 +97,9 @@ struct LutK {
 // two saturated values -> two exact table values (v210.ts:68-70 / 148-150).
 // convert_ushort_sat_rte(v * 65535) == RNE(sat(v) * 65535): both ends of the clamp are fixed points
 // of the multiply, and NaN saturates to 0 either way.
-template <int kLutMode>
+// kAffine: 1 = the table model has s != 1 or o != 0 (linear -> gamma direction), 0 = it has not (gamma -> linear: the
+// predicated-off scale/offset FMA and its two constant loads cost issue slots all the same), -1 = decide at run time
+template <int kLutMode, int kAffine = -1>
 __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const LutParams &lp) {
 	const float2 u = mul2_unfusable(z, f2s(65535.0f));
 	const float2 v = __fadd2_rn(u, f2s(k.magic));   // RNE to an integer, held in the low mantissa bits
@@ -110,7 +112,7 @@ __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const 
 	const float2 x = __ffma2_rn(fi, f2s(lp.p), f2s(lp.q));
 	const float2 y = __fmul2_rn(f2(lg2_approx(x.x), lg2_approx(x.y)), f2s(lp.G));
 	float2 pw = f2(ex2_approx(y.x), ex2_approx(y.y));
-	if (lp.affine) pw = __ffma2_rn(pw, f2s(lp.s), f2s(lp.o));
+	if (kAffine < 0 ? lp.affine != 0 : kAffine != 0) pw = __ffma2_rn(pw, f2s(lp.s), f2s(lp.o));
 	const float2 toe = mul2_unfusable(fi, f2s(lp.kt));   // feeds a packed add below
 	const float h0 = __saturatef(add(fi.x, lp.cJ)), h1 = __saturatef(add(fi.y, lp.cJ));
 	const float2 base = __ffma2_rn(f2(h0, h1), __fadd2_rn(pw, f2(-toe.x, -toe.y)), toe);
@@ -120,7 +122,7 @@ __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const 
 // Two horizontally adjacent pixels sharing one chroma pair -> linear RGB in the working gamut
 // (v210.ts:65-77).  ya/yb are the exponent-trick floats 2^23 + y; cb/cr are 2^23 + s*c with s = 1
 // (SCB/SCR = 0) or 1024 (= 1: a field at bit 10 taken without a shift, met by a coefficient / 1024).
-template <int kLutMode, bool kSparse, int SCB, int SCR>
+template <int kLutMode, bool kSparse, int kReadAffine, int SCB, int SCR>
 __device__ __forceinline__ void convert_pair(uint32_t ya, uint32_t yb, uint32_t cb, uint32_t cr, const ReadConsts &rc, const ReadK &rk,
                                              const LutK<kLutMode> &lut, const LutParams &lp, float2 &R, float2 &G, float2 &B) {
 	// dot(yuva, colMatrix row) as LLVM contracts it: t = cb*m1; t = fma(y, m0, t); t = fma(cr, m2, t); t = fma(1, m3, t).
@@ -136,12 +138,13 @@ __device__ __forceinline__ void convert_pair(uint32_t ya, uint32_t yb, uint32_t 
 	const float2 Y = __fadd2_rn(Yb, f2s(-kTwo23));
 	tg = __ffma2_rn(Y, f2s(rk.mY[1]), f2s(mul(C.x, rk.mCb[1][SCB])));
 	tb = __ffma2_rn(Y, f2s(rk.mY[2]), f2s(mul(C.x, rk.mCb[2][SCB])));
-	tr = f2(fma_(C.y, rk.mCr[0][SCR], tr.x), fma_(C.y, rk.mCr[0][SCR], tr.y));
-	tg = f2(fma_(C.y, rk.mCr[1][SCR], tg.x), fma_(C.y, rk.mCr[1][SCR], tg.y));
-	if (!kSparse) tb = f2(fma_(C.y, rk.mCr[2][SCR], tb.x), fma_(C.y, rk.mCr[2][SCR], tb.y));   // cm[10] == 0: fma(cr, 0, t) == t
-	const float2 r = lut2<kLutMode>(f2(__saturatef(add(tr.x, rc.cm[3])), __saturatef(add(tr.y, rc.cm[3]))), lut, lp);
-	const float2 g = lut2<kLutMode>(f2(__saturatef(add(tg.x, rc.cm[7])), __saturatef(add(tg.y, rc.cm[7]))), lut, lp);
-	const float2 b = lut2<kLutMode>(f2(__saturatef(add(tb.x, rc.cm[11])), __saturatef(add(tb.y, rc.cm[11]))), lut, lp);
+	// the Cr term of both pixels in one packed FMA (broadcast operands): RN(cr * m + t) per lane, as the scalar form
+	tr = __ffma2_rn(f2s(C.y), f2s(rk.mCr[0][SCR]), tr);
+	tg = __ffma2_rn(f2s(C.y), f2s(rk.mCr[1][SCR]), tg);
+	if (!kSparse) tb = __ffma2_rn(f2s(C.y), f2s(rk.mCr[2][SCR]), tb);   // cm[10] == 0: fma(cr, 0, t) == t
+	const float2 r = lut2<kLutMode, kReadAffine>(f2(__saturatef(add(tr.x, rc.cm[3])), __saturatef(add(tr.y, rc.cm[3]))), lut, lp);
+	const float2 g = lut2<kLutMode, kReadAffine>(f2(__saturatef(add(tg.x, rc.cm[7])), __saturatef(add(tg.y, rc.cm[7]))), lut, lp);
+	const float2 b = lut2<kLutMode, kReadAffine>(f2(__saturatef(add(tb.x, rc.cm[11])), __saturatef(add(tb.y, rc.cm[11]))), lut, lp);
 	// gamut 3x3, dot(rgb, row): t = g*m1; t = fma(r, m0, t); t = fma(b, m2, t)
 	R = __ffma2_rn(b, f2s(rc.gamut[2]), __ffma2_rn(r, f2s(rc.gamut[0]), __fmul2_rn(g, f2s(rc.gamut[1]))));
 	G = __ffma2_rn(b, f2s(rc.gamut[5]), __ffma2_rn(r, f2s(rc.gamut[3]), __fmul2_rn(g, f2s(rc.gamut[4]))));
@@ -157,28 +160,28 @@ __device__ __forceinline__ uint32_t mask_or(uint32_t w, uint32_t mask, uint32_t 
 }
 
 // one v210 group (6 texels, v210.ts:58-63) -> planar row slot `row` (plane stride `cap` texels) at texel column 6g
-template <int kLutMode, bool kSparse>
+template <int kLutMode, bool kSparse, int kReadAffine>
 __device__ __forceinline__ void convert_group(const uint4 &w, int g, uint32_t E, const ReadConsts &rc, const ReadK &rk,
                                               const LutK<kLutMode> &lut, const LutParams &lp, SPtr row, int cap) {
 	const SPtr pr = row + g * 6, pg = row + (cap + g * 6), pb_ = row + (2 * cap + g * 6);
 	constexpr uint32_t M0 = 0x3ffu, M10 = 0xffc00u;
 	float2 R, G, B;
 	// word 0: Cr0 | Y0 | Cb0     word 1: Y2 | Cb1 | Y1     word 2: Cb2 | Y3 | Cr1     word 3: Y5 | Cr2 | Y4
-	convert_pair<kLutMode, kSparse, 0, 0>(mask_or(w.x >> 10, M0, E), mask_or(w.y, M0, E), mask_or(w.x, M0, E), mask_or(w.x >> 20, M0, E), rc, rk, lut, lp,
+	convert_pair<kLutMode, kSparse, kReadAffine, 0, 0>(mask_or(w.x >> 10, M0, E), mask_or(w.y, M0, E), mask_or(w.x, M0, E), mask_or(w.x >> 20, M0, E), rc, rk, lut, lp,
 	                                      R, G, B);
 	pr.st2(0, R); pg.st2(0, G); pb_.st2(0, B);
 	PB_PAIR_FENCE();
-	convert_pair<kLutMode, kSparse, 1, 0>(mask_or(w.y >> 20, M0, E), mask_or(w.z >> 10, M0, E), mask_or(w.y, M10, E), mask_or(w.z, M0, E), rc, rk, lut, lp,
+	convert_pair<kLutMode, kSparse, kReadAffine, 1, 0>(mask_or(w.y >> 20, M0, E), mask_or(w.z >> 10, M0, E), mask_or(w.y, M10, E), mask_or(w.z, M0, E), rc, rk, lut, lp,
 	                                      R, G, B);
 	pr.st2(2, R); pg.st2(2, G); pb_.st2(2, B);
 	PB_PAIR_FENCE();
-	convert_pair<kLutMode, kSparse, 0, 1>(mask_or(w.w, M0, E), mask_or(w.w >> 20, M0, E), mask_or(w.z >> 20, M0, E), mask_or(w.w, M10, E), rc, rk, lut, lp,
+	convert_pair<kLutMode, kSparse, kReadAffine, 0, 1>(mask_or(w.w, M0, E), mask_or(w.w >> 20, M0, E), mask_or(w.z >> 20, M0, E), mask_or(w.w, M10, E), rc, rk, lut, lp,
 	                                      R, G, B);
 	pr.st2(4, R); pg.st2(4, G); pb_.st2(4, B);
 }
 
 // value of one leaf at the 3 pixels of this lane -> p[r] = (r, g, b, alpha)
-template <int kLutMode, bool kSparse, bool kSingleRc>
+template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine>
 __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, SPtr buf, int lane, int strip, int y,
                                           int x_first, int x_last, float4 (&p)[kRounds]) {
 	// (strips / lines where the whole layer is border colour never get here: FusedDesc::strip_ops & line_ops)
@@ -240,7 +243,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		constexpr int cap = 96, slot_floats = 3 * cap;   // two row slots of 16 groups
 		{
 			const int hi = lane >> 4, g = lane & 15;
-			if (g < ng && (hi ? ok1 : ok0)) convert_group<kLutMode, kSparse>(wa, g, E, rc, rk, lut, lp, buf + hi * slot_floats, cap);
+			if (g < ng && (hi ? ok1 : ok0)) convert_group<kLutMode, kSparse, kReadAffine>(wa, g, E, rc, rk, lut, lp, buf + hi * slot_floats, cap);
 		}
 		__syncwarp();
 		if (!has_xf) {   // 1:1 read of texel (x, y): exact passthrough, alpha = 1 (leaf_value in pb_device.cuh)
@@ -293,11 +296,11 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 #pragma unroll 1
 	for (int rr = 0; rr < 2; ++rr) {
 		if (!(rr ? ok1 : ok0)) continue;   // border row: all its taps are (0,0,0,0)
-		if (lane < ng) convert_group<kLutMode, kSparse>(rr ? wb : wa, lane, E, rc, rk, lut, lp, buf, cap);
+		if (lane < ng) convert_group<kLutMode, kSparse, kReadAffine>(rr ? wb : wa, lane, E, rc, rk, lut, lp, buf, cap);
 #pragma unroll 1
 		for (int g = lane + 32; g < ng; g += 32) {   // only strips wider than 96 px get here
 			const uint4 w = ld_stream(reinterpret_cast<const uint4 *>(row0 + (rr ? lf.pitch : 0)) + g);
-			convert_group<kLutMode, kSparse>(w, g, E, rc, rk, lut, lp, buf, cap);
+			convert_group<kLutMode, kSparse, kReadAffine>(w, g, E, rc, rk, lut, lp, buf, cap);
 		}
 		__syncwarp();
 		const float wr = rr == 0 ? rb : b;
@@ -333,7 +336,9 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	}
 }
 
-template <int kLutMode, bool kSparse, bool kSingleRc>
+// kPlain: every read table is a non-affine model and the write table an affine one (what colourMaths.ts produces:
+// gamma -> linear on the way in, linear -> gamma on the way out), so both selects are compile-time constants
+template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			eval_leaf<kLutMode, kSparse, kSingleRc>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
+			eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1)>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
 				const float rmix = sub(1.0f, op.mix);
@@ -464,9 +469,9 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		const SPtr stage = buf;
 #pragma unroll
 		for (int r = 0; r + 1 < kRounds; r += 2) {   // two rounds at a time
-			const float2 gr = lut2<kLutMode>(f2(__saturatef(acc[r].x), __saturatef(acc[r + 1].x)), wlut, wlp);
-			const float2 gg = lut2<kLutMode>(f2(__saturatef(acc[r].y), __saturatef(acc[r + 1].y)), wlut, wlp);
-			const float2 gb = lut2<kLutMode>(f2(__saturatef(acc[r].z), __saturatef(acc[r + 1].z)), wlut, wlp);
+			const float2 gr = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].x), __saturatef(acc[r + 1].x)), wlut, wlp);
+			const float2 gg = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].y), __saturatef(acc[r + 1].y)), wlut, wlp);
+			const float2 gb = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].z), __saturatef(acc[r + 1].z)), wlut, wlp);
 			uint32_t code0 = 0, code1 = 0;
 #pragma unroll
 			for (int c = 0; c < 3; ++c) {   // dot(rgba, colMatrix row): t = g*m1; fma(r, m0, t); fma(b, m2, t); fma(1, m3, t) = RN(t + m3)
@@ -481,8 +486,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		}
 		if (kRounds & 1) {   // the odd round out: (r, g) as one pair, b alone
 			constexpr int r = kRounds - 1;
-			const float2 hrg = lut2<kLutMode>(f2(__saturatef(acc[r].x), __saturatef(acc[r].y)), wlut, wlp);
-			const float2 hb = lut2<kLutMode>(f2s(__saturatef(acc[r].z)), wlut, wlp);
+			const float2 hrg = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].x), __saturatef(acc[r].y)), wlut, wlp);
+			const float2 hb = lut2<kLutMode, (kPlain ? 1 : -1)>(f2s(__saturatef(acc[r].z)), wlut, wlp);
 			uint32_t code = 0;
 #pragma unroll
 			for (int c = 0; c < 3; ++c) {
@@ -539,6 +544,9 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 	};
 	const bool single = d.n_rc == 1;
 	if (d.n_luts > 0) {
+		bool plain = d.wlp.affine != 0;
+		for (int i = 0; i < d.n_rc; ++i) plain = plain && d.luts[d.rc[i].lut_slot].lp.affine == 0;
+		if (plain && d.sparse_cm) return single ? launch(k_fused_march<1, true, true, true>) : launch(k_fused_march<1, true, false, true>);
 		if (d.sparse_cm) return single ? launch(k_fused_march<1, true, true>) : launch(k_fused_march<1, true, false>);
 		return single ? launch(k_fused_march<1, false, true>) : launch(k_fused_march<1, false, false>);
 	}
