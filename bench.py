@@ -37,7 +37,17 @@ E2E_WARM = 8                    # pipelined frames before the e2e clock starts
 E2E_FRAMES_PER_STEP = 24       # public-API leg (PCIe bound: ~133 MB H2D + 22 MB D2H per frame)
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "2160p50 v210 4-layer composite frames/sec"
-REF_SAMPLE_LINES = 144         # --impl reference: each step composites a 3840x144 band (1/15 frame)
+REF_ARM_LINES = 720            # --impl reference: each step composites a 3840x720 band (1/3 frame)
+REF_SAMPLE_LINES = 144         # cpu_baseline of the default run: 3840x144 bands (1/15 frame)
+
+
+_JSON_OUT = None   # the real stdout when fd 1 has been pointed at stderr (multi-rank runs)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def env_int(name, default):
@@ -117,14 +127,15 @@ def pin_scene(lib, scene):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_fps(steps, warmup, inputs, threads):
+def cpu_reference_fps(steps, warmup, inputs, threads, lines=None):
     """the reference's unfused stage sequence as restated in oracle/ on the host cores"""
     import oracle
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from scene_oracle import SceneOracle
     from phaneron_b200.scenes import layered_scene
     oracle.set_threads(threads)
-    scene = layered_scene(WIDTH, REF_SAMPLE_LINES, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
+    lines = lines or REF_SAMPLE_LINES
+    scene = layered_scene(WIDTH, lines, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
     so = SceneOracle(scene)
     for _ in range(warmup):
         so.packed()
@@ -132,7 +143,7 @@ def cpu_reference_fps(steps, warmup, inputs, threads):
     for _ in range(steps):
         so.packed()
     dt = time.perf_counter() - t0
-    frames = steps * REF_SAMPLE_LINES / HEIGHT
+    frames = steps * lines / HEIGHT
     return frames / dt, dt
 
 
@@ -164,9 +175,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    fps, dt = cpu_reference_fps(args.steps, max(args.warmup, 1), args.inputs, threads)
+    fps, dt = cpu_reference_fps(args.steps, max(args.warmup, 1), args.inputs, threads, REF_ARM_LINES)
     sample = (f"{args.steps} steps, each the full unfused chain (5x v210 read, 5x transform, dissolve, combine_4, v210 write, "
-              f"RGBA-f32 intermediates) on a {WIDTH}x{REF_SAMPLE_LINES} band = {REF_SAMPLE_LINES}/{HEIGHT} of a frame; fps scaled to whole frames")
+              f"RGBA-f32 intermediates) on a {WIDTH}x{REF_ARM_LINES} band = {REF_ARM_LINES}/{HEIGHT} of a frame; fps scaled to whole frames")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -201,6 +212,9 @@ async def run_ours(args, rank, world, local_rank):
     from phaneron_b200.harness import ChannelHarness
     from phaneron_b200.scenes import layered_scene
 
+    # one process per GPU, on the GPU's own CPU cores / NUMA node (pinned frame buffers are first-touched after this)
+    from phaneron_b200.affinity import bind_to_gpu
+    cpus = None if os.environ.get("PB_NO_AFFINITY") else bind_to_gpu(local_rank, world, local_rank)
     dist = None
     if world > 1:
         import torch
@@ -368,6 +382,7 @@ async def run_ours(args, rank, world, local_rank):
             "config": {"workload": workload_name(args.inputs), "frames_per_step": fps_n, "kernel": kernel_name, "input_sets": n_sets,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating sets x {set_bytes} B = {n_sets * set_bytes} B > 126 MiB",
                        "channels": world, "parallelism": f"{world} independent channel(s), one per GPU",
+                       "cpu_affinity_rank0": (f"{len(cpus)} CPUs local to the GPU" if cpus else "unchanged"),
                        "launches_per_frame": launches_per_frame,
                        "occlusion_culling": bool(st_k["march_launches"]) and not args.no_culling,
                        "occlusion_culling_note": "exact: ops under a layer whose alpha is 1.0f bit for bit over a whole strip line are skipped "
@@ -391,7 +406,7 @@ async def run_ours(args, rank, world, local_rank):
                                     "sample": f"{n} x {WIDTH}x{REF_SAMPLE_LINES} bands ({REF_SAMPLE_LINES}/{HEIGHT} frame each) of the same scene, "
                                               f"oracle/ unfused chain, {dt:.1f} s",
                                     "reference_kernels_on_gpu": reference_kernels_on_gpu(args.inputs)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     barrier()
     if dist:
         dist.destroy_process_group()
@@ -412,6 +427,12 @@ def main():
                          "from the raw tables; generic: the fallback fused kernel")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world > 1:
+        # libraries (NCCL's version banner, torchrun notices) write to fd 1: everything but the JSON line goes to stderr
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun like the driver does
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
