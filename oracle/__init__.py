@@ -291,3 +291,15 @@ def yuv420_write(nv12: bool, rgba, width: int, height: int, interlace: int, col_
     lib().orc_yuv420_write(int(nv12), rgba.ctypes.data_as(C.c_void_p), *ptrs, width, height, interlace,
                            _f(col_matrix).ctypes.data_as(C.c_void_p), _f(gamma_lut).ctypes.data_as(C.c_void_p))
     return outs
+
+
+# ---- Lanczos Transform filter (not in the reference; definition in oracle.c) -----------------------------------------
+def transform_lanczos(img, mat, out_w: int, out_h: int, lobes: int = 3) -> np.ndarray:
+    img = _f(img)
+    sh, sw = img.shape[:2]
+    out = np.empty((out_h, out_w, 4), np.float32)
+    rc = lib().orc_transform_lanczos(img.ctypes.data_as(C.c_void_p), sw, sh, _f(mat).ctypes.data_as(C.c_void_p), int(lobes),
+                                     out.ctypes.data_as(C.c_void_p), out_w, out_h)
+    if rc != 0:
+        raise ValueError("lanczos: axis-aligned transforms with at most 64 taps per axis only")
+    return out

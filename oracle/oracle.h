@@ -90,6 +90,10 @@ void orc_yuv420_write(int nv12, const float *input, uint8_t *outY, uint8_t *outU
                       uint32_t width, uint32_t height, uint32_t interlace, const float *col_matrix12,
                       const float *gamma_lut);
 
+/* Lanczos filter for axis-aligned Transforms: NOT in the reference (BASELINE.json config 5 / SURVEY 8f row 4); the
+   definition lives in oracle.c.  Returns 0, or -1 for rotated transforms / more than 64 taps per axis. */
+int orc_transform_lanczos(const float *in, int sw, int sh, const float *mat9, int lobes, float *out, int w, int h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,11 @@ struct Leaf {
 	const int2 *col_tab;
 	const int2 *row_tab;
 	const int4 *strip_tab;
+	// Lanczos filter (not in the reference; definition in oracle/oracle.c): lz_tx / lz_ty taps per axis, host-built tables
+	// {first tap index} per output column / line and lz_t* normalised weights each.  0 taps = the reference's bilinear sampler.
+	int lz_tx, lz_ty;
+	const int *lz_i0, *lz_j0;
+	const float *lz_wx, *lz_wy;
 	// strips [s0, s1] and output lines [y0, y1] outside of which every tap of this leaf is a border
 	// texel: the kernel skips the leaf there without touching memory
 	int s0, s1, y0, y1;

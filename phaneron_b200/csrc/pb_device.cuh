@@ -227,9 +227,37 @@ __device__ __forceinline__ float2 transform_pos(const float *m, int x, int y, in
 	return p;
 }
 
+// Lanczos-filtered sample (definition: oracle/oracle.c): sum_j wy_j * (sum_i wx_i * T(i0 + i, j0 + j)), ascending
+// fma chains from +0, weights from the host-built tables; texels outside the image are (0,0,0,0)
+__device__ __forceinline__ float4 lanczos_sample(const Leaf &lf, const ReadConsts *rcs, int x, int y) {
+	const int i0 = __ldg(lf.lz_i0 + x), j0 = __ldg(lf.lz_j0 + y);
+	const float *wx = lf.lz_wx + (size_t)x * lf.lz_tx, *wy = lf.lz_wy + (size_t)y * lf.lz_ty;
+	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+	for (int j = 0; j < lf.lz_ty; ++j) {
+		float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+		for (int i = 0; i < lf.lz_tx; ++i) {
+			const float4 t = leaf_texel(lf, rcs, i0 + i, j0 + j);
+			const float w = __ldg(wx + i);
+			row.x = fma_(w, t.x, row.x);
+			row.y = fma_(w, t.y, row.y);
+			row.z = fma_(w, t.z, row.z);
+			row.w = fma_(w, t.w, row.w);
+		}
+		const float w = __ldg(wy + j);
+		acc.x = fma_(w, row.x, acc.x);
+		acc.y = fma_(w, row.y, acc.y);
+		acc.z = fma_(w, row.z, acc.z);
+		acc.w = fma_(w, row.w, acc.w);
+	}
+	return acc;
+}
+
 // value of one leaf at output pixel (x, y)
 __device__ __forceinline__ float4 leaf_value(const Leaf &lf, const ReadConsts *rcs, int x, int y) {
 	if (!lf.has_xf) return leaf_texel(lf, rcs, x, y);
+	if (lf.lz_tx) return lanczos_sample(lf, rcs, x, y);
 	const float2 p = transform_pos(lf.m, x, y, lf.xf_w, lf.xf_h);
 	return sample_linear_clamp(lf.w, lf.h, p.x, p.y, [&](int i, int j) { return leaf_texel(lf, rcs, i, j); });
 }

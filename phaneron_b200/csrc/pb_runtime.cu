@@ -144,6 +144,15 @@ struct pb_ctx {
 	};
 	std::vector<SampleTab> tabs;
 	int next_tab_id = 0;
+	// Lanczos tap tables, cached per (matrix, source dims, output dims, lobes)
+	struct LanczosTab {
+		float m[4];   // m0, m2, m4, m5
+		int sw, sh, W, H, lobes, tx, ty;
+		void *dev = nullptr;
+		int *i0 = nullptr, *j0 = nullptr;
+		float *wx = nullptr, *wy = nullptr;
+	};
+	std::vector<LanczosTab> lanczos_tabs;
 	// blocking-sync events for waits on the copy queues: a host thread waiting for a frame-sized DMA sleeps instead of
 	// spinning, and waits for ITS copy only, not for whatever other producers have queued behind it
 	std::vector<cudaEvent_t> copy_events;
@@ -220,6 +229,7 @@ struct Node {
 	pb_buf *lut_buf = nullptr;   // packed leaves: referenced gamma LUT buffer
 	pb::ReadConsts rc{};         // packed leaves
 	float mat[6] = {0};          // transform
+	int lanczos = 0;             // transform: 0 = the reference's bilinear sampler, else Lanczos lobes
 	float mix = 0.f;             // dissolve
 	void *mat_dev = nullptr;     // RGBA-f32 copy if this node had to be materialised
 	~Node();
@@ -367,6 +377,103 @@ int input_expr(pb_buf *b, NodeP *out) {
 
 int materialise_node(pb_ctx *c, const NodeP &n, const void **dev_out);
 
+// ---- Lanczos tap tables (definition: oracle/oracle.c "Lanczos Transform filter"; same arithmetic, same libm) ----
+constexpr int kLanczosMaxTaps = 64;
+
+double lanczos_kernel(double t, int lobes) {
+	if (t == 0.0) return 1.0;
+	if (fabs(t) >= (double)lobes) return 0.0;
+	const double pt = 3.14159265358979323846 * t;
+	return (double)lobes * sin(pt) * sin(pt / (double)lobes) / (pt * pt);
+}
+
+// taps of one output coordinate along one axis from its sampling position p (normalised source coordinate)
+int lanczos_axis(int out_n, int src_n, float p, float m_scale, int lobes, int *first, float *w) {
+	const float um = p * (float)src_n - 0.5f;
+	const float fu = floorf(um);
+	const float a = um - fu;
+	const double step = fabs((double)m_scale) * (double)src_n / (double)out_n;
+	const double fs = step > 1.0 ? step : 1.0;
+	const int R = (int)ceil((double)lobes * fs);
+	if (2 * R > kLanczosMaxTaps) return 0;
+	float fuc = fu;
+	if (!(fuc >= -1.0e6f)) fuc = -1.0e6f;
+	if (fuc > 1.0e6f) fuc = 1.0e6f;
+	*first = (int)fuc - R + 1;
+	double wd[kLanczosMaxTaps], sum = 0.0;
+	for (int k = 0; k < 2 * R; ++k) {
+		wd[k] = lanczos_kernel(((double)a - (double)(k - R + 1)) / fs, lobes);
+		sum += wd[k];
+	}
+	for (int k = 0; k < 2 * R; ++k) w[k] = (float)(wd[k] / sum);
+	return 2 * R;
+}
+
+// dot3(m_row, (ix, iy, 1)) + 1/2 with the cross term exactly zero, as pb_device.cuh transform_pos evaluates it
+inline float lanczos_pos(int o, int out_n, float m_scale, float m_off, bool is_x) {
+	const float ic = (float)o / (float)out_n - 0.5f;
+	float t;
+	if (is_x) {
+		t = -0.5f * 0.0f;                 // iy * m1 (m1 == 0; any finite iy gives a zero)
+		t = fmaf(ic, m_scale, t);
+	} else {
+		t = ic * m_scale;                 // iy * m4
+		t = fmaf(-0.5f, 0.0f, t);         // ix * m3 (m3 == 0)
+	}
+	t = fmaf(1.0f, m_off, t);
+	return t + 0.5f;
+}
+
+int attach_lanczos(pb_ctx *c, pb::Leaf *lf, int lobes) {
+	if (lobes < 1 || lobes > 8) return fail(PB_ERR_ARG, "lanczos lobes must be 1..8, found %d", lobes);
+	if (lf->m[1] != 0.0f || lf->m[3] != 0.0f) return fail(PB_ERR_ARG, "the lanczos filter needs an axis-aligned transform (no rotation)");
+	const int W = lf->xf_w, H = lf->xf_h;
+	const float key[4] = {lf->m[0], lf->m[2], lf->m[4], lf->m[5]};
+	pb_ctx::LanczosTab *t = nullptr;
+	for (auto &e : c->lanczos_tabs)
+		if (e.sw == lf->w && e.sh == lf->h && e.W == W && e.H == H && e.lobes == lobes && 0 == memcmp(e.m, key, sizeof key)) t = &e;
+	if (!t) {
+		if (c->lanczos_tabs.size() >= 64) {   // parameters are animating: start over
+			CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));
+			for (auto &e : c->lanczos_tabs) cudaFree(e.dev);
+			c->lanczos_tabs.clear();
+		}
+		std::vector<int> i0((size_t)W + H);
+		std::vector<float> wx((size_t)kLanczosMaxTaps * W), wy((size_t)kLanczosMaxTaps * H);
+		int tx = 0, ty = 0;
+		for (int x = 0; x < W; ++x) {
+			tx = lanczos_axis(W, lf->w, lanczos_pos(x, W, lf->m[0], lf->m[2], true), lf->m[0], lobes, &i0[x], &wx[(size_t)kLanczosMaxTaps * x]);
+			if (!tx) return fail(PB_ERR_ARG, "lanczos: more than %d taps per axis (scale too small)", kLanczosMaxTaps);
+		}
+		for (int y = 0; y < H; ++y) {
+			ty = lanczos_axis(H, lf->h, lanczos_pos(y, H, lf->m[4], lf->m[5], false), lf->m[4], lobes, &i0[(size_t)W + y], &wy[(size_t)kLanczosMaxTaps * y]);
+			if (!ty) return fail(PB_ERR_ARG, "lanczos: more than %d taps per axis (scale too small)", kLanczosMaxTaps);
+		}
+		// compact: [i0 (W) | j0 (H)] ints, then wx (W * tx), wy (H * ty) floats
+		std::vector<float> packed((size_t)W * tx + (size_t)H * ty);
+		for (int x = 0; x < W; ++x) memcpy(&packed[(size_t)x * tx], &wx[(size_t)kLanczosMaxTaps * x], sizeof(float) * tx);
+		for (int y = 0; y < H; ++y) memcpy(&packed[(size_t)W * tx + (size_t)y * ty], &wy[(size_t)kLanczosMaxTaps * y], sizeof(float) * ty);
+		pb_ctx::LanczosTab e;
+		memcpy(e.m, key, sizeof key);
+		e.sw = lf->w; e.sh = lf->h; e.W = W; e.H = H; e.lobes = lobes; e.tx = tx; e.ty = ty;
+		const size_t ib = i0.size() * sizeof(int), fb = packed.size() * sizeof(float);
+		CU(cudaMalloc(&e.dev, ib + fb));
+		CU(cudaMemcpyAsync(e.dev, i0.data(), ib, cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+		CU(cudaMemcpyAsync((char *)e.dev + ib, packed.data(), fb, cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+		CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // the staging vectors are locals; once per new transform
+		e.i0 = (int *)e.dev;
+		e.j0 = e.i0 + W;
+		e.wx = (float *)((char *)e.dev + ib);
+		e.wy = e.wx + (size_t)W * tx;
+		c->lanczos_tabs.push_back(e);
+		t = &c->lanczos_tabs.back();
+	}
+	lf->lz_tx = t->tx; lf->lz_ty = t->ty;
+	lf->lz_i0 = t->i0; lf->lz_j0 = t->j0;
+	lf->lz_wx = t->wx; lf->lz_wy = t->wy;
+	return PB_OK;
+}
+
 struct Compiler {
 	pb_ctx *c;
 	pb::FusedDesc d;
@@ -445,6 +552,7 @@ struct Compiler {
 			lf->xf_w = n->w;
 			lf->xf_h = n->h;
 			memcpy(lf->m, n->mat, sizeof lf->m);
+			if (n->lanczos) return attach_lanczos(c, lf, n->lanczos);
 			return PB_OK;
 		}
 		return as_rgba_leaf(n, lf);
@@ -804,7 +912,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
 		for (int q = 0; q < nleaf; ++q) {
 			pb::Leaf &lf = *ll[q];
-			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) return 0;
+			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0 || lf.lz_tx) return 0;
 			if (lf.has_xf) {
 				for (float v : lf.m)
 					if (!(v == v) || v > 1e30f || v < -1e30f) return 0;
@@ -1542,15 +1650,22 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 				return r;
 			if ((r = host_floats(mb, 9, m9, "transformMatrix"))) return r;
 			if ((r = check_image(out, W, H, "output"))) return r;
-			if (defer) {
+			double lanczos = 0;   // extension (not in the reference): Transform.run({..., filter: 'lanczos3'}) binds lanczos = 3
+			if (find(p, n, "lanczos") && (r = need_num(p, n, "lanczos", &lanczos))) return r;
+			if (defer || lanczos != 0) {
 				NodeP child;
 				if ((r = input_expr(in, &child))) return r;
 				NodeP nd = new_node(c, N_TRANSFORM, W, H);
 				nd->in = {child};
 				memcpy(nd->mat, m9, sizeof nd->mat);
+				nd->lanczos = (int)lanczos;
 				out->w = W;
 				out->h = H;
 				set_deferred(out, nd);
+				if (!defer) {   // eager mode: evaluate the one-node expression now (the generic kernel holds the only Lanczos sampler)
+					if ((r = materialise_buf(out))) return r;
+					return PB_OK;
+				}
 				return PB_OK;
 			}
 			if (in->w <= 0 || in->h <= 0) return fail(PB_ERR_ARG, "transform input was created without imageDims");
@@ -1643,6 +1758,7 @@ int pb_ctx_destroy(pb_ctx *c) {
 	}
 	for (auto &lo : c->line_ops) cudaFree(lo.dev);
 	for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+	for (auto &e : c->lanczos_tabs) cudaFree(e.dev);
 	cudaFree(c->lut_cands_dev);
 	cudaFree(c->lut_res_dev);
 	cudaFree(c->lut_scratch);

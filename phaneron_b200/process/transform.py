@@ -49,7 +49,15 @@ class Transform(ProcessImpl):   # transform.ts:62-189
             await self.clContext.waitFinish(self.clContext.queue.load)
         self.curParams = params
         if self.matrixBuffer: self.matrixBuffer.addRef()
-        return {"input": params["input"], "transformMatrix": self.matrixBuffer, "output": params["output"]}
+        kp = {"input": params["input"], "transformMatrix": self.matrixBuffer, "output": params["output"]}
+        # extension (not in the reference, BASELINE.json config 5): filter 'lanczosN' selects an N-lobe Lanczos filter
+        # for axis-aligned transforms; default = the reference's bilinear image sampler
+        flt = params.get("filter")
+        if flt:
+            if not (isinstance(flt, str) and flt.startswith("lanczos") and flt[7:].isdigit()):
+                raise RuntimeError(f"Transform filter must be 'lanczosN', found '{flt}'")
+            kp["lanczos"] = int(flt[7:])
+        return kp
 
     def releaseRefs(self) -> None:
         if self.matrixBuffer: self.matrixBuffer.release()

@@ -51,6 +51,9 @@ class SceneOracle:
         rgba = self.read(src, sw, sh, fmt, colRead)
         if xf is None:
             return rgba
+        flt = xf.get("filter")
+        if flt:   # extension: 'lanczosN' (definition in oracle/oracle.c)
+            return oracle.transform_lanczos(rgba, xf_matrix(self.W, self.H, xf), self.W, self.H, int(flt[7:]))
         return oracle.transform(rgba, xf_matrix(self.W, self.H, xf), self.W, self.H)
 
     def layer(self, L):

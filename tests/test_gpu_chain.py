@@ -438,3 +438,14 @@ def test_mixed_sources_into_a_planar_sink_one_launch():
     out, st = run(_run_scene_variant(scene, "march"))
     assert st["kernel_launches"] == 1 and st["materialised"] == 0, st
     assert np.array_equal(out, ref)
+
+
+def test_lanczos_layers_fuse_into_one_launch():
+    """BASELINE.json config 5's shape (2 layers, the upper one a resized PiP) with the Lanczos filter on both layers' Transforms,
+    v210 and yuv420p sources: one launch, bit-exact against the unfused oracle chain (oracle.transform_lanczos)"""
+    scene = _mixed_format_scene(960, 540, [("v210", None, _xf(filter="lanczos3")),
+                                           ("yuv420p", "709", _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.25, offsetY=-0.2, filter="lanczos3"))])
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0 and st["march_launches"] == 0, st
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"

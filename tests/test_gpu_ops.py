@@ -214,6 +214,51 @@ def test_transform(xf, deferred):
     run(go())
 
 
+# ---- Lanczos filter for Transform: NOT in the reference (BASELINE.json config 5); definition = oracle/oracle.c ----
+LANCZOS_XFS = [
+    dict(anchorX=-0.5, anchorY=-0.5),                                                    # scale 1: a = 1/2 everywhere (Q6)
+    dict(anchorX=-0.5, anchorY=-0.5, scaleX=0.5, scaleY=0.5, offsetX=-0.2, offsetY=-0.1),   # 2x down-scale: widened support
+    dict(anchorX=-0.5, anchorY=-0.5, scaleX=0.37, scaleY=0.61, offsetX=-0.3),
+    dict(anchorX=-0.5, anchorY=-0.5, scaleX=1.7, scaleY=2.3, offsetX=0.2, offsetY=0.1),     # up-scale
+    dict(anchorX=-0.5, anchorY=-0.5, scaleX=0.8, scaleY=0.8, flipH=True, flipV=True),
+    dict(anchorX=-0.5, anchorY=-0.5, scaleX=0.5, scaleY=0.5, offsetX=-0.9, offsetY=0.7),    # mostly outside
+]
+
+
+@pytest.mark.parametrize("deferred", [False, True])
+@pytest.mark.parametrize("lobes", [2, 3])
+@pytest.mark.parametrize("xf", LANCZOS_XFS)
+def test_transform_lanczos(xf, lobes, deferred):
+    async def go():
+        async with Env(deferred) as env:
+            sw, sh, w, h = 160, 90, 192, 108
+            img = rand_rgba(sh, sw, 23)
+            src = await env.image(img)
+            got = await env.run_op(Transform(env.ctx, w, h), dict(input=src, filter=f"lanczos{lobes}", **xf), w, h)
+            from scene_oracle import xf_matrix
+            assert_bits_equal(got, oracle.transform_lanczos(img, xf_matrix(w, h, xf), w, h, lobes), f"lanczos{lobes} {xf}")
+    run(go())
+
+
+def test_transform_lanczos_properties_and_errors():
+    async def go():
+        async with Env(True) as env:
+            sw, sh, w, h = 96, 64, 96, 64
+            flat = np.full((sh, sw, 4), 0.25, np.float32)
+            src = await env.image(flat)
+            got = await env.run_op(Transform(env.ctx, w, h), dict(input=src, filter="lanczos3", anchorX=-0.5, anchorY=-0.5, scaleX=0.75, scaleY=0.75), w, h)
+            inside = got[8:36, 8:56]                        # well inside the shrunken picture (72 x 48, top left): weights sum to 1
+            assert np.abs(inside - 0.25).max() < 1e-6
+            assert got[-1, -1, 3] == 0.0                    # outside: border colour
+            with pytest.raises(Exception, match="axis-aligned"):
+                await env.run_op(Transform(env.ctx, w, h), dict(input=src, filter="lanczos3", rotate=0.1), w, h)
+            with pytest.raises(Exception, match="taps"):
+                await env.run_op(Transform(env.ctx, w, h), dict(input=src, filter="lanczos3", scaleX=0.05, scaleY=0.05), w, h)
+            with pytest.raises(RuntimeError, match="lanczosN"):
+                await env.run_op(Transform(env.ctx, w, h), dict(input=src, filter="bicubic"), w, h)
+    run(go())
+
+
 def test_resize():
     async def go():
         async with Env(False) as env:

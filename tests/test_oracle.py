@@ -257,3 +257,23 @@ def test_yuv420_field_writes_share_the_chroma_plane():
     assert np.array_equal(outs[0], prog[0])
     swapped = rgba.reshape(h // 2, 2, w, 4)[:, ::-1].reshape(h, w, 4).copy()   # bottom lines moved to the top slots
     assert np.array_equal(outs[1], oracle.yuv420_write(False, swapped, w, h, 0, cm, lut)[1])
+
+
+def test_lanczos_definition_properties():
+    """the Lanczos Transform filter is this repo's own definition (oracle.c; not in the reference): partition of unity,
+    interpolation at integer positions when the source grid is hit exactly, rejection of rotated transforms"""
+    from scene_oracle import xf_matrix
+    sw, sh = 64, 48
+    flat = np.full((sh, sw, 4), 0.5, np.float32)
+    m = xf_matrix(sw, sh, dict(anchorX=-0.5, anchorY=-0.5, scaleX=0.5, scaleY=0.5))
+    out = oracle.transform_lanczos(flat, m, sw, sh, 3)
+    assert np.abs(out[10:14, 10:20] - 0.5).max() < 1e-6
+    assert out[-1, -1, 3] == 0.0
+    rng = np.random.default_rng(3)
+    img = rng.random((sh, sw, 4), dtype=np.float32)
+    # shift by exactly half a texel so that the sampling position lands on texel centres (Q6: um = x - 1/2 at identity)
+    m = xf_matrix(sw, sh, dict(anchorX=-0.5, anchorY=-0.5, offsetX=0.5 / sw, offsetY=0.5 / sh))
+    out = oracle.transform_lanczos(img, m, sw, sh, 3)
+    assert np.abs(out[8:40, 8:56] - img[8:40, 8:56]).max() < 1e-5
+    with pytest.raises(ValueError):
+        oracle.transform_lanczos(img, xf_matrix(sw, sh, dict(rotate=0.05)), sw, sh, 3)
