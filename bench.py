@@ -187,7 +187,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def ncu_traffic(kernel, inputs):
