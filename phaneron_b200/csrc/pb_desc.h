@@ -167,6 +167,7 @@ struct FusedDesc {
 	int dbg;           // experiment switches (PB_DBG environment variable), 0 in production
 	uint32_t e_magic;  // 0x4B000000, handed to the kernel as data so that (w & mask) | e stays one LOP3
 	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
+	int any_planar;    // some leaf is a planar 4:2:2 / 4:2:0 source
 	LutDesc luts[kMaxLuts];   // slot 0 = rc[0]'s table
 	LutParams wlp;            // = luts[wc.lut_slot].lp, at a fixed offset for the encoder
 	WriteConsts wc;

@@ -180,8 +180,98 @@ __device__ __forceinline__ void convert_group(const uint4 &w, int g, uint32_t E,
 	pr.st2(4, R); pg.st2(4, G); pb_.st2(4, B);
 }
 
+// ---- source group loads -----------------------------------------------------------------------------------------
+// The conversion consumes a v210 group: 6 texels as three 10-bit fields in each of four words.  A v210 leaf loads it with
+// one 128-bit access; a planar leaf (yuv422p10 / yuv422p8 / yuv420p / nv12: the FFmpegProducer formats) gathers the same 6
+// luma + 3 + 3 chroma samples from its planes and lays them out the same way, so everything downstream is shared.  (8-bit
+// samples simply occupy the low 8 bits of a field; the leaf's own colour matrix carries the 8-bit ranges.)
+__device__ __forceinline__ uint32_t ldg_u16(const void *p) {
+	uint32_t v;
+	asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldg_u8(const void *p) {
+	uint32_t v;
+	asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32(const void *p) {
+	uint32_t v;
+	asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+// word 0: Cr0 | Y0 | Cb0     word 1: Y2 | Cb1 | Y1     word 2: Cb2 | Y3 | Cr1     word 3: Y5 | Cr2 | Y4   (v210.ts:58-63)
+__device__ __forceinline__ uint4 as_v210_group(const uint32_t (&y)[6], const uint32_t (&cb)[3], const uint32_t (&cr)[3]) {
+	uint4 w;
+	w.x = cr[0] << 20 | y[0] << 10 | cb[0];
+	w.y = y[2] << 20 | cb[1] << 10 | y[1];
+	w.z = cb[2] << 20 | y[3] << 10 | cr[1];
+	w.w = y[5] << 20 | cr[2] << 10 | y[4];
+	return w;
+}
+// group g (texels 6g .. 6g+5) of source line j.  kPlanar = false: every leaf of the launch is v210 (no format test at all).
+template <bool kPlanar>
+__device__ __forceinline__ uint4 load_group(const Leaf &lf, int j, int g) {
+	if (!kPlanar || lf.kind == LEAF_V210) return ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);
+	const int pitch = (lf.w + 7) / 8 * 8;   // samples per luma line (yuv422p10.ts:222, yuv420p.ts:240)
+	uint32_t y[6], cb[3], cr[3];
+	if (lf.kind == LEAF_YUV422P10) {
+		const char *Y = reinterpret_cast<const char *>(lf.ptr) + ((size_t)j * pitch + 6 * g) * 2;   // 12 bytes, 4-byte aligned
+		const uint32_t y01 = ldg_u32(Y), y23 = ldg_u32(Y + 4), y45 = ldg_u32(Y + 8);
+		y[0] = y01 & 0xffffu; y[1] = y01 >> 16; y[2] = y23 & 0xffffu; y[3] = y23 >> 16; y[4] = y45 & 0xffffu; y[5] = y45 >> 16;
+		const char *U = reinterpret_cast<const char *>(lf.ptr_u) + ((size_t)j * (pitch / 2) + 3 * g) * 2;
+		const char *V = reinterpret_cast<const char *>(lf.ptr_v) + ((size_t)j * (pitch / 2) + 3 * g) * 2;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) { cb[k] = ldg_u16(U + 2 * k); cr[k] = ldg_u16(V + 2 * k); }
+		// The planes hold 16-bit words and the reference's reader converts whatever is there (yuv422p10.ts:60-75).  A sample
+		// above 1023 -- no legal stream carries one -- does not fit a 10-bit field: the group is flagged (bit 31 of word 0,
+		// unused by v210) and converted sample by sample with the reader's own arithmetic (convert_group_exact).
+		uint32_t top = y[0] | y[1] | y[2] | y[3] | y[4] | y[5] | cb[0] | cb[1] | cb[2] | cr[0] | cr[1] | cr[2];
+		uint4 w = as_v210_group(y, cb, cr);
+		if (top > 1023u) w.x = 0x80000000u;
+		return w;
+	}
+	const char *Y = reinterpret_cast<const char *>(lf.ptr) + (size_t)j * pitch + 6 * g;   // 6 bytes, 2-byte aligned
+	const uint32_t y01 = ldg_u16(Y), y23 = ldg_u16(Y + 2), y45 = ldg_u16(Y + 4);
+	y[0] = y01 & 0xffu; y[1] = y01 >> 8; y[2] = y23 & 0xffu; y[3] = y23 >> 8; y[4] = y45 & 0xffu; y[5] = y45 >> 8;
+	if (lf.kind == LEAF_NV12) {   // interleaved (U, V) pairs, one chroma line per line pair
+		const char *C = reinterpret_cast<const char *>(lf.ptr_u) + (size_t)(j >> 1) * pitch + 6 * g;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const uint32_t uv = ldg_u16(C + 2 * k);
+			cb[k] = uv & 0xffu;
+			cr[k] = uv >> 8;
+		}
+	} else {
+		const size_t crow = (size_t)(lf.kind == LEAF_YUV420P ? (j >> 1) : j) * (pitch / 2) + 3 * g;
+		const char *U = reinterpret_cast<const char *>(lf.ptr_u) + crow, *V = reinterpret_cast<const char *>(lf.ptr_v) + crow;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) { cb[k] = ldg_u8(U + k); cr[k] = ldg_u8(V + k); }
+	}
+	return as_v210_group(y, cb, cr);
+}
+
+// flagged yuv422p10 group (see load_group): re-read the 16-bit samples and convert them as the stand-alone reader does
+__device__ __noinline__ void convert_group_exact(const Leaf &lf, const ReadConsts &rc, int j, int g, SPtr row, int cap, int local_g) {
+	const int pitch = (lf.w + 7) / 8 * 8;
+	const uint16_t *Y = reinterpret_cast<const uint16_t *>(lf.ptr) + (size_t)j * pitch + 6 * g;
+	const uint16_t *U = reinterpret_cast<const uint16_t *>(lf.ptr_u) + (size_t)j * (pitch / 2) + 3 * g;
+	const uint16_t *V = reinterpret_cast<const uint16_t *>(lf.ptr_v) + (size_t)j * (pitch / 2) + 3 * g;
+	for (int p = 0; p < 6; ++p) {
+		Ycc c;
+		c.y = __ldg(Y + p);
+		c.cb = __ldg(U + p / 2);
+		c.cr = __ldg(V + p / 2);
+		const float3 rgb = ycc_to_linear(c, 1.0f, rc);
+		const uint32_t a = row.a + 4u * (uint32_t)(local_g * 6 + p);
+		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(rgb.x) : "memory");
+		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 4u * (uint32_t)cap), "f"(rgb.y) : "memory");
+		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 8u * (uint32_t)cap), "f"(rgb.z) : "memory");
+	}
+}
+
 // value of one leaf at the 3 pixels of this lane -> p[r] = (r, g, b, alpha)
-template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine>
+template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine, bool kPlanar>
 __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, SPtr buf, int lane, int strip, int y,
                                           int x_first, int x_last, float4 (&p)[kRounds]) {
 	// (strips / lines where the whole layer is border colour never get here: FusedDesc::strip_ops & line_ops)
@@ -201,15 +291,14 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	const bool paired = ng <= 16;   // both rows fit one 32-lane pass
 
 	// issue every HBM load of this leaf up front
-	const char *row0 = reinterpret_cast<const char *>(lf.ptr) + (size_t)j0 * lf.pitch + (size_t)g_lo * 16;
 	const uint4 z4 = make_uint4(0, 0, 0, 0);
 	uint4 wa = z4, wb = z4;
 	if (paired) {   // lanes 0-15: row j0, lanes 16-31: row j0 + 1
 		const int hi = lane >> 4, g = lane & 15;
-		if (g < ng && (hi ? ok1 : ok0)) wa = ld_stream(reinterpret_cast<const uint4 *>(row0 + (hi ? lf.pitch : 0)) + g);
+		if (g < ng && (hi ? ok1 : ok0)) wa = load_group<kPlanar>(lf, j0 + hi, g_lo + g);
 	} else {
-		if (lane < ng && ok0) wa = ld_stream(reinterpret_cast<const uint4 *>(row0) + lane);
-		if (lane < ng && ok1) wb = ld_stream(reinterpret_cast<const uint4 *>(row0 + lf.pitch) + lane);
+		if (lane < ng && ok0) wa = load_group<kPlanar>(lf, j0, g_lo + lane);
+		if (lane < ng && ok1) wb = load_group<kPlanar>(lf, j0 + 1, g_lo + lane);
 	}
 	// sampling columns of this lane's pixels (exact host tables): buffer column of tap 0 and the weight a
 	int c0[kRounds];
@@ -243,7 +332,10 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		constexpr int cap = 96, slot_floats = 3 * cap;   // two row slots of 16 groups
 		{
 			const int hi = lane >> 4, g = lane & 15;
-			if (g < ng && (hi ? ok1 : ok0)) convert_group<kLutMode, kSparse, kReadAffine>(wa, g, E, rc, rk, lut, lp, buf + hi * slot_floats, cap);
+			if (g < ng && (hi ? ok1 : ok0)) {
+				if (kPlanar && (wa.x >> 31)) convert_group_exact(lf, rc, j0 + hi, g_lo + g, buf + hi * slot_floats, cap, g);
+				else convert_group<kLutMode, kSparse, kReadAffine>(wa, g, E, rc, rk, lut, lp, buf + hi * slot_floats, cap);
+			}
 		}
 		__syncwarp();
 		if (!has_xf) {   // 1:1 read of texel (x, y): exact passthrough, alpha = 1 (leaf_value in pb_device.cuh)
@@ -296,11 +388,16 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 #pragma unroll 1
 	for (int rr = 0; rr < 2; ++rr) {
 		if (!(rr ? ok1 : ok0)) continue;   // border row: all its taps are (0,0,0,0)
-		if (lane < ng) convert_group<kLutMode, kSparse, kReadAffine>(rr ? wb : wa, lane, E, rc, rk, lut, lp, buf, cap);
+		if (lane < ng) {
+			const uint4 wr_ = rr ? wb : wa;
+			if (kPlanar && (wr_.x >> 31)) convert_group_exact(lf, rc, j0 + rr, g_lo + lane, buf, cap, lane);
+			else convert_group<kLutMode, kSparse, kReadAffine>(wr_, lane, E, rc, rk, lut, lp, buf, cap);
+		}
 #pragma unroll 1
 		for (int g = lane + 32; g < ng; g += 32) {   // only strips wider than 96 px get here
-			const uint4 w = ld_stream(reinterpret_cast<const uint4 *>(row0 + (rr ? lf.pitch : 0)) + g);
-			convert_group<kLutMode, kSparse, kReadAffine>(w, g, E, rc, rk, lut, lp, buf, cap);
+			const uint4 w = load_group<kPlanar>(lf, j0 + rr, g_lo + g);
+			if (kPlanar && (w.x >> 31)) convert_group_exact(lf, rc, j0 + rr, g_lo + g, buf, cap, g);
+			else convert_group<kLutMode, kSparse, kReadAffine>(w, g, E, rc, rk, lut, lp, buf, cap);
 		}
 		__syncwarp();
 		const float wr = rr == 0 ? rb : b;
@@ -338,7 +435,8 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 
 // kPlain: every read table is a non-affine model and the write table an affine one (what colourMaths.ts produces:
 // gamma -> linear on the way in, linear -> gamma on the way out), so both selects are compile-time constants
-template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false>
+// kPlanar: some leaf is a planar 4:2:2 / 4:2:0 source (load_group gathers it into the v210 group layout)
+template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false, bool kPlanar = false>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
@@ -424,7 +522,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1)>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
+			eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1), kPlanar>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
 				const float rmix = sub(1.0f, op.mix);
@@ -546,6 +644,10 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 	if (d.n_luts > 0) {
 		bool plain = d.wlp.affine != 0;
 		for (int i = 0; i < d.n_rc; ++i) plain = plain && d.luts[d.rc[i].lut_slot].lp.affine == 0;
+		if (d.any_planar) {   // prepare_march admits planar leaves only with shared-memory tables and sparse matrices
+			if (plain) return single ? launch(k_fused_march<1, true, true, true, true>) : launch(k_fused_march<1, true, false, true, true>);
+			return launch(k_fused_march<1, true, false, false, true>);
+		}
 		if (plain && d.sparse_cm) return single ? launch(k_fused_march<1, true, true, true>) : launch(k_fused_march<1, true, false, true>);
 		if (d.sparse_cm) return single ? launch(k_fused_march<1, true, true>) : launch(k_fused_march<1, true, false>);
 		return single ? launch(k_fused_march<1, false, true>) : launch(k_fused_march<1, false, false>);

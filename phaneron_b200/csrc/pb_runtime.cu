@@ -903,7 +903,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (d.sink != pb::SINK_V210) return 0;   // the march kernel packs v210 only
 	if (d.out_w % 48 != 0 || d.out_h < 1) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
 	if (d.interlace != 0 && d.out_h < 2) return 0;
-	bool any_xf = false;
+	bool any_xf = false, any_planar = false;
 	pb::Leaf *leaves[3 * pb::kMaxLayers];
 	int n_leaves = 0;
 	for (int l = 0; l < d.n_layers; ++l) {
@@ -912,7 +912,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
 		for (int q = 0; q < nleaf; ++q) {
 			pb::Leaf &lf = *ll[q];
-			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0 || lf.lz_tx) return 0;
+			// packed 4:2:2 / 4:2:0 YCbCr sources convert through the v210 group path; rgba8 / bgra8 (alpha) and RGBA-f32 leaves do not
+			const bool ycc = lf.kind == pb::LEAF_V210 || lf.kind == pb::LEAF_YUV422P10 || lf.kind == pb::LEAF_YUV422P8 ||
+			                 lf.kind == pb::LEAF_YUV420P || lf.kind == pb::LEAF_NV12;
+			if (!ycc || lf.w % 6 != 0 || lf.lz_tx) return 0;
+			if (lf.kind != pb::LEAF_V210) any_planar = true;
 			if (lf.has_xf) {
 				for (float v : lf.m)
 					if (!(v == v) || v > 1e30f || v < -1e30f) return 0;
@@ -1090,6 +1094,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.wc.lut_slot = slot_of(wt);
 	if (d.wc.lut_slot < 0) all_d8 = false;
 	d.n_luts = all_d8 ? n_slots : 0;
+	d.any_planar = any_planar;
+	if (any_planar && !(d.n_luts > 0 && d.sparse_cm)) return 0;   // planar variants exist for the common configuration only
 	for (int i = 0; i < d.n_luts; ++i) {
 		d.luts[i].d8 = c->lut_tables[slots[i]].d8;
 		d.luts[i].lp = c->lut_tables[slots[i]].lp;

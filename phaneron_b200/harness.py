@@ -244,10 +244,10 @@ class ChannelHarness:
         return chain, dests
 
     def algorithmic_bytes(self) -> int:
-        """(distinct packed inputs read + 1 packed output) x v210 frame bytes"""
-        total = v210.getPitchBytes(self.width) * self.height
+        """(distinct packed inputs read + 1 packed output) x packed frame bytes, in each one's own format"""
+        total = sum(make_writer(self.scene.get("outFmt", "v210"), self.width, self.height, self.interlaced).numBytes)
         for L in self.scene["layers"]:
-            total += v210.getPitchBytes(L["sw"]) * L["sh"]
+            total += sum(make_reader(L.get("fmt", "v210"), L["sw"], L["sh"]).numBytes)
             t = L.get("transition")
             if t:
                 total += v210.getPitchBytes(t["sw"]) * t["sh"]

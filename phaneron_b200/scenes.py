@@ -101,3 +101,31 @@ def single_layer_scene(width: int, height: int, inputs: str = "ramp", with_mixer
     return dict(width=width, height=height, colRead=colRead, colWork=colWork, interlaced=False,
                 layers=[dict(src=make_frame(inputs, width, height, frame_set * 16), sw=width, sh=height,
                              xf=dict(IDENTITY_XF) if with_mixer else None, transition=None)])
+
+
+def planar_frame(fmt: str, width: int, height: int, seed: int) -> List[np.ndarray]:
+    """seeded legal-range samples in the plane layout of an FFmpegProducer format (yuv422p10 / yuv422p8 / yuv420p / nv12)"""
+    rng = np.random.default_rng(seed)
+    pitch = (width + 7) // 8 * 8
+    if fmt == "yuv422p10":
+        mk = lambda n, lo, hi: rng.integers(lo, hi, n, dtype=np.uint16).astype("<u2").view(np.uint8)
+        return [mk(pitch * height, 64, 941), mk(pitch // 2 * height, 64, 961), mk(pitch // 2 * height, 64, 961)]
+    mk8 = lambda n, lo, hi: rng.integers(lo, hi, n, dtype=np.uint8)
+    if fmt == "yuv422p8":
+        return [mk8(pitch * height, 16, 236), mk8(pitch // 2 * height, 16, 241), mk8(pitch // 2 * height, 16, 241)]
+    if fmt == "yuv420p":
+        return [mk8(pitch * height, 16, 236), mk8(pitch * height // 4, 16, 241), mk8(pitch * height // 4, 16, 241)]
+    if fmt == "nv12":
+        return [mk8(pitch * height, 16, 236), mk8(pitch * height // 2, 16, 241)]
+    raise ValueError(fmt)
+
+
+def planar_layered_scene(width: int, height: int, fmt: str = "yuv422p10", n_layers: int = 4, colRead: str = "709", colWork: str = "2020",
+                         frame_set: int = 0) -> Dict[str, Any]:
+    """the layered scene of SURVEY 8(d) with FFmpegProducer-format sources instead of v210"""
+    offsets = [(0.05, 0.05), (0.45, 0.10), (0.25, 0.45), (0.10, 0.40)]
+    layers = []
+    for i in range(n_layers):
+        xf = dict(IDENTITY_XF) if i == 0 else pip(0.5, *offsets[(i - 1) % len(offsets)])
+        layers.append(dict(src=planar_frame(fmt, width, height, 2000 + frame_set * 16 + i), sw=width, sh=height, xf=xf, transition=None, fmt=fmt))
+    return dict(width=width, height=height, colRead=colRead, colWork=colWork, interlaced=False, layers=layers)

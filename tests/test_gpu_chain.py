@@ -449,3 +449,37 @@ def test_lanczos_layers_fuse_into_one_launch():
     out, st = run(_run_scene_variant(scene, "march"))
     assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0 and st["march_launches"] == 0, st
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+
+
+# ---- planar YCbCr leaves in the march kernel (gathered into the v210 group layout, pb_march.cu load_group) ----
+PLANAR_MARCH_SCENES = {
+    "yuv422p10_stack": lambda: _mixed_format_scene(960, 540, [("yuv422p10", "709", _xf()), ("yuv422p10", "709", pip(0.5, 0.05, 0.05)),
+                                                              ("yuv422p10", "709", pip(0.5, 0.45, 0.1))]),
+    "all_ycbcr_formats": lambda: _mixed_format_scene(960, 540, [("yuv420p", "709", _xf()), ("nv12", "601_525", pip(0.5, 0.05, 0.05)),
+                                                                ("yuv422p8", "709", pip(0.5, 0.45, 0.1)), ("v210", None, pip(0.5, 0.25, 0.45)),
+                                                                ("yuv422p10", "2020", pip(0.75, 0.2, 0.2))]),
+    "yuv420p_direct": lambda: _mixed_format_scene(768, 64, [("yuv420p", "709", None)]),
+    "nv12_upscaled_flipped": lambda: _mixed_format_scene(960, 270, [("v210", None, _xf()), ("nv12", "709", _xf(scaleX=1.5, scaleY=2.0, flipH=True, offsetX=0.1))]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PLANAR_MARCH_SCENES))
+def test_planar_sources_take_the_march_kernel(name):
+    scene = PLANAR_MARCH_SCENES[name]()
+    ref = SceneOracle(scene).packed()
+    slow, st0 = run(_run_scene_variant(scene, "generic"))
+    assert st0["march_launches"] == 0 and np.array_equal(slow, ref)
+    for mode in ("march", "march_nocull"):
+        out, st = run(_run_scene_variant(scene, mode))
+        assert st["march_launches"] == 1 and st["kernel_launches"] == 1 and st["materialised"] == 0, (mode, st)
+        assert np.array_equal(out, ref), f"{mode}: {int((out != ref).sum())} bytes differ"
+
+
+def test_planar_10bit_samples_above_1023_match_the_reader():
+    """yuv422p10 planes are 16-bit: out-of-range samples must convert exactly as the stand-alone reader converts them"""
+    scene = _mixed_format_scene(480, 64, [("yuv422p10", "709", _xf())])
+    rng = np.random.default_rng(9)
+    scene["layers"][0]["src"] = [rng.integers(0, 65536, p.size // 2, dtype=np.uint16).astype("<u2").view(np.uint8) for p in scene["layers"][0]["src"]]
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert np.array_equal(out, ref), (st, int((out != ref).sum()))
