@@ -900,10 +900,13 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 // tables and gamma-table slots.  Returns 1 = march, 0 = use the generic kernel, <0 = error.
 int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (!c->allow_march) return 0;
-	if (d.sink != pb::SINK_V210) return 0;   // the march kernel packs v210 only
+	// sinks: v210 and the planar YCbCr formats (the same 3 codes per pixel, stored by plane); rgba8 / bgra8 take the generic kernel
+	const bool planar_sink = d.sink == pb::SINK_YUV422P10 || d.sink == pb::SINK_YUV422P8 || d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12;
+	if (d.sink != pb::SINK_V210 && !planar_sink) return 0;
+	if ((d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12) && (d.out_h & 1)) return 0;
 	if (d.out_w % 48 != 0 || d.out_h < 1) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
 	if (d.interlace != 0 && d.out_h < 2) return 0;
-	bool any_xf = false, any_planar = false;
+	bool any_xf = false, any_planar = planar_sink;
 	pb::Leaf *leaves[3 * pb::kMaxLayers];
 	int n_leaves = 0;
 	for (int l = 0; l < d.n_layers; ++l) {
@@ -1053,17 +1056,19 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		}
 		d.line_ops = found->dev;
 	}
-	// the write side packs three codes into one word while regrouping: they must fit 10 bits
+	// the write side packs three codes into one word while regrouping: they must fit 10 bits (8 for the 8-bit sinks, whose
+	// uchar stores would otherwise wrap, Q11)
 	const int wt = lut_table_by_raw(c, d.wc.lut);
 	if (wt < 0 || !c->lut_tables[wt].unit_range) return 0;
-	// (and, being inside [0, 1023], need no saturation: the encoder drops the clamp of convert_ushort_sat_rte)
+	// (and, being inside the code range, need no saturation: the encoder drops the clamp of convert_ushort_sat_rte)
+	const double code_max = (d.sink == pb::SINK_V210 || d.sink == pb::SINK_YUV422P10) ? 1023.0 : 255.0;
 	for (int row = 0; row < 3; ++row) {
 		double hi = d.wc.cm[row * 4 + 3], lo = hi;
 		for (int k = 0; k < 3; ++k) {
 			hi += std::max(0.0, (double)d.wc.cm[row * 4 + k]);
 			lo += std::min(0.0, (double)d.wc.cm[row * 4 + k]);
 		}
-		if (!(hi < 1023.25 && lo > -0.25)) return 0;
+		if (!(hi < code_max + 0.25 && lo > -0.25)) return 0;
 	}
 	// gamma tables: all in the one-byte form (shared memory) or all raw (global memory)
 	d.sparse_cm = 1;
@@ -1178,9 +1183,11 @@ int launch_fused_sink(pb_ctx *c, cudaStream_t s, pb_buf *in, int sink, pb_buf *c
 	cc.d.out = outs[0]->dev;
 	cc.d.out_u = n_outs > 1 ? outs[1]->dev : nullptr;
 	cc.d.out_v = n_outs > 2 ? outs[2]->dev : nullptr;
-	if ((r = launch_desc(c, s, cc.d, nullptr, nullptr))) return r;
+	bool march = false;
+	if ((r = launch_desc(c, s, cc.d, nullptr, &march))) return r;
 	c->stats.fused_launches++;
-	record_launch(c, cc, nullptr, outs[0]);
+	if (march) c->stats.march_launches++;
+	record_launch(c, cc, nullptr, outs[0], march);
 	for (int i = 1; i < n_outs; ++i) record_extra_output(c, outs[i]);
 	return PB_OK;
 }

@@ -427,8 +427,12 @@ def test_consumer_formats_are_fused_sinks(out_fmt, w, h):
     ref = SceneOracle(scene).packed()
     out, st = run(_run_scene_variant(scene, "march"))
     assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0, st
+    # the planar YCbCr consumer formats at march-kernel widths are written by the march kernel itself
+    assert st["march_launches"] == (1 if (w % 48 == 0 and out_fmt not in ("rgba8", "bgra8")) else 0), st
     assert out.shape == ref.shape
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+    slow, st2 = run(_run_scene_variant(scene, "generic"))
+    assert st2["march_launches"] == 0 and np.array_equal(slow, ref)
 
 
 def test_mixed_sources_into_a_planar_sink_one_launch():
@@ -483,3 +487,42 @@ def test_planar_10bit_samples_above_1023_match_the_reader():
     ref = SceneOracle(scene).packed()
     out, st = run(_run_scene_variant(scene, "march"))
     assert np.array_equal(out, ref), (st, int((out != ref).sum()))
+
+
+@pytest.mark.parametrize("out_fmt", ["yuv422p8", "yuv422p10", "yuv420p", "nv12"])
+def test_march_kernel_planar_sink_two_fields(out_fmt):
+    """interlaced consumer: top then bottom field into one set of planes; 4:2:0 keeps the bottom field's chroma (yuv420p.ts:153-200)"""
+    async def go():
+        scene = layered_scene(480, 270 if out_fmt.startswith("yuv422") else 268, 3, "noise", "mix", "709", "2020")
+        scene["interlaced"] = True
+        scene["outFmt"] = out_fmt
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            dests = await h.fromRGBA.createDests("il")
+            for d in dests:
+                d.fill(0)
+                await d.hostAccess("writeonly")
+            for il in (Interlace.TopField, Interlace.BottomField):
+                ups = await h.upload_all(int(il))
+                frame = await h.compose(ups, int(il))
+                await h.consume(frame, dests, il, download=(il == Interlace.BottomField))
+            assert env.ctx.stats()["march_launches"] == 2
+            so = SceneOracle(scene)
+            comp = so.composite()
+            cw, W, H = scene["colWork"], scene["width"], scene["height"]
+            lut = oracle.linear2gamma_lut(cw)
+            if out_fmt.startswith("yuv422"):
+                bits = 10 if out_fmt == "yuv422p10" else 8
+                cm = oracle.rgb2ycbcr_matrix(cw, *((10, 64, 940, 896) if bits == 10 else (8, 16, 235, 224)))
+                ref = [np.zeros(n, np.uint8) for n in oracle.yuv422p_plane_bytes(bits, W, H)]
+                for il in (1, 3):
+                    oracle.yuv422p_write(bits, comp, W, H, il, cm, lut, ref)
+            else:
+                cm = oracle.rgb2ycbcr_matrix(cw, 8, 16, 235, 224)
+                ref = [np.zeros(n, np.uint8) for n in oracle.yuv420_plane_bytes(out_fmt == "nv12", W, H)]
+                for il in (1, 3):
+                    oracle.yuv420_write(out_fmt == "nv12", comp, W, H, il, cm, lut, ref)
+            for d, r in zip(dests, ref):
+                assert np.array_equal(d.host, r)
+    run(go())
