@@ -565,11 +565,26 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		// The host has checked that every code lies in [0, 1023] for table values in [0, 1], so
 		// convert_ushort_sat_rte reduces to the RNE add and the three codes share one word.
 		const SPtr stage = buf;
+		const bool rgba_sink = kPlanar && (d.sink == SINK_RGBA8 || d.sink == SINK_BGRA8);   // ScreenConsumer: one word per pixel, no regroup
 #pragma unroll
 		for (int r = 0; r + 1 < kRounds; r += 2) {   // two rounds at a time
 			const float2 gr = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].x), __saturatef(acc[r + 1].x)), wlut, wlp);
 			const float2 gg = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].y), __saturatef(acc[r + 1].y)), wlut, wlp);
 			const float2 gb = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].z), __saturatef(acc[r + 1].z)), wlut, wlp);
+			if (kPlanar && rgba_sink) {   // rgba8.ts:83-101: convert_uchar_sat_rte(gamma * 255), alpha 255 (table values lie in [0, 1])
+				const float2 r8 = __fadd2_rn(mul2_unfusable(gr, f2s(255.0f)), f2s(kTwo23)), g8 = __fadd2_rn(mul2_unfusable(gg, f2s(255.0f)), f2s(kTwo23)),
+				             b8 = __fadd2_rn(mul2_unfusable(gb, f2s(255.0f)), f2s(kTwo23));
+				const bool bgra = d.sink == SINK_BGRA8;
+				uint32_t *o = reinterpret_cast<uint32_t *>(d.out) + (size_t)y * d.out_w;
+				const int xa = x_first + r * 32 + lane, xb = xa + 32;
+				const uint32_t ca = (__float_as_uint(bgra ? b8.x : r8.x) & 0xffu) | (__float_as_uint(g8.x) & 0xffu) << 8 |
+				                    (__float_as_uint(bgra ? r8.x : b8.x) & 0xffu) << 16 | 0xff000000u;
+				const uint32_t cb_ = (__float_as_uint(bgra ? b8.y : r8.y) & 0xffu) | (__float_as_uint(g8.y) & 0xffu) << 8 |
+				                     (__float_as_uint(bgra ? r8.y : b8.y) & 0xffu) << 16 | 0xff000000u;
+				if (xa <= x_last) o[xa] = ca;
+				if (xb <= x_last) o[xb] = cb_;
+				continue;
+			}
 			uint32_t code0 = 0, code1 = 0;
 #pragma unroll
 			for (int c = 0; c < 3; ++c) {   // dot(rgba, colMatrix row): t = g*m1; fma(r, m0, t); fma(b, m2, t); fma(1, m3, t) = RN(t + m3)
@@ -586,6 +601,15 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			constexpr int r = kRounds - 1;
 			const float2 hrg = lut2<kLutMode, (kPlain ? 1 : -1)>(f2(__saturatef(acc[r].x), __saturatef(acc[r].y)), wlut, wlp);
 			const float2 hb = lut2<kLutMode, (kPlain ? 1 : -1)>(f2s(__saturatef(acc[r].z)), wlut, wlp);
+			if (kPlanar && rgba_sink) {
+				const float r8 = add(mul(hrg.x, 255.0f), kTwo23), g8 = add(mul(hrg.y, 255.0f), kTwo23), b8 = add(mul(hb.x, 255.0f), kTwo23);
+				const bool bgra = d.sink == SINK_BGRA8;
+				const int xa = x_first + r * 32 + lane;
+				if (xa <= x_last)
+					reinterpret_cast<uint32_t *>(d.out)[(size_t)y * d.out_w + xa] = (__float_as_uint(bgra ? b8 : r8) & 0xffu) | (__float_as_uint(g8) & 0xffu) << 8 |
+					                                                                 (__float_as_uint(bgra ? r8 : b8) & 0xffu) << 16 | 0xff000000u;
+				continue;   // next item: nothing to regroup
+			}
 			uint32_t code = 0;
 #pragma unroll
 			for (int c = 0; c < 3; ++c) {

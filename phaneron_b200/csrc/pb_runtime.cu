@@ -844,12 +844,13 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 	t.sw = lf.w; t.sh = lf.h; t.W = W; t.H = H; t.has_xf = lf.has_xf; t.strip_groups = strip_groups;
 	const int strip_px = strip_groups * 6;
 	const int n_strips = (W + strip_px - 1) / strip_px;
-	// one allocation: int2 col[W] | int2 row[H] | int4 strip[n_strips]
+	// one allocation: int4 strip[n_strips] | int2 col[W] | int2 row[H]  (the 16-byte entries first: W + H may be odd)
 	const size_t bytes = ((size_t)W + H) * sizeof(int2) + (size_t)n_strips * sizeof(int4);
-	std::vector<char> host(bytes);
-	int2 *hcol = reinterpret_cast<int2 *>(host.data());
+	std::vector<int4> host_store((bytes + sizeof(int4) - 1) / sizeof(int4));
+	struct { char *p; char *data() const { return p; } } host{reinterpret_cast<char *>(host_store.data())};
+	int4 *hstrip = reinterpret_cast<int4 *>(host.data());
+	int2 *hcol = reinterpret_cast<int2 *>(hstrip + n_strips);
 	int2 *hrow = hcol + W;
-	int4 *hstrip = reinterpret_cast<int4 *>(hrow + H);
 	for (int x = 0; x < W; ++x) hcol[x] = axis_entry(x, W, lf.w, lf.m[0], lf.m[1], lf.m[2], true, lf.has_xf != 0);
 	for (int y = 0; y < H; ++y) hrow[y] = axis_entry(y, H, lf.h, lf.m[4], lf.m[3], lf.m[5], false, lf.has_xf != 0);
 	t.fits = 1;
@@ -887,9 +888,9 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 	CU(cudaMalloc(&t.dev, bytes));
 	CU(cudaMemcpyAsync(t.dev, host.data(), bytes, cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
 	CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // `host` is a local; once per new transform only
-	t.dcol = reinterpret_cast<int2 *>(t.dev);
+	t.dstrip = reinterpret_cast<int4 *>(t.dev);
+	t.dcol = reinterpret_cast<int2 *>(t.dstrip + n_strips);
 	t.drow = t.dcol + W;
-	t.dstrip = reinterpret_cast<int4 *>(t.drow + H);
 	c->tabs.push_back(std::move(t));
 	*out = &c->tabs.back();
 	*fits = c->tabs.back().fits;
@@ -900,8 +901,9 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 // tables and gamma-table slots.  Returns 1 = march, 0 = use the generic kernel, <0 = error.
 int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (!c->allow_march) return 0;
-	// sinks: v210 and the planar YCbCr formats (the same 3 codes per pixel, stored by plane); rgba8 / bgra8 take the generic kernel
-	const bool planar_sink = d.sink == pb::SINK_YUV422P10 || d.sink == pb::SINK_YUV422P8 || d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12;
+	// sinks: v210, the planar YCbCr formats (the same 3 codes per pixel, stored by plane) and rgba8 / bgra8 (one word per pixel)
+	const bool planar_sink = d.sink == pb::SINK_YUV422P10 || d.sink == pb::SINK_YUV422P8 || d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12 ||
+	                         d.sink == pb::SINK_RGBA8 || d.sink == pb::SINK_BGRA8;
 	if (d.sink != pb::SINK_V210 && !planar_sink) return 0;
 	if ((d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12) && (d.out_h & 1)) return 0;
 	if (d.out_w % 48 != 0 || d.out_h < 1) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
