@@ -167,7 +167,9 @@ struct FusedDesc {
 	int dbg;           // experiment switches (PB_DBG environment variable), 0 in production
 	uint32_t e_magic;  // 0x4B000000, handed to the kernel as data so that (w & mask) | e stays one LOP3
 	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
-	int any_planar;    // some leaf is a planar 4:2:2 / 4:2:0 source
+	int any_planar;    // general load path: some leaf is planar 4:2:2 / 4:2:0, or a source width is not a multiple of 6, or the sink is not v210
+	int march_w;       // output pixels the march kernel writes: out_w rounded down to whole v210 groups
+	int g_first;       // generic kernel, v210 sink: first output group column to write (the ragged tail after a march launch), else 0
 	LutDesc luts[kMaxLuts];   // slot 0 = rc[0]'s table
 	LutParams wlp;            // = luts[wc.lut_slot].lp, at a fixed offset for the encoder
 	WriteConsts wc;

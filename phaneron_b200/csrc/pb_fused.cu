@@ -19,10 +19,11 @@ constexpr int kFusedThreads = 128;
 template <bool kToRgba>
 __global__ void __launch_bounds__(kFusedThreads) k_fused_generic(const __grid_constant__ FusedDesc d, float4 *__restrict__ out_rgba) {
 	const int pitch16 = kToRgba ? (d.out_w + 5) / 6 : d.out_pitch / 16;
+	const int g_first = kToRgba ? 0 : d.g_first, cols = pitch16 - g_first;   // g_first > 0: only the ragged tail columns of each line
 	const int lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
 	const size_t tid = (size_t)blockIdx.x * kFusedThreads + threadIdx.x;
-	if (tid >= (size_t)pitch16 * lines) return;
-	const int gl = (int)(tid / pitch16), g = (int)(tid - (size_t)gl * pitch16);
+	if (tid >= (size_t)cols * lines) return;
+	const int gl = (int)(tid / cols), g = g_first + (int)(tid - (size_t)gl * cols);
 	const int line = gl * (d.interlace == 0 ? 1 : 2) + (d.interlace == 3 ? 1 : 0);
 	const int x0 = g * 6;
 	uint4 w = make_uint4(0, 0, 0, 0);
@@ -112,7 +113,7 @@ cudaError_t launch_fused(cudaStream_t s, const FusedDesc &d, void *out_rgba) {
 		const size_t n = (size_t)((d.out_w + 5) / 6) * lines;
 		k_fused_generic<true><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, (float4 *)out_rgba);
 	} else {
-		const size_t n = (size_t)(d.out_pitch / 16) * lines;
+		const size_t n = (size_t)(d.out_pitch / 16 - d.g_first) * lines;
 		k_fused_generic<false><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, nullptr);
 	}
 	return cudaGetLastError();

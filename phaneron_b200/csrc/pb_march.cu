@@ -209,10 +209,20 @@ __device__ __forceinline__ uint4 as_v210_group(const uint32_t (&y)[6], const uin
 	w.w = y[5] << 20 | cr[2] << 10 | y[4];
 	return w;
 }
-// group g (texels 6g .. 6g+5) of source line j.  kPlanar = false: every leaf of the launch is v210 (no format test at all).
+// group g (texels 6g .. 6g+5) of source line j.  kPlanar = false: every leaf of the launch is v210 with a width that is a
+// multiple of 6 (no format test, no flag).  Otherwise bit 31 of word 0 (unused by v210) flags a group that must be converted
+// texel by texel with the readers' own code (convert_group_exact): the partial last group of a line whose width is not a
+// multiple of 6 (1280-wide 720p: 213 groups + 2 pixels, read with the Q1 semantics of v210.ts:90-110) -- flagged WITHOUT
+// touching memory, the group may straddle the end of the line -- and yuv422p10 groups holding words above 1023.
 template <bool kPlanar>
 __device__ __forceinline__ uint4 load_group(const Leaf &lf, int j, int g) {
-	if (!kPlanar || lf.kind == LEAF_V210) return ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);
+	if (!kPlanar) return ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);
+	if (6 * g + 6 > lf.w) return make_uint4(0x80000000u, 0, 0, 0);
+	if (lf.kind == LEAF_V210) {
+		uint4 w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);
+		w.x &= 0x7fffffffu;   // the reference masks the fields, so stray top bits are legal input: keep them out of the flag
+		return w;
+	}
 	const int pitch = (lf.w + 7) / 8 * 8;   // samples per luma line (yuv422p10.ts:222, yuv420p.ts:240)
 	uint32_t y[6], cb[3], cr[3];
 	if (lf.kind == LEAF_YUV422P10) {
@@ -251,22 +261,15 @@ __device__ __forceinline__ uint4 load_group(const Leaf &lf, int j, int g) {
 	return as_v210_group(y, cb, cr);
 }
 
-// flagged yuv422p10 group (see load_group): re-read the 16-bit samples and convert them as the stand-alone reader does
-__device__ __noinline__ void convert_group_exact(const Leaf &lf, const ReadConsts &rc, int j, int g, SPtr row, int cap, int local_g) {
-	const int pitch = (lf.w + 7) / 8 * 8;
-	const uint16_t *Y = reinterpret_cast<const uint16_t *>(lf.ptr) + (size_t)j * pitch + 6 * g;
-	const uint16_t *U = reinterpret_cast<const uint16_t *>(lf.ptr_u) + (size_t)j * (pitch / 2) + 3 * g;
-	const uint16_t *V = reinterpret_cast<const uint16_t *>(lf.ptr_v) + (size_t)j * (pitch / 2) + 3 * g;
+// flagged group (see load_group): every texel through pb_device.cuh leaf_texel -- the code of the stand-alone readers and
+// of the generic fused kernel (Q1 for v210 line tails, raw 16-bit words for yuv422p10, zeros outside the image)
+__device__ __noinline__ void convert_group_exact(const Leaf &lf, const ReadConsts *rcs, int j, int g, SPtr row, int cap, int local_g) {
 	for (int p = 0; p < 6; ++p) {
-		Ycc c;
-		c.y = __ldg(Y + p);
-		c.cb = __ldg(U + p / 2);
-		c.cr = __ldg(V + p / 2);
-		const float3 rgb = ycc_to_linear(c, 1.0f, rc);
+		const float4 t = leaf_texel(lf, rcs, 6 * g + p, j);
 		const uint32_t a = row.a + 4u * (uint32_t)(local_g * 6 + p);
-		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(rgb.x) : "memory");
-		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 4u * (uint32_t)cap), "f"(rgb.y) : "memory");
-		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 8u * (uint32_t)cap), "f"(rgb.z) : "memory");
+		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(t.x) : "memory");
+		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 4u * (uint32_t)cap), "f"(t.y) : "memory");
+		asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 8u * (uint32_t)cap), "f"(t.z) : "memory");
 	}
 }
 
@@ -333,7 +336,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		{
 			const int hi = lane >> 4, g = lane & 15;
 			if (g < ng && (hi ? ok1 : ok0)) {
-				if (kPlanar && (wa.x >> 31)) convert_group_exact(lf, rc, j0 + hi, g_lo + g, buf + hi * slot_floats, cap, g);
+				if (kPlanar && (wa.x >> 31)) convert_group_exact(lf, d.rc, j0 + hi, g_lo + g, buf + hi * slot_floats, cap, g);
 				else convert_group<kLutMode, kSparse, kReadAffine>(wa, g, E, rc, rk, lut, lp, buf + hi * slot_floats, cap);
 			}
 		}
@@ -390,13 +393,13 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 		if (!(rr ? ok1 : ok0)) continue;   // border row: all its taps are (0,0,0,0)
 		if (lane < ng) {
 			const uint4 wr_ = rr ? wb : wa;
-			if (kPlanar && (wr_.x >> 31)) convert_group_exact(lf, rc, j0 + rr, g_lo + lane, buf, cap, lane);
+			if (kPlanar && (wr_.x >> 31)) convert_group_exact(lf, d.rc, j0 + rr, g_lo + lane, buf, cap, lane);
 			else convert_group<kLutMode, kSparse, kReadAffine>(wr_, lane, E, rc, rk, lut, lp, buf, cap);
 		}
 #pragma unroll 1
 		for (int g = lane + 32; g < ng; g += 32) {   // only strips wider than 96 px get here
 			const uint4 w = load_group<kPlanar>(lf, j0 + rr, g_lo + g);
-			if (kPlanar && (w.x >> 31)) convert_group_exact(lf, rc, j0 + rr, g_lo + g, buf, cap, g);
+			if (kPlanar && (w.x >> 31)) convert_group_exact(lf, d.rc, j0 + rr, g_lo + g, buf, cap, g);
 			else convert_group<kLutMode, kSparse, kReadAffine>(w, g, E, rc, rk, lut, lp, buf, cap);
 		}
 		__syncwarp();
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		}
 		const int y = first_line + k * step;
 		const int x_first = strip * strip_px;
-		const int x_last = min(x_first + strip_px, d.out_w) - 1;
+		const int x_last = min(x_first + strip_px, d.march_w) - 1;   // whole output groups only: a ragged tail is the generic kernel's
 
 		// The host flattened the layer graph into ops (a leaf evaluation + an action) and marked, per strip, the ops
 		// that can touch it: leaves that lie elsewhere cost nothing here.  acc starts at 0 and every layer, the bottom

@@ -906,7 +906,12 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	                         d.sink == pb::SINK_RGBA8 || d.sink == pb::SINK_BGRA8;
 	if (d.sink != pb::SINK_V210 && !planar_sink) return 0;
 	if ((d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12) && (d.out_h & 1)) return 0;
-	if (d.out_w % 48 != 0 || d.out_h < 1) return 0;   // ragged widths carry the Q2 tail semantics: generic kernel
+	// Widths: the march kernel writes whole v210 groups.  With a v210 sink a ragged width (1280-wide 720p = 213 groups + 2 pixels,
+	// 27 x 128-byte pitch) is split: the march kernel takes the whole groups, a second small launch of the generic kernel the
+	// tail columns of every line (the partial group with its Q2 semantics, v210.ts:166-192, and the padding groups).  The other
+	// sinks have their own 8-pixel tail quirks: whole multiples of 48 only.
+	if (d.out_h < 1 || d.out_w < 6 || (d.out_w & 1)) return 0;
+	if (d.sink != pb::SINK_V210 && d.out_w % 48 != 0) return 0;
 	if (d.interlace != 0 && d.out_h < 2) return 0;
 	bool any_xf = false, any_planar = planar_sink;
 	pb::Leaf *leaves[3 * pb::kMaxLayers];
@@ -920,8 +925,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			// packed 4:2:2 / 4:2:0 YCbCr sources convert through the v210 group path; rgba8 / bgra8 (alpha) and RGBA-f32 leaves do not
 			const bool ycc = lf.kind == pb::LEAF_V210 || lf.kind == pb::LEAF_YUV422P10 || lf.kind == pb::LEAF_YUV422P8 ||
 			                 lf.kind == pb::LEAF_YUV420P || lf.kind == pb::LEAF_NV12;
-			if (!ycc || lf.w % 6 != 0 || lf.lz_tx) return 0;
-			if (lf.kind != pb::LEAF_V210) any_planar = true;
+			if (!ycc || lf.w < 6 || lf.lz_tx) return 0;
+			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) any_planar = true;   // general load path (formats, partial last groups)
 			if (lf.has_xf) {
 				for (float v : lf.m)
 					if (!(v == v) || v > 1e30f || v < -1e30f) return 0;
@@ -936,6 +941,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	}
 	if (const char *dbg = getenv("PB_DBG")) d.dbg = atoi(dbg);
 	d.e_magic = 0x4B000000u;
+	d.march_w = d.out_w / 6 * 6;
+	d.g_first = 0;
 	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
 	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
 	if (d.n_strips > pb::kMaxStrips) return 0;
@@ -1144,6 +1151,21 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	return 1;
 }
 
+// issue the launch(es) of a prepared descriptor: the march or the generic kernel, plus -- after a march launch on a ragged
+// v210 width -- the generic kernel on the tail columns (prepare_march).  Also the replay path of recorded chains.
+int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d, bool march, void *out_rgba) {
+	cudaError_t e = march ? pb::launch_fused_march(s, d, c->prop.multiProcessorCount) : pb::launch_fused(s, d, out_rgba);
+	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (%s): %s", march ? "march" : "generic", cudaGetErrorString(e));
+	if (march && d.sink == pb::SINK_V210 && d.out_w % 48 != 0) {
+		pb::FusedDesc tail = d;
+		tail.g_first = d.march_w / 6;
+		e = pb::launch_fused(s, tail, nullptr);
+		if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (line tails): %s", cudaGetErrorString(e));
+		c->stats.kernel_launches++;   // the caller counts the main launch
+	}
+	return PB_OK;
+}
+
 // launch a compiled descriptor (march kernel when eligible); *march_out reports the choice
 int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, bool *march_out) {
 	bool march = false;
@@ -1152,8 +1174,8 @@ int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, boo
 		if (r < 0) return r;
 		march = r == 1;
 	}
-	cudaError_t e = march ? pb::launch_fused_march(s, d, c->prop.multiProcessorCount) : pb::launch_fused(s, d, out_rgba);
-	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (%s): %s", march ? "march" : "generic", cudaGetErrorString(e));
+	int r = launch_compiled(c, s, d, march, out_rgba);
+	if (r) return r;
 	if (march_out) *march_out = march;
 	return PB_OK;
 }
@@ -2136,8 +2158,8 @@ int pb_chain_replay(pb_chain *ch, int queue) {
 	std::lock_guard<std::recursive_mutex> lk(c->mu);
 	CU(cudaSetDevice(c->dev));
 	for (const auto &it : ch->items) {
-		cudaError_t e = it.march ? pb::launch_fused_march(c->q[queue], it.d, c->prop.multiProcessorCount) : pb::launch_fused(c->q[queue], it.d, it.out_rgba);
-		if (e != cudaSuccess) return fail(PB_ERR_CUDA, "chain replay: %s", cudaGetErrorString(e));
+		int r = launch_compiled(c, c->q[queue], it.d, it.march, it.out_rgba);
+		if (r) return r;
 		c->stats.kernel_launches++;
 		c->stats.fused_launches++;
 		if (it.march) c->stats.march_launches++;

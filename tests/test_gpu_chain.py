@@ -241,6 +241,7 @@ MARCH_SCENES = {
                                            _xf(flipH=True, flipV=True, scaleX=0.75, scaleY=0.6, offsetY=-0.2)]),
     "odd_fractions": lambda: _with_xf(layered_scene(480, 270, 2, "noise", "plain", "709", "709"),
                                       [_xf(scaleX=1.0001, scaleY=0.9999, offsetX=0.00013), _xf(scaleX=0.731, scaleY=0.577, offsetX=0.21, offsetY=0.13)]),
+    "stray_top_bits": lambda: _ragged_scene(480, 48, [(480, 48, _xf()), (480, 48, pip(0.5, 0.3, 0.3))]),
     "mostly_outside": lambda: _with_xf(layered_scene(480, 270, 2, "noise", "plain", "709", "709"),
                                        [_xf(offsetX=0.97, offsetY=-0.96), _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.7)]),
 }
@@ -316,14 +317,94 @@ def test_gamma_tables_are_deduplicated_and_compressed():
 
 
 def test_march_kernel_declines_what_it_cannot_do():
-    """rotation, a deep downscale (footprint wider than a row buffer) and ragged widths fall back to the generic kernel"""
+    """rotation and a deep downscale (footprint wider than a row buffer) fall back to the generic kernel"""
     rot = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(rotate=0.01)])
     deep = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(scaleX=0.2, scaleY=0.2)])
-    ragged = layered_scene(1280, 36, 2, "ramp", "plain")
-    for scene in (rot, deep, ragged):
+    for scene in (rot, deep):
         out, st = run(_run_scene_variant(scene, "march"))
         assert st["march_launches"] == 0 and st["fused_launches"] == 1
         assert np.array_equal(out, SceneOracle(scene).packed())
+
+
+# ---- widths that are not whole v210 groups / 48-pixel blocks: 1280-wide 720p (213 groups + 2 pixels per line) ----
+def _random_v210(w, h, seed):
+    """any 32-bit words: 10-bit fields of all values, and stray bits 30-31 (the reference masks the fields: legal input)"""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 2 ** 32, v210_pitch(w) * h // 4, dtype=np.uint64).astype(np.uint32).view(np.uint8)
+
+
+def v210_pitch(w):
+    return (w + 47) // 48 * 128
+
+
+def _ragged_scene(w, h, specs, variant="plain"):
+    """specs: [(source width, source height, xf)]"""
+    layers = [dict(src=_random_v210(sw, sh, 70 + i), sw=sw, sh=sh, xf=xf, transition=None) for i, (sw, sh, xf) in enumerate(specs)]
+    if variant == "mix":
+        sw, sh, xf = specs[-1]
+        layers[-1]["transition"] = dict(type="dissolve", mix=0.5, src=_random_v210(sw, sh, 99), sw=sw, sh=sh, xf=xf)
+    return dict(width=w, height=h, colRead="709", colWork="2020", interlaced=False, layers=layers)
+
+
+RAGGED_SCENES = {
+    "720p_direct": lambda: _ragged_scene(1280, 40, [(1280, 40, None)]),
+    "720p_identity_transform": lambda: _ragged_scene(1280, 40, [(1280, 40, _xf())]),
+    "720p_four_layers_mix": lambda: _ragged_scene(1280, 72, [(1280, 72, _xf()), (1280, 72, pip(0.5, 0.05, 0.05)), (1280, 72, pip(0.5, 0.45, 0.1)),
+                                                             (1280, 72, pip(0.75, 0.3, 0.3))], "mix"),
+    "720p_source_into_1080p": lambda: _ragged_scene(1920, 54, [(1920, 54, _xf()), (1280, 36, _xf(scaleX=0.6, scaleY=0.6, offsetX=-0.3))]),
+    "1080p_source_into_720p": lambda: _ragged_scene(1280, 36, [(1280, 36, _xf()), (1920, 54, pip(0.8, 0.1, 0.1))]),
+    "2k_dci": lambda: _ragged_scene(2048, 24, [(2048, 24, _xf()), (2048, 24, pip(0.5, 0.5, 0.2))]),
+    "narrow_50": lambda: _ragged_scene(50, 20, [(50, 20, _xf())]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RAGGED_SCENES))
+def test_ragged_widths_take_the_march_kernel_plus_a_tail_launch(name):
+    """the march kernel writes the whole v210 groups, the generic kernel the tail columns of every line (partial group with the
+    reference's Q2 rounding, padding groups); sources read their partial last group with Q1 (v210.ts:90-110)"""
+    scene = RAGGED_SCENES[name]()
+    ref = SceneOracle(scene).packed()
+    slow, st0 = run(_run_scene_variant(scene, "generic"))
+    assert st0["march_launches"] == 0 and np.array_equal(slow, ref)
+    out, st = run(_run_scene_variant(scene, "march"))
+    ragged_out = scene["width"] % 48 != 0
+    assert st["march_launches"] == 1 and st["kernel_launches"] == (2 if ragged_out else 1) and st["materialised"] == 0, st
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+
+
+def test_ragged_width_interlaced_and_replay():
+    async def go():
+        scene = _ragged_scene(1280, 72, [(1280, 72, _xf()), (1280, 72, pip(0.5, 0.2, 0.2))])
+        scene["interlaced"] = True
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            dests = await h.fromRGBA.createDests("il")
+            dests[0].fill(0)
+            await dests[0].hostAccess("writeonly")
+            for il in (Interlace.TopField, Interlace.BottomField):
+                ups = await h.upload_all(int(il))
+                frame = await h.compose(ups, int(il))
+                await h.consume(frame, dests, il, download=(il == Interlace.BottomField))
+            so = SceneOracle(scene)
+            ref = np.zeros_like(dests[0].host)
+            so.packed(1, ref)
+            so.packed(3, ref)
+            assert np.array_equal(dests[0].host, ref)
+            # a recorded chain re-issues both launches
+            scene["interlaced"] = False
+            h2 = ChannelHarness(env.ctx, scene, env.pj)
+            await h2.init()
+            chain, d2 = await h2.record_chain()
+            assert chain.complete and chain.launches == 1
+            d2[0].fill(0)
+            await d2[0].hostAccess("writeonly")
+            await d2[0].hostAccess("none")
+            chain.replay()
+            await env.ctx.waitFinish(env.ctx.queue.process)
+            await d2[0].hostAccess("readonly")
+            assert np.array_equal(d2[0].host, SceneOracle(scene).packed())
+    run(go())
 
 
 def test_march_kernel_interlaced_fields():
