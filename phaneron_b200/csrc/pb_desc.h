@@ -168,6 +168,7 @@ struct FusedDesc {
 	uint32_t e_magic;  // 0x4B000000, handed to the kernel as data so that (w & mask) | e stays one LOP3
 	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
 	int any_planar;    // general load path: some leaf is planar 4:2:2 / 4:2:0, or a source width is not a multiple of 6, or the sink is not v210
+	int big_rows;      // row buffers of 64 source groups (a leaf is scaled down below ~0.47); implies any_planar
 	int march_w;       // output pixels the march kernel writes: out_w rounded down to whole v210 groups
 	int g_first;       // generic kernel, v210 sink: first output group column to write (the ragged tail after a march launch), else 0
 	LutDesc luts[kMaxLuts];   // slot 0 = rc[0]'s table

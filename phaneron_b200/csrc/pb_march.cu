@@ -274,7 +274,7 @@ __device__ __noinline__ void convert_group_exact(const Leaf &lf, const ReadConst
 }
 
 // value of one leaf at the 3 pixels of this lane -> p[r] = (r, g, b, alpha)
-template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine, bool kPlanar>
+template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine, bool kPlanar, bool kBigRows>
 __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, SPtr buf, int lane, int strip, int y,
                                           int x_first, int x_last, float4 (&p)[kRounds]) {
 	// (strips / lines where the whole layer is border colour never get here: FusedDesc::strip_ops & line_ops)
@@ -386,7 +386,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	}
 
 	// wide footprint (more than 16 groups per row): one pass per row, the canonical chain continues across them
-	constexpr int cap = kRowGroups * 6;
+	constexpr int cap = (kBigRows ? 2 : 1) * kRowGroups * 6;   // big rows: down-scales to ~0.24 (64 source groups per 90-px strip)
 	border();
 #pragma unroll 1
 	for (int rr = 0; rr < 2; ++rr) {
@@ -439,7 +439,8 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 // kPlain: every read table is a non-affine model and the write table an affine one (what colourMaths.ts produces:
 // gamma -> linear on the way in, linear -> gamma on the way out), so both selects are compile-time constants
 // kPlanar: some leaf is a planar 4:2:2 / 4:2:0 source (load_group gathers it into the v210 group layout)
-template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false, bool kPlanar = false>
+// kBigRows: the warps' row buffers hold 64 source groups instead of 32 (deep down-scales; needs <= 2 resident tables)
+template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false, bool kPlanar = false, bool kBigRows = false>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	const int lane = tid_x & 31, warp = tid_x >> 5;
 	SPtr buf;   // this warp's row buffer
 	{
-		const uint32_t addr = lut_saddr + (kLutMode ? (uint32_t)d.n_luts * 65536u : 0u) + (uint32_t)warp * (kRowFloats * 4u);
+		const uint32_t addr = lut_saddr + (kLutMode ? (uint32_t)d.n_luts * 65536u : 0u) + (uint32_t)warp * ((kBigRows ? 2u : 1u) * kRowFloats * 4u);
 		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));   // opaque: keep it in a register, do not re-derive it
 	}
 
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1), kPlanar>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
+			eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
 				const float rmix = sub(1.0f, op.mix);
@@ -680,7 +681,9 @@ cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *
 	return cudaGetLastError();
 }
 
-size_t march_smem_bytes(const FusedDesc &d) { return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kRowFloats * sizeof(float); }
+size_t march_smem_bytes(const FusedDesc &d) {
+	return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * (d.big_rows ? 2 : 1) * kRowFloats * sizeof(float);
+}
 
 cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) {
 	const size_t smem = march_smem_bytes(d);
@@ -708,6 +711,10 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 	if (d.n_luts > 0) {
 		bool plain = d.wlp.affine != 0;
 		for (int i = 0; i < d.n_rc; ++i) plain = plain && d.luts[d.rc[i].lut_slot].lp.affine == 0;
+		if (d.big_rows) {   // (prepare_march sets any_planar with it: the general variants carry the big-row form)
+			if (plain) return single ? launch(k_fused_march<1, true, true, true, true, true>) : launch(k_fused_march<1, true, false, true, true, true>);
+			return launch(k_fused_march<1, true, false, false, true, true>);
+		}
 		if (d.any_planar) {   // prepare_march admits planar leaves only with shared-memory tables and sparse matrices
 			if (plain) return single ? launch(k_fused_march<1, true, true, true, true>) : launch(k_fused_march<1, true, false, true, true>);
 			return launch(k_fused_march<1, true, false, false, true>);

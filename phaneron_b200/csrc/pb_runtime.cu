@@ -868,7 +868,8 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 			hi = std::min(hi, lf.w - 1);
 			e.y = lo / 6;
 			e.z = hi / 6 - e.y + 1;
-			if (e.z > pb::kRowGroups) t.fits = 0;
+			if (e.z > 2 * pb::kRowGroups) t.fits = 0;   // beyond even the big row buffers
+			else if (e.z > pb::kRowGroups && t.fits) t.fits = 2;   // needs the big row buffers
 		}
 		hstrip[sidx] = e;
 		if (e.x & 1) {
@@ -947,12 +948,14 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
 	if (d.n_strips > pb::kMaxStrips) return 0;
 	std::shared_ptr<const pb_ctx::SampleTab::Opq> opq[3 * pb::kMaxLayers];
+	bool big_rows = false;
 	for (int i = 0; i < n_leaves; ++i) {
 		pb_ctx::SampleTab *t;
 		int fits = 0;
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
 		if (r) return r;
 		if (!fits) return 0;
+		if (fits == 2) big_rows = true;
 		opq[i] = t->opq;
 		leaves[i]->col_tab = t->dcol;
 		leaves[i]->row_tab = t->drow;
@@ -1108,6 +1111,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.wc.lut_slot = slot_of(wt);
 	if (d.wc.lut_slot < 0) all_d8 = false;
 	d.n_luts = all_d8 ? n_slots : 0;
+	d.big_rows = big_rows;
+	if (big_rows) {   // 2 x 64 KiB of tables + 20 x 4.5 KiB of rows is what an SM holds
+		if (d.n_luts > 2) return 0;
+		any_planar = true;
+	}
 	d.any_planar = any_planar;
 	if (any_planar && !(d.n_luts > 0 && d.sparse_cm)) return 0;   // planar variants exist for the common configuration only
 	for (int i = 0; i < d.n_luts; ++i) {

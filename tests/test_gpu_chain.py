@@ -241,6 +241,10 @@ MARCH_SCENES = {
                                            _xf(flipH=True, flipV=True, scaleX=0.75, scaleY=0.6, offsetY=-0.2)]),
     "odd_fractions": lambda: _with_xf(layered_scene(480, 270, 2, "noise", "plain", "709", "709"),
                                       [_xf(scaleX=1.0001, scaleY=0.9999, offsetX=0.00013), _xf(scaleX=0.731, scaleY=0.577, offsetX=0.21, offsetY=0.13)]),
+    # deep down-scales (multiviewer tiles): up to 64 source groups per 90-px strip, the big row buffers
+    "multiview_thirds": lambda: _with_xf(layered_scene(960, 270, 4, "noise", "plain", "709", "2020"),
+                                         [_xf(), pip(1 / 3, 0.0, 0.0), pip(1 / 3, 1 / 3, 0.2), pip(0.3, 0.6, 0.5)]),
+    "quarter_tiles_mix": lambda: _with_xf(layered_scene(960, 270, 3, "noise", "mix", "709", "2020"), [_xf(), pip(0.25, 0.1, 0.1), pip(0.26, 0.5, 0.4)]),
     "stray_top_bits": lambda: _ragged_scene(480, 48, [(480, 48, _xf()), (480, 48, pip(0.5, 0.3, 0.3))]),
     "mostly_outside": lambda: _with_xf(layered_scene(480, 270, 2, "noise", "plain", "709", "709"),
                                        [_xf(offsetX=0.97, offsetY=-0.96), _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.7)]),
