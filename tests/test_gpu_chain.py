@@ -260,7 +260,9 @@ def test_march_kernel_matches_generic_and_oracle(name):
     assert np.array_equal(slow, ref)
     for mode in ("march", "march_raw"):
         fast, st = run(_run_scene_variant(scene, mode))
-        assert st["march_launches"] == 1 and st["kernel_launches"] == 1, (mode, st)
+        # (the big-row and general-load variants exist for the shared-memory tables only: raw-table mode falls back there)
+        want = 0 if (mode == "march_raw" and name in ("multiview_thirds", "quarter_tiles_mix")) else 1
+        assert st["march_launches"] == want and st["kernel_launches"] == 1, (mode, st)
         assert np.array_equal(fast, ref), f"{mode}: {int((fast != ref).sum())} bytes differ"
 
 
