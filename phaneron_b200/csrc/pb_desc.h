@@ -65,7 +65,7 @@ struct ReadConsts {
 	float gamut[9];
 	const float *lut;     // raw table in global memory (always valid)
 	int lut_slot;         // march kernel: index into FusedDesc::luts, -1 if the table has no compressed form
-	int pad_;
+	int t256_slot;        // march kernel, constants of rgba8 / bgra8 leaves: index of the 256-entry table (lut[c * 257]) in shared memory, else -1
 };
 
 // march kernel: ReadConsts::cm rearranged.  oY = -2^23 * mY folds the bias of the exponent-trick luma
@@ -168,6 +168,7 @@ struct FusedDesc {
 	uint32_t e_magic;  // 0x4B000000, handed to the kernel as data so that (w & mask) | e stays one LOP3
 	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
 	int any_planar;    // general load path: some leaf is planar 4:2:2 / 4:2:0, or a source width is not a multiple of 6, or the sink is not v210
+	int n_t256;        // 1 KiB tables of rgba8 / bgra8 leaves staged behind the row buffers (ReadConsts::t256_slot)
 	int big_rows;      // row buffers of 64 source groups (a leaf is scaled down below ~0.47); implies any_planar
 	int march_w;       // output pixels the march kernel writes: out_w rounded down to whole v210 groups
 	int g_first;       // generic kernel, v210 sink: first output group column to write (the ragged tail after a march launch), else 0

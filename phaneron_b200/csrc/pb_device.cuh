@@ -137,15 +137,17 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
 // ---- texels of the other packed formats (same arithmetic as the stand-alone read kernels in pb_kernels.cu) ----
 // rgba8.ts:40-62 / bgra8.ts: 8-bit codes -> LUT index code * 65535 / 255; alpha goes through the LUT too (rgba8.ts:61)
 __device__ __forceinline__ float4 rgba8_to_linear(uchar4 v, bool bgra, const ReadConsts &rc) {
-	const float c0 = u2f(bgra ? v.z : v.x), c1 = u2f(v.y), c2 = u2f(bgra ? v.x : v.z), c3 = u2f(v.w);
-	const float r = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c0, 65535.0f), 255.0f)));
-	const float g = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c1, 65535.0f), 255.0f)));
-	const float b = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c2, 65535.0f), 255.0f)));
+	// convert_ushort_sat_rte(c * 65535.0f / 255.0f) for a code c in 0..255: c * 65535 < 2^24 is exact, 65535 / 255 = 257, so
+	// the quotient is the integer c * 257 exactly and every rounding step is the identity: the index is c * 257
+	const uint32_t c0 = bgra ? v.z : v.x, c1 = v.y, c2 = bgra ? v.x : v.z, c3 = v.w;
+	const float r = __ldg(rc.lut + c0 * 257u);
+	const float g = __ldg(rc.lut + c1 * 257u);
+	const float b = __ldg(rc.lut + c2 * 257u);
 	float4 o;
 	o.x = dot3(r, g, b, rc.gamut + 0);
 	o.y = dot3(r, g, b, rc.gamut + 3);
 	o.z = dot3(r, g, b, rc.gamut + 6);
-	o.w = __ldg(rc.lut + sat_rte_u16(__fdiv_rn(mul(c3, 65535.0f), 255.0f)));
+	o.w = __ldg(rc.lut + c3 * 257u);   // alpha goes through the LUT too (rgba8.ts:61)
 	return o;
 }
 

@@ -436,6 +436,98 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	}
 }
 
+// ---- rgba8 / bgra8 leaves (graphics with alpha: FFmpegProducer 'rgba' / 'bgra' / any rgb format, rgba8.ts) ----------
+// Four planes (the alpha of these sources is data and is sampled like a colour channel), one pass per source row, every tap
+// validated.  Conversion is lane = texel (coalesced 128-byte loads, 3 texels per lane in flight): a texel costs four table
+// reads at 256 distinct indices and the 3x3 gamut matrix.
+template <bool kUnused = true>
+__device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &lf, SPtr buf, uint32_t t256_saddr, int lane, int strip, int y, int x_first,
+                                               int x_last, float4 (&p)[kRounds]) {
+	constexpr int cap = kRowGroups * 6;   // 4 planes x 192 texels x 4 B = 3 KiB: the big row buffers (kernel variants with kBigRows)
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+	const int4 si = __ldg(lf.strip_tab + strip);
+	const int2 rt = __ldg(lf.row_tab + y);
+	if (!(si.x & 1)) return;
+	const int g_lo = si.y, ng = si.z, origin = g_lo * 6, last = ng * 6 - 1;
+	const int j0 = rt.x;
+	const bool has_xf = lf.has_xf != 0;
+	const bool ok0 = (unsigned)j0 < (unsigned)lf.h, ok1 = has_xf && (unsigned)(j0 + 1) < (unsigned)lf.h;
+	if (!ok0 && !ok1) return;
+	int c0[kRounds];
+	float ca[kRounds];
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		const int x = min(x_first + r * 32 + lane, x_last);
+		if (has_xf) {
+			const int2 ct = __ldg(lf.col_tab + x);
+			c0[r] = ct.x;
+			ca[r] = __int_as_float(ct.y);
+		} else {
+			c0[r] = x;
+			ca[r] = 0.0f;
+		}
+	}
+	const float b = __int_as_float(rt.y), rb = sub(1.0f, b);
+	const ReadConsts &rc = d.rc[lf.rc];
+	const bool bgra = lf.kind == LEAF_BGRA8;
+	const SPtr tab{t256_saddr + (uint32_t)rc.t256_slot * 1024u};   // tab[c] = gammaLut[c * 257] (see rgba8_to_linear in pb_device.cuh)
+	const int ntex = min(ng * 6, lf.w - origin);   // texels of the footprint that exist
+#pragma unroll 1
+	for (int rr = 0; rr < 2; ++rr) {
+		if (!(rr ? ok1 : ok0)) continue;
+		const uchar4 *line = reinterpret_cast<const uchar4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;
+#pragma unroll 1
+		for (int base = 0; base < ntex; base += 96) {
+			uchar4 px[3];
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				const int t = base + k * 32 + lane;
+				px[k] = t < ntex ? __ldg(line + t) : make_uchar4(0, 0, 0, 0);
+			}
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				const int t = base + k * 32 + lane;
+				if (t < ntex) {
+					const float lr = tab[bgra ? px[k].z : px[k].x], lg = tab[px[k].y], lb = tab[bgra ? px[k].x : px[k].z];
+					float4 v;
+					v.x = dot3(lr, lg, lb, rc.gamut + 0);
+					v.y = dot3(lr, lg, lb, rc.gamut + 3);
+					v.z = dot3(lr, lg, lb, rc.gamut + 6);
+					v.w = tab[px[k].w];   // alpha goes through the LUT too (rgba8.ts:61)
+					const uint32_t a = buf.a + 4u * (uint32_t)t;
+					asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v.x) : "memory");
+					asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 4u * cap), "f"(v.y) : "memory");
+					asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 8u * cap), "f"(v.z) : "memory");
+					asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 12u * cap), "f"(v.w) : "memory");
+				}
+			}
+		}
+		__syncwarp();
+		if (!has_xf) {   // 1:1 read of texel (x, y): exact passthrough, alpha included
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const SPtr t = buf + (c0[r] - origin);
+				p[r] = make_float4(t[0], t[cap], t[2 * cap], t[3 * cap]);
+			}
+		} else {
+			const float wr = rr == 0 ? rb : b;
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const int i0 = c0[r];
+				const bool f0 = (unsigned)i0 < (unsigned)lf.w, f1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
+				const SPtr t0 = buf + min(max(i0 - origin, 0), last), t1 = buf + min(max(i0 - origin + 1, 0), last);
+				const float w0 = mul(sub(1.0f, ca[r]), wr), w1 = mul(ca[r], wr);
+				p[r].x = fma_(w1, f1 ? t1[0] : 0.0f, fma_(w0, f0 ? t0[0] : 0.0f, p[r].x));
+				p[r].y = fma_(w1, f1 ? t1[cap] : 0.0f, fma_(w0, f0 ? t0[cap] : 0.0f, p[r].y));
+				p[r].z = fma_(w1, f1 ? t1[2 * cap] : 0.0f, fma_(w0, f0 ? t0[2 * cap] : 0.0f, p[r].z));
+				p[r].w = fma_(w1, f1 ? t1[3 * cap] : 0.0f, fma_(w0, f0 ? t0[3 * cap] : 0.0f, p[r].w));
+			}
+		}
+		__syncwarp();
+	}
+}
+
 // kPlain: every read table is a non-affine model and the write table an affine one (what colourMaths.ts produces:
 // gamma -> linear on the way in, linear -> gamma on the way out), so both selects are compile-time constants
 // kPlanar: some leaf is a planar 4:2:2 / 4:2:0 source (load_group gathers it into the v210 group layout)
@@ -456,6 +548,18 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));   // opaque: keep it in a register, do not re-derive it
 	}
 
+	const uint32_t t256_saddr = buf.a - (uint32_t)warp * ((kBigRows ? 2u : 1u) * kRowFloats * 4u) + (uint32_t)kMarchWarps * ((kBigRows ? 2u : 1u) * kRowFloats * 4u);
+	if (kBigRows && d.n_t256) {   // 256-entry tables of the rgba8 / bgra8 leaves: gammaLut[c * 257], behind the row buffers
+		for (int i = 0; i < d.n_rc; ++i) {
+			const int slot = d.rc[i].t256_slot;
+			if (slot < 0) continue;
+			for (uint32_t cidx = tid_x; cidx < 256u; cidx += kMarchThreads) {
+				const float v = __ldg(d.rc[i].lut + cidx * 257u);
+				asm volatile("st.shared.f32 [%0], %1;" ::"r"(t256_saddr + (uint32_t)slot * 1024u + cidx * 4u), "f"(v) : "memory");
+			}
+		}
+		if (!kLutMode) __syncthreads();
+	}
 	if (kLutMode) {
 		// The byte tables arrive by TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by one thread and
 		// tracked by an mbarrier: 64 KiB per table without a register round trip or a per-thread loop.
@@ -526,7 +630,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
+			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
+			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
 				const float rmix = sub(1.0f, op.mix);
@@ -682,7 +787,7 @@ cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *
 }
 
 size_t march_smem_bytes(const FusedDesc &d) {
-	return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * (d.big_rows ? 2 : 1) * kRowFloats * sizeof(float);
+	return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * (d.big_rows ? 2 : 1) * kRowFloats * sizeof(float) + (size_t)d.n_t256 * 1024;
 }
 
 cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) {
@@ -710,7 +815,8 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 	const bool single = d.n_rc == 1;
 	if (d.n_luts > 0) {
 		bool plain = d.wlp.affine != 0;
-		for (int i = 0; i < d.n_rc; ++i) plain = plain && d.luts[d.rc[i].lut_slot].lp.affine == 0;
+		for (int i = 0; i < d.n_rc; ++i)
+			if (d.rc[i].lut_slot >= 0) plain = plain && d.luts[d.rc[i].lut_slot].lp.affine == 0;   // (< 0: constants of rgba8 leaves only)
 		if (d.big_rows) {   // (prepare_march sets any_planar with it: the general variants carry the big-row form)
 			if (plain) return single ? launch(k_fused_march<1, true, true, true, true, true>) : launch(k_fused_march<1, true, false, true, true, true>);
 			return launch(k_fused_march<1, true, false, false, true, true>);

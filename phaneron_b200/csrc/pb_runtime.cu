@@ -329,6 +329,7 @@ int make_read_consts(pb_ctx *c, const pb_param *p, int n, bool ycbcr, pb::ReadCo
 	if ((r = lut_table_of(c, lut, &table))) return r;
 	rc->lut = c->lut_tables[table].raw;   // one pointer per distinct table content
 	rc->lut_slot = -1;
+	rc->t256_slot = -1;
 	*lut_out = lut;
 	return PB_OK;
 }
@@ -914,7 +915,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (d.out_h < 1 || d.out_w < 6 || (d.out_w & 1)) return 0;
 	if (d.sink != pb::SINK_V210 && d.out_w % 48 != 0) return 0;
 	if (d.interlace != 0 && d.out_h < 2) return 0;
-	bool any_xf = false, any_planar = planar_sink;
+	bool any_xf = false, any_planar = planar_sink, any_rgba = false;
+	bool rc_ycc[pb::kMaxReadConsts] = {};   // read constants used by some YCbCr leaf (their tables go to shared memory)
 	pb::Leaf *leaves[3 * pb::kMaxLayers];
 	int n_leaves = 0;
 	for (int l = 0; l < d.n_layers; ++l) {
@@ -926,8 +928,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			// packed 4:2:2 / 4:2:0 YCbCr sources convert through the v210 group path; rgba8 / bgra8 (alpha) and RGBA-f32 leaves do not
 			const bool ycc = lf.kind == pb::LEAF_V210 || lf.kind == pb::LEAF_YUV422P10 || lf.kind == pb::LEAF_YUV422P8 ||
 			                 lf.kind == pb::LEAF_YUV420P || lf.kind == pb::LEAF_NV12;
-			if (!ycc || lf.w < 6 || lf.lz_tx) return 0;
+			const bool rgba = lf.kind == pb::LEAF_RGBA8 || lf.kind == pb::LEAF_BGRA8;   // graphics with alpha: pb_march.cu eval_leaf_rgba
+			if (!(ycc || rgba) || lf.w < 6 || lf.lz_tx) return 0;
 			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) any_planar = true;   // general load path (formats, partial last groups)
+			if (rgba) any_rgba = true;
+			else rc_ycc[lf.rc] = true;
 			if (lf.has_xf) {
 				for (float v : lf.m)
 					if (!(v == v) || v > 1e30f || v < -1e30f) return 0;
@@ -947,7 +952,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
 	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
 	if (d.n_strips > pb::kMaxStrips) return 0;
-	std::shared_ptr<const pb_ctx::SampleTab::Opq> opq[3 * pb::kMaxLayers];
+	std::shared_ptr<const pb_ctx::SampleTab::Opq> opq[3 * pb::kMaxLayers], tab_of[3 * pb::kMaxLayers];
 	bool big_rows = false;
 	for (int i = 0; i < n_leaves; ++i) {
 		pb_ctx::SampleTab *t;
@@ -955,8 +960,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
 		if (r) return r;
 		if (!fits) return 0;
-		if (fits == 2) big_rows = true;
-		opq[i] = t->opq;
+		const bool leaf_rgba = leaves[i]->kind == pb::LEAF_RGBA8 || leaves[i]->kind == pb::LEAF_BGRA8;
+		if (leaf_rgba && fits != 1) return 0;   // four planes: 32 source groups per row at most
+		if (fits == 2 || leaf_rgba) big_rows = true;
+		opq[i] = leaf_rgba ? nullptr : t->opq;   // the alpha of an rgba8 leaf is data: never certifiably opaque
+		tab_of[i] = t->opq;
 		leaves[i]->col_tab = t->dcol;
 		leaves[i]->row_tab = t->drow;
 		leaves[i]->strip_tab = t->dstrip;
@@ -1000,7 +1008,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			} else if (cull && ly.kind == pb::LAYER_DISSOLVE) {
 				// transition.ts:60-65 on two alphas of 1: fma(1, mix, 1 * (1 - mix)) = RN(mix + RN(1 - mix))
 				const float rmix = 1.0f - ly.mix;
-				if (ly.mix + rmix == 1.0f) { lopq[l][0] = opq[li].get(); lopq[l][1] = opq[li + 1].get(); }
+				if (ly.mix + rmix == 1.0f && opq[li] && opq[li + 1]) { lopq[l][0] = opq[li].get(); lopq[l][1] = opq[li + 1].get(); }
 			}   // wipe: alpha depends on the mask picture
 			li += nleaf;
 		}
@@ -1094,8 +1102,16 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		slots[n_slots] = table;
 		return n_slots++;
 	};
+	int n_t256 = 0;
 	for (int i = 0; i < d.n_rc; ++i) {   // rc[0]'s table takes slot 0
 		if (d.rc[i].cm[1] != 0.0f || d.rc[i].cm[10] != 0.0f) d.sparse_cm = 0;
+		d.rc[i].t256_slot = -1;
+		if (!rc_ycc[i]) {   // constants of rgba8 / bgra8 leaves only: 256 distinct table entries, staged as a 1 KiB table
+			d.rc[i].lut_slot = -1;
+			if (n_t256 >= 4) return 0;
+			d.rc[i].t256_slot = n_t256++;
+			continue;
+		}
 		d.rc[i].lut_slot = slot_of(lut_table_by_raw(c, d.rc[i].lut));
 		if (d.rc[i].lut_slot < 0) all_d8 = false;
 		for (int ch = 0; ch < 3; ++ch) {
@@ -1111,11 +1127,13 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.wc.lut_slot = slot_of(wt);
 	if (d.wc.lut_slot < 0) all_d8 = false;
 	d.n_luts = all_d8 ? n_slots : 0;
+	d.n_t256 = n_t256;
 	d.big_rows = big_rows;
 	if (big_rows) {   // 2 x 64 KiB of tables + 20 x 4.5 KiB of rows is what an SM holds
 		if (d.n_luts > 2) return 0;
 		any_planar = true;
 	}
+	if (any_rgba && d.n_luts == 0) return 0;   // rgba8 leaves ride on the big-row variants, which exist for shared-memory tables
 	d.any_planar = any_planar;
 	if (any_planar && !(d.n_luts > 0 && d.sparse_cm)) return 0;   // planar variants exist for the common configuration only
 	for (int i = 0; i < d.n_luts; ++i) {
@@ -1135,7 +1153,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			int li = 0;   // index of the op's leaf in leaves[] / opq[]
 			for (int l = 0; l < d.ops[oi].layer; ++l) li += layer_n_ops[l];
 			li += d.ops[oi].which;
-			const auto &o = *opq[li];
+			const auto &o = *tab_of[li];
 			for (int sidx = 0; sidx < d.n_strips; ++sidx) {
 				if (!o.strip_ng[sidx]) continue;
 				seen.assign((size_t)o.src_h, 0);

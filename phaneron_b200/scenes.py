@@ -129,3 +129,21 @@ def planar_layered_scene(width: int, height: int, fmt: str = "yuv422p10", n_laye
         xf = dict(IDENTITY_XF) if i == 0 else pip(0.5, *offsets[(i - 1) % len(offsets)])
         layers.append(dict(src=planar_frame(fmt, width, height, 2000 + frame_set * 16 + i), sw=width, sh=height, xf=xf, transition=None, fmt=fmt))
     return dict(width=width, height=height, colRead=colRead, colWork=colWork, interlaced=False, layers=layers)
+
+
+def overlay_scene(width: int, height: int, inputs: str = "noise", colRead: str = "709", colWork: str = "2020", frame_set: int = 0) -> Dict[str, Any]:
+    """video + graphics: L1 full-frame v210, L2-L3 0.5x v210 PiPs, L4 a full-frame rgba8 graphic whose alpha is a soft-edged
+    lower third (opaque band, 32-line ramps, transparent elsewhere) -- the CG-over-video picture of a broadcast channel"""
+    sc = layered_scene(width, height, 3, inputs, "plain", colRead, colWork, frame_set)
+    rng = np.random.default_rng(3000 + frame_set)
+    g = rng.integers(0, 256, (height, width, 4), dtype=np.uint8)
+    alpha = np.zeros(height, np.float32)
+    top, bot = int(height * 0.72), int(height * 0.9)
+    alpha[top:bot] = 1.0
+    ramp = min(32, top, height - bot)
+    if ramp > 0:
+        alpha[top - ramp:top] = np.linspace(0, 1, ramp, endpoint=False)
+        alpha[bot:bot + ramp] = np.linspace(1, 0, ramp, endpoint=False)
+    g[..., 3] = np.rint(alpha * 255).astype(np.uint8)[:, None]
+    sc["layers"].append(dict(src=g.reshape(-1), sw=width, sh=height, xf=dict(IDENTITY_XF), transition=None, fmt="rgba8", colRead="sRGB"))
+    return sc

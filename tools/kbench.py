@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from phaneron_b200 import clContext
 from phaneron_b200.harness import ChannelHarness
-from phaneron_b200.scenes import layered_scene, planar_layered_scene, single_layer_scene
+from phaneron_b200.scenes import layered_scene, overlay_scene, planar_layered_scene, single_layer_scene
 
 L2 = 126 << 20
 
@@ -33,6 +33,8 @@ def make_scene(kind, w, h, inputs, fs):
         return single_layer_scene(w, h, inputs, False, "709", "709", frame_set=fs)
     if kind == "single_xf":
         return single_layer_scene(w, h, inputs, True, "709", "709", frame_set=fs)
+    if kind == "overlay":   # 3 video layers + a full-frame rgba8 graphic with alpha
+        return overlay_scene(w, h, inputs, "709", "2020", frame_set=fs)
     if kind.startswith("planar4:"):   # e.g. planar4:yuv422p10 -- 4 layers of an FFmpegProducer format
         return planar_layered_scene(w, h, kind.split(":")[1], 4, "709", "2020", frame_set=fs)
     raise SystemExit(f"unknown scene {kind}")
