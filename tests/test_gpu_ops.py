@@ -343,3 +343,35 @@ def test_errors_are_loud():
             with pytest.raises(PhaneronError, match="missing buffer parameter"):
                 await env.ctx.runProgram(prog, {"input": small})
     run(go())
+
+
+@pytest.mark.parametrize("deferred", [False, True])
+@pytest.mark.parametrize("wipe,overlays", [(False, 1), (True, 2), (False, 0)])
+def test_switch(wipe, overlays, deferred):
+    """src/process/switch.ts (dead in the reference): Transform x2 -> Mix | Wipe -> Combine with overlays"""
+    from phaneron_b200.process.switch import Switch
+    from scene_oracle import xf_matrix
+
+    async def go():
+        async with Env(deferred) as env:
+            w, h = 192, 108
+            a, b = rand_rgba(h, w, 31), rand_rgba(h, w, 32)
+            ovs = [rand_rgba(h, w, 40 + i) for i in range(overlays)]
+            xfa = dict(anchorX=-0.5, anchorY=-0.5, scaleX=0.9, scaleY=0.9, offsetX=-0.05)
+            xfb = dict(anchorX=-0.5, anchorY=-0.5, scaleX=1.2, scaleY=1.1, rotate=0.03)
+            sw = Switch(env.ctx, "ch1", env.jobs, w, h, 2, overlays)
+            await sw.init()
+            ia, ib = await env.image(a), await env.image(b)
+            ia.timestamp = ib.timestamp = 7
+            ovb = [await env.image(o) for o in ovs]
+            for bf in (sw.rgbaXf0, sw.rgbaXf1, sw.rgbaMx, *ovb):
+                bf.addRef()   # the switcher's callbacks release what they consumed (switch.ts:147,158-175,186-188)
+            out = await env.out_image(w, h)
+            await sw.processFrame([dict(input=ia, **xfa), dict(input=ib, **xfb)], {"wipe": wipe, "frac": 0.4}, ovb, out)
+            await env.jobs.runQueue({"source": "ch1 switch", "timestamp": 7})
+            got = await env.fetch(out, w, h)
+            ta, tb = oracle.transform(a, xf_matrix(w, h, xfa), w, h), oracle.transform(b, xf_matrix(w, h, xfb), w, h)
+            mixed = oracle.wipe(ta, tb, 0.4) if wipe else oracle.mix(ta, tb, 0.4)
+            ref = oracle.combine([mixed, *ovs]) if ovs else mixed
+            assert_bits_equal(got, ref, f"switch wipe={wipe} overlays={overlays}")
+    run(go())
