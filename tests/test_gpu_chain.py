@@ -622,3 +622,18 @@ def test_march_kernel_planar_sink_two_fields(out_fmt):
             for d, r in zip(dests, ref):
                 assert np.array_equal(d.host, r)
     run(go())
+
+
+def test_planar_sources_with_padded_pitch_and_other_sizes():
+    """planar sources whose line pitch (width rounded up to 8 samples) differs from their width, smaller than the channel:
+    714 x 270 (pitch 720) and 1278 x 540 (pitch 1280) into a 960 x 540 channel, through the march kernel"""
+    layers = [dict(src=make_frame("noise", 960, 540, 3), sw=960, sh=540, xf=_xf(), transition=None)]
+    for i, (fmt, sw, sh, xf) in enumerate([("yuv422p10", 714, 270, _xf(scaleX=0.7, scaleY=0.7, offsetX=-0.1)),
+                                           ("yuv420p", 1278, 540, pip(0.6, 0.3, 0.1)), ("nv12", 714, 270, _xf(scaleX=0.9, scaleY=0.8, offsetX=0.2, offsetY=0.1)),
+                                           ("yuv422p8", 1278, 540, pip(0.55, 0.05, 0.4))]):
+        layers.append(dict(src=_rand_source(fmt, sw, sh, 80 + i), sw=sw, sh=sh, xf=xf, transition=None, fmt=fmt, colRead="709"))
+    scene = dict(width=960, height=540, colRead="709", colWork="2020", interlaced=False, layers=layers)
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert st["march_launches"] == 1 and st["kernel_launches"] == 1 and st["materialised"] == 0, st
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
