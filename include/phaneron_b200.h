@@ -117,6 +117,8 @@ const char *pb_version(void);
 /* bit4 = account, per march launch, the distinct packed source bytes the launch reads (pb_stats.march_src_bytes);
    costs a host pass over the op masks, so it is off by default (bench.py uses it for the roofline figure) */
 #define PB_CTX_FOOTPRINT 16u
+/* bit5 = do not use the dedicated 1:1 v210 -> v210 kernel (k_march_direct); A/B tests against the general march kernel */
+#define PB_CTX_NO_DIRECT 32u
 int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out);
 int pb_ctx_destroy(pb_ctx *ctx);
 /* getPlatformInfo() (index.ts:103-107): JSON text into buf */

@@ -21,6 +21,7 @@ CTX_NO_MARCH = 2
 CTX_RAW_LUT = 4
 CTX_NO_CULL = 8
 CTX_FOOTPRINT = 16
+CTX_NO_DIRECT = 32
 
 OPS = {
     "v210_read": 1, "v210_write": 2, "rgba8_read": 3, "rgba8_write": 4, "bgra8_read": 5, "bgra8_write": 6,

@@ -779,6 +779,128 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	}
 }
 
+
+// ---- k_march_direct: one v210 source read 1:1 into a v210 output (ToRGBA -> FromRGBA, BASELINE.json config 2) ----------
+// The general kernel converts a 96-px strip with lanes 0-15 only when the leaf is read 1:1 (one source row of 16 groups per
+// output line).  Here a work item is one line of a 192-px strip: every lane converts one v210 group (same convert_group, same
+// tables), then encodes its 3 + 3 pixels in two halves through the same staging words.  Same arithmetic, bit for bit.
+__global__ void __launch_bounds__(kMarchThreads, 1) k_march_direct(const __grid_constant__ FusedDesc d) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+	uint32_t tid_x;
+	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
+	const int lane = tid_x & 31, warp = tid_x >> 5;
+	SPtr buf;
+	{
+		const uint32_t addr = lut_saddr + (uint32_t)d.n_luts * 65536u + (uint32_t)warp * (kRowFloats * 4u);
+		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));
+	}
+	{
+		__shared__ __align__(8) unsigned long long lut_bar;
+		const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&lut_bar);
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(d.n_luts * 65536) : "memory");
+			for (int t = 0; t < d.n_luts; ++t)
+				for (int c = 0; c < 4; ++c)
+					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+					                 lut_saddr + t * 65536 + c * 16384),
+					             "l"(d.luts[t].d8 + c * 16384), "r"(16384), "r"(bar)
+					             : "memory");
+		}
+		uint32_t done = 0;
+		while (!done)
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+	}
+	const Leaf &lf = d.layers[0].a;
+	const ReadConsts &rc = d.rc[0];
+	const ReadK &rk = d.rk[0];
+	const LutParams &lp = d.luts[rc.lut_slot].lp;
+	LutK<1> lut, wlut;
+	lut.raw = rc.lut;
+	lut.magic = kTwo23 + (float)(lut_saddr + rc.lut_slot * 65536);
+	wlut.raw = d.wc.lut;
+	wlut.magic = kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536);
+	const LutParams &wlp = d.wlp;
+	const uint32_t E = d.e_magic;
+	constexpr int cap = kRowGroups * 6;   // 192 texels per plane
+
+	const int step = d.interlace == 0 ? 1 : 2, first_line = d.interlace == 3 ? 1 : 0;
+	const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
+	const int groups = d.out_w / 6, n_strips = (groups + 31) / 32;
+	const int total = n_lines * n_strips;
+	const int stride = gridDim.x * kMarchWarps;
+#pragma unroll 1
+	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride) {
+		const int k = item / n_strips, strip = item - k * n_strips;
+		const int y = first_line + k * step;
+		const int G = strip * 32 + lane;
+		if (G < groups) {
+			const uint4 w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)y * lf.pitch) + G);
+			convert_group<1, true, 0>(w, lane, E, rc, rk, lut, lp, buf, cap);
+		}
+		__syncwarp();
+#pragma unroll 1
+		for (int h = 0; h < 2; ++h) {
+			// 1:1 read of texel (x, y): exact passthrough; over an empty frame fma(0, 0, p) == p.  The staging words below reuse
+			// texels 0..95 of the first plane: each lane overwrites only what it has just read, and half 1 lives at 96..191.
+			float3 a[kRounds];
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const SPtr t = buf + (h * 96 + r * 32 + lane);
+				a[r] = make_float3(t[0], t[cap], t[2 * cap]);
+			}
+			const SPtr stage = buf;
+#pragma unroll
+			for (int r = 0; r + 1 < kRounds; r += 2) {
+				const float2 gr = lut2<1, 1>(f2(__saturatef(a[r].x), __saturatef(a[r + 1].x)), wlut, wlp);
+				const float2 gg = lut2<1, 1>(f2(__saturatef(a[r].y), __saturatef(a[r + 1].y)), wlut, wlp);
+				const float2 gb = lut2<1, 1>(f2(__saturatef(a[r].z), __saturatef(a[r + 1].z)), wlut, wlp);
+				uint32_t code0 = 0, code1 = 0;
+#pragma unroll
+				for (int c = 0; c < 3; ++c) {
+					float2 v = __ffma2_rn(gb, f2s(d.wc.cm[c * 4 + 2]), __ffma2_rn(gr, f2s(d.wc.cm[c * 4 + 0]), __fmul2_rn(gg, f2s(d.wc.cm[c * 4 + 1]))));
+					v = __fadd2_rn(v, f2s(d.wc.cm[c * 4 + 3]));
+					v = __fadd2_rn(v, f2s(kTwo23));
+					code0 |= (__float_as_uint(v.x) & 0x3ffu) << (10 * c);
+					code1 |= (__float_as_uint(v.y) & 0x3ffu) << (10 * c);
+				}
+				stage.stu(r * 32 + lane, code0);
+				stage.stu((r + 1) * 32 + lane, code1);
+			}
+			if (kRounds & 1) {
+				constexpr int r = kRounds - 1;
+				const float2 hrg = lut2<1, 1>(f2(__saturatef(a[r].x), __saturatef(a[r].y)), wlut, wlp);
+				const float2 hb = lut2<1, 1>(f2s(__saturatef(a[r].z)), wlut, wlp);
+				uint32_t code = 0;
+#pragma unroll
+				for (int c = 0; c < 3; ++c) {
+					const float u = add(add(fma_(hb.x, d.wc.cm[c * 4 + 2], fma_(hrg.x, d.wc.cm[c * 4 + 0], mul(hrg.y, d.wc.cm[c * 4 + 1]))), d.wc.cm[c * 4 + 3]), kTwo23);
+					code |= (__float_as_uint(u) & 0x3ffu) << (10 * c);
+				}
+				stage.stu(r * 32 + lane, code);
+			}
+			__syncwarp();
+			const int Gh = strip * 32 + h * 16 + lane;   // lanes 0-15 regroup and store this half's 16 groups
+			if (lane < 16 && Gh < groups) {
+				const SPtr sp = stage + lane * 6;
+				const uint32_t p0 = sp.ldu(0), p1 = sp.ldu(1), p2 = sp.ldu(2), p3 = sp.ldu(3), p4 = sp.ldu(4), p5 = sp.ldu(5);
+				uint4 w;   // v210.ts:158-163: chroma from even pixels only
+				w.x = (p0 & 0x3ff00000u) | (p0 & 0x3ffu) << 10 | ((p0 >> 10) & 0x3ffu);
+				w.y = (p2 & 0x3ffu) << 20 | (p2 & 0xffc00u) | (p1 & 0x3ffu);
+				w.z = ((p4 >> 10) & 0x3ffu) << 20 | (p3 & 0x3ffu) << 10 | (p2 >> 20);
+				w.w = (p5 & 0x3ffu) << 20 | ((p4 >> 20) << 10) | (p4 & 0x3ffu);
+				st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d.out) + (size_t)y * d.out_pitch) + Gh, w);
+			}
+			__syncwarp();
+		}
+	}
+}
+
 }  // namespace
 
 cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *cands_dev, int n_cands, uint8_t *d8_out, void *results_dev) {
@@ -812,6 +934,25 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		kernel<<<grid, kMarchThreads, smem, s>>>(d);
 		return cudaGetLastError();
 	};
+	if (d.direct_mode) {   // one v210 source 1:1 into a v210 output (prepare_march checks the conditions)
+		static std::mutex mu;
+		static std::set<int> configured;
+		int dev = 0;
+		cudaGetDevice(&dev);
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			if (!configured.count(dev)) {
+				cudaError_t e = cudaFuncSetAttribute(k_march_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+				if (e != cudaSuccess) return e;
+				configured.insert(dev);
+			}
+		}
+		const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
+		const int total = n_lines * ((d.out_w / 6 + 31) / 32);
+		const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
+		k_march_direct<<<grid, kMarchThreads, smem, s>>>(d);
+		return cudaGetLastError();
+	}
 	const bool single = d.n_rc == 1;
 	if (d.n_luts > 0) {
 		bool plain = d.wlp.affine != 0;

@@ -1129,6 +1129,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.n_luts = all_d8 ? n_slots : 0;
 	d.n_t256 = n_t256;
 	d.big_rows = big_rows;
+	// ToRGBA -> FromRGBA of one v210 source with colourMaths-style tables: the dedicated direct kernel
+	d.direct_mode = d.n_ops == 1 && d.layers[0].kind == pb::LAYER_DIRECT && !d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
+	                d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && all_d8 && n_slots <= 2 && d.sparse_cm && !any_planar && !big_rows &&
+	                d.rc[0].lut_slot >= 0 && c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine == 0 &&
+	                d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine != 0 && !(c->flags & PB_CTX_NO_DIRECT);
 	if (big_rows) {   // 2 x 64 KiB of tables + 20 x 4.5 KiB of rows is what an SM holds
 		if (d.n_luts > 2) return 0;
 		any_planar = true;

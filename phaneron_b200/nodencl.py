@@ -184,6 +184,7 @@ class clContext:
         self.rawLut = bool(options.get("rawLut", False))            # True: march kernel gathers from the raw gamma tables
         self.occlusionCulling = bool(options.get("occlusionCulling", True))   # False: evaluate layers hidden under opaque ones too
         self.footprint = bool(options.get("footprint", False))      # True: stats()['march_src_bytes'] per march launch
+        self.directKernel = bool(options.get("directKernel", True))  # False: 1:1 v210 -> v210 frames take the general march kernel (A/B)
         self.queue = _Queues()
         self._h = 0
 
@@ -197,7 +198,7 @@ class clContext:
     def _flags(self) -> int:
         return ((_lib.CTX_DEFER if self.deferred else 0) | (0 if self.marchKernel else _lib.CTX_NO_MARCH)
                 | (_lib.CTX_RAW_LUT if self.rawLut else 0) | (0 if self.occlusionCulling else _lib.CTX_NO_CULL)
-                | (_lib.CTX_FOOTPRINT if self.footprint else 0))
+                | (_lib.CTX_FOOTPRINT if self.footprint else 0) | (0 if self.directKernel else _lib.CTX_NO_DIRECT))
 
     def close(self) -> None:
         if self._h:

@@ -637,3 +637,47 @@ def test_planar_sources_with_padded_pitch_and_other_sizes():
     out, st = run(_run_scene_variant(scene, "march"))
     assert st["march_launches"] == 1 and st["kernel_launches"] == 1 and st["materialised"] == 0, st
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+
+
+# ---- k_march_direct: one v210 source 1:1 into a v210 output (BASELINE.json config 2) ----
+@pytest.mark.parametrize("w,h,inputs,cols", [(1920, 1080, "noise", ("709", "709")), (1920, 270, "ramp", ("709", "2020")), (384, 100, "noise", ("709", "709")),
+                                             (48, 37, "noise", ("2020", "709")), (3840, 64, "noise", ("709", "2020")), (240, 11, "noise", ("601_525", "709"))])
+def test_direct_kernel_matches_the_general_kernel_and_oracle(w, h, inputs, cols):
+    scene = single_layer_scene(w, h, inputs, False, cols[0], cols[1])
+    ref = SceneOracle(scene).packed()
+
+    async def go(direct):
+        async with Env(True) as env:
+            env.ctx.directKernel = direct
+            env.ctx.setOcclusionCulling(True)   # pushes the flags
+            hh = ChannelHarness(env.ctx, scene, env.pj)
+            await hh.init()
+            out = await hh.run_frame()
+            return out, env.ctx.stats()
+    fast, st = run(go(True))
+    slow, st2 = run(go(False))
+    assert st["march_launches"] == 1 and st2["march_launches"] == 1 and st["kernel_launches"] == 1
+    assert np.array_equal(slow, ref)
+    assert np.array_equal(fast, ref), f"{int((fast != ref).sum())} bytes differ"
+
+
+def test_direct_kernel_two_fields():
+    async def go():
+        scene = single_layer_scene(480, 54, "noise", False, "709", "2020")
+        scene["interlaced"] = True
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            dests = await h.fromRGBA.createDests("il")
+            dests[0].fill(0)
+            await dests[0].hostAccess("writeonly")
+            for il in (Interlace.TopField, Interlace.BottomField):
+                ups = await h.upload_all(int(il))
+                frame = await h.compose(ups, int(il))
+                await h.consume(frame, dests, il, download=(il == Interlace.BottomField))
+            so = SceneOracle(scene)
+            ref = np.zeros_like(dests[0].host)
+            so.packed(1, ref)
+            so.packed(3, ref)
+            assert np.array_equal(dests[0].host, ref)
+    run(go())
