@@ -784,7 +784,11 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 // The general kernel converts a 96-px strip with lanes 0-15 only when the leaf is read 1:1 (one source row of 16 groups per
 // output line).  Here a work item is one line of a 192-px strip: every lane converts one v210 group (same convert_group, same
 // tables), then encodes its 3 + 3 pixels in two halves through the same staging words.  Same arithmetic, bit for bit.
-__global__ void __launch_bounds__(kMarchThreads, 1) k_march_direct(const __grid_constant__ FusedDesc d) {
+#ifndef PB_DIRECT_WARPS
+#define PB_DIRECT_WARPS 28
+#endif
+constexpr int kDirectWarps = PB_DIRECT_WARPS;   // 69 registers per thread: more resident warps than the general kernel's 20
+__global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
 	uint32_t tid_x;
@@ -833,9 +837,9 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_direct(const __grid_
 	const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
 	const int groups = d.out_w / 6, n_strips = (groups + 31) / 32;
 	const int total = n_lines * n_strips;
-	const int stride = gridDim.x * kMarchWarps;
+	const int stride = gridDim.x * kDirectWarps;
 #pragma unroll 1
-	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride) {
+	for (int item = blockIdx.x * kDirectWarps + warp; item < total; item += stride) {
 		const int k = item / n_strips, strip = item - k * n_strips;
 		const int y = first_line + k * step;
 		const int G = strip * 32 + lane;
@@ -949,8 +953,9 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		}
 		const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
 		const int total = n_lines * ((d.out_w / 6 + 31) / 32);
-		const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
-		k_march_direct<<<grid, kMarchThreads, smem, s>>>(d);
+		const int grid = max(1, min(num_sms, (total + kDirectWarps - 1) / kDirectWarps));
+		const size_t smem_direct = (size_t)d.n_luts * 65536 + (size_t)kDirectWarps * kRowFloats * sizeof(float);
+		k_march_direct<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
 		return cudaGetLastError();
 	}
 	const bool single = d.n_rc == 1;
