@@ -138,6 +138,7 @@ struct pb_ctx {
 			int id;
 			std::vector<uint8_t> strip_full, row_full;
 			std::vector<int> row_j0, strip_ng;   // first source row each output line reads, source groups per strip (footprint accounting)
+			std::vector<int> col_i0;             // first source column each output column reads (k_march_single strip footprints)
 			int rows_per_line = 1, src_h = 0;
 		};
 		std::shared_ptr<const Opq> opq;
@@ -772,6 +773,8 @@ std::shared_ptr<const pb_ctx::SampleTab::Opq> leaf_opacity(int id, const pb::Lea
 	o->row_full.assign(H, 0);
 	o->row_j0.resize(H);
 	for (int y = 0; y < H; ++y) o->row_j0[y] = hrow[y].x;
+	o->col_i0.resize(W);
+	for (int x = 0; x < W; ++x) o->col_i0[x] = hcol[x].x;
 	if (!lf.has_xf) {   // 1:1 read: alpha = 1 everywhere (the leaf has the output's dimensions)
 		o->strip_full.assign(n_strips, 1);
 		o->row_full.assign(H, 1);
@@ -1129,6 +1132,52 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.n_luts = all_d8 ? n_slots : 0;
 	d.n_t256 = n_t256;
 	d.big_rows = big_rows;
+	// One v210 layer through an axis-aligned Transform (a channel playing one clip through its Mixer): k_march_single walks down
+	// blocks of lines of 186-px strips and converts every source row once.  Needs <= 32 source groups per strip row (horizontal
+	// scale >= ~1) and is worth it when consecutive lines share a source row (vertical step <= 1).
+	d.single_lines = 0;
+	if (d.n_ops == 1 && d.layers[0].kind == pb::LAYER_DIRECT && d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
+	    d.layers[0].a.w % 6 == 0 && d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && d.interlace == 0 && all_d8 && n_slots <= 2 && d.sparse_cm &&
+	    !any_planar && !big_rows && d.rc[0].lut_slot >= 0 && c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine == 0 && d.wc.lut_slot >= 0 &&
+	    c->lut_tables[slots[d.wc.lut_slot]].lp.affine != 0 && !(c->flags & PB_CTX_NO_DIRECT) && tab_of[0] && !tab_of[0]->col_i0.empty()) {
+		const auto &tb = *tab_of[0];
+		const pb::Leaf &lf = d.layers[0].a;
+		constexpr int kSG = 31;   // pb_march.cu kSingleStripGroups
+		const int groups = d.out_w / 6, n_strips = (groups + kSG - 1) / kSG;
+		bool ok = n_strips <= 64;
+		for (int y = 0; y + 1 < d.out_h && ok; ++y) ok = std::abs(tb.row_j0[y + 1] - tb.row_j0[y]) <= 1;
+		for (int sidx = 0; sidx < n_strips && ok; ++sidx) {
+			const int x0 = sidx * kSG * 6, x1 = std::min(x0 + kSG * 6, d.out_w) - 1;
+			int lo = INT32_MAX, hi = INT32_MIN;
+			for (int x = x0; x <= x1; ++x) {
+				lo = std::min(lo, tb.col_i0[x]);
+				hi = std::max(hi, tb.col_i0[x] + 1);
+			}
+			int2 e = make_int2(0, 0);
+			if (!(hi < 0 || lo >= lf.w)) {
+				const bool interior = lo >= 0 && hi < lf.w;   // (before the clamp below) no tap column outside the image
+				lo = std::max(lo, 0);
+				hi = std::min(hi, lf.w - 1);
+				e.x = lo / 6;
+				e.y = hi / 6 - e.x + 1;
+				ok = e.y <= 32;
+				if (interior) e.y |= 0x100;
+			}
+			d.single_strips[sidx] = e;
+		}
+		if (ok) {
+			// Lines per work item: taller blocks reuse more rows (a block of L lines costs L + 1 conversion passes) but leave fewer
+			// items to spread over the grid's warps.  Pick the L that minimises the longest warp's work: rounds x (L lines of
+			// sampling + encoding (~1060 issue slots per 186-px line) + L + 1 ... conversion passes (~360 each)).
+			const long long warps = (long long)c->prop.multiProcessorCount * pb::kMarchWarps;
+			long long best = -1;
+			for (int L = 1; L <= 16; ++L) {
+				const long long items = (long long)n_strips * ((d.out_h + L - 1) / L), rounds = (items + warps - 1) / warps;
+				const long long cost = rounds * (L * 1060LL + 360LL);
+				if (best < 0 || cost < best) { best = cost; d.single_lines = L; }
+			}
+		}
+	}
 	// ToRGBA -> FromRGBA of one v210 source with colourMaths-style tables: the dedicated direct kernel
 	d.direct_mode = d.n_ops == 1 && d.layers[0].kind == pb::LAYER_DIRECT && !d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
 	                d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && all_d8 && n_slots <= 2 && d.sparse_cm && !any_planar && !big_rows &&

@@ -681,3 +681,38 @@ def test_direct_kernel_two_fields():
             so.packed(3, ref)
             assert np.array_equal(dests[0].host, ref)
     run(go())
+
+
+# ---- k_march_single: one v210 layer through an axis-aligned Transform (a channel playing one clip through its Mixer) ----
+SINGLE_XFS = {
+    "identity_1080p": (1920, 1080, _xf()),
+    "identity_small": (480, 135, _xf()),
+    "shifted": (960, 270, _xf(offsetX=0.1, offsetY=-0.07)),
+    "upscaled_flipped": (960, 270, _xf(scaleX=1.6, scaleY=2.2, flipH=True, flipV=True, offsetX=0.05)),
+    "slightly_upscaled": (960, 540, _xf(scaleX=1.0003, scaleY=1.0007)),
+    "mostly_outside": (960, 270, _xf(offsetX=0.9, offsetY=0.95)),
+    "one_strip": (48, 37, _xf()),
+    "uhd_slice": (3840, 48, _xf(scaleX=1.25, scaleY=1.25)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SINGLE_XFS))
+def test_single_layer_kernel_matches_the_general_kernel_and_oracle(name):
+    w, h, xf = SINGLE_XFS[name]
+    scene = single_layer_scene(w, h, "noise", True, "709", "2020")
+    scene["layers"][0]["xf"] = xf
+    ref = SceneOracle(scene).packed()
+
+    async def go(dedicated):
+        async with Env(True) as env:
+            env.ctx.directKernel = dedicated
+            env.ctx.setOcclusionCulling(True)   # pushes the flags
+            hh = ChannelHarness(env.ctx, scene, env.pj)
+            await hh.init()
+            out = await hh.run_frame()
+            return out, env.ctx.stats()
+    fast, st = run(go(True))
+    slow, st2 = run(go(False))
+    assert st["march_launches"] == 1 and st2["march_launches"] == 1 and st["kernel_launches"] == 1
+    assert np.array_equal(slow, ref)
+    assert np.array_equal(fast, ref), f"{int((fast != ref).sum())} bytes differ"

@@ -52,7 +52,9 @@ async def main():
     pk = peak()
     for inputs in a.inputs.split(","):
         for kern in a.kernels.split(","):
-            ctx = clContext({"deviceIndex": 0, "marchKernel": kern != "generic", "rawLut": kern == "march_raw"})
+            ctx = clContext({"deviceIndex": 0, "marchKernel": kern != "generic", "rawLut": kern == "march_raw",
+                             "directKernel": os.environ.get("PB_NO_DIRECT") is None,      # A/B: the dedicated single-layer kernels
+                             "occlusionCulling": os.environ.get("PB_NO_CULL") is None})
             await ctx.initialise()
             hs, chains, keep = [], [], []
             h0 = ChannelHarness(ctx, make_scene(a.scene, w, h, inputs, 0))
