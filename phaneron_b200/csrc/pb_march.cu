@@ -528,11 +528,224 @@ __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &l
 	}
 }
 
+// ---- k_march_single: ONE v210 layer through an axis-aligned Transform with vertical scale >= 1 into a v210 output -------
+// (a channel playing one full-frame clip through its Mixer: mixer.ts always runs the Transform, identity included).
+// The general kernel hands every output line of a 90-px strip to another warp, so each source row is converted twice (once
+// as row j0 + 1 of line y, once as row j0 of line y + 1).  Here a warp walks down a block of consecutive lines of a 186-px
+// strip and keeps the last two converted rows: every line costs ONE conversion pass with all 32 lanes busy, then the
+// same taps (the edge-aware form of eval_leaf) and the same encode for its 6 pixels per lane.  Bit for bit the same results.
+constexpr int kSingleRowFloats = 2 * 3 * 192 + 96;            // two row slots (3 planes x 192 texels) + 96 staging words
+// the item loop of k_march_single.  kMasked: run as the background pass of the general kernel (same launch): only the
+// lines FusedDesc::line_pairs marks for this strip pair -- those on which the bottom layer is the only live op of both strips
+template <bool kMasked>
+__device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf, uint32_t lut_saddr, int lane, int warp) {
+	const Leaf &lf = d.layers[0].a;
+	const ReadConsts &rc = d.rc[lf.rc];
+	const ReadK &rk = d.rk[lf.rc];
+	const LutParams &lp = d.luts[rc.lut_slot].lp;
+	LutK<1> lut, wlut;
+	lut.raw = rc.lut;
+	lut.magic = kTwo23 + (float)(lut_saddr + rc.lut_slot * 65536);
+	wlut.raw = d.wc.lut;
+	wlut.magic = kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536);
+	const LutParams &wlp = d.wlp;
+	const uint32_t E = d.e_magic;
+	constexpr int cap = 192, slot_floats = 3 * cap;
+	const SPtr stage = buf + 2 * slot_floats;
+
+	const int SG = d.single_strip_groups;   // 31 stand-alone, 30 (two strips of the general kernel) as its background pass
+	const int groups = d.out_w / 6, n_strips = (groups + SG - 1) / SG;
+	const int LB = d.single_lines, n_blocks = (d.out_h + LB - 1) / LB;
+	const int total = n_strips * n_blocks;
+	const int stride = gridDim.x * kMarchWarps;
+#pragma unroll 1
+	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride) {
+		const int blk = item / n_strips, strip = item - blk * n_strips;
+		const int x_first = strip * (SG * 6), x_last = min(x_first + SG * 6, d.out_w) - 1;
+		const int2 sg = d.single_strips[strip];   // first source group and group count of this strip's footprint (0 groups: all border)
+		const int g_lo = sg.x, ng = sg.y & 0xff, origin = g_lo * 6, last = ng * 6 - 1;
+		const bool strip_interior = (sg.y & 0x100) != 0;   // every tap column of the strip lies inside the image
+		int have0 = -0x40000000, have1 = -0x40000000;   // source row held by slot 0 / slot 1
+		const int y_end = min((blk + 1) * LB, d.out_h);
+		// the sampling columns of this lane's 6 pixels do not change down the block
+		int c0[2 * kRounds];
+		float cw[2 * kRounds];
+#pragma unroll
+		for (int q = 0; q < 2 * kRounds; ++q) {
+			const int x = min(x_first + (q / kRounds) * 96 + (q % kRounds) * 32 + lane, x_last);
+			const int2 ct = __ldg(lf.col_tab + x);
+			c0[q] = ct.x;
+			cw[q] = __int_as_float(ct.y);
+		}
+		// software pipeline down the block: the row table entry of the next line and the source row that line will need
+		// are loaded while this line is sampled and encoded
+		int2 rt = __ldg(lf.row_tab + blk * LB);
+		int2 rt_next = rt;
+		uint4 w_pref = make_uint4(0, 0, 0, 0);
+		int pref_row = -0x40000000;
+#pragma unroll 1
+		for (int y = blk * LB; y < y_end; ++y, rt = rt_next) {
+			if (kMasked && !((__ldg(d.line_pairs + y) >> strip) & 1ull)) {   // not a background-only line of this strip pair
+				if (y + 1 < y_end) rt_next = __ldg(lf.row_tab + y + 1);
+				continue;
+			}
+			const int j0 = rt.x;
+			const bool ok0 = ng > 0 && (unsigned)j0 < (unsigned)lf.h, ok1 = ng > 0 && (unsigned)(j0 + 1) < (unsigned)lf.h;
+			if (y + 1 < y_end) rt_next = __ldg(lf.row_tab + y + 1);
+#pragma unroll 1
+			for (int rr = 0; rr < 2; ++rr) {   // bring in the rows this line needs and the slots do not hold yet
+				const int row = j0 + rr, slot = row & 1;
+				if (!(rr ? ok1 : ok0) || (slot ? have1 : have0) == row) continue;
+				if (lane < ng) {
+					uint4 w = w_pref;
+					if (row != pref_row) w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)row * lf.pitch) + g_lo + lane);
+					convert_group<1, true, 0>(w, lane, E, rc, rk, lut, lp, buf + slot * slot_floats, cap);
+				}
+				if (slot) have1 = row; else have0 = row;
+			}
+			__syncwarp();
+			if (y + 1 < y_end) {   // the one new row of the next line (vertical step <= 1), if any: its load flies over this line's arithmetic
+				const int jn = rt_next.x;
+				int want = -0x40000000;
+				if ((unsigned)(jn + 1) < (unsigned)lf.h && have0 != jn + 1 && have1 != jn + 1) want = jn + 1;
+				else if ((unsigned)jn < (unsigned)lf.h && have0 != jn && have1 != jn) want = jn;
+				pref_row = want;
+				if (want >= 0 && lane < ng)
+					w_pref = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)want * lf.pitch) + g_lo + lane);
+			}
+			const float b = __int_as_float(rt.y), rb = sub(1.0f, b);
+			const SPtr s0 = buf + (j0 & 1) * slot_floats, s1 = buf + ((j0 + 1) & 1) * slot_floats;
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				float3 a3[kRounds];
+				if (strip_interior && ok0 && ok1) {   // all four taps are texels (eval_leaf's interior form)
+#pragma unroll
+					for (int r = 0; r < kRounds; ++r) {
+						const float ca = cw[h * kRounds + r], ra = sub(1.0f, ca);
+						const SPtr t0 = s0 + (c0[h * kRounds + r] - origin), t1 = s1 + (c0[h * kRounds + r] - origin);
+						const float w00 = mul(ra, rb), w10 = mul(ca, rb), w01 = mul(ra, b), w11 = mul(ca, b);
+						float4 p;
+						p.x = fma_(w11, t1[1], fma_(w01, t1[0], fma_(w10, t0[1], mul(w00, t0[0]))));
+						p.y = fma_(w11, t1[cap + 1], fma_(w01, t1[cap], fma_(w10, t0[cap + 1], mul(w00, t0[cap]))));
+						p.z = fma_(w11, t1[2 * cap + 1], fma_(w01, t1[2 * cap], fma_(w10, t0[2 * cap + 1], mul(w00, t0[2 * cap]))));
+						p.w = add(w11, add(w01, add(w10, w00)));
+						const float kk = sub(1.0f, p.w);   // combine.ts:49-59 over an empty frame: fma(0, 1 - alpha, p)
+						a3[r] = make_float3(fma_(0.0f, kk, p.x), fma_(0.0f, kk, p.y), fma_(0.0f, kk, p.z));
+					}
+				} else {
+#pragma unroll
+				for (int r = 0; r < kRounds; ++r) {
+					const int i0 = c0[h * kRounds + r];
+					const float ca = cw[h * kRounds + r], ra = sub(1.0f, ca);
+					const bool fc0 = (unsigned)i0 < (unsigned)lf.w, fc1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
+					const bool f00 = fc0 && ok0, f10 = fc1 && ok0, f01 = fc0 && ok1, f11 = fc1 && ok1;
+					const int t0 = min(max(i0 - origin, 0), last), t1 = min(max(i0 - origin + 1, 0), last);
+					const float w00 = mul(ra, rb), w10 = mul(ca, rb), w01 = mul(ra, b), w11 = mul(ca, b);
+					const SPtr a0 = s0 + t0, a1 = s0 + t1, b0 = s1 + t0, b1 = s1 + t1;
+#define PB_TAP(flag, ptr, off) ((flag) ? (ptr)[off] : 0.0f)
+					float4 p;
+					p.x = fma_(w11, PB_TAP(f11, b1, 0), fma_(w01, PB_TAP(f01, b0, 0), fma_(w10, PB_TAP(f10, a1, 0), mul(w00, PB_TAP(f00, a0, 0)))));
+					p.y = fma_(w11, PB_TAP(f11, b1, cap), fma_(w01, PB_TAP(f01, b0, cap), fma_(w10, PB_TAP(f10, a1, cap), mul(w00, PB_TAP(f00, a0, cap)))));
+					p.z = fma_(w11, PB_TAP(f11, b1, 2 * cap), fma_(w01, PB_TAP(f01, b0, 2 * cap), fma_(w10, PB_TAP(f10, a1, 2 * cap), mul(w00, PB_TAP(f00, a0, 2 * cap)))));
+#undef PB_TAP
+					float al = f00 ? w00 : 0.0f;
+					al = f10 ? add(w10, al) : al;
+					al = f01 ? add(w01, al) : al;
+					al = f11 ? add(w11, al) : al;
+					// combine.ts:49-59 over an empty frame: fma(0, 1 - alpha, p)
+					const float kk = sub(1.0f, al);
+					a3[r] = make_float3(fma_(0.0f, kk, p.x), fma_(0.0f, kk, p.y), fma_(0.0f, kk, p.z));
+				}
+				}
+#pragma unroll
+				for (int r = 0; r + 1 < kRounds; r += 2) {
+					const float2 gr = lut2<1, 1>(f2(__saturatef(a3[r].x), __saturatef(a3[r + 1].x)), wlut, wlp);
+					const float2 gg = lut2<1, 1>(f2(__saturatef(a3[r].y), __saturatef(a3[r + 1].y)), wlut, wlp);
+					const float2 gb = lut2<1, 1>(f2(__saturatef(a3[r].z), __saturatef(a3[r + 1].z)), wlut, wlp);
+					uint32_t code0 = 0, code1 = 0;
+#pragma unroll
+					for (int c = 0; c < 3; ++c) {
+						float2 v = __ffma2_rn(gb, f2s(d.wc.cm[c * 4 + 2]), __ffma2_rn(gr, f2s(d.wc.cm[c * 4 + 0]), __fmul2_rn(gg, f2s(d.wc.cm[c * 4 + 1]))));
+						v = __fadd2_rn(v, f2s(d.wc.cm[c * 4 + 3]));
+						v = __fadd2_rn(v, f2s(kTwo23));
+						code0 |= (__float_as_uint(v.x) & 0x3ffu) << (10 * c);
+						code1 |= (__float_as_uint(v.y) & 0x3ffu) << (10 * c);
+					}
+					stage.stu(r * 32 + lane, code0);
+					stage.stu((r + 1) * 32 + lane, code1);
+				}
+				if (kRounds & 1) {
+					constexpr int r = kRounds - 1;
+					const float2 hrg = lut2<1, 1>(f2(__saturatef(a3[r].x), __saturatef(a3[r].y)), wlut, wlp);
+					const float2 hb = lut2<1, 1>(f2s(__saturatef(a3[r].z)), wlut, wlp);
+					uint32_t code = 0;
+#pragma unroll
+					for (int c = 0; c < 3; ++c) {
+						const float u = add(add(fma_(hb.x, d.wc.cm[c * 4 + 2], fma_(hrg.x, d.wc.cm[c * 4 + 0], mul(hrg.y, d.wc.cm[c * 4 + 1]))), d.wc.cm[c * 4 + 3]), kTwo23);
+						code |= (__float_as_uint(u) & 0x3ffu) << (10 * c);
+					}
+					stage.stu(r * 32 + lane, code);
+				}
+				__syncwarp();
+				const int xg = x_first + h * 96 + lane * 6;   // lanes 0-15 regroup and store this half's groups
+				if (lane < 16 && xg <= x_last) {
+					const SPtr sp = stage + lane * 6;
+					const uint32_t p0 = sp.ldu(0), p1 = sp.ldu(1), p2 = sp.ldu(2), p3 = sp.ldu(3), p4 = sp.ldu(4), p5 = sp.ldu(5);
+					uint4 w;   // v210.ts:158-163: chroma from even pixels only
+					w.x = (p0 & 0x3ff00000u) | (p0 & 0x3ffu) << 10 | ((p0 >> 10) & 0x3ffu);
+					w.y = (p2 & 0x3ffu) << 20 | (p2 & 0xffc00u) | (p1 & 0x3ffu);
+					w.z = ((p4 >> 10) & 0x3ffu) << 20 | (p3 & 0x3ffu) << 10 | (p2 >> 20);
+					w.w = (p5 & 0x3ffu) << 20 | ((p4 >> 20) << 10) | (p4 & 0x3ffu);
+					st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d.out) + (size_t)y * d.out_pitch) + xg / 6, w);
+				}
+				__syncwarp();
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_constant__ FusedDesc d) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+	uint32_t tid_x;
+	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
+	const int lane = tid_x & 31, warp = tid_x >> 5;
+	SPtr buf;
+	{
+		const uint32_t addr = lut_saddr + (uint32_t)d.n_luts * 65536u + (uint32_t)warp * (kSingleRowFloats * 4u);
+		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));
+	}
+	{
+		__shared__ __align__(8) unsigned long long lut_bar;
+		const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&lut_bar);
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(d.n_luts * 65536) : "memory");
+			for (int t = 0; t < d.n_luts; ++t)
+				for (int c = 0; c < 4; ++c)
+					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+					                 lut_saddr + t * 65536 + c * 16384),
+					             "l"(d.luts[t].d8 + c * 16384), "r"(16384), "r"(bar)
+					             : "memory");
+		}
+		uint32_t done = 0;
+		while (!done)
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+	}
+	march_single_items<false>(d, buf, lut_saddr, lane, warp);
+}
+
 // kPlain: every read table is a non-affine model and the write table an affine one (what colourMaths.ts produces:
 // gamma -> linear on the way in, linear -> gamma on the way out), so both selects are compile-time constants
 // kPlanar: some leaf is a planar 4:2:2 / 4:2:0 source (load_group gathers it into the v210 group layout)
 // kBigRows: the warps' row buffers hold 64 source groups instead of 32 (deep down-scales; needs <= 2 resident tables)
-template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false, bool kPlanar = false, bool kBigRows = false>
+// kBg: the bottom layer is a full-frame-style v210 leaf (scale >= 1): the strip-pair lines on which it is the only live op are
+// left to a second phase of the same launch, march_single_items<true> (every source row converted once: k_march_single)
+template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false, bool kPlanar = false, bool kBigRows = false, bool kBg = false>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
@@ -544,7 +757,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	const int lane = tid_x & 31, warp = tid_x >> 5;
 	SPtr buf;   // this warp's row buffer
 	{
-		const uint32_t addr = lut_saddr + (kLutMode ? (uint32_t)d.n_luts * 65536u : 0u) + (uint32_t)warp * ((kBigRows ? 2u : 1u) * kRowFloats * 4u);
+		const uint32_t addr = lut_saddr + (kLutMode ? (uint32_t)d.n_luts * 65536u : 0u) + (uint32_t)warp * (kBg ? kSingleRowFloats * 4u : (kBigRows ? 2u : 1u) * kRowFloats * 4u);
 		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));   // opaque: keep it in a register, do not re-derive it
 	}
 
@@ -605,6 +818,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			++k;
 		}
 		const int y = first_line + k * step;
+		if (kBg && ((__ldg(d.line_pairs + y) >> (strip >> 1)) & 1ull)) continue;   // a background-only line of this strip pair: second phase
 		const int x_first = strip * strip_px;
 		const int x_last = min(x_first + strip_px, d.march_w) - 1;   // whole output groups only: a ragged tail is the generic kernel's
 
@@ -777,6 +991,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		}
 		__syncwarp();
 	}
+	if (kBg) march_single_items<true>(d, buf, lut_saddr, lane, warp);   // second phase: the background-only strip-pair lines
 }
 
 
@@ -906,206 +1121,6 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 }
 
 
-// ---- k_march_single: ONE v210 layer through an axis-aligned Transform with vertical scale >= 1 into a v210 output -------
-// (a channel playing one full-frame clip through its Mixer: mixer.ts always runs the Transform, identity included).
-// The general kernel hands every output line of a 90-px strip to another warp, so each source row is converted twice (once
-// as row j0 + 1 of line y, once as row j0 of line y + 1).  Here a warp walks down a block of consecutive lines of a 186-px
-// strip and keeps the last two converted rows: every line costs ONE conversion pass with all 32 lanes busy, then the
-// same taps (the edge-aware form of eval_leaf) and the same encode for its 6 pixels per lane.  Bit for bit the same results.
-constexpr int kSingleStripGroups = 31;                        // output groups per strip: <= 32 source groups per row at scale >= 1
-constexpr int kSingleRowFloats = 2 * 3 * 192 + 96;            // two row slots (3 planes x 192 texels) + 96 staging words
-__global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_constant__ FusedDesc d) {
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
-	uint32_t tid_x;
-	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
-	const int lane = tid_x & 31, warp = tid_x >> 5;
-	SPtr buf;
-	{
-		const uint32_t addr = lut_saddr + (uint32_t)d.n_luts * 65536u + (uint32_t)warp * (kSingleRowFloats * 4u);
-		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));
-	}
-	{
-		__shared__ __align__(8) unsigned long long lut_bar;
-		const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&lut_bar);
-		if (threadIdx.x == 0) {
-			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(d.n_luts * 65536) : "memory");
-			for (int t = 0; t < d.n_luts; ++t)
-				for (int c = 0; c < 4; ++c)
-					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-					                 lut_saddr + t * 65536 + c * 16384),
-					             "l"(d.luts[t].d8 + c * 16384), "r"(16384), "r"(bar)
-					             : "memory");
-		}
-		uint32_t done = 0;
-		while (!done)
-			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
-	}
-	const Leaf &lf = d.layers[0].a;
-	const ReadConsts &rc = d.rc[0];
-	const ReadK &rk = d.rk[0];
-	const LutParams &lp = d.luts[rc.lut_slot].lp;
-	LutK<1> lut, wlut;
-	lut.raw = rc.lut;
-	lut.magic = kTwo23 + (float)(lut_saddr + rc.lut_slot * 65536);
-	wlut.raw = d.wc.lut;
-	wlut.magic = kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536);
-	const LutParams &wlp = d.wlp;
-	const uint32_t E = d.e_magic;
-	constexpr int cap = 192, slot_floats = 3 * cap;
-	const SPtr stage = buf + 2 * slot_floats;
-
-	const int groups = d.out_w / 6, n_strips = (groups + kSingleStripGroups - 1) / kSingleStripGroups;
-	const int LB = d.single_lines, n_blocks = (d.out_h + LB - 1) / LB;
-	const int total = n_strips * n_blocks;
-	const int stride = gridDim.x * kMarchWarps;
-#pragma unroll 1
-	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride) {
-		const int blk = item / n_strips, strip = item - blk * n_strips;
-		const int x_first = strip * (kSingleStripGroups * 6), x_last = min(x_first + kSingleStripGroups * 6, d.out_w) - 1;
-		const int2 sg = d.single_strips[strip];   // first source group and group count of this strip's footprint (0 groups: all border)
-		const int g_lo = sg.x, ng = sg.y & 0xff, origin = g_lo * 6, last = ng * 6 - 1;
-		const bool strip_interior = (sg.y & 0x100) != 0;   // every tap column of the strip lies inside the image
-		int have0 = -0x40000000, have1 = -0x40000000;   // source row held by slot 0 / slot 1
-		const int y_end = min((blk + 1) * LB, d.out_h);
-		// the sampling columns of this lane's 6 pixels do not change down the block
-		int c0[2 * kRounds];
-		float cw[2 * kRounds];
-#pragma unroll
-		for (int q = 0; q < 2 * kRounds; ++q) {
-			const int x = min(x_first + (q / kRounds) * 96 + (q % kRounds) * 32 + lane, x_last);
-			const int2 ct = __ldg(lf.col_tab + x);
-			c0[q] = ct.x;
-			cw[q] = __int_as_float(ct.y);
-		}
-		// software pipeline down the block: the row table entry of the next line and the source row that line will need
-		// are loaded while this line is sampled and encoded
-		int2 rt = __ldg(lf.row_tab + blk * LB);
-		int2 rt_next = rt;
-		uint4 w_pref = make_uint4(0, 0, 0, 0);
-		int pref_row = -0x40000000;
-#pragma unroll 1
-		for (int y = blk * LB; y < y_end; ++y, rt = rt_next) {
-			const int j0 = rt.x;
-			const bool ok0 = ng > 0 && (unsigned)j0 < (unsigned)lf.h, ok1 = ng > 0 && (unsigned)(j0 + 1) < (unsigned)lf.h;
-			if (y + 1 < y_end) rt_next = __ldg(lf.row_tab + y + 1);
-#pragma unroll 1
-			for (int rr = 0; rr < 2; ++rr) {   // bring in the rows this line needs and the slots do not hold yet
-				const int row = j0 + rr, slot = row & 1;
-				if (!(rr ? ok1 : ok0) || (slot ? have1 : have0) == row) continue;
-				if (lane < ng) {
-					uint4 w = w_pref;
-					if (row != pref_row) w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)row * lf.pitch) + g_lo + lane);
-					convert_group<1, true, 0>(w, lane, E, rc, rk, lut, lp, buf + slot * slot_floats, cap);
-				}
-				if (slot) have1 = row; else have0 = row;
-			}
-			__syncwarp();
-			if (y + 1 < y_end) {   // the one new row of the next line (vertical step <= 1), if any: its load flies over this line's arithmetic
-				const int jn = rt_next.x;
-				int want = -0x40000000;
-				if ((unsigned)(jn + 1) < (unsigned)lf.h && have0 != jn + 1 && have1 != jn + 1) want = jn + 1;
-				else if ((unsigned)jn < (unsigned)lf.h && have0 != jn && have1 != jn) want = jn;
-				pref_row = want;
-				if (want >= 0 && lane < ng)
-					w_pref = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)want * lf.pitch) + g_lo + lane);
-			}
-			const float b = __int_as_float(rt.y), rb = sub(1.0f, b);
-			const SPtr s0 = buf + (j0 & 1) * slot_floats, s1 = buf + ((j0 + 1) & 1) * slot_floats;
-#pragma unroll
-			for (int h = 0; h < 2; ++h) {
-				float3 a3[kRounds];
-				if (strip_interior && ok0 && ok1) {   // all four taps are texels (eval_leaf's interior form)
-#pragma unroll
-					for (int r = 0; r < kRounds; ++r) {
-						const float ca = cw[h * kRounds + r], ra = sub(1.0f, ca);
-						const SPtr t0 = s0 + (c0[h * kRounds + r] - origin), t1 = s1 + (c0[h * kRounds + r] - origin);
-						const float w00 = mul(ra, rb), w10 = mul(ca, rb), w01 = mul(ra, b), w11 = mul(ca, b);
-						float4 p;
-						p.x = fma_(w11, t1[1], fma_(w01, t1[0], fma_(w10, t0[1], mul(w00, t0[0]))));
-						p.y = fma_(w11, t1[cap + 1], fma_(w01, t1[cap], fma_(w10, t0[cap + 1], mul(w00, t0[cap]))));
-						p.z = fma_(w11, t1[2 * cap + 1], fma_(w01, t1[2 * cap], fma_(w10, t0[2 * cap + 1], mul(w00, t0[2 * cap]))));
-						p.w = add(w11, add(w01, add(w10, w00)));
-						const float kk = sub(1.0f, p.w);   // combine.ts:49-59 over an empty frame: fma(0, 1 - alpha, p)
-						a3[r] = make_float3(fma_(0.0f, kk, p.x), fma_(0.0f, kk, p.y), fma_(0.0f, kk, p.z));
-					}
-				} else {
-#pragma unroll
-				for (int r = 0; r < kRounds; ++r) {
-					const int i0 = c0[h * kRounds + r];
-					const float ca = cw[h * kRounds + r], ra = sub(1.0f, ca);
-					const bool fc0 = (unsigned)i0 < (unsigned)lf.w, fc1 = (unsigned)(i0 + 1) < (unsigned)lf.w;
-					const bool f00 = fc0 && ok0, f10 = fc1 && ok0, f01 = fc0 && ok1, f11 = fc1 && ok1;
-					const int t0 = min(max(i0 - origin, 0), last), t1 = min(max(i0 - origin + 1, 0), last);
-					const float w00 = mul(ra, rb), w10 = mul(ca, rb), w01 = mul(ra, b), w11 = mul(ca, b);
-					const SPtr a0 = s0 + t0, a1 = s0 + t1, b0 = s1 + t0, b1 = s1 + t1;
-#define PB_TAP(flag, ptr, off) ((flag) ? (ptr)[off] : 0.0f)
-					float4 p;
-					p.x = fma_(w11, PB_TAP(f11, b1, 0), fma_(w01, PB_TAP(f01, b0, 0), fma_(w10, PB_TAP(f10, a1, 0), mul(w00, PB_TAP(f00, a0, 0)))));
-					p.y = fma_(w11, PB_TAP(f11, b1, cap), fma_(w01, PB_TAP(f01, b0, cap), fma_(w10, PB_TAP(f10, a1, cap), mul(w00, PB_TAP(f00, a0, cap)))));
-					p.z = fma_(w11, PB_TAP(f11, b1, 2 * cap), fma_(w01, PB_TAP(f01, b0, 2 * cap), fma_(w10, PB_TAP(f10, a1, 2 * cap), mul(w00, PB_TAP(f00, a0, 2 * cap)))));
-#undef PB_TAP
-					float al = f00 ? w00 : 0.0f;
-					al = f10 ? add(w10, al) : al;
-					al = f01 ? add(w01, al) : al;
-					al = f11 ? add(w11, al) : al;
-					// combine.ts:49-59 over an empty frame: fma(0, 1 - alpha, p)
-					const float kk = sub(1.0f, al);
-					a3[r] = make_float3(fma_(0.0f, kk, p.x), fma_(0.0f, kk, p.y), fma_(0.0f, kk, p.z));
-				}
-				}
-#pragma unroll
-				for (int r = 0; r + 1 < kRounds; r += 2) {
-					const float2 gr = lut2<1, 1>(f2(__saturatef(a3[r].x), __saturatef(a3[r + 1].x)), wlut, wlp);
-					const float2 gg = lut2<1, 1>(f2(__saturatef(a3[r].y), __saturatef(a3[r + 1].y)), wlut, wlp);
-					const float2 gb = lut2<1, 1>(f2(__saturatef(a3[r].z), __saturatef(a3[r + 1].z)), wlut, wlp);
-					uint32_t code0 = 0, code1 = 0;
-#pragma unroll
-					for (int c = 0; c < 3; ++c) {
-						float2 v = __ffma2_rn(gb, f2s(d.wc.cm[c * 4 + 2]), __ffma2_rn(gr, f2s(d.wc.cm[c * 4 + 0]), __fmul2_rn(gg, f2s(d.wc.cm[c * 4 + 1]))));
-						v = __fadd2_rn(v, f2s(d.wc.cm[c * 4 + 3]));
-						v = __fadd2_rn(v, f2s(kTwo23));
-						code0 |= (__float_as_uint(v.x) & 0x3ffu) << (10 * c);
-						code1 |= (__float_as_uint(v.y) & 0x3ffu) << (10 * c);
-					}
-					stage.stu(r * 32 + lane, code0);
-					stage.stu((r + 1) * 32 + lane, code1);
-				}
-				if (kRounds & 1) {
-					constexpr int r = kRounds - 1;
-					const float2 hrg = lut2<1, 1>(f2(__saturatef(a3[r].x), __saturatef(a3[r].y)), wlut, wlp);
-					const float2 hb = lut2<1, 1>(f2s(__saturatef(a3[r].z)), wlut, wlp);
-					uint32_t code = 0;
-#pragma unroll
-					for (int c = 0; c < 3; ++c) {
-						const float u = add(add(fma_(hb.x, d.wc.cm[c * 4 + 2], fma_(hrg.x, d.wc.cm[c * 4 + 0], mul(hrg.y, d.wc.cm[c * 4 + 1]))), d.wc.cm[c * 4 + 3]), kTwo23);
-						code |= (__float_as_uint(u) & 0x3ffu) << (10 * c);
-					}
-					stage.stu(r * 32 + lane, code);
-				}
-				__syncwarp();
-				const int xg = x_first + h * 96 + lane * 6;   // lanes 0-15 regroup and store this half's groups
-				if (lane < 16 && xg <= x_last) {
-					const SPtr sp = stage + lane * 6;
-					const uint32_t p0 = sp.ldu(0), p1 = sp.ldu(1), p2 = sp.ldu(2), p3 = sp.ldu(3), p4 = sp.ldu(4), p5 = sp.ldu(5);
-					uint4 w;   // v210.ts:158-163: chroma from even pixels only
-					w.x = (p0 & 0x3ff00000u) | (p0 & 0x3ffu) << 10 | ((p0 >> 10) & 0x3ffu);
-					w.y = (p2 & 0x3ffu) << 20 | (p2 & 0xffc00u) | (p1 & 0x3ffu);
-					w.z = ((p4 >> 10) & 0x3ffu) << 20 | (p3 & 0x3ffu) << 10 | (p2 >> 20);
-					w.w = (p5 & 0x3ffu) << 20 | ((p4 >> 20) << 10) | (p4 & 0x3ffu);
-					st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d.out) + (size_t)y * d.out_pitch) + xg / 6, w);
-				}
-				__syncwarp();
-			}
-		}
-	}
-}
-
 }  // namespace
 
 cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *cands_dev, int n_cands, uint8_t *d8_out, void *results_dev) {
@@ -1114,6 +1129,7 @@ cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *
 }
 
 size_t march_smem_bytes(const FusedDesc &d) {
+	if (d.bg_single) return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
 	return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * (d.big_rows ? 2 : 1) * kRowFloats * sizeof(float) + (size_t)d.n_t256 * 1024;
 }
 
@@ -1139,7 +1155,7 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		kernel<<<grid, kMarchThreads, smem, s>>>(d);
 		return cudaGetLastError();
 	};
-	if (d.single_lines > 0) {   // one v210 layer through an axis-aligned Transform, vertical scale >= 1 (prepare_march checks)
+	if (d.single_lines > 0 && !d.bg_single) {   // one v210 layer through an axis-aligned Transform, vertical scale >= 1 (prepare_march checks)
 		static std::mutex mu;
 		static std::set<int> configured;
 		int dev = 0;
@@ -1152,7 +1168,7 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 				configured.insert(dev);
 			}
 		}
-		const int n_strips = (d.out_w / 6 + kSingleStripGroups - 1) / kSingleStripGroups;
+		const int n_strips = (d.out_w / 6 + d.single_strip_groups - 1) / d.single_strip_groups;
 		const int total = n_strips * ((d.out_h + d.single_lines - 1) / d.single_lines);
 		const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
 		const size_t smem_single = (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
@@ -1192,6 +1208,8 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 			if (plain) return single ? launch(k_fused_march<1, true, true, true, true>) : launch(k_fused_march<1, true, false, true, true>);
 			return launch(k_fused_march<1, true, false, false, true>);
 		}
+		if (d.bg_single)   // (prepare_march: plain tables, sparse matrices, v210 leaves with whole groups)
+			return single ? launch(k_fused_march<1, true, true, true, false, false, true>) : launch(k_fused_march<1, true, false, true, false, false, true>);
 		if (plain && d.sparse_cm) return single ? launch(k_fused_march<1, true, true, true>) : launch(k_fused_march<1, true, false, true>);
 		if (d.sparse_cm) return single ? launch(k_fused_march<1, true, true>) : launch(k_fused_march<1, true, false>);
 		return single ? launch(k_fused_march<1, false, true>) : launch(k_fused_march<1, false, false>);

@@ -179,7 +179,14 @@ struct pb_ctx {
 	struct LineOps {   // per-line op masks of the march kernel
 		std::vector<int> key;
 		uint32_t *dev = nullptr;
+		std::vector<uint32_t> host;   // the same, for the host passes that need it (background-pass masks)
 	};
+	struct LinePairs {   // per-line strip-pair masks of the background pass (FusedDesc::line_pairs)
+		std::vector<int> key;
+		std::vector<uint32_t> strip_ops;
+		unsigned long long *dev = nullptr;
+	};
+	std::vector<LinePairs> line_pairs;
 	std::vector<LineOps> line_ops;
 };
 
@@ -919,6 +926,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (d.sink != pb::SINK_V210 && d.out_w % 48 != 0) return 0;
 	if (d.interlace != 0 && d.out_h < 2) return 0;
 	bool any_xf = false, any_planar = planar_sink, any_rgba = false;
+	const std::vector<uint32_t> *line_ops_host = nullptr;
+	std::vector<int> line_ops_key;
 	bool rc_ycc[pb::kMaxReadConsts] = {};   // read constants used by some YCbCr leaf (their tables go to shared memory)
 	pb::Leaf *leaves[3 * pb::kMaxLayers];
 	int n_leaves = 0;
@@ -1071,6 +1080,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			}
 			pb_ctx::LineOps lo;
 			lo.key = key;
+			lo.host = host;
 			CU(cudaMalloc(&lo.dev, host.size() * sizeof(uint32_t)));
 			CU(cudaMemcpyAsync(lo.dev, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
 			CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // `host` is a local
@@ -1078,6 +1088,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			found = &c->line_ops.back();
 		}
 		d.line_ops = found->dev;
+		line_ops_host = &found->host;
+		line_ops_key = key;
 	}
 	// the write side packs three codes into one word while regrouping: they must fit 10 bits (8 for the 8-bit sinks, whose
 	// uchar stores would otherwise wrap, Q11)
@@ -1132,19 +1144,27 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.n_luts = all_d8 ? n_slots : 0;
 	d.n_t256 = n_t256;
 	d.big_rows = big_rows;
-	// One v210 layer through an axis-aligned Transform (a channel playing one clip through its Mixer): k_march_single walks down
-	// blocks of lines of 186-px strips and converts every source row once.  Needs <= 32 source groups per strip row (horizontal
-	// scale >= ~1) and is worth it when consecutive lines share a source row (vertical step <= 1).
+	// The bottom layer as a row-reuse pass.  One v210 layer through an axis-aligned Transform alone (a channel playing one clip
+	// through its Mixer) takes k_march_single: blocks of lines of 186-px strips, every source row converted once.  With more
+	// layers on top, the same item loop runs as the second phase of the general kernel (bg_single) over the strip-pair lines on
+	// which the bottom layer is the only live op after bounding boxes and occlusion culling.  Needs <= 32 source groups per strip
+	// row (horizontal scale >= ~1) and pays when consecutive lines share a source row (vertical step <= 1).
 	d.single_lines = 0;
-	if (d.n_ops == 1 && d.layers[0].kind == pb::LAYER_DIRECT && d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
-	    d.layers[0].a.w % 6 == 0 && d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && d.interlace == 0 && all_d8 && n_slots <= 2 && d.sparse_cm &&
-	    !any_planar && !big_rows && d.rc[0].lut_slot >= 0 && c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine == 0 && d.wc.lut_slot >= 0 &&
-	    c->lut_tables[slots[d.wc.lut_slot]].lp.affine != 0 && !(c->flags & PB_CTX_NO_DIRECT) && tab_of[0] && !tab_of[0]->col_i0.empty()) {
+	d.bg_single = 0;
+	d.line_pairs = nullptr;
+	d.single_strip_groups = 31;
+	const bool plain_tables = all_d8 && n_slots <= 2 && d.sparse_cm && d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine != 0;
+	bool reads_plain = plain_tables;
+	for (int i = 0; i < d.n_rc && reads_plain; ++i) reads_plain = d.rc[i].lut_slot >= 0 && c->lut_tables[slots[d.rc[i].lut_slot]].lp.affine == 0;
+	if (reads_plain && d.n_ops >= 1 && d.layers[0].kind == pb::LAYER_DIRECT && d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
+	    d.layers[0].a.w % 6 == 0 && d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && d.interlace == 0 && !any_planar && !big_rows &&
+	    !(c->flags & PB_CTX_NO_DIRECT) && tab_of[0] && !tab_of[0]->col_i0.empty() && line_ops_host) {
 		const auto &tb = *tab_of[0];
 		const pb::Leaf &lf = d.layers[0].a;
-		constexpr int kSG = 31;   // pb_march.cu kSingleStripGroups
+		const bool bg = d.n_ops > 1;
+		const int kSG = bg ? 2 * d.strip_groups : 31;   // as a background pass: two strips of the general kernel
 		const int groups = d.out_w / 6, n_strips = (groups + kSG - 1) / kSG;
-		bool ok = n_strips <= 64;
+		bool ok = n_strips <= 64 && (!bg || d.strip_groups == pb::kStripGroupsXf);
 		for (int y = 0; y + 1 < d.out_h && ok; ++y) ok = std::abs(tb.row_j0[y + 1] - tb.row_j0[y]) <= 1;
 		for (int sidx = 0; sidx < n_strips && ok; ++sidx) {
 			const int x0 = sidx * kSG * 6, x1 = std::min(x0 + kSG * 6, d.out_w) - 1;
@@ -1165,6 +1185,56 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			}
 			d.single_strips[sidx] = e;
 		}
+		if (ok && bg) {
+			// which strip-pair lines are background-only: todo == {op 0} on both strips, evaluated as the kernel evaluates it
+			pb_ctx::LinePairs *found = nullptr;
+			std::vector<uint32_t> sops(d.strip_ops, d.strip_ops + d.n_strips);
+			for (auto &lp_ : c->line_pairs)
+				if (lp_.key == line_ops_key && lp_.strip_ops == sops) found = &lp_;
+			if (!found) {
+				if (c->line_pairs.size() >= 64) {
+					CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));
+					for (auto &lp_ : c->line_pairs) cudaFree(lp_.dev);
+					c->line_pairs.clear();
+				}
+				std::vector<unsigned long long> host((size_t)d.out_h, 0ull);
+				auto todo_of = [&](int sidx, int y) {
+					const uint32_t both = d.strip_ops[sidx] & (*line_ops_host)[y];
+					uint32_t todo = both & 0xFFFFFFu;
+					if (both >> 24) todo &= ~0u << d.layer_first_op[(31 - __builtin_clz(both)) - 24];
+					return todo;
+				};
+				long long marked = 0;
+				for (int y = 0; y < d.out_h; ++y) {
+					unsigned long long m = 0;
+					for (int pr = 0; pr < n_strips; ++pr) {
+						const int sa = 2 * pr, sb = 2 * pr + 1;
+						if (todo_of(sa, y) == 1u && (sb >= d.n_strips || todo_of(sb, y) == 1u)) {
+							m |= 1ull << pr;
+							++marked;
+						}
+					}
+					host[y] = m;
+				}
+				pb_ctx::LinePairs e;
+				e.key = line_ops_key;
+				e.strip_ops = sops;
+				// Worth a second phase only when it has work for tall blocks on every warp: measured on B200, 4320p two layers
+				// 426 -> 403 us, but 2160p four layers 165 -> 194 us with blocks too few and too tall to balance
+				const long long warps_ = (long long)c->prop.multiProcessorCount * pb::kMarchWarps;
+				long long min_marked = 32 * warps_;
+				if (const char *ov = getenv("PB_BG_MIN")) min_marked = atoll(ov);   // tests force the pass on small frames
+				if (marked > 0 && marked >= min_marked) {
+					CU(cudaMalloc(&e.dev, host.size() * sizeof(unsigned long long)));
+					CU(cudaMemcpyAsync(e.dev, host.data(), host.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+					CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // `host` is a local
+				}
+				c->line_pairs.push_back(std::move(e));
+				found = &c->line_pairs.back();
+			}
+			ok = found->dev != nullptr;   // no background-only line anywhere: nothing to gain
+			d.line_pairs = found->dev;
+		}
 		if (ok) {
 			// Lines per work item: taller blocks reuse more rows (a block of L lines costs L + 1 conversion passes) but leave fewer
 			// items to spread over the grid's warps.  Pick the L that minimises the longest warp's work: rounds x (L lines of
@@ -1176,6 +1246,9 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 				const long long cost = rounds * (L * 1060LL + 360LL);
 				if (best < 0 || cost < best) { best = cost; d.single_lines = L; }
 			}
+			if (bg) d.single_lines = 16;   // (gated above to frames with enough background-only lines for tall blocks)
+			d.single_strip_groups = kSG;
+			d.bg_single = bg ? 1 : 0;
 		}
 	}
 	// ToRGBA -> FromRGBA of one v210 source with colourMaths-style tables: the dedicated direct kernel
@@ -1876,6 +1949,7 @@ int pb_ctx_destroy(pb_ctx *c) {
 	for (auto &lo : c->line_ops) cudaFree(lo.dev);
 	for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
 	for (auto &e : c->lanczos_tabs) cudaFree(e.dev);
+	for (auto &e : c->line_pairs) cudaFree(e.dev);
 	cudaFree(c->lut_cands_dev);
 	cudaFree(c->lut_res_dev);
 	cudaFree(c->lut_scratch);

@@ -716,3 +716,26 @@ def test_single_layer_kernel_matches_the_general_kernel_and_oracle(name):
     assert st["march_launches"] == 1 and st2["march_launches"] == 1 and st["kernel_launches"] == 1
     assert np.array_equal(slow, ref)
     assert np.array_equal(fast, ref), f"{int((fast != ref).sum())} bytes differ"
+
+
+# ---- the background pass: the bottom layer's background-only strip-pair lines as a second phase of the general kernel ----
+@pytest.mark.parametrize("name", ["north_star_mix", "north_star_wipe", "flips_and_upscale", "odd_fractions", "mostly_outside", "odd_height"])
+def test_background_pass_is_exact(name, monkeypatch):
+    """march_single_items<true>: gated to large frames in production (PB_BG_MIN forces it here); same bytes as without it"""
+    monkeypatch.setenv("PB_BG_MIN", "0")
+    scene = MARCH_SCENES[name]()
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert st["march_launches"] == 1 and st["kernel_launches"] == 1
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+    out2, _ = run(_run_scene_variant(scene, "march_nocull"))
+    assert np.array_equal(out2, ref)
+
+
+def test_background_pass_full_size_4320p():
+    """BASELINE config 5's shape at full size, where the background pass is on by default: march == generic byte for byte"""
+    scene = layered_scene(7680, 4320, 2, "noise", "plain", "709", "2020")
+    slow, _ = run(_run_scene_variant(scene, "generic"))
+    fast, st = run(_run_scene_variant(scene, "march"))
+    assert st["march_launches"] == 1 and st["kernel_launches"] == 1
+    assert np.array_equal(fast, slow)
