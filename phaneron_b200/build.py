@@ -50,10 +50,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(bdir, exist_ok=True)
     nvcc = _nvcc()
     log = []
-    for src in SOURCES:
+    # the translation units compile side by side (pb_march.cu, with its kernel variants, is the long pole)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(bdir, src + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
-        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for src, obj, res in results:
         log.append(res.stderr)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
