@@ -537,7 +537,9 @@ __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &l
 constexpr int kSingleRowFloats = 2 * 3 * 192 + 96;            // two row slots (3 planes x 192 texels) + 96 staging words
 // the item loop of k_march_single.  kMasked: run as the background pass of the general kernel (same launch): only the
 // lines FusedDesc::line_pairs marks for this strip pair -- those on which the bottom layer is the only live op of both strips
-template <bool kMasked>
+// kPlanarSrc: the layer is a planar 4:2:2 / 4:2:0 source (an FFmpegProducer clip): groups come through load_group<true>,
+// flagged groups (yuv422p10 words above 1023) through convert_group_exact
+template <bool kMasked, bool kPlanarSrc = false>
 __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf, uint32_t lut_saddr, int lane, int warp) {
 	const Leaf &lf = d.layers[0].a;
 	const ReadConsts &rc = d.rc[lf.rc];
@@ -598,8 +600,9 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 				if (!(rr ? ok1 : ok0) || (slot ? have1 : have0) == row) continue;
 				if (lane < ng) {
 					uint4 w = w_pref;
-					if (row != pref_row) w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)row * lf.pitch) + g_lo + lane);
-					convert_group<1, true, 0>(w, lane, E, rc, rk, lut, lp, buf + slot * slot_floats, cap);
+					if (row != pref_row) w = load_group<kPlanarSrc>(lf, row, g_lo + lane);
+					if (kPlanarSrc && (w.x >> 31)) convert_group_exact(lf, d.rc, row, g_lo + lane, buf + slot * slot_floats, cap, lane);
+					else convert_group<1, true, 0>(w, lane, E, rc, rk, lut, lp, buf + slot * slot_floats, cap);
 				}
 				if (slot) have1 = row; else have0 = row;
 			}
@@ -610,8 +613,7 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 				if ((unsigned)(jn + 1) < (unsigned)lf.h && have0 != jn + 1 && have1 != jn + 1) want = jn + 1;
 				else if ((unsigned)jn < (unsigned)lf.h && have0 != jn && have1 != jn) want = jn;
 				pref_row = want;
-				if (want >= 0 && lane < ng)
-					w_pref = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)want * lf.pitch) + g_lo + lane);
+				if (want >= 0 && lane < ng) w_pref = load_group<kPlanarSrc>(lf, want, g_lo + lane);
 			}
 			const float b = __int_as_float(rt.y), rb = sub(1.0f, b);
 			const SPtr s0 = buf + (j0 & 1) * slot_floats, s1 = buf + ((j0 + 1) & 1) * slot_floats;
@@ -704,6 +706,7 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 	}
 }
 
+template <bool kPlanarSrc>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -736,7 +739,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 		while (!done)
 			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
 	}
-	march_single_items<false>(d, buf, lut_saddr, lane, warp);
+	march_single_items<false, kPlanarSrc>(d, buf, lut_saddr, lane, warp);
 }
 
 // kPlain: every read table is a non-affine model and the write table an affine one (what colourMaths.ts produces:
@@ -1163,7 +1166,8 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		{
 			std::lock_guard<std::mutex> lk(mu);
 			if (!configured.count(dev)) {
-				cudaError_t e = cudaFuncSetAttribute(k_march_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+				cudaError_t e = cudaFuncSetAttribute(k_march_single<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+				if (e == cudaSuccess) e = cudaFuncSetAttribute(k_march_single<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 				if (e != cudaSuccess) return e;
 				configured.insert(dev);
 			}
@@ -1172,7 +1176,8 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		const int total = n_strips * ((d.out_h + d.single_lines - 1) / d.single_lines);
 		const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
 		const size_t smem_single = (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
-		k_march_single<<<grid, kMarchThreads, smem_single, s>>>(d);
+		if (d.layers[0].a.kind == LEAF_V210) k_march_single<false><<<grid, kMarchThreads, smem_single, s>>>(d);
+		else k_march_single<true><<<grid, kMarchThreads, smem_single, s>>>(d);
 		return cudaGetLastError();
 	}
 	if (d.direct_mode) {   // one v210 source 1:1 into a v210 output (prepare_march checks the conditions)

@@ -1156,8 +1156,13 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	const bool plain_tables = all_d8 && n_slots <= 2 && d.sparse_cm && d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine != 0;
 	bool reads_plain = plain_tables;
 	for (int i = 0; i < d.n_rc && reads_plain; ++i) reads_plain = d.rc[i].lut_slot >= 0 && c->lut_tables[slots[d.rc[i].lut_slot]].lp.affine == 0;
-	if (reads_plain && d.n_ops >= 1 && d.layers[0].kind == pb::LAYER_DIRECT && d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
-	    d.layers[0].a.w % 6 == 0 && d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && d.interlace == 0 && !any_planar && !big_rows &&
+	const int k0 = d.layers[0].a.kind;
+	const bool l0_v210 = k0 == pb::LEAF_V210;
+	const bool l0_planar = k0 == pb::LEAF_YUV422P10 || k0 == pb::LEAF_YUV422P8 || k0 == pb::LEAF_YUV420P || k0 == pb::LEAF_NV12;
+	// (stand-alone: v210 or a planar FFmpegProducer clip; as a background pass of the fast variant: v210 only)
+	if (reads_plain && d.n_ops >= 1 && d.layers[0].kind == pb::LAYER_DIRECT && d.layers[0].a.has_xf &&
+	    ((d.n_ops == 1 && (l0_v210 || l0_planar)) || (l0_v210 && !any_planar)) &&
+	    d.layers[0].a.w % 6 == 0 && d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && d.interlace == 0 && !big_rows &&
 	    !(c->flags & PB_CTX_NO_DIRECT) && tab_of[0] && !tab_of[0]->col_i0.empty() && line_ops_host) {
 		const auto &tb = *tab_of[0];
 		const pb::Leaf &lf = d.layers[0].a;

@@ -739,3 +739,31 @@ def test_background_pass_full_size_4320p():
     fast, st = run(_run_scene_variant(scene, "march"))
     assert st["march_launches"] == 1 and st["kernel_launches"] == 1
     assert np.array_equal(fast, slow)
+
+
+@pytest.mark.parametrize("fmt,w,h,xf", [("yuv422p10", 960, 270, _xf()), ("yuv420p", 960, 270, _xf(scaleX=1.3, scaleY=1.6, offsetX=0.05)),
+                                        ("nv12", 480, 136, _xf(flipH=True)), ("yuv422p8", 1920, 64, _xf(offsetY=0.1))])
+def test_single_layer_kernel_planar_clip(fmt, w, h, xf):
+    """a channel playing one FFmpegProducer clip through its Mixer: k_march_single<planar> == general kernel == oracle"""
+    scene = _mixed_format_scene(w, h, [(fmt, "709", xf)])
+    if fmt == "yuv422p10":   # words above 1023 take the sample-exact path inside the single-layer kernel too
+        rng = np.random.default_rng(11)
+        planes = scene["layers"][0]["src"]
+        y16 = planes[0].view("<u2").copy()
+        y16[rng.integers(0, y16.size, 200)] = rng.integers(1024, 65536, 200, dtype=np.uint16)
+        planes[0] = y16.view(np.uint8)
+    ref = SceneOracle(scene).packed()
+
+    async def go(dedicated):
+        async with Env(True) as env:
+            env.ctx.directKernel = dedicated
+            env.ctx.setOcclusionCulling(True)   # pushes the flags
+            hh = ChannelHarness(env.ctx, scene, env.pj)
+            await hh.init()
+            out = await hh.run_frame()
+            return out, env.ctx.stats()
+    fast, st = run(go(True))
+    slow, st2 = run(go(False))
+    assert st["march_launches"] == 1 and st2["march_launches"] == 1 and st["kernel_launches"] == 1
+    assert np.array_equal(slow, ref)
+    assert np.array_equal(fast, ref), f"{int((fast != ref).sum())} bytes differ"

@@ -35,6 +35,8 @@ def make_scene(kind, w, h, inputs, fs):
         return single_layer_scene(w, h, inputs, True, "709", "709", frame_set=fs)
     if kind == "overlay":   # 3 video layers + a full-frame rgba8 graphic with alpha
         return overlay_scene(w, h, inputs, "709", "2020", frame_set=fs)
+    if kind.startswith("planar1:"):   # e.g. planar1:yuv422p10 -- one FFmpegProducer-format clip through the Mixer's identity Transform
+        return planar_layered_scene(w, h, kind.split(":")[1], 1, "709", "2020", frame_set=fs)
     if kind.startswith("planar4:"):   # e.g. planar4:yuv422p10 -- 4 layers of an FFmpegProducer format
         return planar_layered_scene(w, h, kind.split(":")[1], 4, "709", "2020", frame_set=fs)
     raise SystemExit(f"unknown scene {kind}")
