@@ -528,6 +528,54 @@ __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &l
 	}
 }
 
+// ---- one output group (6 pixels) from its staged codes: word k = Y | Cb << 10 | Cr << 20 of pixel k -----------------------
+// kSinks = false: v210 only (the fast variants).  Otherwise also the planar consumer formats (FFmpegConsumer's yuv422p8 and its
+// siblings): the same codes, stored by plane.  Chroma comes from the even pixels (v210.ts:158-163, yuv422p10.ts:170-171);
+// 4:2:0 keeps one chroma line per line pair, written from the first line of the pair the launch processes (yuv420p.ts:160-200).
+template <bool kSinks>
+__device__ __forceinline__ void store_group(const FusedDesc &d, int y, int G, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4, uint32_t p5) {
+	if (kSinks && d.sink != SINK_V210) {
+		const int pitch = (d.out_w + 7) / 8 * 8;
+		const uint32_t y0 = p0 & 0x3ffu, y1 = p1 & 0x3ffu, y2 = p2 & 0x3ffu, y3 = p3 & 0x3ffu, y4 = p4 & 0x3ffu, y5 = p5 & 0x3ffu;
+		const uint32_t u0 = (p0 >> 10) & 0x3ffu, u1 = (p2 >> 10) & 0x3ffu, u2 = (p4 >> 10) & 0x3ffu;
+		const uint32_t v0 = p0 >> 20, v1 = p2 >> 20, v2 = p4 >> 20;
+		if (d.sink == SINK_YUV422P10) {
+			uint32_t *Y = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(d.out) + ((size_t)y * pitch + 6 * G) * 2);
+			Y[0] = y0 | y1 << 16; Y[1] = y2 | y3 << 16; Y[2] = y4 | y5 << 16;
+			uint16_t *U = reinterpret_cast<uint16_t *>(d.out_u) + (size_t)y * (pitch / 2) + 3 * G;
+			uint16_t *V = reinterpret_cast<uint16_t *>(d.out_v) + (size_t)y * (pitch / 2) + 3 * G;
+			U[0] = (uint16_t)u0; U[1] = (uint16_t)u1; U[2] = (uint16_t)u2;
+			V[0] = (uint16_t)v0; V[1] = (uint16_t)v1; V[2] = (uint16_t)v2;
+		} else {
+			uint16_t *Y = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(d.out) + (size_t)y * pitch + 6 * G);
+			Y[0] = (uint16_t)(y0 | y1 << 8); Y[1] = (uint16_t)(y2 | y3 << 8); Y[2] = (uint16_t)(y4 | y5 << 8);
+			if (d.sink == SINK_YUV422P8) {
+				uint8_t *U = reinterpret_cast<uint8_t *>(d.out_u) + (size_t)y * (pitch / 2) + 3 * G;
+				uint8_t *V = reinterpret_cast<uint8_t *>(d.out_v) + (size_t)y * (pitch / 2) + 3 * G;
+				U[0] = (uint8_t)u0; U[1] = (uint8_t)u1; U[2] = (uint8_t)u2;
+				V[0] = (uint8_t)v0; V[1] = (uint8_t)v1; V[2] = (uint8_t)v2;
+			} else if ((y & 1) == (d.interlace == 3 ? 1 : 0)) {   // 4:2:0: the pair's first processed line carries the chroma
+				if (d.sink == SINK_YUV420P) {
+					uint8_t *U = reinterpret_cast<uint8_t *>(d.out_u) + (size_t)(y >> 1) * (pitch / 2) + 3 * G;
+					uint8_t *V = reinterpret_cast<uint8_t *>(d.out_v) + (size_t)(y >> 1) * (pitch / 2) + 3 * G;
+					U[0] = (uint8_t)u0; U[1] = (uint8_t)u1; U[2] = (uint8_t)u2;
+					V[0] = (uint8_t)v0; V[1] = (uint8_t)v1; V[2] = (uint8_t)v2;
+				} else {   // SINK_NV12
+					uint16_t *C = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(d.out_u) + (size_t)(y >> 1) * pitch + 6 * G);
+					C[0] = (uint16_t)(u0 | v0 << 8); C[1] = (uint16_t)(u1 | v1 << 8); C[2] = (uint16_t)(u2 | v2 << 8);
+				}
+			}
+		}
+		return;
+	}
+	uint4 w;   // v210.ts:158-163
+	w.x = (p0 & 0x3ff00000u) | (p0 & 0x3ffu) << 10 | ((p0 >> 10) & 0x3ffu);
+	w.y = (p2 & 0x3ffu) << 20 | (p2 & 0xffc00u) | (p1 & 0x3ffu);
+	w.z = ((p4 >> 10) & 0x3ffu) << 20 | (p3 & 0x3ffu) << 10 | (p2 >> 20);
+	w.w = (p5 & 0x3ffu) << 20 | ((p4 >> 20) << 10) | (p4 & 0x3ffu);
+	st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d.out) + (size_t)y * d.out_pitch) + G, w);
+}
+
 // ---- k_march_single: ONE v210 layer through an axis-aligned Transform with vertical scale >= 1 into a v210 output -------
 // (a channel playing one full-frame clip through its Mixer: mixer.ts always runs the Transform, identity included).
 // The general kernel hands every output line of a 90-px strip to another warp, so each source row is converted twice (once
@@ -693,12 +741,7 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 				if (lane < 16 && xg <= x_last) {
 					const SPtr sp = stage + lane * 6;
 					const uint32_t p0 = sp.ldu(0), p1 = sp.ldu(1), p2 = sp.ldu(2), p3 = sp.ldu(3), p4 = sp.ldu(4), p5 = sp.ldu(5);
-					uint4 w;   // v210.ts:158-163: chroma from even pixels only
-					w.x = (p0 & 0x3ff00000u) | (p0 & 0x3ffu) << 10 | ((p0 >> 10) & 0x3ffu);
-					w.y = (p2 & 0x3ffu) << 20 | (p2 & 0xffc00u) | (p1 & 0x3ffu);
-					w.z = ((p4 >> 10) & 0x3ffu) << 20 | (p3 & 0x3ffu) << 10 | (p2 >> 20);
-					w.w = (p5 & 0x3ffu) << 20 | ((p4 >> 20) << 10) | (p4 & 0x3ffu);
-					st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d.out) + (size_t)y * d.out_pitch) + xg / 6, w);
+					store_group<kPlanarSrc>(d, y, xg / 6, p0, p1, p2, p3, p4, p5);   // (the <true> variant also writes the planar consumer formats)
 				}
 				__syncwarp();
 			}
@@ -948,49 +991,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		if (x_first + lane * 6 <= x_last) {
 			const SPtr sp = stage + lane * 6;
 			const uint32_t p0 = sp.ldu(0), p1 = sp.ldu(1), p2 = sp.ldu(2), p3 = sp.ldu(3), p4 = sp.ldu(4), p5 = sp.ldu(5);
-			if (kPlanar && d.sink != SINK_V210) {
-				// planar consumer formats (FFmpegConsumer's yuv422p8 and its siblings): the same codes, stored by plane.
-				// Chroma comes from the even pixels (yuv422p10.ts:170-171); 4:2:0 keeps one chroma line per line pair,
-				// written from the first line of the pair this launch processes (yuv420p.ts:160-200).
-				const int G = strip * d.strip_groups + lane, pitch = (d.out_w + 7) / 8 * 8;
-				const uint32_t y0 = p0 & 0x3ffu, y1 = p1 & 0x3ffu, y2 = p2 & 0x3ffu, y3 = p3 & 0x3ffu, y4 = p4 & 0x3ffu, y5 = p5 & 0x3ffu;
-				const uint32_t u0 = (p0 >> 10) & 0x3ffu, u1 = (p2 >> 10) & 0x3ffu, u2 = (p4 >> 10) & 0x3ffu;
-				const uint32_t v0 = p0 >> 20, v1 = p2 >> 20, v2 = p4 >> 20;
-				if (d.sink == SINK_YUV422P10) {
-					uint32_t *Y = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(d.out) + ((size_t)y * pitch + 6 * G) * 2);
-					Y[0] = y0 | y1 << 16; Y[1] = y2 | y3 << 16; Y[2] = y4 | y5 << 16;
-					uint16_t *U = reinterpret_cast<uint16_t *>(d.out_u) + (size_t)y * (pitch / 2) + 3 * G;
-					uint16_t *V = reinterpret_cast<uint16_t *>(d.out_v) + (size_t)y * (pitch / 2) + 3 * G;
-					U[0] = (uint16_t)u0; U[1] = (uint16_t)u1; U[2] = (uint16_t)u2;
-					V[0] = (uint16_t)v0; V[1] = (uint16_t)v1; V[2] = (uint16_t)v2;
-				} else {
-					uint16_t *Y = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(d.out) + (size_t)y * pitch + 6 * G);
-					Y[0] = (uint16_t)(y0 | y1 << 8); Y[1] = (uint16_t)(y2 | y3 << 8); Y[2] = (uint16_t)(y4 | y5 << 8);
-					if (d.sink == SINK_YUV422P8) {
-						uint8_t *U = reinterpret_cast<uint8_t *>(d.out_u) + (size_t)y * (pitch / 2) + 3 * G;
-						uint8_t *V = reinterpret_cast<uint8_t *>(d.out_v) + (size_t)y * (pitch / 2) + 3 * G;
-						U[0] = (uint8_t)u0; U[1] = (uint8_t)u1; U[2] = (uint8_t)u2;
-						V[0] = (uint8_t)v0; V[1] = (uint8_t)v1; V[2] = (uint8_t)v2;
-					} else if ((y & 1) == (d.interlace == 3 ? 1 : 0)) {   // 4:2:0: the pair's first processed line carries the chroma
-						if (d.sink == SINK_YUV420P) {
-							uint8_t *U = reinterpret_cast<uint8_t *>(d.out_u) + (size_t)(y >> 1) * (pitch / 2) + 3 * G;
-							uint8_t *V = reinterpret_cast<uint8_t *>(d.out_v) + (size_t)(y >> 1) * (pitch / 2) + 3 * G;
-							U[0] = (uint8_t)u0; U[1] = (uint8_t)u1; U[2] = (uint8_t)u2;
-							V[0] = (uint8_t)v0; V[1] = (uint8_t)v1; V[2] = (uint8_t)v2;
-						} else {   // SINK_NV12
-							uint16_t *C = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(d.out_u) + (size_t)(y >> 1) * pitch + 6 * G);
-							C[0] = (uint16_t)(u0 | v0 << 8); C[1] = (uint16_t)(u1 | v1 << 8); C[2] = (uint16_t)(u2 | v2 << 8);
-						}
-					}
-				}
-			} else {
-			uint4 w;   // v210.ts:158-163: chroma from even pixels only
-			w.x = (p0 & 0x3ff00000u) | (p0 & 0x3ffu) << 10 | ((p0 >> 10) & 0x3ffu);
-			w.y = (p2 & 0x3ffu) << 20 | (p2 & 0xffc00u) | (p1 & 0x3ffu);
-			w.z = ((p4 >> 10) & 0x3ffu) << 20 | (p3 & 0x3ffu) << 10 | (p2 >> 20);
-			w.w = (p5 & 0x3ffu) << 20 | ((p4 >> 20) << 10) | (p4 & 0x3ffu);
-			st_stream(reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d.out) + (size_t)y * d.out_pitch) + strip * d.strip_groups + lane, w);
-			}
+			store_group<kPlanar>(d, y, strip * d.strip_groups + lane, p0, p1, p2, p3, p4, p5);
 		}
 		__syncwarp();
 	}
@@ -1176,7 +1177,7 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		const int total = n_strips * ((d.out_h + d.single_lines - 1) / d.single_lines);
 		const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
 		const size_t smem_single = (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
-		if (d.layers[0].a.kind == LEAF_V210) k_march_single<false><<<grid, kMarchThreads, smem_single, s>>>(d);
+		if (d.layers[0].a.kind == LEAF_V210 && d.sink == SINK_V210) k_march_single<false><<<grid, kMarchThreads, smem_single, s>>>(d);
 		else k_march_single<true><<<grid, kMarchThreads, smem_single, s>>>(d);
 		return cudaGetLastError();
 	}

@@ -1161,8 +1161,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	const bool l0_planar = k0 == pb::LEAF_YUV422P10 || k0 == pb::LEAF_YUV422P8 || k0 == pb::LEAF_YUV420P || k0 == pb::LEAF_NV12;
 	// (stand-alone: v210 or a planar FFmpegProducer clip; as a background pass of the fast variant: v210 only)
 	if (reads_plain && d.n_ops >= 1 && d.layers[0].kind == pb::LAYER_DIRECT && d.layers[0].a.has_xf &&
-	    ((d.n_ops == 1 && (l0_v210 || l0_planar)) || (l0_v210 && !any_planar)) &&
-	    d.layers[0].a.w % 6 == 0 && d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && d.interlace == 0 && !big_rows &&
+	    ((d.n_ops == 1 && (l0_v210 || l0_planar)) || (l0_v210 && !any_planar && d.sink == pb::SINK_V210)) &&
+	    d.layers[0].a.w % 6 == 0 && d.sink != pb::SINK_RGBA8 && d.sink != pb::SINK_BGRA8 && d.out_w % 48 == 0 && d.interlace == 0 && !big_rows &&
 	    !(c->flags & PB_CTX_NO_DIRECT) && tab_of[0] && !tab_of[0]->col_i0.empty() && line_ops_host) {
 		const auto &tb = *tab_of[0];
 		const pb::Leaf &lf = d.layers[0].a;

@@ -767,3 +767,26 @@ def test_single_layer_kernel_planar_clip(fmt, w, h, xf):
     assert st["march_launches"] == 1 and st2["march_launches"] == 1 and st["kernel_launches"] == 1
     assert np.array_equal(slow, ref)
     assert np.array_equal(fast, ref), f"{int((fast != ref).sum())} bytes differ"
+
+
+@pytest.mark.parametrize("src_fmt,out_fmt,w,h", [("yuv422p10", "yuv422p8", 960, 270), ("v210", "yuv420p", 960, 270), ("nv12", "nv12", 480, 136),
+                                                 ("yuv420p", "yuv422p10", 1920, 64), ("v210", "yuv422p8", 480, 135)])
+def test_single_layer_kernel_transcodes(src_fmt, out_fmt, w, h):
+    """one clip through the Mixer into an FFmpegConsumer-style planar output: k_march_single<true> == general kernel == oracle"""
+    scene = _mixed_format_scene(w, h, [(src_fmt, None if src_fmt == "v210" else "709", _xf(scaleX=1.1, scaleY=1.1))])
+    scene["outFmt"] = out_fmt
+    ref = SceneOracle(scene).packed()
+
+    async def go(dedicated):
+        async with Env(True) as env:
+            env.ctx.directKernel = dedicated
+            env.ctx.setOcclusionCulling(True)   # pushes the flags
+            hh = ChannelHarness(env.ctx, scene, env.pj)
+            await hh.init()
+            out = await hh.run_frame()
+            return out, env.ctx.stats()
+    fast, st = run(go(True))
+    slow, st2 = run(go(False))
+    assert st["march_launches"] == 1 and st2["march_launches"] == 1 and st["kernel_launches"] == 1
+    assert np.array_equal(slow, ref)
+    assert np.array_equal(fast, ref), f"{int((fast != ref).sum())} bytes differ"
