@@ -790,3 +790,31 @@ def test_single_layer_kernel_transcodes(src_fmt, out_fmt, w, h):
     assert st["march_launches"] == 1 and st2["march_launches"] == 1 and st["kernel_launches"] == 1
     assert np.array_equal(slow, ref)
     assert np.array_equal(fast, ref), f"{int((fast != ref).sum())} bytes differ"
+
+
+@pytest.mark.parametrize("kind", ["direct", "single", "single_planar", "background"])
+def test_chain_replay_of_the_dedicated_kernels(kind, monkeypatch):
+    """a recorded chain re-issues k_march_direct / k_march_single / the two-phase general kernel with their descriptors"""
+    if kind == "background":
+        monkeypatch.setenv("PB_BG_MIN", "0")
+    scene = {"direct": lambda: single_layer_scene(480, 135, "noise", False, "709", "2020"),
+             "single": lambda: single_layer_scene(480, 135, "noise", True, "709", "2020"),
+             "single_planar": lambda: _mixed_format_scene(480, 136, [("yuv420p", "709", _xf(scaleX=1.2, scaleY=1.2))]),
+             "background": lambda: layered_scene(480, 270, 3, "noise", "plain", "709", "2020")}[kind]()
+
+    async def go():
+        async with Env() as env:
+            h = ChannelHarness(env.ctx, scene, env.pj)
+            await h.init()
+            chain, dests = await h.record_chain()
+            assert chain.complete and chain.launches == 1
+            dests[0].fill(0)
+            await dests[0].hostAccess("writeonly")
+            await dests[0].hostAccess("none")
+            for _ in range(2):
+                chain.replay()
+            await env.ctx.waitFinish(env.ctx.queue.process)
+            await dests[0].hostAccess("readonly")
+            assert np.array_equal(dests[0].host, SceneOracle(scene).packed())
+            chain.destroy()
+    run(go())
