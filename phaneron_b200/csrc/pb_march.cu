@@ -608,8 +608,19 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 	const int LB = d.single_lines, n_blocks = (d.out_h + LB - 1) / LB;
 	const int total = n_strips * n_blocks;
 	const int stride = gridDim.x * kMarchWarps;
+	// Stand-alone the items are dealt round-robin.  As the background pass they are claimed from a counter in global memory:
+	// warps reach this phase at different times and the blocks are coarse, so a static deal leaves a long tail.  The counter
+	// is never reset: the host hands every launch the value it starts from (each warp of the grid claims exactly one item
+	// past the end, so a launch advances it by total + warps; unsigned arithmetic, wrap-around safe).
+	int item = blockIdx.x * kMarchWarps + warp;
+	auto claim = [&]() -> int {
+		unsigned v = 0;
+		if (lane == 0) v = atomicAdd(d.bg_counter, 1u) - d.bg_base;
+		return (int)__shfl_sync(0xffffffffu, v, 0);
+	};
+	if (kMasked) item = claim();
 #pragma unroll 1
-	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride) {
+	for (; (unsigned)item < (unsigned)total; item = kMasked ? claim() : item + stride) {
 		const int blk = item / n_strips, strip = item - blk * n_strips;
 		const int x_first = strip * (SG * 6), x_last = min(x_first + SG * 6, d.out_w) - 1;
 		const int2 sg = d.single_strips[strip];   // first source group and group count of this strip's footprint (0 groups: all border)

@@ -187,6 +187,8 @@ struct pb_ctx {
 		unsigned long long *dev = nullptr;
 	};
 	std::vector<LinePairs> line_pairs;
+	unsigned int *bg_counter = nullptr;   // device counter of the background pass (never reset) and the value the next launch starts from
+	unsigned int bg_next_base = 0;
 	std::vector<LineOps> line_ops;
 };
 
@@ -1224,10 +1226,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 				pb_ctx::LinePairs e;
 				e.key = line_ops_key;
 				e.strip_ops = sops;
-				// Worth a second phase only when it has work for tall blocks on every warp: measured on B200, 4320p two layers
-				// 426 -> 403 us, but 2160p four layers 165 -> 194 us with blocks too few and too tall to balance
+				// Worth a second phase only when it has a few blocks for every warp of the grid.  Measured on B200 with the items
+				// claimed dynamically: 4320p two layers 426 -> 361 us, 2160p two layers 113 -> 106 us; the 2160p four-layer bench
+				// scene (17 k marked lines) is neutral, smaller frames lose
 				const long long warps_ = (long long)c->prop.multiProcessorCount * pb::kMarchWarps;
-				long long min_marked = 32 * warps_;
+				long long min_marked = 8 * warps_;
 				if (const char *ov = getenv("PB_BG_MIN")) min_marked = atoll(ov);   // tests force the pass on small frames
 				if (marked > 0 && marked >= min_marked) {
 					CU(cudaMalloc(&e.dev, host.size() * sizeof(unsigned long long)));
@@ -1251,7 +1254,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 				const long long cost = rounds * (L * 1060LL + 360LL);
 				if (best < 0 || cost < best) { best = cost; d.single_lines = L; }
 			}
-			if (bg) d.single_lines = 16;   // (gated above to frames with enough background-only lines for tall blocks)
+			if (bg) d.single_lines = 6;   // (items are claimed dynamically: moderately tall blocks balance and still reuse 5 rows of 6)
 			d.single_strip_groups = kSG;
 			d.bg_single = bg ? 1 : 0;
 		}
@@ -1311,7 +1314,27 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 
 // issue the launch(es) of a prepared descriptor: the march or the generic kernel, plus -- after a march launch on a ragged
 // v210 width -- the generic kernel on the tail columns (prepare_march).  Also the replay path of recorded chains.
-int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d, bool march, void *out_rgba) {
+int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool march, void *out_rgba) {
+	pb::FusedDesc bg_copy;
+	const pb::FusedDesc *dp = &d_in;
+	if (march && d_in.bg_single) {   // the second phase claims its items from a counter that is never reset (pb_march.cu)
+		if (!c->bg_counter) {
+			CU(cudaMalloc(&c->bg_counter, sizeof(unsigned int)));
+			CU(cudaMemsetAsync(c->bg_counter, 0, sizeof(unsigned int), s));
+			c->bg_next_base = 0;
+		}
+		bg_copy = d_in;
+		bg_copy.bg_counter = c->bg_counter;
+		bg_copy.bg_base = c->bg_next_base;
+		const int n_lines = d_in.out_h;
+		const int pairs = (d_in.out_w / 6 + d_in.single_strip_groups - 1) / d_in.single_strip_groups;
+		const unsigned total = (unsigned)pairs * (unsigned)((n_lines + d_in.single_lines - 1) / d_in.single_lines);
+		const unsigned items1 = (unsigned)n_lines * (unsigned)d_in.n_strips;   // the grid launch_fused_march picks (phase-1 items)
+		const unsigned grid = std::max(1u, std::min((unsigned)c->prop.multiProcessorCount, (items1 + pb::kMarchWarps - 1) / pb::kMarchWarps));
+		c->bg_next_base += total + grid * pb::kMarchWarps;
+		dp = &bg_copy;
+	}
+	const pb::FusedDesc &d = *dp;
 	cudaError_t e = march ? pb::launch_fused_march(s, d, c->prop.multiProcessorCount) : pb::launch_fused(s, d, out_rgba);
 	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (%s): %s", march ? "march" : "generic", cudaGetErrorString(e));
 	if (march && d.sink == pb::SINK_V210 && d.out_w % 48 != 0) {
@@ -1955,6 +1978,7 @@ int pb_ctx_destroy(pb_ctx *c) {
 	for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
 	for (auto &e : c->lanczos_tabs) cudaFree(e.dev);
 	for (auto &e : c->line_pairs) cudaFree(e.dev);
+	cudaFree(c->bg_counter);
 	cudaFree(c->lut_cands_dev);
 	cudaFree(c->lut_res_dev);
 	cudaFree(c->lut_scratch);
