@@ -34,7 +34,7 @@ WIDTH, HEIGHT, LAYERS, VARIANT = 3840, 2160, 4, "mix"
 COL_READ, COL_WORK = "709", "2020"
 FRAMES_PER_STEP = 240          # device-resident leg
 E2E_WARM = 8                    # pipelined frames before the e2e clock starts
-E2E_FRAMES_PER_STEP = 24       # public-API leg (PCIe bound: ~133 MB H2D + 22 MB D2H per frame)
+E2E_FRAMES_PER_STEP = 48       # public-API leg (PCIe bound: ~133 MB H2D + 22 MB D2H per frame)
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "2160p50 v210 4-layer composite frames/sec"
 REF_ARM_LINES = 720            # --impl reference: each step composites a 3840x720 band (1/3 frame)
