@@ -476,7 +476,30 @@ __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &l
 #pragma unroll 1
 	for (int rr = 0; rr < 2; ++rr) {
 		if (!(rr ? ok1 : ok0)) continue;
-		const uchar4 *line = reinterpret_cast<const uchar4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;
+		const uchar4 *line = reinterpret_cast<const uchar4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;   // (rgba8 / bgra8)
+		if (lf.kind == LEAF_RGBA_F32) {   // an RGBA-f32 frame (a Yadif output, a materialised sub-expression): nothing to convert
+			const float4 *linef = reinterpret_cast<const float4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;
+#pragma unroll 1
+			for (int base = 0; base < ntex; base += 64) {
+				float4 v[2];
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					const int t = base + k * 32 + lane;
+					v[k] = t < ntex ? __ldg(linef + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+				}
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					const int t = base + k * 32 + lane;
+					if (t < ntex) {
+						const uint32_t a = buf.a + 4u * (uint32_t)t;
+						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v[k].x) : "memory");
+						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 4u * cap), "f"(v[k].y) : "memory");
+						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 8u * cap), "f"(v[k].z) : "memory");
+						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 12u * cap), "f"(v[k].w) : "memory");
+					}
+				}
+			}
+		} else
 #pragma unroll 1
 		for (int base = 0; base < ntex; base += 96) {
 			uchar4 px[3];
@@ -901,7 +924,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
+			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
 			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))

@@ -927,7 +927,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (d.out_h < 1 || d.out_w < 6 || (d.out_w & 1)) return 0;
 	if (d.sink != pb::SINK_V210 && d.out_w % 48 != 0) return 0;
 	if (d.interlace != 0 && d.out_h < 2) return 0;
-	bool any_xf = false, any_planar = planar_sink, any_rgba = false;
+	bool any_xf = false, any_planar = planar_sink, any_rgba = false, any_f32 = false;
 	const std::vector<uint32_t> *line_ops_host = nullptr;
 	std::vector<int> line_ops_key;
 	bool rc_ycc[pb::kMaxReadConsts] = {};   // read constants used by some YCbCr leaf (their tables go to shared memory)
@@ -942,7 +942,9 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			// packed 4:2:2 / 4:2:0 YCbCr sources convert through the v210 group path; rgba8 / bgra8 (alpha) and RGBA-f32 leaves do not
 			const bool ycc = lf.kind == pb::LEAF_V210 || lf.kind == pb::LEAF_YUV422P10 || lf.kind == pb::LEAF_YUV422P8 ||
 			                 lf.kind == pb::LEAF_YUV420P || lf.kind == pb::LEAF_NV12;
-			const bool rgba = lf.kind == pb::LEAF_RGBA8 || lf.kind == pb::LEAF_BGRA8;   // graphics with alpha: pb_march.cu eval_leaf_rgba
+			// graphics with alpha, and RGBA-f32 frames (Yadif outputs, materialised sub-expressions): pb_march.cu eval_leaf_rgba
+			const bool rgba = lf.kind == pb::LEAF_RGBA8 || lf.kind == pb::LEAF_BGRA8 || lf.kind == pb::LEAF_RGBA_F32;
+			if (lf.kind == pb::LEAF_RGBA_F32) any_f32 = true;
 			if (!(ycc || rgba) || lf.w < 6 || lf.lz_tx) return 0;
 			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) any_planar = true;   // general load path (formats, partial last groups)
 			if (rgba) any_rgba = true;
@@ -974,7 +976,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
 		if (r) return r;
 		if (!fits) return 0;
-		const bool leaf_rgba = leaves[i]->kind == pb::LEAF_RGBA8 || leaves[i]->kind == pb::LEAF_BGRA8;
+		const bool leaf_rgba = leaves[i]->kind == pb::LEAF_RGBA8 || leaves[i]->kind == pb::LEAF_BGRA8 || leaves[i]->kind == pb::LEAF_RGBA_F32;
 		if (leaf_rgba && fits != 1) return 0;   // four planes: 32 source groups per row at most
 		if (fits == 2 || leaf_rgba) big_rows = true;
 		opq[i] = leaf_rgba ? nullptr : t->opq;   // the alpha of an rgba8 leaf is data: never certifiably opaque
@@ -1006,7 +1008,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	}
 	// exact occlusion culling: which layers are opaque (alpha == 1.0f) over whole strips / whole lines.
 	// Needs finite values below (NaN * 0 != 0): every read table must lie in [0, 1].
-	bool cull = !(c->flags & PB_CTX_NO_CULL);
+	bool cull = !(c->flags & PB_CTX_NO_CULL) && !any_f32;   // (an RGBA-f32 frame may hold NaN / inf: NaN * 0 != 0)
 	for (int i = 0; i < d.n_rc && cull; ++i) {
 		const int t = lut_table_by_raw(c, d.rc[i].lut);
 		cull = t >= 0 && c->lut_tables[t].unit_range;

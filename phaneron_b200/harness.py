@@ -64,18 +64,27 @@ class _Source:
     def __init__(self, h: "ChannelHarness", sid: str, sw: int, sh: int, xf: Optional[Dict[str, Any]], fmt: str = "v210",
                  colRead: Optional[str] = None):
         self.h, self.sid, self.sw, self.sh, self.xf = h, sid, sw, sh, xf
-        self.toRGBA = ToRGBA(h.ctx, colRead or h.colRead, h.colWork, make_reader(fmt, sw, sh), h.clJobs)
+        # fmt 'rgbaf32': the source already is an RGBA-f32 frame in the working colour space (what a Yadif stage or any other
+        # image process hands on): uploaded as an image buffer, no Reader
+        self.rgbaf32 = fmt == "rgbaf32"
+        self.toRGBA = None if self.rgbaf32 else ToRGBA(h.ctx, colRead or h.colRead, h.colWork, make_reader(fmt, sw, sh), h.clJobs)
         self.transform: Optional[ImageProcess] = None
         if xf is not None:
             self.transform = ImageProcess(h.ctx, Transform(h.ctx, h.width, h.height), h.clJobs)
         self.resident: Optional[List[OpenCLBuffer]] = None
 
     async def init(self) -> None:
-        await self.toRGBA.init()
+        if self.toRGBA:
+            await self.toRGBA.init()
         if self.transform:
             await self.transform.init()
 
     async def upload(self, frame: np.ndarray, timestamp: int) -> List[OpenCLBuffer]:
+        if self.rgbaf32:
+            img = await self.h.ctx.createBuffer(self.sw * self.sh * 16, "readwrite", "coarse", {"width": self.sw, "height": self.sh}, self.sid)
+            img.timestamp = timestamp
+            await img.hostAccess("writeonly", self.h.ctx.queue.load, np.ascontiguousarray(frame, np.float32).view(np.uint8).reshape(-1))
+            return [img]
         srcs = await self.toRGBA.createSources(self.sid)        # macadamProducer.ts:171-191
         for s in srcs:
             s.timestamp = timestamp
@@ -85,12 +94,17 @@ class _Source:
 
     async def frame(self, srcs: List[OpenCLBuffer], timestamp: int) -> OpenCLBuffer:
         h = self.h
-        dest = await self.toRGBA.createDest({"width": self.sw, "height": self.sh}, self.sid)   # macadamProducer.ts:193-210
-        dest.timestamp = timestamp
-        self.toRGBA.processFrame(self.sid, srcs, dest)
-        if not self.transform:
-            await h.clJobs.runQueue({"source": self.sid, "timestamp": timestamp})
-            return dest
+        if self.rgbaf32:
+            dest = srcs[0]
+            if not self.transform:
+                return dest
+        else:
+            dest = await self.toRGBA.createDest({"width": self.sw, "height": self.sh}, self.sid)   # macadamProducer.ts:193-210
+            dest.timestamp = timestamp
+            self.toRGBA.processFrame(self.sid, srcs, dest)
+            if not self.transform:
+                await h.clJobs.runQueue({"source": self.sid, "timestamp": timestamp})
+                return dest
         xfDest = await h.ctx.createBuffer(h.width * h.height * 16, "readwrite", "coarse",          # mixer.ts:196-207
                                           {"width": h.width, "height": h.height}, f"mixer {self.sid} {timestamp}")
         xfDest.timestamp = timestamp

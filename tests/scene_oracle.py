@@ -33,6 +33,8 @@ class SceneOracle:
 
     def read(self, src, sw, sh, fmt="v210", colRead=None):
         """the Reader kernel of the layer's source format with the constants its Loader would upload (loadSave.ts:41-64)"""
+        if fmt == "rgbaf32":   # already an RGBA-f32 frame in the working space
+            return np.ascontiguousarray(src, np.float32).reshape(sh, sw, 4)
         if fmt == "v210" and colRead is None:
             return oracle.v210_read(src, sw, sh, self.cm_r, self.lut_r, self.gamut)
         cr = colRead or self.s.get("colRead", "709")

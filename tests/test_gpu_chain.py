@@ -818,3 +818,43 @@ def test_chain_replay_of_the_dedicated_kernels(kind, monkeypatch):
             assert np.array_equal(dests[0].host, SceneOracle(scene).packed())
             chain.destroy()
     run(go())
+
+
+# ---- RGBA-f32 frames as leaves of the march kernel (Yadif outputs, materialised sub-expressions, image-process results) ----
+def _f32_scene(w, h, specs, nan=False):
+    """specs: [(fmt, xf)] with fmt 'v210' or 'rgbaf32'"""
+    layers = []
+    for i, (fmt, xf) in enumerate(specs):
+        if fmt == "rgbaf32":
+            rng = np.random.default_rng(120 + i)
+            img = rng.random((h, w, 4), dtype=np.float32)
+            img[..., :3] *= img[..., 3:4]          # premultiplied, like the frames the chain hands on
+            if nan:
+                img[h // 2, w // 3] = np.float32("nan")
+                img[h // 3, w // 2, 1] = np.float32("inf")
+            src = img
+        else:
+            src = make_frame("noise", w, h, 130 + i)
+        layers.append(dict(src=src, sw=w, sh=h, xf=xf, transition=None, fmt=fmt))
+    return dict(width=w, height=h, colRead="709", colWork="2020", interlaced=False, layers=layers)
+
+
+F32_SCENES = {
+    "f32_over_video": lambda: _f32_scene(960, 270, [("v210", _xf()), ("rgbaf32", _xf()), ("v210", pip(0.5, 0.3, 0.3))]),
+    "f32_background_upscaled": lambda: _f32_scene(480, 135, [("rgbaf32", _xf(scaleX=1.5, scaleY=1.2, flipH=True)), ("v210", pip(0.5, 0.1, 0.1))]),
+    "f32_pip_direct_under": lambda: _f32_scene(480, 136, [("rgbaf32", None), ("rgbaf32", pip(0.6, 0.2, 0.2))]),
+    "f32_with_nan_under_opaque_video": lambda: _f32_scene(480, 135, [("rgbaf32", _xf()), ("v210", pip(0.5, 0.2, 0.2))], nan=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(F32_SCENES))
+def test_rgba_f32_leaves_take_the_march_kernel(name):
+    """bit-exact against the oracle chain and the generic kernel; NaN / inf in a frame propagate exactly as the reference's
+    fma(prev, 1 - alpha, layer) propagates them (no culling under opaque layers when an RGBA-f32 frame is in the graph)"""
+    scene = F32_SCENES[name]()
+    ref = SceneOracle(scene).packed()
+    slow, st0 = run(_run_scene_variant(scene, "generic"))
+    assert st0["march_launches"] == 0 and np.array_equal(slow, ref)
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert st["march_launches"] == 1 and st["kernel_launches"] == 1 and st["materialised"] == 0, st
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
