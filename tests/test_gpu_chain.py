@@ -858,3 +858,84 @@ def test_rgba_f32_leaves_take_the_march_kernel(name):
     out, st = run(_run_scene_variant(scene, "march"))
     assert st["march_launches"] == 1 and st["kernel_launches"] == 1 and st["materialised"] == 0, st
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+
+
+@pytest.mark.parametrize("use_march", [True, False])
+def test_interlaced_source_through_yadif_composites_on_the_march_kernel(use_march):
+    """the north star's whole chain with its de-interlace stage: v210 (1080i-style) -> ToRGBA -> Yadif (3-frame window) ->
+    Mixer Transform -> Combine with a PiP layer -> FromRGBA v210.  The Yadif output is an RGBA-f32 frame; the composite that
+    follows it is one march-kernel launch, bit-exact against the oracle's stage-by-stage chain"""
+    from phaneron_b200.process import v210 as v210m
+    from phaneron_b200.process.combine import Combine
+    from phaneron_b200.process.image_process import ImageProcess
+    from phaneron_b200.process.io import FromRGBA, ToRGBA
+    from phaneron_b200.process.transform import Transform
+    from phaneron_b200.process.yadif import Yadif
+    from scene_oracle import xf_matrix
+    w, h = 480, 136
+    fields = [make_frame("noise", w, h, 140 + i) for i in range(3)]
+    pip_src = make_frame("noise", w, h, 150)
+    pip_xf = pip(0.5, 0.3, 0.2)
+
+    async def go():
+        async with Env(True) as env:
+            env.ctx.setMarchKernel(use_march)
+            ctx, jobs = env.ctx, env.jobs
+            to_a = ToRGBA(ctx, "709", "2020", v210m.Reader(w, h), jobs)
+            to_b = ToRGBA(ctx, "709", "2020", v210m.Reader(w, h), jobs)
+            frm = FromRGBA(ctx, "2020", v210m.Writer(w, h, False), jobs)
+            xa = ImageProcess(ctx, Transform(ctx, w, h), jobs)
+            xb = ImageProcess(ctx, Transform(ctx, w, h), jobs)
+            comb = ImageProcess(ctx, Combine(2, w, h), jobs)
+            yad = Yadif(ctx, jobs, w, h, {"mode": "send_frame", "tff": True}, True)
+            for o in (to_a, to_b, frm, xa, xb, comb, yad):
+                await o.init()
+            outs = []
+            for t, f in enumerate(fields):   # producer side: load, convert, de-interlace (yadif.ts:115-145)
+                srcs = await to_a.createSources("src")
+                for s_ in srcs:
+                    s_.timestamp = t * 2
+                await to_a.loadFrame(f, srcs, ctx.queue.load)
+                rgba = await to_a.createDest({"width": w, "height": h}, "src")
+                rgba.timestamp = t * 2
+                to_a.processFrame("src", srcs, rgba)
+                await yad.processFrame(rgba, outs, "src")
+            assert len(outs) == 1   # the window fills at the third field: one de-interlaced frame
+            deint = outs[0]
+            deint.addRef()
+            got_deint = await env.fetch(deint, w, h)
+            before = ctx.stats()
+            # mixer + second layer + combiner + consumer
+            xfa = await ctx.createBuffer(w * h * 16, "readwrite", "coarse", {"width": w, "height": h}, "mixer a")
+            await xa.run(dict(input=deint, output=xfa, **_xf()), {"source": "L0", "timestamp": 2}, lambda: None)
+            await jobs.runQueue({"source": "L0", "timestamp": 2})
+            srcs = await to_b.createSources("pip")
+            await to_b.loadFrame(pip_src, srcs, ctx.queue.load)
+            rgb = await to_b.createDest({"width": w, "height": h}, "pip")
+            to_b.processFrame("pip", srcs, rgb)
+            xfb = await ctx.createBuffer(w * h * 16, "readwrite", "coarse", {"width": w, "height": h}, "mixer b")
+            await xb.run(dict(input=rgb, output=xfb, **pip_xf), {"source": "pip", "timestamp": 0}, lambda: None)
+            await jobs.runQueue({"source": "pip", "timestamp": 0})
+            cdest = await ctx.createBuffer(w * h * 16, "readwrite", "coarse", {"width": w, "height": h}, "comb")
+            cdest.timestamp = 2
+            await comb.run({"inputs": [xfa, xfb], "output": cdest}, {"source": "ch", "timestamp": 2}, lambda: None)
+            await jobs.runQueue({"source": "ch", "timestamp": 2})
+            dests = await frm.createDests("out")
+            frm.processFrame("out", cdest, dests, Interlace.Progressive)
+            await jobs.runQueue({"source": "out", "timestamp": 2})
+            await frm.saveFrame(dests)
+            after = ctx.stats()
+            return dests[0].host.copy(), {k: after[k] - before[k] for k in after}, got_deint
+    out, st, got_deint = run(go())
+    cm_r, lut_r, gam = oracle.ycbcr2rgb_matrix("709"), oracle.gamma2linear_lut("709"), oracle.rgb2rgb_matrix("709", "2020")
+    # (the Yadif stage itself is pinned in tests/test_gpu_ops.py; here its actual output is the oracle's input for the stages
+    # that follow it, which is what this test is about)
+    c_ = oracle.v210_read(fields[1], w, h, cm_r, lut_r, gam)
+    kept = (got_deint.view(np.uint32) == c_.view(np.uint32)).all(axis=(1, 2))
+    assert kept.sum() == h // 2, "one field of the de-interlaced frame is the current frame's"
+    deint = got_deint
+    la = oracle.transform(deint, xf_matrix(w, h, _xf()), w, h)
+    lb = oracle.transform(oracle.v210_read(pip_src, w, h, cm_r, lut_r, gam), xf_matrix(w, h, pip_xf), w, h)
+    ref = oracle.v210_write(oracle.combine([la, lb]), w, h, 0, oracle.rgb2ycbcr_matrix("2020"), oracle.linear2gamma_lut("2020"))
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+    assert st["march_launches"] == (1 if use_march else 0) and st["fused_launches"] == 1 and st["kernel_launches"] == 1, st
