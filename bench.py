@@ -37,8 +37,7 @@ E2E_WARM = 8                    # pipelined frames before the e2e clock starts
 E2E_FRAMES_PER_STEP = 48       # public-API leg (PCIe bound: ~133 MB H2D + 22 MB D2H per frame)
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "2160p50 v210 4-layer composite frames/sec"
-REF_ARM_LINES = 720            # --impl reference: each step composites a 3840x720 band (1/3 frame)
-REF_SAMPLE_LINES = 144         # cpu_baseline of the default run: 3840x144 bands (1/15 frame)
+CPU_BASELINE_FRAMES = 12       # cpu_baseline of the default run: whole 3840x2160 frames (about 1 s each on 16 cores)
 
 
 _JSON_OUT = None   # the real stdout when fd 1 has been pointed at stderr (multi-rank runs)
@@ -127,15 +126,17 @@ def pin_scene(lib, scene):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_fps(steps, warmup, inputs, threads, lines=None):
-    """the reference's unfused stage sequence as restated in oracle/ on the host cores"""
+def cpu_reference_fps(steps, warmup, inputs, threads):
+    """the reference's unfused stage sequence as restated in oracle/ on the host cores: WHOLE frames of the bench scene
+    (5x v210 read, 5x transform, dissolve, combine_4, v210 write with RGBA-f32 intermediates in host memory), one per step,
+    compiled -O3 -march=native on this machine"""
     import oracle
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from scene_oracle import SceneOracle
     from phaneron_b200.scenes import layered_scene
+    native = oracle.use_native()
     oracle.set_threads(threads)
-    lines = lines or REF_SAMPLE_LINES
-    scene = layered_scene(WIDTH, lines, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
+    scene = layered_scene(WIDTH, HEIGHT, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
     so = SceneOracle(scene)
     for _ in range(warmup):
         so.packed()
@@ -143,8 +144,7 @@ def cpu_reference_fps(steps, warmup, inputs, threads, lines=None):
     for _ in range(steps):
         so.packed()
     dt = time.perf_counter() - t0
-    frames = steps * lines / HEIGHT
-    return frames / dt, dt
+    return steps / dt, dt, native
 
 
 def reference_kernels_on_gpu(inputs, frames=6):
@@ -175,9 +175,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    fps, dt = cpu_reference_fps(args.steps, max(args.warmup, 1), args.inputs, threads, REF_ARM_LINES)
-    sample = (f"{args.steps} steps, each the full unfused chain (5x v210 read, 5x transform, dissolve, combine_4, v210 write, "
-              f"RGBA-f32 intermediates) on a {WIDTH}x{REF_ARM_LINES} band = {REF_ARM_LINES}/{HEIGHT} of a frame; fps scaled to whole frames")
+    fps, dt, native = cpu_reference_fps(args.steps, max(args.warmup, 1), args.inputs, threads)
+    sample = (f"{args.steps} steps, each ONE whole {WIDTH}x{HEIGHT} frame through the full unfused chain (5x v210 read, 5x transform, dissolve, "
+              f"combine_4, v210 write, RGBA-f32 intermediates), oracle/ built {'-O3 -march=native on this host' if native else '-O3'}, {dt:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -191,14 +191,18 @@ def run_reference(args, rank, world):
 
 
 def ncu_traffic(kernel, inputs):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same scene (profiles/r01_march_ncu_summary.json); None if not captured"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_march_ncu_summary.json")) as f:
-            j = json.load(f)
-        return j.get(f"{kernel}_{inputs}", {}).get("dram_bytes_per_launch")
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the NEWEST committed
+    `ncu --set full` capture of this same scene (profiles/rNN_march_ncu_summary.json); None if not captured"""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_march_ncu_summary.json")), reverse=True):
+        try:
+            with open(path) as f:
+                v = json.load(f).get(f"{kernel}_{inputs}", {}).get("dram_bytes_per_launch")
+            if v:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 def workload_name(inputs):
@@ -238,7 +242,7 @@ async def run_ours(args, rank, world, local_rank):
     n_in = LAYERS + (1 if VARIANT == "mix" else 2 if VARIANT == "wipe" else 0)
     set_bytes = (n_in + 1) * frame_bytes
     n_sets = max(3, -(-2 * L2_BYTES // set_bytes) + 1)
-    harnesses, chains, keep = [], [], []
+    harnesses, chains, keep, chain_dests = [], [], [], []
     chains_nocull = []   # the same frames with occlusion culling off (reported beside the default)
     for s in range(n_sets):
         scene = layered_scene(WIDTH, HEIGHT, LAYERS, args.inputs, VARIANT, COL_READ, COL_WORK, frame_set=s + rank * n_sets)
@@ -250,6 +254,7 @@ async def run_ours(args, rank, world, local_rank):
         harnesses.append(h)
         chains.append(chain)
         keep.append(dests)
+        chain_dests.append(dests)
         if not args.no_culling and args.kernel != "generic":
             ctx.setOcclusionCulling(False)
             chain2, dests2 = await h.record_chain()
@@ -269,6 +274,25 @@ async def run_ours(args, rank, world, local_rank):
     alg_bytes = harnesses[0].algorithmic_bytes()
     launches_per_frame = chains[0].launches
     await ctx.waitFinish(ctx.queue.process)
+
+    # ---- parity, untimed: the frames the timed region replays are the oracle's frames, byte for byte (rank 0) ----
+    async def replayed_frame(s):
+        chains[s].replay()
+        await ctx.waitFinish(ctx.queue.process)
+        await harnesses[s].fromRGBA.saveFrame(chain_dests[s], ctx.queue.unload)
+        await ctx.waitFinish(ctx.queue.unload)
+        return chain_dests[s][0].host
+
+    parity = {"checked": False}
+    ref0 = None
+    if rank == 0 and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from scene_oracle import SceneOracle
+        ref0 = SceneOracle(harnesses[0].scene).packed()
+        got = await replayed_frame(0)
+        if not np.array_equal(got, ref0):
+            raise RuntimeError(f"bench: the replayed frame differs from the oracle in {int((got != ref0).sum())} bytes")
+        parity = {"checked": True, "what": "replayed frame of input set 0 == oracle (unfused CPU chain), byte for byte, before and after the timed region"}
 
     fps_n = args.frames_per_step
 
@@ -322,6 +346,11 @@ async def run_ours(args, rank, world, local_rank):
     frames = args.steps * fps_n
     fps_rank = frames / (ms * 1e-3)
     launches = st1["kernel_launches"] - st0["kernel_launches"]
+    if ref0 is not None:   # what the timed replays left in set 0's destination (then once more, freshly replayed)
+        await harnesses[0].fromRGBA.saveFrame(chain_dests[0], ctx.queue.unload)
+        await ctx.waitFinish(ctx.queue.unload)
+        if not np.array_equal(chain_dests[0][0].host, ref0) or not np.array_equal(await replayed_frame(0), ref0):
+            raise RuntimeError("bench: a frame written inside the timed region differs from the oracle")
 
     # ---- end-to-end leg through the public API ------------------------------------------------
     e2e_scene = pin_scene(lib, layered_scene(WIDTH, HEIGHT, LAYERS, args.inputs, VARIANT, COL_READ, COL_WORK, frame_set=rank * n_sets))
@@ -332,7 +361,7 @@ async def run_ours(args, rank, world, local_rank):
     e2e_steps = max(1, min(args.steps, 5))
     barrier()
     await ctx.waitFinish(ctx.queue.process)
-    checksum = 0
+    e2e_first = e2e_last = None
     # Frames are pipelined the way phaneron's redioactive pipes run them: while frame i is composed, packed and
     # read back, the sources of the next frames are already being copied in (every call is async work, see nodencl.py;
     # PB_E2E_DEPTH frame times of uploads in flight keep the H2D copy engine busy across the host-side hand-over).
@@ -352,12 +381,51 @@ async def run_ours(args, rank, world, local_rank):
             pending.append(asyncio.ensure_future(he.upload_all(1000 + i + depth)))
         frame = await he.compose(ups, 1000 + i)              # operators + job queue (records the expression)
         dests = await he.consume(frame, download=True)       # fused launch + D2H of the packed result
-        checksum ^= int(dests[0].host[:64].view(np.uint64).sum())
+        if i == n_all - 1:
+            te1 = time.perf_counter()
+            e2e_last = dests[0].host.copy()                  # (after the clock: the last timed frame)
+        elif i == E2E_WARM - 1:
+            e2e_first = dests[0].host.copy()                 # (before the clock: the last warm-up frame)
         for d in dests:
             d.release()
-    te1 = time.perf_counter()
     s1 = ctx.stats()
     e2e_dt = te1 - te0
+    e2e_parity = False
+    if ref0 is not None:   # rank 0's e2e scene is input set 0: the downloaded frames must be the oracle's frame
+        for nm, fr in (("first", e2e_first), ("last", e2e_last)):
+            if fr is None or not np.array_equal(fr, ref0):
+                raise RuntimeError(f"bench: the {nm} frame downloaded by the end-to-end leg differs from the oracle")
+        e2e_parity = True
+
+    # ---- host cost of the public-API path with device-resident inputs (no H2D, no D2H): what pb_chain_replay skips ----
+    host_frames = 40
+    ups = await he.upload_all(5000)
+    await ctx.waitFinish(ctx.queue.process)
+    hs0 = ctx.stats()
+    th0 = time.perf_counter()
+    for i in range(host_frames):
+        for per_layer in ups:   # the sources stay resident: one more reference per frame for the release callbacks
+            for bufs in per_layer.values():
+                for b in bufs:
+                    b.addRef()
+                    b.timestamp = 6000 + i
+        frame = await he.compose(ups, 6000 + i)
+        dests = await he.consume(frame, download=False)
+        for d in dests:
+            d.release()
+    th1 = time.perf_counter()
+    await ctx.waitFinish(ctx.queue.process)
+    th2 = time.perf_counter()
+    hs1 = ctx.stats()
+    for per_layer in ups:
+        for bufs in per_layer.values():
+            for b in bufs:
+                b.release()
+    host_cost = {"frames": host_frames,
+                 "api_us_per_frame": (th1 - th0) / host_frames * 1e6,          # Python mirror of the TS operators + C ABI, launches issued
+                 "c_abi_us_per_frame": (hs1["run_program_ns"] - hs0["run_program_ns"]) / host_frames * 1e-3,   # inside pb_run_program only
+                 "run_program_calls_per_frame": (hs1["run_program_calls"] - hs0["run_program_calls"]) / host_frames,
+                 "wall_us_per_frame_incl_gpu": (th2 - th0) / host_frames * 1e6}
     if dist:
         import torch
         t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
@@ -394,17 +462,19 @@ async def run_ours(args, rank, world, local_rank):
                          "launch_us": launch_ms * 1e3},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": n_in * frame_bytes * E2E_FRAMES_PER_STEP,
                     "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // e2e_steps, "frames_per_step": E2E_FRAMES_PER_STEP,
-                    "steps": e2e_steps, "checksum": checksum & 0xFFFFFFFF},
+                    "steps": e2e_steps, "parity_checked": e2e_parity},
+            "parity_checked": parity["checked"], "parity": parity,
+            "host_us_per_frame": host_cost,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = 150   # ~1 s of wall clock on 16 cores = ~15-20 core-seconds of CPU work
-            fps, dt = cpu_reference_fps(n, 1, args.inputs, threads)
+            n = CPU_BASELINE_FRAMES   # whole frames: ~10-20 core-seconds of CPU work
+            fps, dt, native = cpu_reference_fps(n, 1, args.inputs, threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n} x {WIDTH}x{REF_SAMPLE_LINES} bands ({REF_SAMPLE_LINES}/{HEIGHT} frame each) of the same scene, "
-                                              f"oracle/ unfused chain, {dt:.1f} s",
+                                    "sample": f"{n} whole {WIDTH}x{HEIGHT} frames of the same scene, oracle/ unfused chain "
+                                              f"({'-O3 -march=native' if native else '-O3'}), {dt:.1f} s",
                                     "reference_kernels_on_gpu": reference_kernels_on_gpu(args.inputs)}
         emit(line)
     barrier()
@@ -421,6 +491,7 @@ def main():
     ap.add_argument("--inputs", default="noise", choices=["ramp", "noise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-culling", action="store_true", help="evaluate layers hidden under opaque ones too (A/B)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle comparison of the replayed and downloaded frames")
     ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP, help="frames per device-resident step (profiling runs use a few)")
     ap.add_argument("--kernel", default="march", choices=["march", "march_raw", "generic"],
                     help="march: fused kernel, gamma tables in shared memory (default); march_raw: same kernel gathering "

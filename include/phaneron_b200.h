@@ -96,6 +96,9 @@ typedef struct pb_stats {
 	uint64_t lut_tables;        /* distinct gamma tables seen (by content) */
 	uint64_t lut_tables_d8;     /* of which: held in the lossless one-byte form the march kernel keeps in shared memory */
 	uint64_t march_src_bytes;   /* PB_CTX_FOOTPRINT: distinct packed source bytes read by the last march launch */
+	uint64_t lut_tables_poly;   /* of lut_tables_d8: decoded without MUFU (polynomial power segment) */
+	uint64_t run_program_ns;    /* host time spent inside pb_run_program (recording, flattening, launch issue), nanoseconds */
+	uint64_t run_program_calls;
 } pb_stats;
 
 const char *pb_last_error(void);

@@ -27,6 +27,21 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def use_native() -> bool:
+    """bench.py's CPU-baseline legs: switch this process to a -O3 -march=native build made on THIS machine
+    (oracle/_native/, git-ignored).  Same source, same -ffp-contract=off: same results, the host's full ISA."""
+    global _lib
+    path = os.path.join(_HERE, "_native", "liboracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "_native/liboracle_native.so"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        l = C.CDLL(path)
+        _declare(l)
+        _lib = l
+        return True
+    except Exception:
+        return False
+
+
 _lib = None
 
 

@@ -55,7 +55,7 @@ class Timings(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "kernel_launches", "fused_launches", "march_launches", "deferred_nodes", "materialised", "h2d_bytes", "d2h_bytes",
-        "dev_bytes_live", "dev_bytes_pooled", "lut_tables", "lut_tables_d8", "march_src_bytes")]
+        "dev_bytes_live", "dev_bytes_pooled", "lut_tables", "lut_tables_d8", "march_src_bytes", "lut_tables_poly", "run_program_ns", "run_program_calls")]
 
 
 class PhaneronError(RuntimeError):

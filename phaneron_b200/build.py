@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libphaneron_b200.so")
+LIB = os.environ.get("PB_LIB_OUT") or os.path.join(HERE, "libphaneron_b200.so")   # PB_LIB_OUT: kernel-variant experiments (load with PB_LIB)
 SOURCES = ["pb_kernels.cu", "pb_fused.cu", "pb_march.cu", "pb_runtime.cu", "pb_colour.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
     "-Xptxas", "-v",
 ]
-for _k in ("PB_MARCH_WARPS", "PB_MARCH_ROUNDS"):   # kernel-variant experiments
+for _k in ("PB_MARCH_WARPS", "PB_MARCH_ROUNDS", "PB_DIRECT_WARPS", "PB_EXP"):   # kernel-variant experiments
     if os.environ.get(_k):
         NVCC_FLAGS += [f"-D{_k}={int(os.environ[_k])}"]
 
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     objs = []
-    bdir = os.path.join(HERE, "build")
+    bdir = os.environ.get("PB_BUILD_DIR") or os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     nvcc = _nvcc()
     log = []

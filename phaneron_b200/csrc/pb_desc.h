@@ -54,9 +54,15 @@ enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2
 // The d8 bytes are produced ON the device by the same code that decodes them (pb_lut.cuh).
 // The toe / power select is arithmetic (FMA pipe, no predicate): with h = sat(i + cJ) = (i >= J),
 //   base(i) = i*kt + h * (pw(i) - i*kt)          -- exactly i*kt below the knee, pw(i) to a few ulp above it
+// A third, MUFU-free model (affine == 2) evaluates the power segment as a degree-7 polynomial in x = i*p + q (x in
+// [-1, 1] over [J, 65535]): seven FMAs on the FMA pipe instead of MUFU.LG2 + MUFU.EX2 on the quarter-rate XU pipe.  The
+// host fits the coefficients per transfer function (pb_lut_cache.cpp lut_candidates); the byte table absorbs the residue as
+// for the MUFU models, and a table the polynomial misses by more than a byte falls back to the MUFU model.
+constexpr int kLutPolyDeg = 7;
 struct LutParams {
 	float p, q, G, s, o, kt, cJ;   // cJ = 1 - J
-	int affine;                    // 0: s == 1 and o == 0 (gamma -> linear direction)
+	int affine;                    // 0: s == 1 and o == 0 (gamma -> linear direction); 1: affine; 2: polynomial power segment
+	float c[kLutPolyDeg + 1];      // affine == 2: pw(x) = (((c[7] x + c[6]) x + ...) x + c[0]
 };
 
 // Loader constants (loadSave.ts:41-64): YCbCr->RGB 3x4, gamma->linear LUT, gamut 3x3
@@ -166,6 +172,7 @@ struct FusedDesc {
 	int n_luts;        // tables to stage in shared memory (0: gather from the raw tables in global memory)
 	int dbg;           // experiment switches (PB_DBG environment variable), 0 in production
 	uint32_t e_magic;  // 0x4B000000, handed to the kernel as data so that (w & mask) | e stays one LOP3
+	uint32_t lds_koff; // -0x4B000000 (mod 2^32) as data of its own: stays in a uniform register, the operand of LDS.U8 [R + UR] (pb_march.cu LutK::koff)
 	int sparse_cm;     // every rc has cm[1] == 0 and cm[10] == 0 (true for all colourMaths YCbCr matrices)
 	int any_planar;    // general load path: some leaf is planar 4:2:2 / 4:2:0, or a source width is not a multiple of 6, or the sink is not v210
 	int single_strip_groups;   // output groups per strip of the single-layer item loop: 31 stand-alone, 30 as the background pass

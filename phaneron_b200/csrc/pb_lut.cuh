@@ -38,8 +38,15 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // operation is IEEE round-to-nearest or an SFU approximation, so both forms agree bit for bit.
 __device__ __forceinline__ float lut_base(float fi, const LutParams &lp) {
 	const float x = __fmaf_rn(fi, lp.p, lp.q);
-	float pw = ex2_approx(__fmul_rn(lg2_approx(x), lp.G));
-	if (lp.affine) pw = __fmaf_rn(pw, lp.s, lp.o);
+	float pw;
+	if (lp.affine == 2) {   // MUFU-free model: Horner, highest coefficient first (the march kernel runs the same chain as FFMA2)
+		pw = lp.c[kLutPolyDeg];
+#pragma unroll
+		for (int k = kLutPolyDeg - 1; k >= 0; --k) pw = __fmaf_rn(pw, x, lp.c[k]);
+	} else {
+		pw = ex2_approx(__fmul_rn(lg2_approx(x), lp.G));
+		if (lp.affine) pw = __fmaf_rn(pw, lp.s, lp.o);
+	}
 	const float toe = __fmul_rn(fi, lp.kt);
 	const float h = __saturatef(__fadd_rn(fi, lp.cJ));   // 0 below the knee, 1 from it on
 	// below the knee exactly the toe; above it RN(RN(pw - toe) + toe), a few ulp from pw -- any deterministic

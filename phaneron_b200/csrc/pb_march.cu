@@ -92,12 +92,17 @@ template <int kLutMode>
 struct LutK {
 	float magic;        // mode 1: 2^23 + shared-memory byte address of the d8 table (even); mode 0: 2^23
 	const float *raw;   // mode 0: the raw table in global memory
+	// mode 1: -0x4B000000 as run-time data (FusedDesc::lds_koff).  bits(RN(u + magic)) = 0x4B000000 + table address + index,
+	// so the byte's address is bits + koff (32-bit wrap-around): a uniform-register operand of the load itself, LDS.U8 [R + UR],
+	// where an immediate mask would cost a LOP3 per lookup (profiles/r02_kbench_lds_ur.txt)
+	uint32_t koff;
 };
 
 // two saturated values -> two exact table values (v210.ts:68-70 / 148-150).
 // convert_ushort_sat_rte(v * 65535) == RNE(sat(v) * 65535): both ends of the clamp are fixed points
 // of the multiply, and NaN saturates to 0 either way.
-// kAffine: 1 = the table model has s != 1 or o != 0 (linear -> gamma direction), 0 = it has not (gamma -> linear: the
+// kAffine: the table model (LutParams::affine) as a compile-time constant: 2 = polynomial power segment (no MUFU),
+// 1 = the table model has s != 1 or o != 0 (linear -> gamma direction), 0 = it has not (gamma -> linear: the
 // predicated-off scale/offset FMA and its two constant loads cost issue slots all the same), -1 = decide at run time
 template <int kLutMode, int kAffine = -1>
 __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const LutParams &lp) {
@@ -106,13 +111,20 @@ __device__ __forceinline__ float2 lut2(float2 z, const LutK<kLutMode> &k, const 
 	if (kLutMode == 0) {
 		return f2(__ldg(k.raw + (__float_as_uint(v.x) & 0xFFFFu)), __ldg(k.raw + (__float_as_uint(v.y) & 0xFFFFu)));
 	}
-	const uint32_t d0 = lds_u8(__float_as_uint(v.x) & 0x7FFFFFu), d1 = lds_u8(__float_as_uint(v.y) & 0x7FFFFFu);
+	const uint32_t d0 = lds_u8(__float_as_uint(v.x) + k.koff), d1 = lds_u8(__float_as_uint(v.y) + k.koff);
 	const float2 fi = __fadd2_rn(v, f2s(-k.magic));   // the index as an exact float
 	// lut_base() of pb_lut.cuh, two lanes wide
 	const float2 x = __ffma2_rn(fi, f2s(lp.p), f2s(lp.q));
-	const float2 y = __fmul2_rn(f2(lg2_approx(x.x), lg2_approx(x.y)), f2s(lp.G));
-	float2 pw = f2(ex2_approx(y.x), ex2_approx(y.y));
-	if (kAffine < 0 ? lp.affine != 0 : kAffine != 0) pw = __ffma2_rn(pw, f2s(lp.s), f2s(lp.o));
+	float2 pw;
+	if (kAffine < 0 ? lp.affine == 2 : kAffine == 2) {   // MUFU-free model: degree-7 Horner chain on the FMA pipe (LutParams::c)
+		pw = f2s(lp.c[kLutPolyDeg]);
+#pragma unroll
+		for (int k = kLutPolyDeg - 1; k >= 0; --k) pw = __ffma2_rn(pw, x, f2s(lp.c[k]));
+	} else {
+		const float2 y = __fmul2_rn(f2(lg2_approx(x.x), lg2_approx(x.y)), f2s(lp.G));
+		pw = f2(ex2_approx(y.x), ex2_approx(y.y));
+		if (kAffine < 0 ? lp.affine == 1 : kAffine == 1) pw = __ffma2_rn(pw, f2s(lp.s), f2s(lp.o));
+	}
 	const float2 toe = mul2_unfusable(fi, f2s(lp.kt));   // feeds a packed add below
 	const float h0 = __saturatef(add(fi.x, lp.cJ)), h1 = __saturatef(add(fi.y, lp.cJ));
 	const float2 base = __ffma2_rn(f2(h0, h1), __fadd2_rn(pw, f2(-toe.x, -toe.y)), toe);
@@ -328,6 +340,7 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	LutK<kLutMode> lut;
 	lut.raw = rc.lut;
 	lut.magic = kLutMode ? kTwo23 + (float)(lut_saddr + (kSingleRc ? 0 : slot) * 65536) : kTwo23;
+	lut.koff = d.lds_koff;
 	const uint32_t E = d.e_magic;
 	const SPtr bufo = buf + (-origin);   // row buffer addressed by source column
 
@@ -610,7 +623,7 @@ constexpr int kSingleRowFloats = 2 * 3 * 192 + 96;            // two row slots (
 // lines FusedDesc::line_pairs marks for this strip pair -- those on which the bottom layer is the only live op of both strips
 // kPlanarSrc: the layer is a planar 4:2:2 / 4:2:0 source (an FFmpegProducer clip): groups come through load_group<true>,
 // flagged groups (yuv422p10 words above 1023) through convert_group_exact
-template <bool kMasked, bool kPlanarSrc = false>
+template <bool kMasked, bool kPlanarSrc = false, int kReadMode = 0>
 __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf, uint32_t lut_saddr, int lane, int warp) {
 	const Leaf &lf = d.layers[0].a;
 	const ReadConsts &rc = d.rc[lf.rc];
@@ -619,8 +632,10 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 	LutK<1> lut, wlut;
 	lut.raw = rc.lut;
 	lut.magic = kTwo23 + (float)(lut_saddr + rc.lut_slot * 65536);
+	lut.koff = d.lds_koff;
 	wlut.raw = d.wc.lut;
 	wlut.magic = kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536);
+	wlut.koff = d.lds_koff;
 	const LutParams &wlp = d.wlp;
 	const uint32_t E = d.e_magic;
 	constexpr int cap = 192, slot_floats = 3 * cap;
@@ -684,7 +699,7 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 					uint4 w = w_pref;
 					if (row != pref_row) w = load_group<kPlanarSrc>(lf, row, g_lo + lane);
 					if (kPlanarSrc && (w.x >> 31)) convert_group_exact(lf, d.rc, row, g_lo + lane, buf + slot * slot_floats, cap, lane);
-					else convert_group<1, true, 0>(w, lane, E, rc, rk, lut, lp, buf + slot * slot_floats, cap);
+					else convert_group<1, true, kReadMode>(w, lane, E, rc, rk, lut, lp, buf + slot * slot_floats, cap);
 				}
 				if (slot) have1 = row; else have0 = row;
 			}
@@ -783,7 +798,7 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 	}
 }
 
-template <bool kPlanarSrc>
+template <bool kPlanarSrc, int kReadMode>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -816,16 +831,17 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 		while (!done)
 			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
 	}
-	march_single_items<false, kPlanarSrc>(d, buf, lut_saddr, lane, warp);
+	march_single_items<false, kPlanarSrc, kReadMode>(d, buf, lut_saddr, lane, warp);
 }
 
-// kPlain: every read table is a non-affine model and the write table an affine one (what colourMaths.ts produces:
-// gamma -> linear on the way in, linear -> gamma on the way out), so both selects are compile-time constants
+// kPlain: 1 = every read table is a non-affine MUFU model and the write table an affine one (what colourMaths.ts produces:
+// gamma -> linear on the way in, linear -> gamma on the way out), so both selects are compile-time constants; 2 = the same with
+// every read table in the MUFU-free polynomial model (LutParams::affine == 2); 0 = decide per table at run time
 // kPlanar: some leaf is a planar 4:2:2 / 4:2:0 source (load_group gathers it into the v210 group layout)
 // kBigRows: the warps' row buffers hold 64 source groups instead of 32 (deep down-scales; needs <= 2 resident tables)
 // kBg: the bottom layer is a full-frame-style v210 leaf (scale >= 1): the strip-pair lines on which it is the only live op are
 // left to a second phase of the same launch, march_single_items<true> (every source row converted once: k_march_single)
-template <int kLutMode, bool kSparse, bool kSingleRc, bool kPlain = false, bool kPlanar = false, bool kBigRows = false, bool kBg = false>
+template <int kLutMode, bool kSparse, bool kSingleRc, int kPlain = 0, bool kPlanar = false, bool kBigRows = false, bool kBg = false>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
@@ -886,6 +902,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	LutK<kLutMode> wlut;
 	wlut.raw = d.wc.lut;
 	wlut.magic = kLutMode ? kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536) : kTwo23;
+	wlut.koff = d.lds_koff;
 	const LutParams &wlp = d.wlp;
 
 	// item -> (line k, strip) is kept incrementally: no integer division per item
@@ -925,7 +942,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
 			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
-			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
+			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
 				const float rmix = sub(1.0f, op.mix);
@@ -1029,7 +1046,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		}
 		__syncwarp();
 	}
-	if (kBg) march_single_items<true>(d, buf, lut_saddr, lane, warp);   // second phase: the background-only strip-pair lines
+	if (kBg) march_single_items<true, false, (kPlain == 2 ? 2 : 0)>(d, buf, lut_saddr, lane, warp);   // second phase: the background-only strip-pair lines
 }
 
 
@@ -1041,6 +1058,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 #define PB_DIRECT_WARPS 28
 #endif
 constexpr int kDirectWarps = PB_DIRECT_WARPS;   // 69 registers per thread: more resident warps than the general kernel's 20
+template <int kReadMode>
 __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -1080,8 +1098,10 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 	LutK<1> lut, wlut;
 	lut.raw = rc.lut;
 	lut.magic = kTwo23 + (float)(lut_saddr + rc.lut_slot * 65536);
+	lut.koff = d.lds_koff;
 	wlut.raw = d.wc.lut;
 	wlut.magic = kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536);
+	wlut.koff = d.lds_koff;
 	const LutParams &wlp = d.wlp;
 	const uint32_t E = d.e_magic;
 	constexpr int cap = kRowGroups * 6;   // 192 texels per plane
@@ -1098,7 +1118,7 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 		const int G = strip * 32 + lane;
 		if (G < groups) {
 			const uint4 w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)y * lf.pitch) + G);
-			convert_group<1, true, 0>(w, lane, E, rc, rk, lut, lp, buf, cap);
+			convert_group<1, true, kReadMode>(w, lane, E, rc, rk, lut, lp, buf, cap);
 		}
 		__syncwarp();
 #pragma unroll 1
@@ -1201,8 +1221,9 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		{
 			std::lock_guard<std::mutex> lk(mu);
 			if (!configured.count(dev)) {
-				cudaError_t e = cudaFuncSetAttribute(k_march_single<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-				if (e == cudaSuccess) e = cudaFuncSetAttribute(k_march_single<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+				cudaError_t e = cudaSuccess;
+				for (auto *k : {k_march_single<false, 0>, k_march_single<true, 0>, k_march_single<false, 2>, k_march_single<true, 2>})
+					if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 				if (e != cudaSuccess) return e;
 				configured.insert(dev);
 			}
@@ -1211,8 +1232,9 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		const int total = n_strips * ((d.out_h + d.single_lines - 1) / d.single_lines);
 		const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
 		const size_t smem_single = (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
-		if (d.layers[0].a.kind == LEAF_V210 && d.sink == SINK_V210) k_march_single<false><<<grid, kMarchThreads, smem_single, s>>>(d);
-		else k_march_single<true><<<grid, kMarchThreads, smem_single, s>>>(d);
+		const bool poly = d.luts[d.rc[d.layers[0].a.rc].lut_slot].lp.affine == 2;   // the layer's read table in the MUFU-free model
+		const bool plain_fmt = d.layers[0].a.kind == LEAF_V210 && d.sink == SINK_V210;
+		(plain_fmt ? (poly ? k_march_single<false, 2> : k_march_single<false, 0>) : (poly ? k_march_single<true, 2> : k_march_single<true, 0>))<<<grid, kMarchThreads, smem_single, s>>>(d);
 		return cudaGetLastError();
 	}
 	if (d.direct_mode) {   // one v210 source 1:1 into a v210 output (prepare_march checks the conditions)
@@ -1223,7 +1245,8 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		{
 			std::lock_guard<std::mutex> lk(mu);
 			if (!configured.count(dev)) {
-				cudaError_t e = cudaFuncSetAttribute(k_march_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+				cudaError_t e = cudaFuncSetAttribute(k_march_direct<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+				if (e == cudaSuccess) e = cudaFuncSetAttribute(k_march_direct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 				if (e != cudaSuccess) return e;
 				configured.insert(dev);
 			}
@@ -1232,25 +1255,36 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		const int total = n_lines * ((d.out_w / 6 + 31) / 32);
 		const int grid = max(1, min(num_sms, (total + kDirectWarps - 1) / kDirectWarps));
 		const size_t smem_direct = (size_t)d.n_luts * 65536 + (size_t)kDirectWarps * kRowFloats * sizeof(float);
-		k_march_direct<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
+		(d.luts[d.rc[0].lut_slot].lp.affine == 2 ? k_march_direct<2> : k_march_direct<0>)<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
 		return cudaGetLastError();
 	}
 	const bool single = d.n_rc == 1;
 	if (d.n_luts > 0) {
-		bool plain = d.wlp.affine != 0;
-		for (int i = 0; i < d.n_rc; ++i)
-			if (d.rc[i].lut_slot >= 0) plain = plain && d.luts[d.rc[i].lut_slot].lp.affine == 0;   // (< 0: constants of rgba8 leaves only)
+		// plain: the write table is the affine MUFU model and the read tables are all the non-affine MUFU model (1) or all the
+		// MUFU-free polynomial model (2): the selects inside lut2 become compile-time constants
+		int plain = d.wlp.affine == 1 ? -1 : 0;
+		for (int i = 0; i < d.n_rc && plain; ++i) {
+			if (d.rc[i].lut_slot < 0) continue;   // (< 0: constants of rgba8 leaves only)
+			const int m = d.luts[d.rc[i].lut_slot].lp.affine == 0 ? 1 : d.luts[d.rc[i].lut_slot].lp.affine == 2 ? 2 : 0;
+			plain = (plain < 0 || plain == m) ? m : 0;
+		}
+		if (plain < 0) plain = 1;   // no YCbCr read table at all
 		if (d.big_rows) {   // (prepare_march sets any_planar with it: the general variants carry the big-row form)
-			if (plain) return single ? launch(k_fused_march<1, true, true, true, true, true>) : launch(k_fused_march<1, true, false, true, true, true>);
-			return launch(k_fused_march<1, true, false, false, true, true>);
+			if (plain == 2) return single ? launch(k_fused_march<1, true, true, 2, true, true>) : launch(k_fused_march<1, true, false, 2, true, true>);
+			if (plain) return single ? launch(k_fused_march<1, true, true, 1, true, true>) : launch(k_fused_march<1, true, false, 1, true, true>);
+			return launch(k_fused_march<1, true, false, 0, true, true>);
 		}
 		if (d.any_planar) {   // prepare_march admits planar leaves only with shared-memory tables and sparse matrices
-			if (plain) return single ? launch(k_fused_march<1, true, true, true, true>) : launch(k_fused_march<1, true, false, true, true>);
-			return launch(k_fused_march<1, true, false, false, true>);
+			if (plain == 2) return single ? launch(k_fused_march<1, true, true, 2, true>) : launch(k_fused_march<1, true, false, 2, true>);
+			if (plain) return single ? launch(k_fused_march<1, true, true, 1, true>) : launch(k_fused_march<1, true, false, 1, true>);
+			return launch(k_fused_march<1, true, false, 0, true>);
 		}
-		if (d.bg_single)   // (prepare_march: plain tables, sparse matrices, v210 leaves with whole groups)
-			return single ? launch(k_fused_march<1, true, true, true, false, false, true>) : launch(k_fused_march<1, true, false, true, false, false, true>);
-		if (plain && d.sparse_cm) return single ? launch(k_fused_march<1, true, true, true>) : launch(k_fused_march<1, true, false, true>);
+		if (d.bg_single) {   // (prepare_march: plain tables, sparse matrices, v210 leaves with whole groups)
+			if (plain == 2) return single ? launch(k_fused_march<1, true, true, 2, false, false, true>) : launch(k_fused_march<1, true, false, 2, false, false, true>);
+			return single ? launch(k_fused_march<1, true, true, 1, false, false, true>) : launch(k_fused_march<1, true, false, 1, false, false, true>);
+		}
+		if (plain == 2 && d.sparse_cm) return single ? launch(k_fused_march<1, true, true, 2>) : launch(k_fused_march<1, true, false, 2>);
+		if (plain && d.sparse_cm) return single ? launch(k_fused_march<1, true, true, 1>) : launch(k_fused_march<1, true, false, 1>);
 		if (d.sparse_cm) return single ? launch(k_fused_march<1, true, true>) : launch(k_fused_march<1, true, false>);
 		return single ? launch(k_fused_march<1, false, true>) : launch(k_fused_march<1, false, false>);
 	}

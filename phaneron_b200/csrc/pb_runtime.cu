@@ -173,7 +173,7 @@ struct pb_ctx {
 	};
 	std::vector<LutTable> lut_tables;
 	std::vector<LutFit> lut_fits;
-	pb::LutParams lut_cands[4];
+	pb::LutParams lut_cands[6];
 	void *lut_cands_dev = nullptr, *lut_res_dev = nullptr, *lut_scratch = nullptr;
 	uint64_t version_counter = 0;
 	struct LineOps {   // per-line op masks of the march kernel
@@ -633,10 +633,66 @@ constexpr TransferSet kTransferSets[] = {
 	{1.099, 0.018, 0.45, 4.5},                   // 601 / 709 / 2020
 	{1.055, 0.0031308, 1.0 / 2.4, 12.92},        // sRGB
 };
-constexpr int kLutCands = 4;
+constexpr int kLutCands = 6;   // per transfer set: gamma->linear as a polynomial (MUFU-free), gamma->linear and linear->gamma as MUFU models
+
+// Coefficients of the MUFU-free model (pb_desc.h LutParams::affine == 2): the power segment of gamma2linearLUT,
+// ((i / 65535 + alpha - 1) / alpha) ^ (1 / gamma) for i in [J, 65535], as a degree-7 polynomial in x = i * p + q in [-1, 1].
+// Least squares on 1024 Chebyshev nodes in the Chebyshev basis, weighted by 1 / f (relative error, i.e. roughly ulps), then
+// converted to monomials.  Any deterministic coefficients would do: the byte table holds the distance to the exact table
+// value and lut_fit_kernel verifies that it fits a byte for all 65536 entries (else the MUFU model of the same curve is taken).
+void fit_power_poly(double alpha, double gamma, int J, pb::LutParams *g) {
+	constexpr int N = pb::kLutPolyDeg + 1, K = 1024;
+	const double pp = 2.0 / (65535.0 - J), qq = -1.0 - pp * J;
+	long double A[N][N + 1] = {};
+	for (int k = 0; k < K; ++k) {
+		const double t = std::cos(M_PI * (k + 0.5) / K);
+		const double i = (t - qq) / pp;
+		const double f = std::pow((i / 65535.0 + alpha - 1.0) / alpha, 1.0 / gamma);
+		double T[N];
+		T[0] = 1.0;
+		T[1] = t;
+		for (int n = 2; n < N; ++n) T[n] = 2.0 * t * T[n - 1] - T[n - 2];
+		for (int r = 0; r < N; ++r) {
+			for (int cidx = 0; cidx < N; ++cidx) A[r][cidx] += (long double)(T[r] / f) * (T[cidx] / f);
+			A[r][N] += (long double)(T[r] / f);
+		}
+	}
+	for (int col = 0; col < N; ++col) {   // Gauss-Jordan with partial pivoting
+		int piv = col;
+		for (int r = col + 1; r < N; ++r)
+			if (fabsl(A[r][col]) > fabsl(A[piv][col])) piv = r;
+		for (int k = 0; k <= N; ++k) std::swap(A[col][k], A[piv][k]);
+		for (int r = 0; r < N; ++r) {
+			if (r == col) continue;
+			const long double m = A[r][col] / A[col][col];
+			for (int k = col; k <= N; ++k) A[r][k] -= m * A[col][k];
+		}
+	}
+	long double mono[N] = {}, Tm2[N] = {1}, Tm1[N] = {0, 1};   // Chebyshev -> monomial: T_n = 2 t T_{n-1} - T_{n-2}
+	for (int n = 0; n < N; ++n) {
+		long double Tn[N] = {};
+		if (n == 0) Tn[0] = 1;
+		else if (n == 1) Tn[1] = 1;
+		else {
+			for (int k = 0; k + 1 < N; ++k) Tn[k + 1] += 2 * Tm1[k];
+			for (int k = 0; k < N; ++k) Tn[k] -= Tm2[k];
+			for (int k = 0; k < N; ++k) { Tm2[k] = Tm1[k]; Tm1[k] = Tn[k]; }
+		}
+		const long double cn = A[n][N] / A[n][n];
+		for (int k = 0; k < N; ++k) mono[k] += cn * Tn[k];
+	}
+	g->p = (float)pp;
+	g->q = (float)qq;
+	for (int k = 0; k < N; ++k) g->c[k] = (float)mono[k];
+	g->affine = 2;
+}
 
 void lut_candidates(pb::LutParams *out) {
 	int n = 0;
+	// The MUFU-free polynomial model is exact (the whole GPU suite passes with it) but costs one more issue slot per lookup than
+	// MUFU.LG2 + MUFU.EX2, and the kernels are issue-bound, not XU-bound: 170.0 vs 164.5 us on the 2160p bench scene
+	// (profiles/r02_kbench_poly_ab.txt).  Opt-in for A/B runs.
+	const bool no_poly = getenv("PB_LUT_POLY") == nullptr;
 	for (const TransferSet &t : kTransferSets) {
 		pb::LutParams g{};   // gamma2linearLUT (colourMaths.ts:130-149)
 		g.p = (float)(1.0 / (65535.0 * t.alpha));
@@ -649,6 +705,10 @@ void lut_candidates(pb::LutParams *out) {
 		while (J < 65536 && J / 65535.0 < t.beta * t.delta) ++J;
 		g.cJ = (float)(1 - J);
 		g.affine = 0;
+		pb::LutParams gp = g;   // the same curve, MUFU-free: preferred when it fits (listed first)
+		fit_power_poly(t.alpha, t.gamma, J, &gp);
+		if (no_poly) gp = g;
+		out[n++] = gp;
 		out[n++] = g;
 		pb::LutParams l{};   // linear2gammaLUT (colourMaths.ts:151-169)
 		l.p = (float)(1.0 / 65535.0);
@@ -963,6 +1023,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	}
 	if (const char *dbg = getenv("PB_DBG")) d.dbg = atoi(dbg);
 	d.e_magic = 0x4B000000u;
+	d.lds_koff = 0u - 0x4B000000u;
 	d.march_w = d.out_w / 6 * 6;
 	d.g_first = 0;
 	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
@@ -1157,9 +1218,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.bg_single = 0;
 	d.line_pairs = nullptr;
 	d.single_strip_groups = 31;
-	const bool plain_tables = all_d8 && n_slots <= 2 && d.sparse_cm && d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine != 0;
-	bool reads_plain = plain_tables;
-	for (int i = 0; i < d.n_rc && reads_plain; ++i) reads_plain = d.rc[i].lut_slot >= 0 && c->lut_tables[slots[d.rc[i].lut_slot]].lp.affine == 0;
+	const bool plain_tables = all_d8 && n_slots <= 2 && d.sparse_cm && d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine == 1;
+	bool reads_plain = plain_tables;   // all read tables in the same non-affine model: MUFU (0) or polynomial (2)
+	for (int i = 0; i < d.n_rc && reads_plain; ++i)
+		reads_plain = d.rc[i].lut_slot >= 0 && c->lut_tables[slots[d.rc[i].lut_slot]].lp.affine != 1 &&
+		              c->lut_tables[slots[d.rc[i].lut_slot]].lp.affine == c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine;
 	const int k0 = d.layers[0].a.kind;
 	const bool l0_v210 = k0 == pb::LEAF_V210;
 	const bool l0_planar = k0 == pb::LEAF_YUV422P10 || k0 == pb::LEAF_YUV422P8 || k0 == pb::LEAF_YUV420P || k0 == pb::LEAF_NV12;
@@ -1264,8 +1327,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	// ToRGBA -> FromRGBA of one v210 source with colourMaths-style tables: the dedicated direct kernel
 	d.direct_mode = d.n_ops == 1 && d.layers[0].kind == pb::LAYER_DIRECT && !d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
 	                d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && all_d8 && n_slots <= 2 && d.sparse_cm && !any_planar && !big_rows &&
-	                d.rc[0].lut_slot >= 0 && c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine == 0 &&
-	                d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine != 0 && !(c->flags & PB_CTX_NO_DIRECT);
+	                d.rc[0].lut_slot >= 0 && c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine != 1 &&
+	                d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine == 1 && !(c->flags & PB_CTX_NO_DIRECT);
 	if (big_rows) {   // 2 x 64 KiB of tables + 20 x 4.5 KiB of rows is what an SM holds
 		if (d.n_luts > 2) return 0;
 		any_planar = true;
@@ -2009,7 +2072,11 @@ int pb_ctx_stats(pb_ctx *c, pb_stats *out) {
 	out->dev_bytes_pooled = c->pool.dev_pooled;
 	out->lut_tables = c->lut_tables.size();
 	out->lut_tables_d8 = 0;
-	for (const auto &t : c->lut_tables) out->lut_tables_d8 += t.d8 ? 1 : 0;
+	out->lut_tables_poly = 0;
+	for (const auto &t : c->lut_tables) {
+		out->lut_tables_d8 += t.d8 ? 1 : 0;
+		out->lut_tables_poly += (t.d8 && t.lp.affine == 2) ? 1 : 0;
+	}
 	return PB_OK;
 }
 
@@ -2272,7 +2339,10 @@ int pb_run_program(pb_ctx *c, pb_prog *g, const pb_param *params, int num_params
 		CU(cudaEventRecord(c->ev0, s));
 	}
 	const uint64_t before = c->stats.kernel_launches;
+	const auto h0 = std::chrono::steady_clock::now();
 	int r = run_locked(c, g, params, num_params, s);
+	c->stats.run_program_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - h0).count();
+	c->stats.run_program_calls += 1;
 	if (r) return r;
 	if (t && c->stats.kernel_launches != before) {
 		CU(cudaEventRecord(c->ev1, s));

@@ -83,7 +83,7 @@ async def main():
             gbs = set_bytes / (us * 1e-6) / 1e9
             print(f"{a.scene:9s} {w}x{h} {inputs:5s} {kern:9s} {us:9.1f} us/frame {1e6 / us:9.0f} fps {gbs:8.1f} GB/s "
                   f"frac {gbs / pk:6.3f}  launches/frame {chains[0].launches} march {st['march_launches']} "
-                  f"luts {st['lut_tables']}/{st['lut_tables_d8']} sets {n_sets}", flush=True)
+                  f"luts {st['lut_tables']}/{st['lut_tables_d8']}/poly {st['lut_tables_poly']} sets {n_sets}", flush=True)
             for c in chains:
                 c.destroy() if hasattr(c, "destroy") else None
             ctx.close()
