@@ -266,7 +266,7 @@ def test_march_kernel_matches_generic_and_oracle(name):
         assert np.array_equal(fast, ref), f"{mode}: {int((fast != ref).sum())} bytes differ"
 
 
-# ---- exact occlusion culling (pb_runtime.cu leaf_opacity) -------------------------------
+# ---- exact occlusion culling (pb_march_prep.cu leaf_opacity) -------------------------------
 def _stack(w, h, xfs, variant="plain", inputs="noise"):
     return _with_xf(layered_scene(w, h, len(xfs), inputs, variant, "709", "2020"), xfs)
 
