@@ -209,6 +209,37 @@ int pb_transform_matrix(int width, int height, int flip_h, int flip_v, double an
                         double anchor_y, double scale_x, double scale_y, double offset_x,
                         double offset_y, double rotate_turns, float *out9);
 
+/* ---- ROUTE between channels on different GPUs ------------------------------------------------------------------
+   The reference's ROUTE producer forks another channel's pipes: the routed frame is a REFERENCE to that channel's
+   combined RGBA-f32 OpenCLBuffer (routeProducer.ts:63-73, channel.ts:289-300, routeSource.ts:26-31), all inside one
+   process and one device.  With channels sharded one per GPU the frame has to cross: these calls are that hand-off
+   (csrc/pb_route.cu).  One process per GPU: NCCL point-to-point (ncclSend / ncclRecv over NVLink) on a side stream of the
+   context, one group per frame period; the host never blocks in the steady state.  libnccl.so.2 is loaded on first use.
+
+     rank 0: pb_comm_unique_id(id); the host carries the 128 bytes to the other ranks (its control plane)
+     every rank: pb_comm_init(ctx, rank, world, id, &comm)
+     every frame period: pb_route_begin; pb_route_send(frame, peer) / pb_route_recv(landing, peer) ...; pb_route_end;
+                         pb_route_wait(comm, PB_QUEUE_PROCESS) where a received frame is first consumed
+   Sent frames (materialised on demand if still deferred) and landing buffers stay referenced until the exchange has
+   completed; the next pb_route_begin (or pb_route_sync) gives them back. */
+typedef struct pb_comm pb_comm;
+#define PB_COMM_ID_BYTES 128
+int pb_comm_unique_id(void *out128);
+int pb_comm_init(pb_ctx *ctx, int rank, int world, const void *id128, pb_comm **out);
+int pb_comm_info(pb_comm *comm, int *rank, int *world, uint64_t *bytes_sent, uint64_t *bytes_received);
+int pb_comm_destroy(pb_comm *comm);
+int pb_route_begin(pb_comm *comm);
+int pb_route_send(pb_comm *comm, pb_buf *frame, int peer);
+int pb_route_recv(pb_comm *comm, pb_buf *landing, int peer);
+int pb_route_end(pb_comm *comm);
+/* make `queue` wait, on the device, for the exchange last ended */
+int pb_route_wait(pb_comm *comm, int queue);
+/* block the host until the exchange last ended has completed and release the buffers it held */
+int pb_route_sync(pb_comm *comm);
+/* one process, one context per GPU (a Node.js host): peer-to-peer copy of a routed frame into a buffer of another
+   context, on the destination's load queue, ordered after the source's process queue */
+int pb_route_copy_peer(pb_buf *src, pb_buf *dst);
+
 #ifdef __cplusplus
 }
 #endif

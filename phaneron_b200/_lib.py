@@ -41,6 +41,8 @@ SYMBOLS = [
     "pb_chain_begin", "pb_chain_end", "pb_chain_info", "pb_chain_replay", "pb_chain_destroy",
     "pb_gamma2linear_lut", "pb_linear2gamma_lut", "pb_ycbcr2rgb_matrix", "pb_rgb2ycbcr_matrix",
     "pb_rgb2rgb_matrix", "pb_transform_matrix",
+    "pb_comm_unique_id", "pb_comm_init", "pb_comm_info", "pb_comm_destroy", "pb_route_begin", "pb_route_send",
+    "pb_route_recv", "pb_route_end", "pb_route_wait", "pb_route_sync", "pb_route_copy_peer",
 ]
 
 
@@ -120,6 +122,17 @@ def lib() -> C.CDLL:
         "pb_rgb2ycbcr_matrix": (i, [cp, i, i, i, i, vp]),
         "pb_rgb2rgb_matrix": (i, [cp, cp, vp]),
         "pb_transform_matrix": (i, [i, i, i, i] + [C.c_double] * 7 + [vp]),
+        "pb_comm_unique_id": (i, [vp]),
+        "pb_comm_init": (i, [vp, i, i, vp, C.POINTER(vp)]),
+        "pb_comm_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "pb_comm_destroy": (i, [vp]),
+        "pb_route_begin": (i, [vp]),
+        "pb_route_send": (i, [vp, vp, i]),
+        "pb_route_recv": (i, [vp, vp, i]),
+        "pb_route_end": (i, [vp]),
+        "pb_route_wait": (i, [vp, i]),
+        "pb_route_sync": (i, [vp]),
+        "pb_route_copy_peer": (i, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(l, name)
@@ -132,3 +145,16 @@ def lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != PB_OK:
         raise PhaneronError(lib().pb_last_error().decode() or f"phaneron_b200 error {rc}")
+
+
+def call_in_worker(fn, *args):
+    """for run_in_executor: pb_last_error() is thread-local, so the message of a failed call has to be fetched on the worker
+    thread that made it (the event-loop thread would read its own, stale or empty, message).  -> (rc, message)"""
+    rc = fn(*args)
+    return rc, (lib().pb_last_error().decode() if rc != PB_OK else "")
+
+
+def check_worker(res) -> None:
+    rc, msg = res
+    if rc != PB_OK:
+        raise PhaneronError(msg or f"phaneron_b200 error {rc}")

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("PB_LIB_OUT") or os.path.join(HERE, "libphaneron_b200.so")   # PB_LIB_OUT: kernel-variant experiments (load with PB_LIB)
-SOURCES = ["pb_kernels.cu", "pb_fused.cu", "pb_march.cu", "pb_recorder.cu", "pb_lut_cache.cu", "pb_march_prep.cu", "pb_abi.cu", "pb_colour.cpp"]
+SOURCES = ["pb_kernels.cu", "pb_fused.cu", "pb_march.cu", "pb_recorder.cu", "pb_lut_cache.cu", "pb_march_prep.cu", "pb_abi.cu", "pb_route.cu", "pb_colour.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs]  # static cudart: self-contained .so
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-ldl"]  # static cudart: self-contained .so (libnccl is dlopen'ed by pb_route.cu)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

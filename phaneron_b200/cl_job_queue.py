@@ -123,6 +123,11 @@ class ClProcessJobs:
                 await self.clContext.waitFinish(self.clContext.queue.process)
             except BaseException as e:  # reject the runQueue() promise instead of wedging the loop
                 del self.requests[chan]
+                for j in req.jobs:      # the release callbacks still run (as clearQueue does, clJobQueue.ts:87-94): no buffer leaks
+                    try:
+                        j.cb()
+                    except Exception:
+                        pass
                 if req.error:
                     req.error(e)
                 continue

@@ -21,6 +21,7 @@ int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out) {
 	c->allow_march = !(flags & PB_CTX_NO_MARCH);
 	CU(cudaGetDeviceProperties(&c->prop, gpu_index));
 	for (auto &q : c->q) CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+	c->pool.queues = c->q;
 	CU(cudaEventCreate(&c->ev0));
 	CU(cudaEventCreate(&c->ev1));
 	CU(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
@@ -100,6 +101,10 @@ int pb_buf_create(pb_ctx *c, size_t bytes, int dir, int svm, int image_w, int im
 	b->w = image_w;
 	b->h = image_h;
 	if (owner) b->owner = owner;
+	{   // a fresh content id: two buffers never share one (the gamma-table cache is keyed by it), and 0 is never cached
+		std::lock_guard<std::recursive_mutex> lk(c->mu);
+		b->version = ++c->version_counter;
+	}
 	*out = b;
 	return PB_OK;
 }

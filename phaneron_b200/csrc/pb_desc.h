@@ -177,8 +177,8 @@ struct FusedDesc {
 	int any_planar;    // general load path: some leaf is planar 4:2:2 / 4:2:0, or a source width is not a multiple of 6, or the sink is not v210
 	int single_strip_groups;   // output groups per strip of the single-layer item loop: 31 stand-alone, 30 as the background pass
 	int bg_single;             // the general kernel leaves the background-only strip-pair lines to march_single_items<true>
-	unsigned int *bg_counter;   // bg_single: item counter of the second phase (never reset; see march_single_items)
-	unsigned int bg_base;       // its value when this launch starts (set at launch time)
+	unsigned int *bg_counter;   // bg_single: item counter of the second phase, this launch's own (zeroed on the stream before the launch)
+	unsigned int bg_base;       // its value when this launch starts: 0
 	const unsigned long long *line_pairs;   // bg_single: per output line, bit p set = strip pair p is background-only there
 	int single_lines;  // > 0: k_march_single (one v210 layer through an axis-aligned Transform): output lines per work item
 	int2 single_strips[64];   // k_march_single: {first source group, source groups} of each 186-px output strip

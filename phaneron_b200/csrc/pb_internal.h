@@ -47,15 +47,45 @@ using NodeP = std::shared_ptr<Node>;
 // performs no cudaMalloc/cudaFree (the reference allocates a fresh SVM buffer per stage per
 // frame: mixer.ts:196, transitioner.ts:152, combiner.ts:230)
 struct Pool {
-	std::unordered_map<size_t, std::vector<void *>> dev, host;
+	// A block goes back to its free list while kernels / copies that use it may still be in flight: the owner's last
+	// reference often drops right after the launch was ISSUED (deferred frames release their packed sources as soon as the
+	// fused launch is queued).  So every pooled block carries two events, recorded when it was returned on the process and the
+	// load queue; whoever takes the block next makes all three queues wait for the ones that have not completed yet
+	// (device-side waits, no host stall).  Without this an upload on the load queue could overwrite a source that a kernel
+	// on the process queue was still reading.
+	struct Block {
+		void *p;
+		cudaEvent_t ev[2];
+	};
+	std::unordered_map<size_t, std::vector<Block>> dev;
+	std::unordered_map<size_t, std::vector<void *>> host;
+	std::vector<cudaEvent_t> events;   // spare events
+	cudaStream_t *queues = nullptr;    // the context's three queues (load, process, unload)
 	size_t dev_pooled = 0, dev_live = 0;
 	static constexpr size_t kMaxPooled = size_t(24) << 30;
 
+	cudaEvent_t take_event() {
+		if (!events.empty()) {
+			cudaEvent_t e = events.back();
+			events.pop_back();
+			return e;
+		}
+		cudaEvent_t e = nullptr;
+		cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+		return e;
+	}
 	cudaError_t dev_get(size_t n, void **p) {
 		auto &v = dev[n];
 		if (!v.empty()) {
-			*p = v.back();
+			Block b = v.back();
 			v.pop_back();
+			for (cudaEvent_t e : b.ev) {
+				if (!e) continue;
+				if (queues && cudaEventQuery(e) != cudaSuccess)
+					for (int q = 0; q < 3; ++q) cudaStreamWaitEvent(queues[q], e, 0);
+				events.push_back(e);
+			}
+			*p = b.p;
 			dev_pooled -= n;
 			dev_live += n;
 			return cudaSuccess;
@@ -72,10 +102,17 @@ struct Pool {
 		if (!p) return;
 		dev_live -= n;
 		if (dev_pooled + n > kMaxPooled) {
-			cudaFree(p);
+			cudaFree(p);   // (synchronises with outstanding work on the block)
 			return;
 		}
-		dev[n].push_back(p);
+		Block b{p, {nullptr, nullptr}};
+		if (queues) {
+			b.ev[0] = take_event();
+			b.ev[1] = take_event();
+			if (b.ev[0]) cudaEventRecord(b.ev[0], queues[1]);   // PB_QUEUE_PROCESS
+			if (b.ev[1]) cudaEventRecord(b.ev[1], queues[0]);   // PB_QUEUE_LOAD
+		}
+		dev[n].push_back(b);
 		dev_pooled += n;
 	}
 	cudaError_t host_get(size_t n, void **p) {
@@ -92,12 +129,18 @@ struct Pool {
 	}
 	void trim() {
 		for (auto &kv : dev)
-			for (void *p : kv.second) cudaFree(p);
+			for (Block &b : kv.second) {
+				cudaFree(b.p);
+				for (cudaEvent_t e : b.ev)
+					if (e) events.push_back(e);
+			}
 		dev.clear();
 		dev_pooled = 0;
 	}
 	void destroy() {
 		trim();
+		for (cudaEvent_t e : events) cudaEventDestroy(e);
+		events.clear();
 		for (auto &kv : host)
 			for (void *p : kv.second) cudaFreeHost(p);
 		host.clear();
@@ -179,8 +222,8 @@ struct pb_ctx {
 		unsigned long long *dev = nullptr;
 	};
 	std::vector<LinePairs> line_pairs;
-	unsigned int *bg_counter = nullptr;   // device counter of the background pass (never reset) and the value the next launch starts from
-	unsigned int bg_next_base = 0;
+	unsigned int *bg_counter = nullptr;   // ring of device counters of the background pass: one per launch, zeroed on its stream (launch_compiled)
+	unsigned int bg_next_base = 0;        // next ring slot
 	std::vector<LineOps> line_ops;
 };
 

@@ -118,7 +118,7 @@ struct FitResultHost {   // mirrors pb::LutFitResult
 
 int lut_table_of(pb_ctx *c, pb_buf *lut, int *table_out) {
 	for (const auto &f : c->lut_fits)
-		if (f.version == lut->version) {
+		if (lut->version != 0 && f.version == lut->version) {
 			*table_out = f.table;
 			return PB_OK;
 		}
@@ -140,8 +140,15 @@ int lut_table_of(pb_ctx *c, pb_buf *lut, int *table_out) {
 	CU(cudaMemcpyAsync(res, c->lut_res_dev, sizeof res, cudaMemcpyDeviceToHost, s));
 	CU(cudaStreamSynchronize(s));
 	int table = -1;
-	for (size_t i = 0; i < c->lut_tables.size(); ++i)
-		if (c->lut_tables[i].hash == res[0].hash) table = (int)i;
+	for (size_t i = 0; i < c->lut_tables.size() && table < 0; ++i) {
+		if (c->lut_tables[i].hash != res[0].hash) continue;
+		// same 64-bit hash: confirm the contents before sharing the table (a collision would mean wrong colours, silently)
+		std::vector<float> a(65536), b(65536);
+		CU(cudaMemcpyAsync(a.data(), c->lut_tables[i].raw, 65536 * sizeof(float), cudaMemcpyDeviceToHost, s));
+		CU(cudaMemcpyAsync(b.data(), lut->dev, 65536 * sizeof(float), cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+		if (0 == memcmp(a.data(), b.data(), 65536 * sizeof(float))) table = (int)i;
+	}
 	if (table < 0) {
 		pb_ctx::LutTable t;
 		t.hash = res[0].hash;
@@ -162,7 +169,7 @@ int lut_table_of(pb_ctx *c, pb_buf *lut, int *table_out) {
 		table = (int)c->lut_tables.size() - 1;
 	}
 	if (c->lut_fits.size() >= 4096) c->lut_fits.erase(c->lut_fits.begin(), c->lut_fits.begin() + 2048);
-	c->lut_fits.push_back({lut->version, table});
+	if (lut->version != 0) c->lut_fits.push_back({lut->version, table});
 	*table_out = table;
 	return PB_OK;
 }

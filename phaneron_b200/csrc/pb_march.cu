@@ -648,8 +648,7 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 	const int stride = gridDim.x * kMarchWarps;
 	// Stand-alone the items are dealt round-robin.  As the background pass they are claimed from a counter in global memory:
 	// warps reach this phase at different times and the blocks are coarse, so a static deal leaves a long tail.  The counter
-	// is never reset: the host hands every launch the value it starts from (each warp of the grid claims exactly one item
-	// past the end, so a launch advances it by total + warps; unsigned arithmetic, wrap-around safe).
+	// belongs to this launch alone: the host zeroes it on the launching stream right before the launch (launch_compiled).
 	int item = blockIdx.x * kMarchWarps + warp;
 	auto claim = [&]() -> int {
 		unsigned v = 0;

@@ -696,21 +696,17 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool march, void *out_rgba) {
 	pb::FusedDesc bg_copy;
 	const pb::FusedDesc *dp = &d_in;
-	if (march && d_in.bg_single) {   // the second phase claims its items from a counter that is never reset (pb_march.cu)
-		if (!c->bg_counter) {
-			CU(cudaMalloc(&c->bg_counter, sizeof(unsigned int)));
-			CU(cudaMemsetAsync(c->bg_counter, 0, sizeof(unsigned int), s));
-			c->bg_next_base = 0;
-		}
+	if (march && d_in.bg_single) {
+		// The second phase claims its items from a counter in global memory (pb_march.cu march_single_items).  Every launch gets
+		// a counter of its own out of a ring, zeroed on the launching stream just before the launch: nothing to predict on the
+		// host, nothing shared between launches on different queues, and a failed launch leaves no state behind.
+		constexpr unsigned kRing = 256;
+		if (!c->bg_counter) CU(cudaMalloc(&c->bg_counter, kRing * sizeof(unsigned int)));
+		unsigned int *ctr = c->bg_counter + (c->bg_next_base++ % kRing);
+		CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
 		bg_copy = d_in;
-		bg_copy.bg_counter = c->bg_counter;
-		bg_copy.bg_base = c->bg_next_base;
-		const int n_lines = d_in.out_h;
-		const int pairs = (d_in.out_w / 6 + d_in.single_strip_groups - 1) / d_in.single_strip_groups;
-		const unsigned total = (unsigned)pairs * (unsigned)((n_lines + d_in.single_lines - 1) / d_in.single_lines);
-		const unsigned items1 = (unsigned)n_lines * (unsigned)d_in.n_strips;   // the grid launch_fused_march picks (phase-1 items)
-		const unsigned grid = std::max(1u, std::min((unsigned)c->prop.multiProcessorCount, (items1 + pb::kMarchWarps - 1) / pb::kMarchWarps));
-		c->bg_next_base += total + grid * pb::kMarchWarps;
+		bg_copy.bg_counter = ctr;
+		bg_copy.bg_base = 0;
 		dp = &bg_copy;
 	}
 	const pb::FusedDesc &d = *dp;

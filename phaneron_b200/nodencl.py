@@ -166,8 +166,7 @@ class OpenCLBuffer:
             # nodencl runs every call as async work on the libuv pool: frame-sized copies go to a
             # worker thread (ctypes drops the GIL), so `await Promise.all([...])`-style callers overlap H2D, D2H
             # and kernel launches exactly as they do under Node
-            rc = await asyncio.get_running_loop().run_in_executor(None, _lib.lib().pb_buf_host_access, h, m, q, ptr, n)
-            check(rc)
+            _lib.check_worker(await asyncio.get_running_loop().run_in_executor(None, _lib.call_in_worker, _lib.lib().pb_buf_host_access, h, m, q, ptr, n))
         else:
             check(_lib.lib().pb_buf_host_access(h, m, q, ptr, n))
 
@@ -291,7 +290,7 @@ class clContext:
             return
         # the copy queues are waited on from a worker thread, like nodencl's waitFinish on the libuv pool: a producer
         # waiting for its upload (macadamProducer.ts:186) must not stall the loop that is composing the previous frame
-        check(await asyncio.get_running_loop().run_in_executor(None, _lib.lib().pb_wait_finish, self._need(), q))
+        _lib.check_worker(await asyncio.get_running_loop().run_in_executor(None, _lib.call_in_worker, _lib.lib().pb_wait_finish, self._need(), q))
 
 
 class Chain:

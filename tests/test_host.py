@@ -148,12 +148,13 @@ def test_job_queue_semantics():
         assert fired == ["cb1", "cb2", "cb3"]
         assert len(ctx.log) == 3
         # a failing kernel rejects the runQueue awaitable and the loop keeps serving later requests
-        jobs.add({"source": "b", "timestamp": 0}, "bad", "boom", {}, lambda: fired.append("never"))
+        jobs.add({"source": "b", "timestamp": 0}, "bad", "boom", {}, lambda: fired.append("released-b"))
         with pytest.raises(RuntimeError, match="kernel failed"):
             await jobs.runQueue({"source": "b", "timestamp": 0})
         jobs.add({"source": "c", "timestamp": 0}, "ok", "p4", {}, lambda: fired.append("cb4"))
         await jobs.runQueue({"source": "c", "timestamp": 0})
-        assert fired[-1] == "cb4" and "never" not in fired
+        # the failed request's release callbacks ran too (its buffers must not leak; the reference would wedge here)
+        assert fired[-2:] == ["released-b", "cb4"]
 
     asyncio.run(go())
 
