@@ -493,6 +493,10 @@ def main():
     ap.add_argument("--no-culling", action="store_true", help="evaluate layers hidden under opaque ones too (A/B)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle comparison of the replayed and downloaded frames")
     ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP, help="frames per device-resident step (profiling runs use a few)")
+    ap.add_argument("--config", default="3", choices=["3", "route", "5"],
+                    help="3: BASELINE.json configs[2], the 2160p 4-layer composite (default, the headline metric); route: configs[3], 1080p "
+                         "channels one per GPU with ROUTE cross-feed over NCCL; 5: configs[4], 4320p 2-layer composite with a Lanczos-3 PiP")
+    ap.add_argument("--route-frames-per-step", type=int, default=200)
     ap.add_argument("--kernel", default="march", choices=["march", "march_raw", "generic"],
                     help="march: fused kernel, gamma tables in shared memory (default); march_raw: same kernel gathering "
                          "from the raw tables; generic: the fallback fused kernel")
@@ -512,6 +516,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config == "route":
+        from phaneron_b200 import bench_route
+        asyncio.run(bench_route.run(args, rank, world, local_rank, emit, ClockSampler, measured_peak))
         return
     asyncio.run(run_ours(args, rank, world, local_rank))
 

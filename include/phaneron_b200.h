@@ -1,6 +1,6 @@
 /*
  * phaneron_b200.h -- C ABI of libphaneron_b200.so, the B200 (sm_100a) replacement
- * for the `nodencl` OpenCL addon that Streampunk/phaneron's src/process/*.ts and
+ * for the `nodencl` OpenCL addon that the .ts files of Streampunk/phaneron's src/process and
  * src/clJobQueue.ts bind to.
  *
  * Every entry point cites the nodencl call (by its call sites in the reference,
@@ -137,6 +137,10 @@ int pb_buf_wrap(pb_ctx *ctx, void *dev_ptr, size_t bytes, int image_w, int image
 int pb_buf_addref(pb_buf *buf);   /* OpenCLBuffer.addRef()  */
 int pb_buf_release(pb_buf *buf);  /* OpenCLBuffer.release() */
 int pb_buf_refs(pb_buf *buf);
+/* give the device memory (and any deferred expression) of a buffer back to the pool while keeping the handle and its
+   pinned host face: what the N-API wrapper calls when the last USER reference has gone and only the node Buffer's own
+   reference keeps the bytes visible to JavaScript until the garbage collector runs */
+int pb_buf_trim(pb_buf *buf);
 size_t pb_buf_bytes(pb_buf *buf);
 /* host-addressable storage of the Buffer subclass (pinned); valid until release */
 void *pb_buf_host_ptr(pb_buf *buf);
@@ -234,6 +238,9 @@ int pb_route_recv(pb_comm *comm, pb_buf *landing, int peer);
 int pb_route_end(pb_comm *comm);
 /* make `queue` wait, on the device, for the exchange last ended */
 int pb_route_wait(pb_comm *comm, int queue);
+/* ... or for the one `age` exchanges before it (age 0 = the last one; up to 2): a host that composes frame n + 1 from what
+   exchange n - 1 delivered lets exchange n overlap that frame's kernels */
+int pb_route_wait_age(pb_comm *comm, int queue, int age);
 /* block the host until the exchange last ended has completed and release the buffers it held */
 int pb_route_sync(pb_comm *comm);
 /* one process, one context per GPU (a Node.js host): peer-to-peer copy of a routed frame into a buffer of another

@@ -34,7 +34,7 @@ OPS = {
 SYMBOLS = [
     "pb_last_error", "pb_version", "pb_ctx_create", "pb_ctx_destroy", "pb_ctx_info", "pb_ctx_stats",
     "pb_ctx_set_flags", "pb_buf_create", "pb_buf_wrap", "pb_buf_addref", "pb_buf_release", "pb_buf_refs",
-    "pb_buf_bytes", "pb_buf_host_ptr", "pb_buf_dev_ptr", "pb_buf_is_deferred", "pb_buf_host_access",
+    "pb_buf_bytes", "pb_buf_trim", "pb_buf_host_ptr", "pb_buf_dev_ptr", "pb_buf_is_deferred", "pb_buf_host_access",
     "pb_buf_upload_async", "pb_buf_download_async", "pb_host_alloc", "pb_host_free", "pb_prog_create",
     "pb_prog_destroy", "pb_run_program", "pb_wait_finish", "pb_queue_wait_queue", "pb_ctx_stream",
     "pb_event_create", "pb_event_record", "pb_event_sync", "pb_event_elapsed_ms", "pb_event_destroy",
@@ -42,7 +42,7 @@ SYMBOLS = [
     "pb_gamma2linear_lut", "pb_linear2gamma_lut", "pb_ycbcr2rgb_matrix", "pb_rgb2ycbcr_matrix",
     "pb_rgb2rgb_matrix", "pb_transform_matrix",
     "pb_comm_unique_id", "pb_comm_init", "pb_comm_info", "pb_comm_destroy", "pb_route_begin", "pb_route_send",
-    "pb_route_recv", "pb_route_end", "pb_route_wait", "pb_route_sync", "pb_route_copy_peer",
+    "pb_route_recv", "pb_route_end", "pb_route_wait", "pb_route_wait_age", "pb_route_sync", "pb_route_copy_peer",
 ]
 
 
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         "pb_buf_release": (i, [vp]),
         "pb_buf_refs": (i, [vp]),
         "pb_buf_bytes": (sz, [vp]),
+        "pb_buf_trim": (i, [vp]),
         "pb_buf_host_ptr": (vp, [vp]),
         "pb_buf_dev_ptr": (vp, [vp]),
         "pb_buf_is_deferred": (i, [vp]),
@@ -131,6 +132,7 @@ def lib() -> C.CDLL:
         "pb_route_recv": (i, [vp, vp, i]),
         "pb_route_end": (i, [vp]),
         "pb_route_wait": (i, [vp, i]),
+        "pb_route_wait_age": (i, [vp, i, i]),
         "pb_route_sync": (i, [vp]),
         "pb_route_copy_peer": (i, [vp, vp]),
     }

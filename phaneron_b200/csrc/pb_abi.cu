@@ -134,6 +134,17 @@ int pb_buf_release(pb_buf *b) {
 }
 
 int pb_buf_refs(pb_buf *b) { return b ? b->refs.load() : 0; }
+
+int pb_buf_trim(pb_buf *b) {
+	if (!b) return fail(PB_ERR_ARG, "null buffer");
+	pb_ctx *c = b->ctx;
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	b->expr.reset();
+	if (b->dev && !b->dev_external) c->pool.dev_put(b->bytes, b->dev);
+	b->dev = nullptr;
+	b->host_dirty = false;
+	return PB_OK;
+}
 size_t pb_buf_bytes(pb_buf *b) { return b ? b->bytes : 0; }
 
 void *pb_buf_host_ptr(pb_buf *b) {

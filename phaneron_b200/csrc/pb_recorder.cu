@@ -535,9 +535,13 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 			if (interlace != 0 && (r = flush_host(out, s))) return r;
 			out->host_dirty = false;
 			if ((r = ensure_dev(out))) return r;
-			if (v210 && in->expr) {
+			// (while a chain is being recorded a frame that already is real memory goes through the fused path too, as an RGBA
+			// leaf: a recorded chain replays fused launches only -- the ROUTE payload frame that FromRGBA packs, bench_route.py)
+			if (v210 && (in->expr || (c->recording && in->w > 0 && (c->flags & PB_CTX_DEFER)))) {
+				NodeP root;
+				if ((r = input_expr(in, &root))) return r;
 				Compiler cc{c};
-				if ((r = cc.compile(in->expr))) return r;
+				if ((r = cc.compile(root))) return r;
 				cc.d.wc = wc;
 				cc.d.interlace = interlace;
 				cc.d.out = out->dev;

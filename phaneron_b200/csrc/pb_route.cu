@@ -97,18 +97,25 @@ struct pb_comm {
 	int rank = 0, world = 1;
 	cudaStream_t rs = nullptr;           // the side stream the exchanges run on
 	cudaEvent_t ev_ready = nullptr;      // process queue -> side stream
-	cudaEvent_t ev_done = nullptr;       // side stream -> whoever consumes the received frames
-	bool open = false, pending = false;  // between begin and end / an ended exchange whose buffers are still held
-	std::vector<pb_buf *> held;
+	// The last kRing exchanges, newest at `head`: the event recorded at their end on the side stream and the buffers they hold.
+	// Keeping several lets exchange n run while frame n + 1 is composed from what exchange n - 1 delivered (pb_route_wait_age).
+	static constexpr int kRing = 4;
+	struct Gen {
+		cudaEvent_t done = nullptr;      // side stream -> whoever consumes the received frames
+		std::vector<pb_buf *> held;
+		bool pending = false;            // ended, buffers still held
+	} gen[kRing];
+	int head = 0;
+	bool open = false;                   // between begin and end
 	uint64_t bytes_sent = 0, bytes_received = 0;
 };
 
 namespace {
 
-void release_held(pb_comm *m) {   // with ctx->mu held
-	for (pb_buf *b : m->held) buf_release_locked(b);
-	m->held.clear();
-	m->pending = false;
+void release_gen(pb_comm *m, pb_comm::Gen &g) {   // with ctx->mu held
+	for (pb_buf *b : g.held) buf_release_locked(b);
+	g.held.clear();
+	g.pending = false;
 }
 
 // the side stream must not touch `b` before everything queued so far on the process (and load) queue has run
@@ -153,7 +160,7 @@ int pb_comm_init(pb_ctx *c, int rank, int world, const void *id128, pb_comm **ou
 	}
 	CU(cudaStreamCreateWithFlags(&m->rs, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&m->ev_ready, cudaEventDisableTiming));
-	CU(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+	for (auto &g : m->gen) CU(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
 	*out = m;
 	return PB_OK;
 }
@@ -173,12 +180,12 @@ int pb_comm_destroy(pb_comm *m) {
 	cudaStreamSynchronize(m->rs);
 	{
 		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
-		release_held(m);
+		for (auto &g : m->gen) release_gen(m, g);
 	}
 	if (m->comm && nccl()->CommDestroy) nccl()->CommDestroy(m->comm);
 	cudaStreamDestroy(m->rs);
 	cudaEventDestroy(m->ev_ready);
-	cudaEventDestroy(m->ev_done);
+	for (auto &g : m->gen) cudaEventDestroy(g.done);
 	delete m;
 	return PB_OK;
 }
@@ -187,10 +194,18 @@ int pb_route_begin(pb_comm *m) {
 	if (!m) return fail(PB_ERR_ARG, "null comm");
 	if (m->open) return fail(PB_ERR_STATE, "pb_route_begin: an exchange is already open");
 	CU(cudaSetDevice(m->ctx->dev));
-	if (m->pending) {   // the previous exchange (normally finished a frame period ago) gives its buffers back
-		CU(cudaEventSynchronize(m->ev_done));
+	{   // earlier exchanges that have completed give their buffers back; the slot about to be reused has to (normally it
+		// finished several frame periods ago, so this does not block)
 		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
-		release_held(m);
+		const int next = (m->head + 1) % pb_comm::kRing;
+		for (int k = 0; k < pb_comm::kRing; ++k) {
+			pb_comm::Gen &g = m->gen[k];
+			if (!g.pending) continue;
+			if (k == next) CU(cudaEventSynchronize(g.done));
+			else if (cudaEventQuery(g.done) != cudaSuccess) continue;
+			release_gen(m, g);
+		}
+		m->head = next;
 	}
 	NC(nccl()->GroupStart());
 	m->open = true;
@@ -211,7 +226,7 @@ int pb_route_send(pb_comm *m, pb_buf *frame, int peer) {
 	if ((r = order_after_queues(m))) return r;
 	NC(nccl()->Send(frame->dev, frame->bytes, kNcclUint8, peer, m->comm, m->rs));
 	frame->refs.fetch_add(1);
-	m->held.push_back(frame);
+	m->gen[m->head].held.push_back(frame);
 	m->bytes_sent += frame->bytes;
 	return PB_OK;
 }
@@ -231,7 +246,7 @@ int pb_route_recv(pb_comm *m, pb_buf *landing, int peer) {
 	NC(nccl()->Recv(landing->dev, landing->bytes, kNcclUint8, peer, m->comm, m->rs));
 	landing->version = ++m->ctx->version_counter;
 	landing->refs.fetch_add(1);
-	m->held.push_back(landing);
+	m->gen[m->head].held.push_back(landing);
 	m->bytes_received += landing->bytes;
 	return PB_OK;
 }
@@ -242,29 +257,32 @@ int pb_route_end(pb_comm *m) {
 	CU(cudaSetDevice(m->ctx->dev));
 	m->open = false;
 	NC(nccl()->GroupEnd());
-	CU(cudaEventRecord(m->ev_done, m->rs));
-	m->pending = true;
+	CU(cudaEventRecord(m->gen[m->head].done, m->rs));
+	m->gen[m->head].pending = true;
 	return PB_OK;
 }
 
-int pb_route_wait(pb_comm *m, int queue) {
+int pb_route_wait_age(pb_comm *m, int queue, int age) {
 	if (!m) return fail(PB_ERR_ARG, "null comm");
 	if (queue < 0 || queue > 2) return fail(PB_ERR_ARG, "bad queue %d", queue);
+	if (age < 0 || age >= pb_comm::kRing - 1) return fail(PB_ERR_ARG, "age %d: the last %d exchanges can be waited for", age, pb_comm::kRing - 1);
 	if (m->open) return fail(PB_ERR_STATE, "pb_route_wait inside an open exchange");
 	CU(cudaSetDevice(m->ctx->dev));
-	if (m->pending) CU(cudaStreamWaitEvent(m->ctx->q[queue], m->ev_done, 0));
+	// (an exchange that has been released already has completed; its event still says so)
+	pb_comm::Gen &g = m->gen[(m->head + pb_comm::kRing - age) % pb_comm::kRing];
+	CU(cudaStreamWaitEvent(m->ctx->q[queue], g.done, 0));
 	return PB_OK;
 }
+
+int pb_route_wait(pb_comm *m, int queue) { return pb_route_wait_age(m, queue, 0); }
 
 int pb_route_sync(pb_comm *m) {
 	if (!m) return fail(PB_ERR_ARG, "null comm");
 	if (m->open) return fail(PB_ERR_STATE, "pb_route_sync inside an open exchange");
 	CU(cudaSetDevice(m->ctx->dev));
-	if (m->pending) {
-		CU(cudaEventSynchronize(m->ev_done));
-		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
-		release_held(m);
-	}
+	CU(cudaStreamSynchronize(m->rs));
+	std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
+	for (auto &g : m->gen) release_gen(m, g);
 	return PB_OK;
 }
 

@@ -86,9 +86,10 @@ class RouteComm:
     def end(self) -> None:
         check(_lib.lib().pb_route_end(self._h))
 
-    def wait(self, queue: int = _lib.QUEUE_PROCESS) -> None:
-        """device-side: `queue` waits for the exchange last ended; the host does not block"""
-        check(_lib.lib().pb_route_wait(self._h, int(queue)))
+    def wait(self, queue: int = _lib.QUEUE_PROCESS, age: int = 0) -> None:
+        """device-side: `queue` waits for the exchange last ended (age 0) or the one `age` exchanges before it; the host
+        does not block"""
+        check(_lib.lib().pb_route_wait_age(self._h, int(queue), int(age)))
 
     def sync(self) -> None:
         check(_lib.lib().pb_route_sync(self._h))

@@ -169,3 +169,45 @@ def test_requests_are_fifo_across_sources():
         assert [e[1] for e in ctx.log if e[0] == "run"] == ["prog-x", "prog-y", "prog-z"]
 
     asyncio.run(go())
+
+
+# ---- the N-API addon and the TypeScript-face edits ----------------------------------------------------
+def test_napi_shim_compiles_against_the_stub_and_binds_only_declared_entry_points():
+    """napi/phaneron_napi.cc: node-addon-api is absent from the image, so the shim is type-checked against napi/stub/napi.h;
+    every pb_* function it calls is declared in include/phaneron_b200.h and exported by the shared library"""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of the image"
+    res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Inapi/stub", "-Iinclude", "napi/phaneron_napi.cc"],
+                         cwd=root, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    src = open(os.path.join(root, "napi", "phaneron_napi.cc")).read()
+    hdr = open(os.path.join(root, "include", "phaneron_b200.h")).read()
+    called = set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", src))
+    declared = set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", hdr))
+    assert called and called <= declared, sorted(called - declared)
+    from phaneron_b200 import _lib
+    l = _lib.lib()
+    assert all(hasattr(l, s) for s in called)
+    # the nodencl surface phaneron's sources use (SURVEY.md 8b) is all there
+    for method in ("initialise", "getPlatformInfo", "createBuffer", "createProgram", "runProgram", "waitFinish", "hostAccess", "addRef", "release"):
+        assert f'"{method}"' in src, method
+    assert "..." not in re.sub(r"//.*", "", src), "no elisions in the shim"
+
+
+def test_typescript_patches_apply_to_the_reference():
+    """ts/*.patch are real unified diffs against the reference's files (checked with patch --dry-run where the reference is present)"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    patches = sorted(f for f in os.listdir(os.path.join(root, "ts")) if f.endswith(".patch"))
+    assert {"packer.ts.patch", "index.ts.patch", "package.json.patch"} <= set(patches)
+    if not os.path.isdir("/root/reference/src") or not shutil.which("patch"):
+        pytest.skip("reference tree or patch(1) not present")
+    for p in patches:
+        res = subprocess.run(["patch", "--dry-run", "-p1", "-d", "/root/reference", "-i", os.path.join(root, "ts", p), "-o", "/dev/null"],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, (p, res.stdout + res.stderr)
