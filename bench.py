@@ -37,6 +37,26 @@ E2E_WARM = 8                    # pipelined frames before the e2e clock starts
 E2E_FRAMES_PER_STEP = 48       # public-API leg (PCIe bound: ~133 MB H2D + 22 MB D2H per frame)
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "2160p50 v210 4-layer composite frames/sec"
+LANCZOS = 0                    # > 0: the upper layers' Transforms use an N-lobe Lanczos filter (config 5)
+
+
+def select_config(name: str) -> None:
+    """--config: '3' = BASELINE.json configs[2] (the headline metric, default); '5' = configs[4]: 4320p, 2 layers, the upper
+    one a half-size PiP resized with a Lanczos-3 filter (an extension: the reference has only the bilinear sampler)"""
+    global WIDTH, HEIGHT, LAYERS, VARIANT, METRIC, LANCZOS, FRAMES_PER_STEP, CPU_BASELINE_FRAMES
+    if name == "5":
+        WIDTH, HEIGHT, LAYERS, VARIANT, LANCZOS = 7680, 4320, 2, "plain", 3
+        METRIC = "4320p50 v210 2-layer composite with Lanczos-3 resize frames/sec"
+        FRAMES_PER_STEP, CPU_BASELINE_FRAMES = 60, 4
+
+
+def bench_scene(inputs: str, frame_set: int = 0):
+    from phaneron_b200.scenes import layered_scene
+    scene = layered_scene(WIDTH, HEIGHT, LAYERS, inputs, VARIANT, COL_READ, COL_WORK, frame_set=frame_set)
+    if LANCZOS:
+        for L in scene["layers"][1:]:
+            L["xf"] = dict(L["xf"], filter=f"lanczos{LANCZOS}")
+    return scene
 CPU_BASELINE_FRAMES = 12       # cpu_baseline of the default run: whole 3840x2160 frames (about 1 s each on 16 cores)
 
 
@@ -136,7 +156,7 @@ def cpu_reference_fps(steps, warmup, inputs, threads):
     from phaneron_b200.scenes import layered_scene
     native = oracle.use_native()
     oracle.set_threads(threads)
-    scene = layered_scene(WIDTH, HEIGHT, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
+    scene = bench_scene(inputs)
     so = SceneOracle(scene)
     for _ in range(warmup):
         so.packed()
@@ -151,6 +171,8 @@ def reference_kernels_on_gpu(inputs, frames=6):
     """Baseline A: the reference's OWN OpenCL kernels (extracted from its .ts sources into the
     git-ignored oracle/_ref/) launched in the reference's unfused sequence on the same B200 through NVIDIA's
     OpenCL driver, buffers resident.  None when the driver or the extracted kernels are absent."""
+    if LANCZOS:
+        return {"unavailable": "the reference has no Lanczos filter (transform.ts:26-29 samples with CLK_FILTER_LINEAR)"}
     try:
         from oracle import ref_ocl
         if not ref_ocl.available():
@@ -159,7 +181,7 @@ def reference_kernels_on_gpu(inputs, frames=6):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from scene_oracle import xf_matrix
         from phaneron_b200.scenes import layered_scene
-        scene = layered_scene(WIDTH, HEIGHT, LAYERS, inputs, VARIANT, COL_READ, COL_WORK)
+        scene = bench_scene(inputs)
         consts = (oracle.ycbcr2rgb_matrix(COL_READ), oracle.gamma2linear_lut(COL_READ), oracle.rgb2rgb_matrix(COL_READ, COL_WORK),
                   oracle.rgb2ycbcr_matrix(COL_WORK), oracle.linear2gamma_lut(COL_WORK))
         chain = ref_ocl.ReferenceChain(scene, consts, xf_matrix)
@@ -176,8 +198,8 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     fps, dt, native = cpu_reference_fps(args.steps, max(args.warmup, 1), args.inputs, threads)
-    sample = (f"{args.steps} steps, each ONE whole {WIDTH}x{HEIGHT} frame through the full unfused chain (5x v210 read, 5x transform, dissolve, "
-              f"combine_4, v210 write, RGBA-f32 intermediates), oracle/ built {'-O3 -march=native on this host' if native else '-O3'}, {dt:.1f} s")
+    sample = (f"{args.steps} steps, each ONE whole {WIDTH}x{HEIGHT} frame through the full unfused chain (a v210 read + transform per source, "
+              f"{'dissolve, ' if VARIANT == 'mix' else ''}combine_{LAYERS}, v210 write, RGBA-f32 intermediates), oracle/ built {'-O3 -march=native on this host' if native else '-O3'}, {dt:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -206,6 +228,9 @@ def ncu_traffic(kernel, inputs):
 
 
 def workload_name(inputs):
+    if LANCZOS:
+        return (f"{WIDTH}x{HEIGHT} v210, {LAYERS}-layer composite (L1 identity, L2 MIXER FILL 0.5 PiP resized with a Lanczos-{LANCZOS} filter), "
+                f"{COL_READ}->{COL_WORK}, inputs={inputs}")
     return (f"{WIDTH}x{HEIGHT} v210, {LAYERS}-layer composite (L1 identity, L2-L4 MIXER FILL 0.5 PiP, top layer dissolve mix=0.5 "
             f"with a 5th source), {COL_READ}->{COL_WORK}, inputs={inputs}")
 
@@ -245,7 +270,7 @@ async def run_ours(args, rank, world, local_rank):
     harnesses, chains, keep, chain_dests = [], [], [], []
     chains_nocull = []   # the same frames with occlusion culling off (reported beside the default)
     for s in range(n_sets):
-        scene = layered_scene(WIDTH, HEIGHT, LAYERS, args.inputs, VARIANT, COL_READ, COL_WORK, frame_set=s + rank * n_sets)
+        scene = bench_scene(args.inputs, s + rank * n_sets)
         h = ChannelHarness(ctx, scene, chanID=f"ch{rank}s{s}")
         await h.init()
         chain, dests = await h.record_chain()
@@ -353,7 +378,7 @@ async def run_ours(args, rank, world, local_rank):
             raise RuntimeError("bench: a frame written inside the timed region differs from the oracle")
 
     # ---- end-to-end leg through the public API ------------------------------------------------
-    e2e_scene = pin_scene(lib, layered_scene(WIDTH, HEIGHT, LAYERS, args.inputs, VARIANT, COL_READ, COL_WORK, frame_set=rank * n_sets))
+    e2e_scene = pin_scene(lib, bench_scene(args.inputs, rank * n_sets))
     he = ChannelHarness(ctx, e2e_scene, chanID=f"e2e{rank}")
     await he.init()
     for _ in range(3):
@@ -514,9 +539,12 @@ def main():
                "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    select_config(args.config)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.frames_per_step == 240:
+        args.frames_per_step = FRAMES_PER_STEP
     if args.config == "route":
         from phaneron_b200 import bench_route
         asyncio.run(bench_route.run(args, rank, world, local_rank, emit, ClockSampler, measured_peak))

@@ -41,7 +41,10 @@ int pb_ctx_destroy(pb_ctx *c) {
 	}
 	for (auto &lo : c->line_ops) cudaFree(lo.dev);
 	for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
-	for (auto &e : c->lanczos_tabs) cudaFree(e.dev);
+	for (auto &e : c->lanczos_tabs) {
+		cudaFree(e.dev);
+		cudaFree(e.dstrip);
+	}
 	for (auto &e : c->line_pairs) cudaFree(e.dev);
 	cudaFree(c->bg_counter);
 	cudaFree(c->lut_cands_dev);

@@ -117,6 +117,7 @@ struct Leaf {
 	int lz_tx, lz_ty;
 	const int *lz_i0, *lz_j0;
 	const float *lz_wx, *lz_wy;
+	const float *lz_wxt;   // march kernel: the horizontal weights tap-major, [tap][output column]: a warp's lanes (consecutive columns) read one line
 	// strips [s0, s1] and output lines [y0, y1] outside of which every tap of this leaf is a border
 	// texel: the kernel skips the leaf there without touching memory
 	int s0, s1, y0, y1;

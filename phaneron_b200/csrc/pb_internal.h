@@ -186,7 +186,13 @@ struct pb_ctx {
 		int sw, sh, W, H, lobes, tx, ty;
 		void *dev = nullptr;
 		int *i0 = nullptr, *j0 = nullptr;
-		float *wx = nullptr, *wy = nullptr;
+		float *wx = nullptr, *wy = nullptr, *wxt = nullptr;
+		// march kernel: first tap per output column / line on the host, and (built on demand for one strip width) the per-strip
+		// source footprints {flags, first group, groups, 0} with the strips / lines outside of which all taps are border texels
+		std::vector<int> h_i0, h_j0;
+		int strip_groups = 0, fits = 1, s0 = 0, s1 = -1, y0 = 0, y1 = -1;
+		int4 *dstrip = nullptr;
+		std::shared_ptr<const SampleTab::Opq> opq;   // footprint accounting only (never opaque: the alpha is a weight sum)
 	};
 	std::vector<LanczosTab> lanczos_tabs;
 	// blocking-sync events for waits on the copy queues: a host thread waiting for a frame-sized DMA sleeps instead of

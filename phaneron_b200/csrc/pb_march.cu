@@ -449,6 +449,119 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	}
 }
 
+// ---- Lanczos leaves (extension; definition in oracle/oracle.c) ----------------------------------------------
+// value = sum_j wy_j * (sum_i wx_i * T(i0 + i, j0 + j)): ascending fma chains from +0, weights and first taps from the
+// host-built tables (Leaf::lz_*), texels outside the image (0,0,0,0) -- pb_device.cuh lanczos_sample, bit for bit.  One
+// conversion pass per source row of the vertical support, like the wide bilinear form: the row is converted once into the
+// warp's row buffer, every lane takes the horizontal taps of its pixels from it and continues its vertical chain.
+// (A border texel leaves a chain as it is -- fma(w, 0, s) == s up to the sign of a zero -- so taps and rows outside the image
+// are skipped.)
+template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine, bool kBigRows>
+__device__ __noinline__ void eval_leaf_lanczos(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, SPtr buf, int lane, int strip, int y, int x_first,
+                                               int x_last, float4 (&p)[kRounds]) {
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+	const int4 si = __ldg(lf.strip_tab + strip);
+	if (!(si.x & 1)) return;
+	const int g_lo = si.y, ng = si.z, origin = g_lo * 6;
+	const int tx = lf.lz_tx, ty = lf.lz_ty, j0 = __ldg(lf.lz_j0 + y);
+	int i0[kRounds];
+	const float *wxp[kRounds];   // this pixel's weights in the tap-major table: tap i at wxp[r][i * W]
+	const int xw = lf.xf_w;
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		const int x = min(x_first + r * 32 + lane, x_last);
+		i0[r] = __ldg(lf.lz_i0 + x);
+		wxp[r] = lf.lz_wxt + x;
+	}
+	const int rci = kSingleRc ? 0 : lf.rc;
+	const ReadConsts &rc = d.rc[rci];
+	const ReadK &rk = d.rk[rci];
+	const int slot = kLutMode ? rc.lut_slot : 0;
+	const LutParams &lp = d.luts[kSingleRc ? 0 : slot].lp;
+	LutK<kLutMode> lut;
+	lut.raw = rc.lut;
+	lut.magic = kLutMode ? kTwo23 + (float)(lut_saddr + (kSingleRc ? 0 : slot) * 65536) : kTwo23;
+	lut.koff = d.lds_koff;
+	const uint32_t E = d.e_magic;
+	constexpr int cap = (kBigRows ? 2 : 1) * kRowGroups * 6;
+	const SPtr bufo = buf + (-origin);   // row buffer addressed by source column
+	const float *wy = lf.lz_wy + (size_t)y * ty;
+	const bool edge = (si.x & 2) != 0;   // some tap column of the strip lies outside the image
+	// the alpha taps are all 1 inside the image: the horizontal alpha sum of a pixel is the same for every source row
+	float hw[kRounds];
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) hw[r] = 0.f;
+#pragma unroll 4
+	for (int i = 0; i < tx; ++i) {
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r)
+			if (!edge || (unsigned)(i0[r] + i) < (unsigned)lf.w) hw[r] = fma_(__ldg(wxp[r] + (size_t)i * xw), 1.0f, hw[r]);
+	}
+	// software pipeline down the vertical support: the groups of the next source row are loaded while this row is converted
+	// and sampled (a row costs one HBM round trip; with 12 of them per line the latency would otherwise add up)
+	const int j_lo = max(0, -j0), j_hi = min(ty, lf.h - j0);   // rows of the support inside the image
+	uint4 w_next = make_uint4(0, 0, 0, 0);
+	if (j_lo < j_hi && lane < ng) w_next = load_group<true>(lf, j0 + j_lo, g_lo + lane);
+#pragma unroll 1
+	for (int j = j_lo; j < j_hi; ++j) {
+		const int row = j0 + j;
+		const uint4 w_cur = w_next;
+		if (j + 1 < j_hi && lane < ng) w_next = load_group<true>(lf, row + 1, g_lo + lane);
+		if (lane < ng) {
+			if (w_cur.x >> 31) convert_group_exact(lf, d.rc, row, g_lo + lane, buf, cap, lane);
+			else convert_group<kLutMode, kSparse, kReadAffine>(w_cur, lane, E, rc, rk, lut, lp, buf, cap);
+		}
+#pragma unroll 1
+		for (int g = lane + 32; g < ng; g += 32) {   // (footprints wider than 32 groups: the big-row variants)
+			const uint4 w = load_group<true>(lf, row, g_lo + g);
+			if (w.x >> 31) convert_group_exact(lf, d.rc, row, g_lo + g, buf, cap, g);
+			else convert_group<kLutMode, kSparse, kReadAffine>(w, g, E, rc, rk, lut, lp, buf, cap);
+		}
+		__syncwarp();
+		const float wyj = __ldg(wy + j);
+		float3 h[kRounds];
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) h[r] = make_float3(0.f, 0.f, 0.f);
+		// the three pixels of a lane advance tap by tap together: three independent fma chains per channel in flight
+		if (!edge) {
+#pragma unroll 4
+			for (int i = 0; i < tx; ++i) {
+#pragma unroll
+				for (int r = 0; r < kRounds; ++r) {
+					const float w = __ldg(wxp[r] + (size_t)i * xw);
+					const SPtr t = bufo + (i0[r] + i);
+					h[r].x = fma_(w, t[0], h[r].x);
+					h[r].y = fma_(w, t[cap], h[r].y);
+					h[r].z = fma_(w, t[2 * cap], h[r].z);
+				}
+			}
+		} else {
+#pragma unroll 2
+			for (int i = 0; i < tx; ++i) {
+#pragma unroll
+				for (int r = 0; r < kRounds; ++r) {
+					const int cidx = i0[r] + i;
+					if ((unsigned)cidx >= (unsigned)lf.w) continue;   // border texel
+					const float w = __ldg(wxp[r] + (size_t)i * xw);
+					const SPtr t = bufo + cidx;
+					h[r].x = fma_(w, t[0], h[r].x);
+					h[r].y = fma_(w, t[cap], h[r].y);
+					h[r].z = fma_(w, t[2 * cap], h[r].z);
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) {
+			p[r].x = fma_(wyj, h[r].x, p[r].x);
+			p[r].y = fma_(wyj, h[r].y, p[r].y);
+			p[r].z = fma_(wyj, h[r].z, p[r].z);
+			p[r].w = fma_(wyj, hw[r], p[r].w);
+		}
+		__syncwarp();
+	}
+}
+
 // ---- rgba8 / bgra8 leaves (graphics with alpha: FFmpegProducer 'rgba' / 'bgra' / any rgb format, rgba8.ts) ----------
 // Four planes (the alpha of these sources is data and is sampled like a colour channel), one pass per source row, every tap
 // validated.  Conversion is lane = texel (coalesced 128-byte loads, 3 texels per lane in flight): a texel costs four table
@@ -941,6 +1054,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
 			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
+			else if (kPlanar && lf.lz_tx) eval_leaf_lanczos<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))

@@ -63,7 +63,10 @@ int attach_lanczos(pb_ctx *c, pb::Leaf *lf, int lobes) {
 	if (!t) {
 		if (c->lanczos_tabs.size() >= 64) {   // parameters are animating: start over
 			CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));
-			for (auto &e : c->lanczos_tabs) cudaFree(e.dev);
+			for (auto &e : c->lanczos_tabs) {
+				cudaFree(e.dev);
+				cudaFree(e.dstrip);
+			}
 			c->lanczos_tabs.clear();
 		}
 		std::vector<int> i0((size_t)W + H);
@@ -78,9 +81,13 @@ int attach_lanczos(pb_ctx *c, pb::Leaf *lf, int lobes) {
 			if (!ty) return fail(PB_ERR_ARG, "lanczos: more than %d taps per axis (scale too small)", kLanczosMaxTaps);
 		}
 		// compact: [i0 (W) | j0 (H)] ints, then wx (W * tx), wy (H * ty) floats
-		std::vector<float> packed((size_t)W * tx + (size_t)H * ty);
+		// ... and wx once more tap-major (W per tap) for the march kernel's coalesced reads
+		std::vector<float> packed((size_t)2 * W * tx + (size_t)H * ty);
 		for (int x = 0; x < W; ++x) memcpy(&packed[(size_t)x * tx], &wx[(size_t)kLanczosMaxTaps * x], sizeof(float) * tx);
 		for (int y = 0; y < H; ++y) memcpy(&packed[(size_t)W * tx + (size_t)y * ty], &wy[(size_t)kLanczosMaxTaps * y], sizeof(float) * ty);
+		float *wxt = &packed[(size_t)W * tx + (size_t)H * ty];
+		for (int x = 0; x < W; ++x)
+			for (int i = 0; i < tx; ++i) wxt[(size_t)i * W + x] = wx[(size_t)kLanczosMaxTaps * x + i];
 		pb_ctx::LanczosTab e;
 		memcpy(e.m, key, sizeof key);
 		e.sw = lf->w; e.sh = lf->h; e.W = W; e.H = H; e.lobes = lobes; e.tx = tx; e.ty = ty;
@@ -93,12 +100,76 @@ int attach_lanczos(pb_ctx *c, pb::Leaf *lf, int lobes) {
 		e.j0 = e.i0 + W;
 		e.wx = (float *)((char *)e.dev + ib);
 		e.wy = e.wx + (size_t)W * tx;
+		e.wxt = e.wy + (size_t)H * ty;
+		e.h_i0.assign(i0.begin(), i0.begin() + W);
+		e.h_j0.assign(i0.begin() + W, i0.end());
 		c->lanczos_tabs.push_back(e);
 		t = &c->lanczos_tabs.back();
 	}
 	lf->lz_tx = t->tx; lf->lz_ty = t->ty;
 	lf->lz_i0 = t->i0; lf->lz_j0 = t->j0;
 	lf->lz_wx = t->wx; lf->lz_wy = t->wy;
+	lf->lz_wxt = t->wxt;
+	return PB_OK;
+}
+
+// march kernel: per-strip source footprints of a Lanczos leaf (the counterpart of get_tabs for the bilinear sampler)
+int get_lanczos_tabs(pb_ctx *c, pb::Leaf *lf, int W, int H, int strip_groups, pb_ctx::LanczosTab **out) {
+	pb_ctx::LanczosTab *t = nullptr;
+	for (auto &e : c->lanczos_tabs)
+		if (e.i0 == lf->lz_i0) t = &e;
+	if (!t) return fail(PB_ERR_STATE, "lanczos tables of a leaf are gone");
+	*out = t;
+	if (t->strip_groups == strip_groups && t->dstrip) return PB_OK;
+	if (t->dstrip) {
+		CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));
+		cudaFree(t->dstrip);
+		t->dstrip = nullptr;
+	}
+	const int strip_px = strip_groups * 6, n_strips = (W + strip_px - 1) / strip_px;
+	std::vector<int4> hstrip((size_t)n_strips);
+	auto o = std::make_shared<pb_ctx::SampleTab::Opq>();
+	o->id = c->next_tab_id++;
+	o->strip_full.assign((size_t)n_strips, 0);
+	o->row_full.assign((size_t)H, 0);
+	o->row_j0 = t->h_j0;
+	o->strip_ng.assign((size_t)n_strips, 0);
+	o->rows_per_line = t->ty;
+	o->src_h = lf->h;
+	t->fits = 1;
+	t->s0 = 0; t->s1 = -1; t->y0 = 0; t->y1 = -1;
+	for (int sidx = 0; sidx < n_strips; ++sidx) {
+		const int x0 = sidx * strip_px, x1 = std::min(x0 + strip_px, W) - 1;
+		int lo = INT32_MAX, hi = INT32_MIN;
+		for (int x = x0; x <= x1; ++x) {
+			lo = std::min(lo, t->h_i0[x]);
+			hi = std::max(hi, t->h_i0[x] + t->tx - 1);
+		}
+		int4 e = make_int4(0, 0, 0, 0);
+		if (!(hi < 0 || lo >= lf->w)) {
+			e.x = 1 | ((lo < 0 || hi >= lf->w) ? 2 : 0);
+			lo = std::max(lo, 0);
+			hi = std::min(hi, lf->w - 1);
+			e.y = lo / 6;
+			e.z = hi / 6 - e.y + 1;
+			if (e.z > 2 * pb::kRowGroups) t->fits = 0;
+			else if (e.z > pb::kRowGroups && t->fits) t->fits = 2;
+			if (t->s1 < t->s0) t->s0 = sidx;
+			t->s1 = sidx;
+		}
+		hstrip[sidx] = e;
+		o->strip_ng[sidx] = e.z;
+	}
+	for (int y = 0; y < H; ++y)
+		if (t->h_j0[y] + t->ty - 1 >= 0 && t->h_j0[y] < lf->h) {
+			if (t->y1 < t->y0) t->y0 = y;
+			t->y1 = y;
+		}
+	CU(cudaMalloc(&t->dstrip, hstrip.size() * sizeof(int4)));
+	CU(cudaMemcpyAsync(t->dstrip, hstrip.data(), hstrip.size() * sizeof(int4), cudaMemcpyHostToDevice, c->q[PB_QUEUE_PROCESS]));
+	CU(cudaStreamSynchronize(c->q[PB_QUEUE_PROCESS]));   // `hstrip` is a local; once per new transform
+	t->strip_groups = strip_groups;
+	t->opq = o;
 	return PB_OK;
 }
 
@@ -319,8 +390,9 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			// graphics with alpha, and RGBA-f32 frames (Yadif outputs, materialised sub-expressions): pb_march.cu eval_leaf_rgba
 			const bool rgba = lf.kind == pb::LEAF_RGBA8 || lf.kind == pb::LEAF_BGRA8 || lf.kind == pb::LEAF_RGBA_F32;
 			if (lf.kind == pb::LEAF_RGBA_F32) any_f32 = true;
-			if (!(ycc || rgba) || lf.w < 6 || lf.lz_tx) return 0;
-			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) any_planar = true;   // general load path (formats, partial last groups)
+			if (!(ycc || rgba) || lf.w < 6 || (lf.lz_tx && !ycc)) return 0;
+			// (a Lanczos leaf -- the extension of DESIGN.md 4.6 -- takes the general variants: eval_leaf_lanczos)
+			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0 || lf.lz_tx) any_planar = true;   // general load path (formats, partial last groups)
 			if (rgba) any_rgba = true;
 			else rc_ycc[lf.rc] = true;
 			if (lf.has_xf) {
@@ -341,11 +413,48 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.march_w = d.out_w / 6 * 6;
 	d.g_first = 0;
 	d.strip_groups = any_xf ? pb::kStripGroupsXf : pb::kStripGroupsDirect;
+	// Lanczos leaves: a strip's source footprint is its taps wider than the bilinear one, and a row of more than 32 groups
+	// costs a second conversion pass with one or two lanes busy.  Narrow the strips until every Lanczos footprint fits one pass
+	// (0.5x with 12 taps: 14 groups = 84 px -> at most 31 source groups); if nothing fits, stay wide and take the big rows.
+	{
+		bool any_lz = false;
+		for (int i = 0; i < n_leaves; ++i) any_lz = any_lz || leaves[i]->lz_tx;
+		if (any_lz) {
+			int pick = 0;
+			for (int sg = d.strip_groups; sg >= 8 && !pick; --sg) {
+				if ((d.out_w / 6 + sg - 1) / sg > pb::kMaxStrips) break;
+				bool ok = true;
+				for (int i = 0; i < n_leaves && ok; ++i) {
+					if (!leaves[i]->lz_tx) continue;
+					pb_ctx::LanczosTab *lt;
+					int r = get_lanczos_tabs(c, leaves[i], d.out_w, d.out_h, sg, &lt);
+					if (r) return r;
+					ok = lt->fits == 1;
+				}
+				if (ok) pick = sg;
+			}
+			if (pick) d.strip_groups = pick;
+		}
+	}
 	d.n_strips = (d.out_w / 6 + d.strip_groups - 1) / d.strip_groups;
 	if (d.n_strips > pb::kMaxStrips) return 0;
 	std::shared_ptr<const pb_ctx::SampleTab::Opq> opq[3 * pb::kMaxLayers], tab_of[3 * pb::kMaxLayers];
 	bool big_rows = false;
 	for (int i = 0; i < n_leaves; ++i) {
+		if (leaves[i]->lz_tx) {   // separable Lanczos taps: footprints from the tap tables
+			pb_ctx::LanczosTab *lt;
+			int r = get_lanczos_tabs(c, leaves[i], d.out_w, d.out_h, d.strip_groups, &lt);
+			if (r) return r;
+			if (!lt->fits) return 0;
+			if (lt->fits == 2) big_rows = true;
+			opq[i] = nullptr;
+			tab_of[i] = lt->opq;
+			leaves[i]->col_tab = nullptr;
+			leaves[i]->row_tab = nullptr;
+			leaves[i]->strip_tab = lt->dstrip;
+			leaves[i]->s0 = lt->s0; leaves[i]->s1 = lt->s1; leaves[i]->y0 = lt->y0; leaves[i]->y1 = lt->y1;
+			continue;
+		}
 		pb_ctx::SampleTab *t;
 		int fits = 0;
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);

@@ -547,8 +547,38 @@ def test_lanczos_layers_fuse_into_one_launch():
                                            ("yuv420p", "709", _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.25, offsetY=-0.2, filter="lanczos3"))])
     ref = SceneOracle(scene).packed()
     out, st = run(_run_scene_variant(scene, "march"))
-    assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0 and st["march_launches"] == 0, st
+    # Lanczos leaves ride the march kernel (pb_march.cu eval_leaf_lanczos): still ONE launch, now the fast one
+    assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0 and st["march_launches"] == 1, st
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+    slow, st0 = run(_run_scene_variant(scene, "generic"))
+    assert st0["march_launches"] == 0 and np.array_equal(slow, ref)
+
+
+LANCZOS_MARCH_SCENES = {
+    # BASELINE.json config 5's layer structure: full-frame bilinear background, Lanczos-3 half-size PiP
+    "config5_shape": lambda: _lanczos_scene(960, 540, [("v210", _xf()), ("v210", dict(pip(0.5, 0.25, 0.25), filter="lanczos3"))]),
+    "two_lobes_upscale_flip": lambda: _lanczos_scene(768, 432, [("v210", _xf(filter="lanczos2")),
+                                                                ("v210", _xf(scaleX=1.4, scaleY=1.2, offsetX=0.1, flipH=True, filter="lanczos2"))]),
+    "mostly_outside_and_dissolve": lambda: _lanczos_scene(768, 432, [("v210", _xf()), ("v210", dict(pip(0.6, 0.7, 0.65), filter="lanczos3"))], dissolve=True),
+    "deep_downscale_big_rows": lambda: _lanczos_scene(960, 540, [("v210", _xf()), ("v210", dict(pip(0.4, 0.1, 0.3), filter="lanczos3"))]),
+}
+
+
+def _lanczos_scene(w, h, specs, dissolve=False):
+    layers = [dict(src=make_frame("noise", w, h, i), sw=w, sh=h, xf=xf, transition=None) for i, (_, xf) in enumerate(specs)]
+    if dissolve:
+        layers[-1]["transition"] = dict(type="dissolve", mix=0.25, src=make_frame("noise", w, h, 9), sw=w, sh=h, xf=layers[-1]["xf"])
+    return dict(width=w, height=h, colRead="709", colWork="2020", interlaced=False, layers=layers)
+
+
+@pytest.mark.parametrize("name", sorted(LANCZOS_MARCH_SCENES))
+def test_lanczos_leaves_in_the_march_kernel(name):
+    scene = LANCZOS_MARCH_SCENES[name]()
+    ref = SceneOracle(scene).packed()
+    for mode in ("march", "march_nocull"):
+        out, st = run(_run_scene_variant(scene, mode))
+        assert st["march_launches"] == 1 and st["kernel_launches"] == 1 and st["materialised"] == 0, (mode, st)
+        assert np.array_equal(out, ref), f"{mode}: {int((out != ref).sum())} bytes differ"
 
 
 # ---- planar YCbCr leaves in the march kernel (gathered into the v210 group layout, pb_march.cu load_group) ----
