@@ -527,17 +527,17 @@ def main():
                          "from the raw tables; generic: the fallback fused kernel")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if world > 1:
-        # libraries (NCCL's version banner, torchrun notices) write to fd 1: everything but the JSON line goes to stderr
-        global _JSON_OUT
-        sys.stdout.flush()
-        _JSON_OUT = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun like the driver does
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if world > 1 or "route" in sys.argv:
+        # libraries (NCCL's version banner, torchrun notices) write to fd 1: everything but the JSON line goes to stderr
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     select_config(args.config)
     if args.impl == "reference":

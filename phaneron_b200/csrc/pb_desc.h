@@ -154,7 +154,8 @@ enum SinkKind : int {
 	SINK_YUV422P10 = 3,  // yuv422p10.ts:126-219: out = Y, out_u, out_v
 	SINK_YUV422P8 = 4,   // yuv422p8.ts:126-219 (FFmpegConsumer)
 	SINK_YUV420P = 5,    // yuv420p.ts:142-238
-	SINK_NV12 = 6        // nv12.ts:134-240: out = Y, out_u = interleaved chroma
+	SINK_NV12 = 6,       // nv12.ts:134-240: out = Y, out_u = interleaved chroma
+	SINK_RGBA_F32 = 7    // the composite itself as an RGBA-f32 frame (a deferred frame made real: ROUTE payloads, Yadif inputs, host reads)
 };
 
 struct FusedDesc {

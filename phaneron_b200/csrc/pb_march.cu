@@ -1037,16 +1037,19 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		float3 acc[kRounds];
 		float4 p[kRounds], t[kRounds];
 		float m[kRounds];
+		float al[kRounds];   // general variants: the composite's alpha (combine.ts:49-59: fma(prev.a, 0, l.a)), for the RGBA-f32 sink
 #pragma unroll
 		for (int r = 0; r < kRounds; ++r) {
 			acc[r] = make_float3(0.f, 0.f, 0.f);
 			t[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 			m[r] = 0.f;
+			al[r] = 0.f;
 		}
 		const uint32_t both = d.strip_ops[strip] & __ldg(d.line_ops + y);
 		uint32_t todo = both & 0xFFFFFFu;
 		// exact occlusion culling: the topmost layer that is opaque over this whole strip line hides all ops below it
 		if (both >> 24) todo &= ~0u << d.layer_first_op[(31 - __clz(both)) - 24];
+		const bool top_live = (todo >> (d.n_ops - 1)) & 1u;   // the top layer reaches this strip line (else it contributes (0,0,0,0))
 #pragma unroll 1
 		while (todo) {
 			const int oi = __ffs(todo) - 1;
@@ -1091,7 +1094,18 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			for (int r = 0; r < kRounds; ++r) {
 				const float kk = sub(1.0f, p[r].w);
 				acc[r] = make_float3(fma_(acc[r].x, kk, p[r].x), fma_(acc[r].y, kk, p[r].y), fma_(acc[r].z, kk, p[r].z));
+				if (kPlanar) al[r] = fma_(al[r], 0.0f, p[r].w);
 			}
+		}
+
+		if (kPlanar && d.sink == SINK_RGBA_F32) {   // the composite as it is: one float4 per pixel, 512 contiguous bytes per round
+			float4 *o = reinterpret_cast<float4 *>(d.out) + (size_t)y * d.out_w;
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const int x = x_first + r * 32 + lane;
+				if (x <= x_last) o[x] = make_float4(acc[r].x, acc[r].y, acc[r].z, top_live ? al[r] : fma_(al[r], 0.0f, 0.0f));
+			}
+			continue;
 		}
 
 		// ---- encode (v210.ts:145-156) and regroup 6 pixels -> 4 words through the row buffer ----
@@ -1171,7 +1185,9 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 #define PB_DIRECT_WARPS 28
 #endif
 constexpr int kDirectWarps = PB_DIRECT_WARPS;   // 69 registers per thread: more resident warps than the general kernel's 20
-template <int kReadMode>
+// kRgbaOut: the converted pixels are written as an RGBA-f32 frame (a ToRGBA output made real).  kRgbaIn: the source already is
+// an RGBA-f32 frame (a routed channel frame, a Yadif output, a host-written image) that FromRGBA packs: v210.ts:113-195 alone.
+template <int kReadMode, bool kRgbaOut = false, bool kRgbaIn = false>
 __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -1207,10 +1223,10 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 	const Leaf &lf = d.layers[0].a;
 	const ReadConsts &rc = d.rc[0];
 	const ReadK &rk = d.rk[0];
-	const LutParams &lp = d.luts[rc.lut_slot].lp;
+	const LutParams &lp = d.luts[kRgbaIn ? 0 : rc.lut_slot].lp;
 	LutK<1> lut, wlut;
 	lut.raw = rc.lut;
-	lut.magic = kTwo23 + (float)(lut_saddr + rc.lut_slot * 65536);
+	lut.magic = kTwo23 + (float)(lut_saddr + (kRgbaIn ? 0 : rc.lut_slot) * 65536);
 	lut.koff = d.lds_koff;
 	wlut.raw = d.wc.lut;
 	wlut.magic = kTwo23 + (float)(lut_saddr + d.wc.lut_slot * 65536);
@@ -1229,11 +1245,24 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 		const int k = item / n_strips, strip = item - k * n_strips;
 		const int y = first_line + k * step;
 		const int G = strip * 32 + lane;
-		if (G < groups) {
-			const uint4 w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)y * lf.pitch) + G);
-			convert_group<1, true, kReadMode>(w, lane, E, rc, rk, lut, lp, buf, cap);
+		if (!kRgbaIn) {
+			if (G < groups) {
+				const uint4 w = ld_stream(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)y * lf.pitch) + G);
+				convert_group<1, true, kReadMode>(w, lane, E, rc, rk, lut, lp, buf, cap);
+			}
+			__syncwarp();
 		}
-		__syncwarp();
+		if (kRgbaOut) {   // ToRGBA made real (v210.ts:25-111 as a frame in HBM): alpha 1, coalesced float4 stores
+			float4 *o = reinterpret_cast<float4 *>(d.out) + (size_t)y * d.out_w + strip * 192;
+#pragma unroll
+			for (int q = 0; q < 6; ++q) {
+				const int xs = q * 32 + lane;
+				const SPtr t = buf + xs;
+				if (strip * 192 + xs < d.out_w) o[xs] = make_float4(t[0], t[cap], t[2 * cap], 1.0f);
+			}
+			__syncwarp();
+			continue;
+		}
 #pragma unroll 1
 		for (int h = 0; h < 2; ++h) {
 			// 1:1 read of texel (x, y): exact passthrough; over an empty frame fma(0, 0, p) == p.  The staging words below reuse
@@ -1241,8 +1270,14 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 			float3 a[kRounds];
 #pragma unroll
 			for (int r = 0; r < kRounds; ++r) {
-				const SPtr t = buf + (h * 96 + r * 32 + lane);
-				a[r] = make_float3(t[0], t[cap], t[2 * cap]);
+				if (kRgbaIn) {   // pixel (strip * 192 + h * 96 + r * 32 + lane) of the frame itself: 512 contiguous bytes per round
+					const int x = min(strip * 192 + h * 96 + r * 32 + lane, d.out_w - 1);
+					const float4 px = __ldg(reinterpret_cast<const float4 *>(lf.ptr) + (size_t)y * d.out_w + x);
+					a[r] = make_float3(px.x, px.y, px.z);
+				} else {
+					const SPtr t = buf + (h * 96 + r * 32 + lane);
+					a[r] = make_float3(t[0], t[cap], t[2 * cap]);
+				}
 			}
 			const SPtr stage = buf;
 #pragma unroll
@@ -1358,8 +1393,9 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		{
 			std::lock_guard<std::mutex> lk(mu);
 			if (!configured.count(dev)) {
-				cudaError_t e = cudaFuncSetAttribute(k_march_direct<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-				if (e == cudaSuccess) e = cudaFuncSetAttribute(k_march_direct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+				cudaError_t e = cudaSuccess;
+				for (auto *k : {k_march_direct<0, false>, k_march_direct<2, false>, k_march_direct<0, true>, k_march_direct<2, true>, k_march_direct<0, false, true>})
+					if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 				if (e != cudaSuccess) return e;
 				configured.insert(dev);
 			}
@@ -1368,7 +1404,13 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		const int total = n_lines * ((d.out_w / 6 + 31) / 32);
 		const int grid = max(1, min(num_sms, (total + kDirectWarps - 1) / kDirectWarps));
 		const size_t smem_direct = (size_t)d.n_luts * 65536 + (size_t)kDirectWarps * kRowFloats * sizeof(float);
-		(d.luts[d.rc[0].lut_slot].lp.affine == 2 ? k_march_direct<2> : k_march_direct<0>)<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
+		if (d.direct_mode == 2) {   // an RGBA-f32 frame packed to v210
+			k_march_direct<0, false, true><<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
+			return cudaGetLastError();
+		}
+		const bool poly = d.luts[d.rc[0].lut_slot].lp.affine == 2;
+		if (d.sink == SINK_RGBA_F32) (poly ? k_march_direct<2, true> : k_march_direct<0, true>)<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
+		else (poly ? k_march_direct<2, false> : k_march_direct<0, false>)<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
 		return cudaGetLastError();
 	}
 	const bool single = d.n_rc == 1;

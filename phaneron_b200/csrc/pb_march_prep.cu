@@ -361,8 +361,10 @@ int get_tabs(pb_ctx *c, const pb::Leaf &lf, int W, int H, int strip_groups, pb_c
 int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (!c->allow_march) return 0;
 	// sinks: v210, the planar YCbCr formats (the same 3 codes per pixel, stored by plane) and rgba8 / bgra8 (one word per pixel)
+	// ... and the composite itself as an RGBA-f32 frame (deferred frames made real: ROUTE payloads, Yadif inputs, host reads)
+	const bool rgba_f32_sink = d.sink == pb::SINK_RGBA_F32;
 	const bool planar_sink = d.sink == pb::SINK_YUV422P10 || d.sink == pb::SINK_YUV422P8 || d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12 ||
-	                         d.sink == pb::SINK_RGBA8 || d.sink == pb::SINK_BGRA8;
+	                         d.sink == pb::SINK_RGBA8 || d.sink == pb::SINK_BGRA8 || rgba_f32_sink;
 	if (d.sink != pb::SINK_V210 && !planar_sink) return 0;
 	if ((d.sink == pb::SINK_YUV420P || d.sink == pb::SINK_NV12) && (d.out_h & 1)) return 0;
 	// Widths: the march kernel writes whole v210 groups.  With a v210 sink a ragged width (1280-wide 720p = 213 groups + 2 pixels,
@@ -581,11 +583,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	}
 	// the write side packs three codes into one word while regrouping: they must fit 10 bits (8 for the 8-bit sinks, whose
 	// uchar stores would otherwise wrap, Q11)
-	const int wt = lut_table_by_raw(c, d.wc.lut);
-	if (wt < 0 || !c->lut_tables[wt].unit_range) return 0;
+	const int wt = rgba_f32_sink ? -1 : lut_table_by_raw(c, d.wc.lut);   // (an RGBA-f32 sink has no write side)
+	if (!rgba_f32_sink && (wt < 0 || !c->lut_tables[wt].unit_range)) return 0;
 	// (and, being inside the code range, need no saturation: the encoder drops the clamp of convert_ushort_sat_rte)
 	const double code_max = (d.sink == pb::SINK_V210 || d.sink == pb::SINK_YUV422P10) ? 1023.0 : 255.0;
-	for (int row = 0; row < 3; ++row) {
+	for (int row = 0; row < 3 && !rgba_f32_sink; ++row) {
 		double hi = d.wc.cm[row * 4 + 3], lo = hi;
 		for (int k = 0; k < 3; ++k) {
 			hi += std::max(0.0, (double)d.wc.cm[row * 4 + k]);
@@ -627,8 +629,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			}
 		}
 	}
-	d.wc.lut_slot = slot_of(wt);
-	if (d.wc.lut_slot < 0) all_d8 = false;
+	d.wc.lut_slot = rgba_f32_sink ? -1 : slot_of(wt);
+	if (d.wc.lut_slot < 0 && !rgba_f32_sink) all_d8 = false;
 	d.n_luts = all_d8 ? n_slots : 0;
 	d.n_t256 = n_t256;
 	d.big_rows = big_rows;
@@ -641,7 +643,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.bg_single = 0;
 	d.line_pairs = nullptr;
 	d.single_strip_groups = 31;
-	const bool plain_tables = all_d8 && n_slots <= 2 && d.sparse_cm && d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine == 1;
+	const bool write_plain = rgba_f32_sink || (d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine == 1);
+	const bool plain_tables = all_d8 && n_slots <= 2 && d.sparse_cm && write_plain && !rgba_f32_sink;
 	bool reads_plain = plain_tables;   // all read tables in the same non-affine model: MUFU (0) or polynomial (2)
 	for (int i = 0; i < d.n_rc && reads_plain; ++i)
 		reads_plain = d.rc[i].lut_slot >= 0 && c->lut_tables[slots[d.rc[i].lut_slot]].lp.affine != 1 &&
@@ -748,22 +751,37 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		}
 	}
 	// ToRGBA -> FromRGBA of one v210 source with colourMaths-style tables: the dedicated direct kernel
+	// (or into an RGBA-f32 frame: a ToRGBA output made real, k_march_direct<.., true>)
 	d.direct_mode = d.n_ops == 1 && d.layers[0].kind == pb::LAYER_DIRECT && !d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_V210 &&
-	                d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && all_d8 && n_slots <= 2 && d.sparse_cm && !any_planar && !big_rows &&
-	                d.rc[0].lut_slot >= 0 && c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine != 1 &&
-	                d.wc.lut_slot >= 0 && c->lut_tables[slots[d.wc.lut_slot]].lp.affine == 1 && !(c->flags & PB_CTX_NO_DIRECT);
-	if (big_rows) {   // 2 x 64 KiB of tables + 20 x 4.5 KiB of rows is what an SM holds
+	                d.layers[0].a.w % 6 == 0 && (d.sink == pb::SINK_V210 || rgba_f32_sink) && d.out_w % 48 == 0 && all_d8 && n_slots <= 2 && d.sparse_cm &&
+	                (!any_planar || rgba_f32_sink) && !big_rows && d.n_rc == 1 &&
+	                d.rc[0].lut_slot >= 0 && c->lut_tables[slots[d.rc[0].lut_slot]].lp.affine != 1 && write_plain && !(c->flags & PB_CTX_NO_DIRECT);
+	// FromRGBA of a frame that is real memory (one RGBA-f32 leaf read 1:1 into a v210 output: a routed channel frame, a Yadif
+	// output): the direct kernel with the frame itself as the pixel source
+	if (!d.direct_mode && d.n_ops == 1 && d.layers[0].kind == pb::LAYER_DIRECT && !d.layers[0].a.has_xf && d.layers[0].a.kind == pb::LEAF_RGBA_F32 &&
+	    d.sink == pb::SINK_V210 && d.out_w % 48 == 0 && all_d8 && n_slots == 1 && d.wc.lut_slot == 0 && write_plain && !(c->flags & PB_CTX_NO_DIRECT))
+		d.direct_mode = 2;
+	if (big_rows && d.direct_mode != 2) {   // 2 x 64 KiB of tables + 20 x 4.5 KiB of rows is what an SM holds
 		if (d.n_luts > 2) return 0;
 		any_planar = true;
 	}
 	if (any_rgba && d.n_luts == 0) return 0;   // rgba8 leaves ride on the big-row variants, which exist for shared-memory tables
 	d.any_planar = any_planar;
 	if (any_planar && !(d.n_luts > 0 && d.sparse_cm)) return 0;   // planar variants exist for the common configuration only
+	if (rgba_f32_sink && !d.direct_mode) {
+		// A frame made real.  The march kernel pays where packed leaves are sampled through a Transform (every texel converted once
+		// instead of once per tap); a graph of 1:1 packed reads and RGBA-f32 frames is a few gathers per pixel, which the generic
+		// kernel does faster than the row-buffer round trip (a routed channel frame: 17 vs 52 us, profiles/r02_route_launches.txt)
+		bool sampled_packed = false;
+		for (int i = 0; i < n_leaves; ++i) sampled_packed = sampled_packed || (leaves[i]->kind != pb::LEAF_RGBA_F32 && leaves[i]->has_xf);
+		if (!sampled_packed) return 0;
+	}
 	for (int i = 0; i < d.n_luts; ++i) {
 		d.luts[i].d8 = c->lut_tables[slots[i]].d8;
 		d.luts[i].lp = c->lut_tables[slots[i]].lp;
 	}
-	if (d.n_luts) d.wlp = d.luts[d.wc.lut_slot].lp;
+	if (d.n_luts && d.wc.lut_slot >= 0) d.wlp = d.luts[d.wc.lut_slot].lp;
+	else if (rgba_f32_sink) d.wlp.affine = 1;   // (no write table: the kernel variants are picked by the read tables alone)
 	if (c->flags & PB_CTX_FOOTPRINT) {
 		// distinct packed source bytes this launch reads (after bounding-box masks and occlusion culling): per
 		// leaf and strip, the distinct source rows of the lines on which the leaf's op survives
@@ -834,7 +852,7 @@ int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool m
 // launch a compiled descriptor (march kernel when eligible); *march_out reports the choice
 int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, bool *march_out) {
 	bool march = false;
-	if (!out_rgba) {
+	if (!out_rgba || d.sink == pb::SINK_RGBA_F32) {   // (an RGBA-f32 destination: the march kernel where it can, else the generic one into out_rgba)
 		int r = prepare_march(c, d);
 		if (r < 0) return r;
 		march = r == 1;

@@ -362,17 +362,21 @@ int materialise_node(pb_ctx *c, const NodeP &n, const void **dev_out) {
 			c->pool.dev_put((size_t)n->w * n->h * 16, p);
 			return r;
 		}
-		cudaError_t e = pb::launch_fused(c->q[PB_QUEUE_PROCESS], cc.d, p);
-		if (e != cudaSuccess) {
+		cc.d.sink = pb::SINK_RGBA_F32;
+		cc.d.out = p;
+		cc.d.out_pitch = n->w * 16;
+		bool march = false;
+		if ((r = launch_desc(c, c->q[PB_QUEUE_PROCESS], cc.d, p, &march))) {
 			c->pool.dev_put((size_t)n->w * n->h * 16, p);
-			return fail(PB_ERR_CUDA, "fused materialise launch: %s", cudaGetErrorString(e));
+			return r;
 		}
 		c->stats.kernel_launches++;
 		c->stats.fused_launches++;
+		if (march) c->stats.march_launches++;
 		c->stats.materialised++;
 		n->mat_dev = p;
 		cc.keep.push_back(n);   // a recorded chain must keep the node (and its mat_dev) alive
-		record_launch(c, cc, p, nullptr);
+		record_launch(c, cc, p, nullptr, march);
 	}
 	*dev_out = n->mat_dev;
 	return PB_OK;
@@ -392,12 +396,16 @@ int materialise_buf(pb_buf *b) {
 	} else {
 		Compiler cc{c};
 		if ((r = cc.compile(n))) return r;
-		cudaError_t e = pb::launch_fused(c->q[PB_QUEUE_PROCESS], cc.d, b->dev);
-		if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused materialise launch: %s", cudaGetErrorString(e));
+		cc.d.sink = pb::SINK_RGBA_F32;
+		cc.d.out = b->dev;
+		cc.d.out_pitch = n->w * 16;
+		bool march = false;
+		if ((r = launch_desc(c, c->q[PB_QUEUE_PROCESS], cc.d, b->dev, &march))) return r;
 		c->stats.kernel_launches++;
 		c->stats.fused_launches++;
+		if (march) c->stats.march_launches++;
 		c->stats.materialised++;
-		record_launch(c, cc, b->dev, b);
+		record_launch(c, cc, b->dev, b, march);
 	}
 	b->expr.reset();
 	return PB_OK;
