@@ -20,6 +20,7 @@ int pb_ctx_create(int gpu_index, unsigned flags, pb_ctx **out) {
 	c->flags = flags;
 	c->allow_march = !(flags & PB_CTX_NO_MARCH);
 	CU(cudaGetDeviceProperties(&c->prop, gpu_index));
+	c->march_sms = c->prop.multiProcessorCount;
 	for (auto &q : c->q) CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
 	c->pool.queues = c->q;
 	CU(cudaEventCreate(&c->ev0));

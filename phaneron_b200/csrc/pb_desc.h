@@ -43,7 +43,8 @@ enum LeafKind : int {
 	LEAF_YUV422P10 = 5,   // yuv422p10.ts: ptr = Y, ptr_u, ptr_v
 	LEAF_YUV422P8 = 6,    // yuv422p8.ts
 	LEAF_YUV420P = 7,     // yuv420p.ts
-	LEAF_NV12 = 8         // nv12.ts: ptr = Y, ptr_u = interleaved chroma
+	LEAF_NV12 = 8,        // nv12.ts: ptr = Y, ptr_u = interleaved chroma
+	LEAF_YADIF = 9        // yadifCl.ts:105-167 over three RGBA-f32 frames: ptr = cur, ptr_u = prev, ptr_v = next; Leaf::yadif = parity | tff << 1 | skipSpatial << 2
 };
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
 
@@ -102,6 +103,7 @@ struct Leaf {
 	int w, h;          // source dimensions in pixels
 	int pitch;         // bytes per line (v210) / unused for RGBA (w*16)
 	int rc;            // index into FusedDesc::rc (v210 leaves)
+	int yadif;         // LEAF_YADIF: parity | tff << 1 | skipSpatial << 2
 	int has_xf;        // 0: sample texel (x,y) directly; 1: Transform (transform.ts:36-59)
 	int xf_w, xf_h;    // dimensions of the Transform's output image
 	float m[6];        // rows 0 and 1 of the 3x3 transformMatrix

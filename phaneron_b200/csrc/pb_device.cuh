@@ -181,6 +181,83 @@ __device__ __forceinline__ float4 packed_texel(const Leaf &lf, const ReadConsts 
 	return make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
 }
 
+// ---- yadif: yadifCl.ts:28-167 ------------------------------------------------------------------------
+__device__ __forceinline__ float half_sum(float a, float b) { return mul(add(a, b), 0.5f); }   // (a + b) / 2.0f, exact
+__device__ __forceinline__ float ad(float a, float b) { return fabsf(sub(a, b)); }
+
+__device__ __forceinline__ float spatial_predictor(float a, float b, float c, float d, float e, float f, float g, float h,
+                                                    float i, float j, float k, float l, float m, float n) {
+	float pred = half_sum(d, k);
+	float best = add(add(ad(c, j), ad(d, k)), ad(e, l));
+	float score = add(add(ad(b, k), ad(c, l)), ad(d, m));
+	bool cmp = score < best;
+	pred = cmp ? half_sum(c, l) : pred;
+	best = cmp ? score : best;
+	score = cmp ? add(add(ad(a, l), ad(b, m)), ad(c, n)) : score;
+	cmp = cmp && (score < best);
+	pred = cmp ? half_sum(b, m) : pred;
+	best = cmp ? score : best;
+	score = add(add(ad(d, i), ad(e, j)), ad(f, k));
+	cmp = score < best;
+	pred = cmp ? half_sum(e, j) : pred;
+	best = cmp ? score : best;
+	score = cmp ? add(add(ad(e, h), ad(f, i)), ad(g, j)) : score;
+	cmp = cmp && (score < best);
+	pred = cmp ? half_sum(f, i) : pred;
+	return pred;
+}
+
+__device__ __forceinline__ float temporal_predictor(float A, float B, float C, float D, float E, float F, float G, float H,
+                                                     float I, float J, float K, float L, float pred, int skip) {
+	const float p0 = half_sum(C, H), p1 = F, p2 = half_sum(D, I), p3 = G, p4 = half_sum(E, J);
+	const float t0 = ad(D, I);
+	const float t1 = mul(add(ad(A, F), ad(B, G)), 0.5f);
+	const float t2 = mul(add(ad(K, F), ad(G, L)), 0.5f);
+	float diff = fmaxf(fmaxf(t0, t1), t2);
+	if (!skip) {
+		const float p2mp3 = sub(p2, p3), p2mp1 = sub(p2, p1), p0mp1 = sub(p0, p1), p4mp3 = sub(p4, p3);
+		const float maxi = fmaxf(fmaxf(p2mp3, p2mp1), fminf(p0mp1, p4mp3));
+		const float mini = fminf(fminf(p2mp3, p2mp1), fmaxf(p0mp1, p4mp3));
+		diff = fmaxf(fmaxf(diff, mini), -maxi);
+	}
+	const float hi = add(p2, diff), lo = sub(p2, diff);
+	pred = (pred > hi) ? hi : pred;
+	pred = (pred < lo) ? lo : pred;
+	return pred;
+}
+
+// one output pixel of the yadif kernel (yadifCl.ts:105-167) from three RGBA-f32 frames; reads clamp to the edge
+// (CLK_ADDRESS_CLAMP_TO_EDGE).  Shared by the stand-alone kernel (pb_kernels.cu k_yadif) and the fused kernels' Yadif leaves.
+__device__ __forceinline__ float4 yadif_texel(const float4 *__restrict__ prev, const float4 *__restrict__ cur, const float4 *__restrict__ next,
+                                              int w, int h, int parity, int tff, int skip, int xo, int yo) {
+	auto px = [&](const float4 *img, int x, int y) {
+		x = min(max(x, 0), w - 1);
+		y = min(max(y, 0), h - 1);
+		return __ldg(img + (size_t)y * w + x);
+	};
+	if ((yo & 1) == parity) return px(cur, xo, yo);   // the primary field is not modified
+	const int second = !(parity ^ tff);
+	const float4 a = px(cur, xo - 3, yo - 1), b = px(cur, xo - 2, yo - 1), c = px(cur, xo - 1, yo - 1), d = px(cur, xo, yo - 1),
+	             e = px(cur, xo + 1, yo - 1), f = px(cur, xo + 2, yo - 1), g = px(cur, xo + 3, yo - 1);
+	const float4 hh = px(cur, xo - 3, yo + 1), i = px(cur, xo - 2, yo + 1), j = px(cur, xo - 1, yo + 1), k = px(cur, xo, yo + 1),
+	             l = px(cur, xo + 1, yo + 1), m = px(cur, xo + 2, yo + 1), n = px(cur, xo + 3, yo + 1);
+	const float4 A = px(prev, xo, yo - 1), B = px(prev, xo, yo + 1);
+	const float4 C = px(second ? cur : prev, xo, yo - 2), D = px(second ? cur : prev, xo, yo), E = px(second ? cur : prev, xo, yo + 2);
+	const float4 F = d, G = k;
+	const float4 H = px(second ? next : cur, xo, yo - 2), I = px(second ? next : cur, xo, yo), J = px(second ? next : cur, xo, yo + 2);
+	const float4 K = px(next, xo, yo - 1), L = px(next, xo, yo + 1);
+	float4 o;
+#define YADIF_CH(ch) \
+	o.ch = temporal_predictor(A.ch, B.ch, C.ch, D.ch, E.ch, F.ch, G.ch, H.ch, I.ch, J.ch, K.ch, L.ch, \
+	                          spatial_predictor(a.ch, b.ch, c.ch, d.ch, e.ch, f.ch, g.ch, hh.ch, i.ch, j.ch, k.ch, l.ch, m.ch, n.ch), skip)
+	YADIF_CH(x);
+	YADIF_CH(y);
+	YADIF_CH(z);
+#undef YADIF_CH
+	o.w = px(cur, xo, yo).w;   // "Reset Alpha" (yadifCl.ts:164): the w channel's prediction is discarded
+	return o;
+}
+
 // ---- leaves -------------------------------------------------------------------------
 // One texel of a leaf as RGBA-f32; texels outside the image are the CLK_ADDRESS_CLAMP
 // border colour (0,0,0,0).
@@ -189,6 +266,9 @@ __device__ __forceinline__ float4 leaf_texel(const Leaf &lf, const ReadConsts *r
 	if (lf.kind == LEAF_RGBA_F32) {
 		return __ldg(reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + i);
 	}
+	if (lf.kind == LEAF_YADIF)   // a de-interlaced field, computed where it is sampled (ptr = cur, ptr_u = prev, ptr_v = next: RGBA-f32 frames)
+		return yadif_texel(reinterpret_cast<const float4 *>(lf.ptr_u), reinterpret_cast<const float4 *>(lf.ptr), reinterpret_cast<const float4 *>(lf.ptr_v),
+		                   lf.w, lf.h, lf.yadif & 1, (lf.yadif >> 1) & 1, (lf.yadif >> 2) & 1, i, j);
 	if (lf.kind != LEAF_V210) return packed_texel(lf, rcs[lf.rc], i, j);
 	const int g = i / 6, p = i - g * 6;
 	const uint4 w = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);

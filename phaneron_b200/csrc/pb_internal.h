@@ -199,6 +199,7 @@ struct pb_ctx {
 	// spinning, and waits for ITS copy only, not for whatever other producers have queued behind it
 	std::vector<cudaEvent_t> copy_events;
 	bool allow_march = true;
+	int march_sms = 0;   // SMs the persistent march kernels occupy; fewer than all while a ROUTE communicator needs SMs of its own (pb_route.cu)
 	// gamma tables by content (see lut_table_of)
 	struct LutTable {
 		unsigned long long hash = 0;
@@ -268,7 +269,7 @@ struct pb_chain {
 namespace pbrt {
 
 
-enum NodeKind { N_LEAF_V210, N_LEAF_RGBA, N_TRANSFORM, N_DISSOLVE, N_WIPE_MASK, N_COMBINE, N_LEAF_PACKED };
+enum NodeKind { N_LEAF_V210, N_LEAF_RGBA, N_TRANSFORM, N_DISSOLVE, N_WIPE_MASK, N_COMBINE, N_LEAF_PACKED, N_YADIF };
 
 struct Node {
 	NodeKind kind;
@@ -278,6 +279,7 @@ struct Node {
 	pb_buf *src = nullptr;       // leaves: referenced source buffer
 	pb_buf *src_u = nullptr, *src_v = nullptr;   // N_LEAF_PACKED, planar formats: chroma planes
 	int leaf_kind = 0;           // N_LEAF_PACKED: pb::LeafKind (rgba8, bgra8, yuv422p10/8, yuv420p, nv12)
+	int yadif = 0;               // N_YADIF (src = cur, src_u = prev, src_v = next: real RGBA-f32 frames): parity | tff << 1 | skipSpatial << 2
 	pb_buf *lut_buf = nullptr;   // packed leaves: referenced gamma LUT buffer
 	pb::ReadConsts rc{};         // packed leaves
 	float mat[6] = {0};          // transform

@@ -250,85 +250,13 @@ __global__ void __launch_bounds__(kThreads) k_resize(const float4 *__restrict__ 
 }
 
 // ---- yadif: yadifCl.ts:28-167 ------------------------------------------------------------------------
-__device__ __forceinline__ float half_sum(float a, float b) { return mul(add(a, b), 0.5f); }   // (a + b) / 2.0f, exact
-__device__ __forceinline__ float ad(float a, float b) { return fabsf(sub(a, b)); }
-
-__device__ __forceinline__ float spatial_predictor(float a, float b, float c, float d, float e, float f, float g, float h,
-                                                    float i, float j, float k, float l, float m, float n) {
-	float pred = half_sum(d, k);
-	float best = add(add(ad(c, j), ad(d, k)), ad(e, l));
-	float score = add(add(ad(b, k), ad(c, l)), ad(d, m));
-	bool cmp = score < best;
-	pred = cmp ? half_sum(c, l) : pred;
-	best = cmp ? score : best;
-	score = cmp ? add(add(ad(a, l), ad(b, m)), ad(c, n)) : score;
-	cmp = cmp && (score < best);
-	pred = cmp ? half_sum(b, m) : pred;
-	best = cmp ? score : best;
-	score = add(add(ad(d, i), ad(e, j)), ad(f, k));
-	cmp = score < best;
-	pred = cmp ? half_sum(e, j) : pred;
-	best = cmp ? score : best;
-	score = cmp ? add(add(ad(e, h), ad(f, i)), ad(g, j)) : score;
-	cmp = cmp && (score < best);
-	pred = cmp ? half_sum(f, i) : pred;
-	return pred;
-}
-
-__device__ __forceinline__ float temporal_predictor(float A, float B, float C, float D, float E, float F, float G, float H,
-                                                     float I, float J, float K, float L, float pred, int skip) {
-	const float p0 = half_sum(C, H), p1 = F, p2 = half_sum(D, I), p3 = G, p4 = half_sum(E, J);
-	const float t0 = ad(D, I);
-	const float t1 = mul(add(ad(A, F), ad(B, G)), 0.5f);
-	const float t2 = mul(add(ad(K, F), ad(G, L)), 0.5f);
-	float diff = fmaxf(fmaxf(t0, t1), t2);
-	if (!skip) {
-		const float p2mp3 = sub(p2, p3), p2mp1 = sub(p2, p1), p0mp1 = sub(p0, p1), p4mp3 = sub(p4, p3);
-		const float maxi = fmaxf(fmaxf(p2mp3, p2mp1), fminf(p0mp1, p4mp3));
-		const float mini = fminf(fminf(p2mp3, p2mp1), fmaxf(p0mp1, p4mp3));
-		diff = fmaxf(fmaxf(diff, mini), -maxi);
-	}
-	const float hi = add(p2, diff), lo = sub(p2, diff);
-	pred = (pred > hi) ? hi : pred;
-	pred = (pred < lo) ? lo : pred;
-	return pred;
-}
-
 __global__ void __launch_bounds__(kThreads) k_yadif(const float4 *__restrict__ prev, const float4 *__restrict__ cur,
                                                     const float4 *__restrict__ next, int parity, int tff, int skip,
                                                     float4 *__restrict__ out, int w, int h) {
 	const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
 	if (tid >= (size_t)w * h) return;
 	const int yo = (int)(tid / w), xo = (int)(tid - (size_t)yo * w);
-	auto px = [&](const float4 *img, int x, int y) {
-		x = min(max(x, 0), w - 1);
-		y = min(max(y, 0), h - 1);
-		return __ldg(img + (size_t)y * w + x);
-	};
-	if ((yo & 1) == parity) {
-		out[tid] = px(cur, xo, yo);
-		return;
-	}
-	const int second = !(parity ^ tff);
-	const float4 a = px(cur, xo - 3, yo - 1), b = px(cur, xo - 2, yo - 1), c = px(cur, xo - 1, yo - 1), d = px(cur, xo, yo - 1),
-	             e = px(cur, xo + 1, yo - 1), f = px(cur, xo + 2, yo - 1), g = px(cur, xo + 3, yo - 1);
-	const float4 hh = px(cur, xo - 3, yo + 1), i = px(cur, xo - 2, yo + 1), j = px(cur, xo - 1, yo + 1), k = px(cur, xo, yo + 1),
-	             l = px(cur, xo + 1, yo + 1), m = px(cur, xo + 2, yo + 1), n = px(cur, xo + 3, yo + 1);
-	const float4 A = px(prev, xo, yo - 1), B = px(prev, xo, yo + 1);
-	const float4 C = px(second ? cur : prev, xo, yo - 2), D = px(second ? cur : prev, xo, yo), E = px(second ? cur : prev, xo, yo + 2);
-	const float4 F = d, G = k;
-	const float4 H = px(second ? next : cur, xo, yo - 2), I = px(second ? next : cur, xo, yo), J = px(second ? next : cur, xo, yo + 2);
-	const float4 K = px(next, xo, yo - 1), L = px(next, xo, yo + 1);
-	float4 o;
-#define YADIF_CH(ch) \
-	o.ch = temporal_predictor(A.ch, B.ch, C.ch, D.ch, E.ch, F.ch, G.ch, H.ch, I.ch, J.ch, K.ch, L.ch, \
-	                          spatial_predictor(a.ch, b.ch, c.ch, d.ch, e.ch, f.ch, g.ch, hh.ch, i.ch, j.ch, k.ch, l.ch, m.ch, n.ch), skip)
-	YADIF_CH(x);
-	YADIF_CH(y);
-	YADIF_CH(z);
-#undef YADIF_CH
-	o.w = px(cur, xo, yo).w;   // "Reset Alpha" (yadifCl.ts:164): the w channel's prediction is discarded
-	out[tid] = o;
+	out[tid] = yadif_texel(prev, cur, next, w, h, parity, tff, skip, xo, yo);
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------

@@ -603,15 +603,22 @@ __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &l
 	for (int rr = 0; rr < 2; ++rr) {
 		if (!(rr ? ok1 : ok0)) continue;
 		const uchar4 *line = reinterpret_cast<const uchar4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;   // (rgba8 / bgra8)
-		if (lf.kind == LEAF_RGBA_F32) {   // an RGBA-f32 frame (a Yadif output, a materialised sub-expression): nothing to convert
+		if (lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF) {   // an RGBA-f32 frame (a materialised sub-expression, a routed frame):
+			// nothing to convert; or a de-interlaced field computed here from its three RGBA-f32 frames (yadifCl.ts:105-167)
 			const float4 *linef = reinterpret_cast<const float4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;
+			const bool yadif = lf.kind == LEAF_YADIF;
 #pragma unroll 1
 			for (int base = 0; base < ntex; base += 64) {
 				float4 v[2];
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
 					const int t = base + k * 32 + lane;
-					v[k] = t < ntex ? __ldg(linef + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+					if (t >= ntex) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+					else if (yadif)
+						v[k] = yadif_texel(reinterpret_cast<const float4 *>(lf.ptr_u), reinterpret_cast<const float4 *>(lf.ptr),
+						                   reinterpret_cast<const float4 *>(lf.ptr_v), lf.w, lf.h, lf.yadif & 1, (lf.yadif >> 1) & 1, (lf.yadif >> 2) & 1,
+						                   origin + t, j0 + rr);
+					else v[k] = __ldg(linef + t);
 				}
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
@@ -1056,7 +1063,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
+			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
 			else if (kPlanar && lf.lz_tx) eval_leaf_lanczos<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			const int act = op.act;

@@ -390,8 +390,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			const bool ycc = lf.kind == pb::LEAF_V210 || lf.kind == pb::LEAF_YUV422P10 || lf.kind == pb::LEAF_YUV422P8 ||
 			                 lf.kind == pb::LEAF_YUV420P || lf.kind == pb::LEAF_NV12;
 			// graphics with alpha, and RGBA-f32 frames (Yadif outputs, materialised sub-expressions): pb_march.cu eval_leaf_rgba
-			const bool rgba = lf.kind == pb::LEAF_RGBA8 || lf.kind == pb::LEAF_BGRA8 || lf.kind == pb::LEAF_RGBA_F32;
-			if (lf.kind == pb::LEAF_RGBA_F32) any_f32 = true;
+			const bool rgba = lf.kind == pb::LEAF_RGBA8 || lf.kind == pb::LEAF_BGRA8 || lf.kind == pb::LEAF_RGBA_F32 || lf.kind == pb::LEAF_YADIF;
+			if (lf.kind == pb::LEAF_RGBA_F32 || lf.kind == pb::LEAF_YADIF) any_f32 = true;
 			if (!(ycc || rgba) || lf.w < 6 || (lf.lz_tx && !ycc)) return 0;
 			// (a Lanczos leaf -- the extension of DESIGN.md 4.6 -- takes the general variants: eval_leaf_lanczos)
 			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0 || lf.lz_tx) any_planar = true;   // general load path (formats, partial last groups)
@@ -462,7 +462,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
 		if (r) return r;
 		if (!fits) return 0;
-		const bool leaf_rgba = leaves[i]->kind == pb::LEAF_RGBA8 || leaves[i]->kind == pb::LEAF_BGRA8 || leaves[i]->kind == pb::LEAF_RGBA_F32;
+		const bool leaf_rgba = leaves[i]->kind == pb::LEAF_RGBA8 || leaves[i]->kind == pb::LEAF_BGRA8 || leaves[i]->kind == pb::LEAF_RGBA_F32 ||
+		                       leaves[i]->kind == pb::LEAF_YADIF;
 		if (leaf_rgba && fits != 1) return 0;   // four planes: 32 source groups per row at most
 		if (fits == 2 || leaf_rgba) big_rows = true;
 		opq[i] = leaf_rgba ? nullptr : t->opq;   // the alpha of an rgba8 leaf is data: never certifiably opaque
@@ -837,7 +838,7 @@ int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool m
 		dp = &bg_copy;
 	}
 	const pb::FusedDesc &d = *dp;
-	cudaError_t e = march ? pb::launch_fused_march(s, d, c->prop.multiProcessorCount) : pb::launch_fused(s, d, out_rgba);
+	cudaError_t e = march ? pb::launch_fused_march(s, d, c->march_sms) : pb::launch_fused(s, d, out_rgba);
 	if (e != cudaSuccess) return fail(PB_ERR_CUDA, "fused launch (%s): %s", march ? "march" : "generic", cudaGetErrorString(e));
 	if (march && d.sink == pb::SINK_V210 && d.out_w % 48 != 0) {
 		pb::FusedDesc tail = d;

@@ -201,6 +201,17 @@ struct Compiler {
 			lf->pitch = n->w * 16;
 			return PB_OK;
 		}
+		if (n->kind == N_YADIF) {   // a de-interlaced field (yadifCl.ts:105-167), evaluated where it is sampled
+			lf->kind = pb::LEAF_YADIF;
+			lf->ptr = n->src->dev;
+			lf->ptr_u = n->src_u->dev;
+			lf->ptr_v = n->src_v->dev;
+			lf->w = n->w;
+			lf->h = n->h;
+			lf->pitch = n->w * 16;
+			lf->yadif = n->yadif;
+			return PB_OK;
+		}
 		if (n->kind == N_LEAF_PACKED) {   // rgba8 / bgra8 / planar 4:2:2 / 4:2:0 sources, read in place by the fused kernel
 			int idx;
 			if (rc_index(n->rc, &idx)) return 1;
@@ -869,7 +880,29 @@ int run_locked(pb_ctx *c, pb_prog *g, const pb_param *p, int n, cudaStream_t s) 
 			if ((r = check_image(out, W, H, "output"))) return r;
 			const void *a, *b, *d;
 			void *o;
-			if ((r = real_input(prev, &a)) || (r = real_input(cur, &b)) || (r = real_input(next, &d)) || (r = real_output(out, &o))) return r;
+			if ((r = real_input(prev, &a)) || (r = real_input(cur, &b)) || (r = real_input(next, &d))) return r;
+			if (c->flags & PB_CTX_DEFER) {
+				// The three frames of the window are real RGBA-f32 frames now (each ToRGBA output is made real once, by the direct
+				// kernel, and serves six field evaluations).  The field itself is only recorded: it is computed inside the fused
+				// launch that consumes it (Mixer Transform -> Combine -> FromRGBA), pixel by pixel where it is sampled, and never
+				// exists in HBM (yadif.ts:88-113 would write it and the next stage read it back).
+				if (prev->w != W || prev->h != H || cur->w != W || cur->h != H || next->w != W || next->h != H)
+					return fail(PB_ERR_ARG, "yadif: the three frames must be %dx%d images", W, H);
+				NodeP yn = new_node(c, N_YADIF, W, H);
+				yn->src = cur;
+				yn->src_u = prev;
+				yn->src_v = next;
+				cur->refs.fetch_add(1);
+				prev->refs.fetch_add(1);
+				next->refs.fetch_add(1);
+				yn->yadif = ((int)parity & 1) | (tff != 0 ? 2 : 0) | (skip != 0 ? 4 : 0);
+				set_deferred(out, yn);
+				out->w = W;
+				out->h = H;
+				c->stats.deferred_nodes++;
+				return PB_OK;
+			}
+			if ((r = real_output(out, &o))) return r;
 			out->w = W;
 			out->h = H;
 			e = pb::launch_yadif(s, a, b, d, (int)parity, tff != 0, skip != 0, o, W, H);

@@ -144,6 +144,24 @@ int pb_comm_unique_id(void *out128) {
 int pb_comm_init(pb_ctx *c, int rank, int world, const void *id128, pb_comm **out) {
 	if (!c || !id128 || !out) return fail(PB_ERR_ARG, "null argument");
 	if (world < 1 || rank < 0 || rank >= world) return fail(PB_ERR_ARG, "rank %d of %d", rank, world);
+	// The fused kernels are persistent, one CTA per SM with nearly all of its registers: NCCL's copy kernel would only get an
+	// SM when a fused launch ends, and the exchange would serialise with the frames it is meant to overlap.  So while a
+	// communicator spans more than this GPU, the march kernels can leave PB_ROUTE_SMS SMs to NCCL, which is then told to use that
+	// many channels.  Measured (profiles/r02_route_sms.txt, 2 GPUs): NCCL's point-to-point kernel moves ~10 GB/s per CTA, so
+	// a reservation small enough not to hurt the frames (8-16 SMs) starves the exchange (433 / 248 us per frame period against
+	// 152 us with no reservation); the default is therefore 0 and the knob stays for hosts with other trade-offs.
+	int route_sms = 0;
+	if (world > 1) {
+		const char *e = getenv("PB_ROUTE_SMS");
+		route_sms = e ? atoi(e) : 0;
+		route_sms = std::max(0, std::min(route_sms, c->prop.multiProcessorCount / 2));
+		if (route_sms > 0) {
+			char v[16];
+			snprintf(v, sizeof v, "%d", route_sms);
+			setenv("NCCL_MIN_CTAS", v, 0);
+			setenv("NCCL_MAX_CTAS", v, 0);
+		}
+	}
 	Nccl *n = nccl();
 	if (!n->handle) return fail(PB_ERR_STATE, "%s", n->why.c_str());
 	CU(cudaSetDevice(c->dev));
@@ -158,9 +176,17 @@ int pb_comm_init(pb_ctx *c, int rank, int world, const void *id128, pb_comm **ou
 		delete m;
 		return fail(PB_ERR_CUDA, "ncclCommInitRank: %s", n->GetErrorString(r));
 	}
-	CU(cudaStreamCreateWithFlags(&m->rs, cudaStreamNonBlocking));
+	{   // the exchange stream outranks the queues: its copy CTAs take the SMs that free up first
+		int lo = 0, hi = 0;
+		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CU(cudaStreamCreateWithPriority(&m->rs, cudaStreamNonBlocking, hi));
+	}
 	CU(cudaEventCreateWithFlags(&m->ev_ready, cudaEventDisableTiming));
 	for (auto &g : m->gen) CU(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+	{
+		std::lock_guard<std::recursive_mutex> lk(c->mu);
+		c->march_sms = c->prop.multiProcessorCount - route_sms;
+	}
 	*out = m;
 	return PB_OK;
 }
@@ -181,6 +207,10 @@ int pb_comm_destroy(pb_comm *m) {
 	{
 		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
 		for (auto &g : m->gen) release_gen(m, g);
+	}
+	{
+		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
+		m->ctx->march_sms = m->ctx->prop.multiProcessorCount;
 	}
 	if (m->comm && nccl()->CommDestroy) nccl()->CommDestroy(m->comm);
 	cudaStreamDestroy(m->rs);

@@ -969,3 +969,112 @@ def test_interlaced_source_through_yadif_composites_on_the_march_kernel(use_marc
     ref = oracle.v210_write(oracle.combine([la, lb]), w, h, 0, oracle.rgb2ycbcr_matrix("2020"), oracle.linear2gamma_lut("2020"))
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
     assert st["march_launches"] == (1 if use_march else 0) and st["fused_launches"] == 1 and st["kernel_launches"] == 1, st
+
+
+@pytest.mark.parametrize("mode", ["send_field", "send_frame_nospatial"])
+def test_yadif_fields_are_fused_into_the_composite_launch(mode):
+    """Interlaced v210 frames -> ToRGBA -> Yadif (yadif.ts:88-145) -> Mixer Transform -> Combine with a PiP -> FromRGBA.
+    Each ToRGBA output is made real ONCE (one direct-kernel launch per input frame: the window re-reads it for six fields);
+    the de-interlaced field itself never exists in HBM: it is computed inside the ONE march launch of its output frame.
+    Bit-exact against the oracle's stage-by-stage chain (v210 read x3 -> yadif -> transform -> combine -> v210 write)."""
+    from phaneron_b200.process import v210 as v210m
+    from phaneron_b200.process.combine import Combine
+    from phaneron_b200.process.image_process import ImageProcess
+    from phaneron_b200.process.io import FromRGBA, ToRGBA
+    from phaneron_b200.process.transform import Transform
+    from phaneron_b200.process.yadif import Yadif
+    from scene_oracle import xf_matrix
+    w, h = 480, 136
+    frames = [make_frame("noise", w, h, 170 + i) for i in range(4)]
+    pip_src = make_frame("noise", w, h, 180)
+    pip_xf = pip(0.5, 0.3, 0.2)
+
+    async def go():
+        async with Env(True) as env:
+            ctx, jobs = env.ctx, env.jobs
+            to_a = ToRGBA(ctx, "709", "2020", v210m.Reader(w, h), jobs)
+            to_b = ToRGBA(ctx, "709", "2020", v210m.Reader(w, h), jobs)
+            frm = FromRGBA(ctx, "2020", v210m.Writer(w, h, False), jobs)
+            xa = ImageProcess(ctx, Transform(ctx, w, h), jobs)
+            xb = ImageProcess(ctx, Transform(ctx, w, h), jobs)
+            comb = ImageProcess(ctx, Combine(2, w, h), jobs)
+            yad = Yadif(ctx, jobs, w, h, {"mode": mode, "tff": True}, True)
+            for o in (to_a, to_b, frm, xa, xb, comb, yad):
+                await o.init()
+            results, stats = [], []
+            for t, f in enumerate(frames):
+                s0 = ctx.stats()
+                srcs = await to_a.createSources("src")
+                for s_ in srcs:
+                    s_.timestamp = t * 2
+                await to_a.loadFrame(f, srcs, ctx.queue.load)
+                rgba = await to_a.createDest({"width": w, "height": h}, "src")
+                rgba.timestamp = t * 2
+                to_a.processFrame("src", srcs, rgba)
+                # (In the reference the newest frame's read job is still queued under its own timestamp when the window first
+                # uses it as `next` -- yadif.ts:101-112 runs the queue of the CURRENT frame's timestamp -- so `next` is read
+                # before it is written; test_gpu_ops.py covers that order.  Here the read is flushed first: the window holds
+                # three converted frames, which is what the fused path is about.)
+                if len(yad.in_) >= 2:   # (while the window fills, Yadif.processFrame flushes the read itself, yadif.ts:126-130)
+                    await jobs.runQueue({"source": "src", "timestamp": t * 2})
+                outs = []
+                await yad.processFrame(rgba, outs, "src")
+                s1 = ctx.stats()
+                stats.append(("deinterlace", {k: s1[k] - s0[k] for k in s1}))
+                for deint in outs:   # every de-interlaced frame goes down the channel: mixer, second layer, combiner, consumer
+                    assert deint.deferred
+                    b0 = ctx.stats()
+                    ts = deint.timestamp
+                    xfa = await ctx.createBuffer(w * h * 16, "readwrite", "coarse", {"width": w, "height": h}, "mixer a")
+                    await xa.run(dict(input=deint, output=xfa, **_xf()), {"source": "L0", "timestamp": ts}, lambda d=deint: d.release())
+                    await jobs.runQueue({"source": "L0", "timestamp": ts})
+                    psrcs = await to_b.createSources("pip")
+                    for s_ in psrcs:
+                        s_.timestamp = ts
+                    await to_b.loadFrame(pip_src, psrcs, ctx.queue.load)
+                    rgb = await to_b.createDest({"width": w, "height": h}, "pip")
+                    to_b.processFrame("pip", psrcs, rgb)
+                    xfb = await ctx.createBuffer(w * h * 16, "readwrite", "coarse", {"width": w, "height": h}, "mixer b")
+                    await xb.run(dict(input=rgb, output=xfb, **pip_xf), {"source": "pip", "timestamp": ts}, lambda r_=rgb: r_.release())
+                    await jobs.runQueue({"source": "pip", "timestamp": ts})
+                    cdest = await ctx.createBuffer(w * h * 16, "readwrite", "coarse", {"width": w, "height": h}, "comb")
+                    cdest.timestamp = ts
+                    await comb.run({"inputs": [xfa, xfb], "output": cdest}, {"source": "ch", "timestamp": ts}, lambda: None)
+                    await jobs.runQueue({"source": "ch", "timestamp": ts})
+                    xfa.release()
+                    xfb.release()
+                    dests = await frm.createDests("out")
+                    frm.processFrame("out", cdest, dests, Interlace.Progressive)
+                    await jobs.runQueue({"source": "out", "timestamp": ts})
+                    await frm.saveFrame(dests)
+                    b1 = ctx.stats()
+                    results.append(dests[0].host.copy())
+                    stats.append(("compose", {k: b1[k] - b0[k] for k in b1}))
+                    for d_ in dests:
+                        d_.release()
+            yad.release()
+            return results, stats
+    results, stats = run(go())
+    send_field = mode.startswith("send_field")
+    skip = mode.endswith("nospatial")
+    assert len(results) == (4 if send_field else 2)   # the window fills at the third frame; 1 or 2 outputs per frame from then on
+    # launch structure
+    for kind, st in stats:
+        if kind == "compose":
+            assert st["kernel_launches"] == 1 and st["march_launches"] == 1 and st["materialised"] == 0, st
+        else:   # producer side: frames are made real when the window first needs them (one direct-kernel launch each), nothing else
+            assert st["kernel_launches"] == st["materialised"] == st["march_launches"], st
+    assert sum(st["materialised"] for kind, st in stats if kind == "deinterlace") == 4   # each input frame exactly once
+    # oracle chain
+    cm_r, lut_r, gam = oracle.ycbcr2rgb_matrix("709"), oracle.gamma2linear_lut("709"), oracle.rgb2rgb_matrix("709", "2020")
+    rgba = [oracle.v210_read(f, w, h, cm_r, lut_r, gam) for f in frames]
+    lb = oracle.transform(oracle.v210_read(pip_src, w, h, cm_r, lut_r, gam), xf_matrix(w, h, pip_xf), w, h)
+    k = 0
+    for t in (2, 3):   # window (t-2, t-1, t): the de-interlaced frame is frame t-1's
+        for second in ((False, True) if send_field else (False,)):
+            parity = 1 ^ (0 if second else 1)   # tff: (tff ? 1 : 0) ^ (!isSecond ? 1 : 0), yadif.ts:104
+            deint = oracle.yadif(rgba[t - 2], rgba[t - 1], rgba[t], parity, True, skip)
+            la = oracle.transform(deint, xf_matrix(w, h, _xf()), w, h)
+            ref = oracle.v210_write(oracle.combine([la, lb]), w, h, 0, oracle.rgb2ycbcr_matrix("2020"), oracle.linear2gamma_lut("2020"))
+            assert np.array_equal(results[k], ref), f"output {k}: {int((results[k] != ref).sum())} bytes differ"
+            k += 1
