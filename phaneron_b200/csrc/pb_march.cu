@@ -285,10 +285,37 @@ __device__ __noinline__ void convert_group_exact(const Leaf &lf, const ReadConst
 	}
 }
 
+// ---- TMA row prefetch (fast variants) ------------------------------------------------------------------------------------
+// A work item starts with two dependent round trips to memory: the leaf's table entries, then the packed source rows they
+// point at.  Both are taken off the item's critical path, two items deep, without holding registers:
+//   stage A (start of item i): which leaf item i + 1 starts with is known (its line mask was loaded during item i - 1);
+//            lane 0 copies that leaf's {strip, row} table entries into scratch words of the warp (cp.async, LDGSTS);
+//   stage B (item i, before its encode): the entries have arrived; lane 0 hands the two source rows they point at to the
+//            TMA unit (cp.async.bulk into the warp's 1 KiB staging tile, completion on the warp's own mbarrier);
+//   item i + 1: its first leaf finds its 128-bit groups in shared memory (and its table entries in L1).
+constexpr int kPfRowBytes = 512;                 // 32 v210 groups
+constexpr int kPfBytes = 2 * kPfRowBytes + 32;   // two source rows + the scratch words the table entries of the next item's first leaf land in
+struct RowPf {
+	uint32_t raw;      // shared-memory address of the warp's staging tile
+	uint32_t bar;      // ... of its mbarrier
+	uint32_t parity;   // phase the next wait is for
+	int item, op;      // the (item, op) the tile was filled for; item < 0: nothing in flight
+};
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	uint32_t done = 0;
+	while (!done)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+
 // value of one leaf at the 3 pixels of this lane -> p[r] = (r, g, b, alpha)
-template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine, bool kPlanar, bool kBigRows>
+template <int kLutMode, bool kSparse, bool kSingleRc, int kReadAffine, bool kPlanar, bool kBigRows, bool kPf = false>
 __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, uint32_t lut_saddr, SPtr buf, int lane, int strip, int y,
-                                          int x_first, int x_last, float4 (&p)[kRounds]) {
+                                          int x_first, int x_last, float4 (&p)[kRounds], RowPf *pf = nullptr, bool from_pf = false) {
 	// (strips / lines where the whole layer is border colour never get here: FusedDesc::strip_ops & line_ops)
 	const int4 si = __ldg(lf.strip_tab + strip);
 	const int2 rt = __ldg(lf.row_tab + y);
@@ -308,7 +335,17 @@ __device__ __forceinline__ void eval_leaf(const FusedDesc &d, const Leaf &lf, ui
 	// issue every HBM load of this leaf up front
 	const uint4 z4 = make_uint4(0, 0, 0, 0);
 	uint4 wa = z4, wb = z4;
-	if (paired) {   // lanes 0-15: row j0, lanes 16-31: row j0 + 1
+	if (kPf && from_pf) {   // the rows were fetched by the TMA unit while the previous item was encoded
+		mbar_wait(pf->bar, pf->parity);
+		pf->parity ^= 1u;
+		if (paired) {
+			const int hi = lane >> 4, g = lane & 15;
+			if (g < ng && (hi ? ok1 : ok0)) wa = lds_u128(pf->raw + hi * kPfRowBytes + g * 16);
+		} else {
+			if (lane < ng && ok0) wa = lds_u128(pf->raw + lane * 16);
+			if (lane < ng && ok1) wb = lds_u128(pf->raw + kPfRowBytes + lane * 16);
+		}
+	} else if (paired) {   // lanes 0-15: row j0, lanes 16-31: row j0 + 1
 		const int hi = lane >> 4, g = lane & 15;
 		if (g < ng && (hi ? ok1 : ok0)) wa = load_group<kPlanar>(lf, j0 + hi, g_lo + g);
 	} else {
@@ -1024,9 +1061,35 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	wlut.koff = d.lds_koff;
 	const LutParams &wlp = d.wlp;
 
+	// TMA row prefetch (see RowPf): the fast variants only (v210 leaves with whole groups, 32-group row buffers)
+	constexpr bool kPf = kLutMode == 1 && !kPlanar && !kBigRows && !kBg;
+	__shared__ __align__(8) unsigned long long pf_bars[kPf ? kMarchWarps : 1];
+	RowPf pf;
+	pf.raw = lut_saddr + (uint32_t)d.n_luts * 65536u + (uint32_t)kMarchWarps * (kRowFloats * 4u) + (uint32_t)warp * kPfBytes;
+	pf.bar = (uint32_t)__cvta_generic_to_shared(&pf_bars[kPf ? warp : 0]);
+	pf.parity = 0;
+	pf.item = -1;
+	pf.op = 0;
+	// Measured (profiles/r02_kbench_tma_prefetch_v*.txt): bit-exact, and 6-9 % SLOWER than without on the 2160p scenes -- other warps
+	// already cover the load latency, what the prefetch adds is instructions.  Off unless PB_DBG=2 asks for it (A/B runs).
+	const bool pf_on = kPf && (d.dbg & 2);
+	uint32_t lo_next = 0;   // line mask of the next item (loaded one item ahead)
+	if (kPf) {
+		if (lane == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pf.bar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+	}
+
 	// item -> (line k, strip) is kept incrementally: no integer division per item
 	const int stride = gridDim.x * kMarchWarps, stride_k = stride / d.n_strips, stride_s = stride - stride_k * d.n_strips;
 	int k = (blockIdx.x * kMarchWarps + warp) / d.n_strips, strip = (blockIdx.x * kMarchWarps + warp) - k * d.n_strips;
+	if (kPf && pf_on) {   // the line mask of this warp's second item
+		int k2 = k + stride_k, strip2 = strip + stride_s;
+		if (strip2 >= d.n_strips) ++k2;
+		if (blockIdx.x * kMarchWarps + warp + stride < total) lo_next = __ldg(d.line_ops + first_line + k2 * step);
+	}
 #pragma unroll 1
 	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride, k += stride_k, strip += stride_s) {
 		if (strip >= d.n_strips) {
@@ -1034,6 +1097,38 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			++k;
 		}
 		const int y = first_line + k * step;
+		bool pf_stage = false;
+		int pf_op2 = 0;   // first live op of the next item
+		if (kPf && pf_on) {
+			// ---- stage A: the table entries of the leaf the next item starts with; the line mask of the item after it ----
+			pf.item = pf.item == item ? pf.item : -1;
+			const int item2 = item + stride;
+			if (item2 < total) {
+				int k2 = k + stride_k, strip2 = strip + stride_s;
+				if (strip2 >= d.n_strips) {
+					strip2 -= d.n_strips;
+					++k2;
+				}
+				const uint32_t both2 = d.strip_ops[strip2] & lo_next;
+				uint32_t todo2 = both2 & 0xFFFFFFu;
+				if (both2 >> 24) todo2 &= ~0u << d.layer_first_op[(31 - __clz(both2)) - 24];
+				if (todo2) {
+					const int oi2 = __ffs(todo2) - 1;
+					const MarchOp &op2 = d.ops[oi2];
+					const Leaf &lf2 = (&d.layers[op2.layer].a)[op2.which];
+					if (lane == 0) {
+						const uint32_t sc = pf.raw + 2 * kPfRowBytes;
+						asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sc), "l"(lf2.strip_tab + strip2) : "memory");
+						asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sc + 16), "l"(lf2.row_tab + (first_line + k2 * step)) : "memory");
+					}
+					pf_op2 = oi2;
+					pf_stage = true;
+				}
+				int k3 = k2 + stride_k, strip3 = strip2 + stride_s;
+				if (strip3 >= d.n_strips) ++k3;
+				if (item2 + stride < total) lo_next = __ldg(d.line_ops + first_line + k3 * step);
+			}
+		}
 		if (kBg && ((__ldg(d.line_pairs + y) >> (strip >> 1)) & 1ull)) continue;   // a background-only line of this strip pair: second phase
 		const int x_first = strip * strip_px;
 		const int x_last = min(x_first + strip_px, d.march_w) - 1;   // whole output groups only: a ragged tail is the generic kernel's
@@ -1065,7 +1160,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
 			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
 			else if (kPlanar && lf.lz_tx) eval_leaf_lanczos<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
-			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
+			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows, kPf>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p, &pf,
+			                                                                                                                  kPf && pf.item == item && pf.op == oi);
 			const int act = op.act;
 			if (act == ACT_DIS_B) {   // transition.ts:60-65: fma(in0, mix, in1 * (1 - mix))
 				const float rmix = sub(1.0f, op.mix);
@@ -1102,6 +1198,34 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 				const float kk = sub(1.0f, p[r].w);
 				acc[r] = make_float3(fma_(acc[r].x, kk, p[r].x), fma_(acc[r].y, kk, p[r].y), fma_(acc[r].z, kk, p[r].z));
 				if (kPlanar) al[r] = fma_(al[r], 0.0f, p[r].w);
+			}
+		}
+
+		if (kPf && pf_stage) {
+			// ---- stage B: the table entries have arrived in the warp's scratch words: hand the row copies to the TMA unit ----
+			if (lane == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+			__syncwarp();   // (also: every lane has taken its groups out of the tile)
+			const uint32_t sc = pf.raw + 2 * kPfRowBytes;
+			uint32_t sx, sy, sz, rx;
+			asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sx), "=r"(sy) : "r"(sc));
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sz) : "r"(sc + 8));
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rx) : "r"(sc + 16));
+			const Leaf &lf2 = (&d.layers[d.ops[pf_op2].layer].a)[d.ops[pf_op2].which];
+			const int j2 = (int)rx;
+			const bool ok0 = (unsigned)j2 < (unsigned)lf2.h, ok1 = lf2.has_xf != 0 && (unsigned)(j2 + 1) < (unsigned)lf2.h;
+			if ((sx & 1u) && (ok0 || ok1)) {   // (else eval_leaf returns the border colour without loading anything)
+				const uint32_t row_bytes = sz * 16u;
+				const char *src = reinterpret_cast<const char *>(lf2.ptr) + (size_t)j2 * lf2.pitch + (size_t)sy * 16;
+				if (lane == 0) {
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pf.bar), "r"(row_bytes * ((ok0 ? 1u : 0u) + (ok1 ? 1u : 0u))) : "memory");
+					if (ok0)
+						asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pf.raw), "l"(src), "r"(row_bytes), "r"(pf.bar) : "memory");
+					if (ok1)
+						asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pf.raw + kPfRowBytes), "l"(src + lf2.pitch), "r"(row_bytes), "r"(pf.bar) : "memory");
+				}
+				pf.item = item + stride;
+				pf.op = pf_op2;
 			}
 		}
 
@@ -1343,7 +1467,8 @@ cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *
 
 size_t march_smem_bytes(const FusedDesc &d) {
 	if (d.bg_single) return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
-	return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * (d.big_rows ? 2 : 1) * kRowFloats * sizeof(float) + (size_t)d.n_t256 * 1024;
+	const size_t pf_tiles = (d.n_luts > 0 && !d.any_planar && !d.big_rows) ? (size_t)kMarchWarps * kPfBytes : 0;   // TMA row prefetch of the fast variants
+	return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * (d.big_rows ? 2 : 1) * kRowFloats * sizeof(float) + (size_t)d.n_t256 * 1024 + pf_tiles;
 }
 
 cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) {
