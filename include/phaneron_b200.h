@@ -236,6 +236,16 @@ int pb_route_begin(pb_comm *comm);
 int pb_route_send(pb_comm *comm, pb_buf *frame, int peer);
 int pb_route_recv(pb_comm *comm, pb_buf *landing, int peer);
 int pb_route_end(pb_comm *comm);
+/* Copy-engine transport between the GPUs of one node (optional; collective over the communicator, once).  Every rank names
+   the 2..4 landing buffers it will receive into -- in the order it will pass them to pb_route_recv, round robin --, the rank
+   it receives from and the rank it sends to.  The ranks exchange CUDA IPC handles and map each other's buffers; from then on
+   pb_route_send(frame, peer_out) pushes the frame into the receiver's landing buffer with the copy engines (no SM: NCCL's
+   copy kernel would wait for the persistent fused kernels) and two sequence numbers in device memory, written and waited for
+   by the streams themselves, do the flow control.  Contract: the launches that read a received buffer are queued between the
+   pb_route_wait that made a queue wait for it and the next pb_route_begin.  Where mapping is impossible the calls stay on
+   NCCL; pb_route_transport says which it is (1 = copy engines). */
+int pb_route_attach(pb_comm *comm, pb_buf **landing, int n_landing, int peer_in, int peer_out);
+int pb_route_transport(pb_comm *comm);
 /* make `queue` wait, on the device, for the exchange last ended */
 int pb_route_wait(pb_comm *comm, int queue);
 /* ... or for the one `age` exchanges before it (age 0 = the last one; up to 2): a host that composes frame n + 1 from what

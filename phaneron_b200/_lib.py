@@ -42,7 +42,7 @@ SYMBOLS = [
     "pb_gamma2linear_lut", "pb_linear2gamma_lut", "pb_ycbcr2rgb_matrix", "pb_rgb2ycbcr_matrix",
     "pb_rgb2rgb_matrix", "pb_transform_matrix",
     "pb_comm_unique_id", "pb_comm_init", "pb_comm_info", "pb_comm_destroy", "pb_route_begin", "pb_route_send",
-    "pb_route_recv", "pb_route_end", "pb_route_wait", "pb_route_wait_age", "pb_route_sync", "pb_route_copy_peer",
+    "pb_route_recv", "pb_route_end", "pb_route_attach", "pb_route_transport", "pb_route_wait", "pb_route_wait_age", "pb_route_sync", "pb_route_copy_peer",
 ]
 
 
@@ -131,6 +131,8 @@ def lib() -> C.CDLL:
         "pb_route_send": (i, [vp, vp, i]),
         "pb_route_recv": (i, [vp, vp, i]),
         "pb_route_end": (i, [vp]),
+        "pb_route_attach": (i, [vp, C.POINTER(vp), i, i, i]),
+        "pb_route_transport": (i, [vp]),
         "pb_route_wait": (i, [vp, i]),
         "pb_route_wait_age": (i, [vp, i, i]),
         "pb_route_sync": (i, [vp]),

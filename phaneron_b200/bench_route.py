@@ -78,6 +78,9 @@ async def run(args, rank: int, world: int, local_rank: int, emit, clock_sampler_
     for b in landing:
         await b.hostAccess("writeonly", ctx.queue.load, zero)
     await ctx.waitFinish(ctx.queue.load)
+    # between the GPUs of the node the frames cross with the copy engines (CUDA IPC + stream memory operations); NCCL carries
+    # the handles once, and the frames themselves where mapping is impossible (one GPU: rank 0 routes to itself)
+    transport = "copy engines (CUDA IPC push + cuStreamWaitValue32 flow control)" if comm.attach(landing, peer_in, peer_out) else "NCCL point-to-point"
     xfp = dict(pip(0.5, 0.25, 0.25))
 
     # ---- record one chain per slot: chain k composes from landing[(k + 1) % 3] (filled two exchanges ago) into out[k] ----
@@ -120,7 +123,12 @@ async def run(args, rank: int, world: int, local_rank: int, emit, clock_sampler_
 
     lib = _lib.lib()
 
+    counter = {"ex": 0}   # exchange periods so far: the slot rotation continues across timed runs
+
     def period(n: int, exchange: bool) -> None:
+        if exchange:
+            n = counter["ex"]
+            counter["ex"] += 1
         k = n % SLOTS
         if exchange:
             comm.wait(_lib.QUEUE_PROCESS, age=1)   # landing[(k+1)%3] was filled by exchange n-2; out[k] was sent by exchange n-3
@@ -172,7 +180,7 @@ async def run(args, rank: int, world: int, local_rank: int, emit, clock_sampler_
             "config": {"workload": f"BASELINE.json configs[3]: {world} x 1920x1080 v210 channel(s), one per GPU, 2 layers each (own source + 0.5x PiP of the "
                                    f"neighbour channel's ROUTEd RGBA-f32 frame), 709, inputs={args.inputs}",
                        "frames_per_step": args.route_frames_per_step, "launches_per_frame": launches_per_frame,
-                       "route": "pb_route_* (C ABI): ncclSend/ncclRecv on a side stream, one group per frame period, exchange n overlaps frame n+1",
+                       "route": "pb_route_* (C ABI) on a side stream, one exchange per frame period, exchange n overlaps frame n+1; transport: " + transport,
                        "route_bytes_per_frame_per_gpu": frame_bytes, "l2_policy": "each frame period streams 110 MB through HBM (> L2 with the exchange buffers rotating over 3 slots)"},
             "frame_period_us": per_frame_us, "frame_period_us_without_route": ms_local * 1e3 / frames,
             "route_overhead": per_frame_us / (ms_local * 1e3 / frames),

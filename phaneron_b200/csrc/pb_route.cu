@@ -83,6 +83,24 @@ Nccl *nccl() {
 	return &n;
 }
 
+// stream memory operations of the driver API (the runtime hands out the entry points)
+typedef int (*StreamValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+struct DriverOps {
+	StreamValue32Fn wait32 = nullptr, write32 = nullptr;
+};
+DriverOps *driver_ops() {
+	static DriverOps d;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		void *w = nullptr, *r = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) d.wait32 = (StreamValue32Fn)w;
+		if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &r, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) d.write32 = (StreamValue32Fn)r;
+	});
+	return &d;
+}
+constexpr unsigned kWaitGeq = 0x0;   // CU_STREAM_WAIT_VALUE_GEQ
+
 #define NC(call)                                                                                                    \
 	do {                                                                                                            \
 		ncclResult_t r__ = (call);                                                                                  \
@@ -108,6 +126,28 @@ struct pb_comm {
 	int head = 0;
 	bool open = false;                   // between begin and end
 	uint64_t bytes_sent = 0, bytes_received = 0;
+
+	// ---- copy-engine transport (pb_route_attach) ------------------------------------------------------------------------------
+	// NCCL's point-to-point kernel needs SMs, and the fused kernels are persistent: the exchange would wait for the end of a
+	// launch and then run in its place (profiles/r02_route_sms.txt).  Between GPUs of one node the frame can instead be PUSHED
+	// by the copy engines straight into the receiver's landing buffer (CUDA IPC mapping), with two 32-bit sequence numbers in
+	// device memory for flow control, written and waited for by the streams themselves (cuStreamWriteValue32 /
+	// cuStreamWaitValue32): no SM, no host round trip.
+	//   flags[0] "ready":  written by the sender into the RECEIVER's flags after its copy: exchanges delivered so far
+	//   flags[1] "credit": written by the receiver into the SENDER's flags when the frames that read an exchange are done
+	struct Ce {
+		bool on = false;
+		int peer_in = -1, peer_out = -1, slots = 0;
+		pb_buf *landing[4] = {};          // this rank's landing buffers, in the order they are filled
+		void *remote_landing[4] = {};     // peer_out's landing buffers, mapped here
+		uint32_t *flags = nullptr;        // this rank's flags (written by the peers)
+		uint32_t *flags_of_in = nullptr;  // peer_in's flags, mapped: credit goes there
+		uint32_t *flags_of_out = nullptr; // peer_out's flags, mapped: ready goes there
+		uint32_t sent = 0, received = 0;  // exchanges so far (1-based sequence numbers)
+		uint32_t credit_due = 0;          // sequence number of the last exchange a queue was made to wait for
+		uint32_t credit_given = 0;
+	} ce;
+	uint32_t gen_recv_seq[kRing] = {};   // per exchange of the ring: sequence number of its copy-engine receive (0: none)
 };
 
 namespace {
@@ -212,6 +252,16 @@ int pb_comm_destroy(pb_comm *m) {
 		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
 		m->ctx->march_sms = m->ctx->prop.multiProcessorCount;
 	}
+	if (m->ce.flags) {
+		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
+		for (int i = 0; i < 4; ++i) {
+			if (m->ce.remote_landing[i]) cudaIpcCloseMemHandle(m->ce.remote_landing[i]);
+			if (m->ce.landing[i]) buf_release_locked(m->ce.landing[i]);
+		}
+		if (m->ce.flags_of_in && m->ce.flags_of_in != m->ce.flags_of_out) cudaIpcCloseMemHandle(m->ce.flags_of_in);
+		if (m->ce.flags_of_out) cudaIpcCloseMemHandle(m->ce.flags_of_out);
+		cudaFree(m->ce.flags);
+	}
 	if (m->comm && nccl()->CommDestroy) nccl()->CommDestroy(m->comm);
 	cudaStreamDestroy(m->rs);
 	cudaEventDestroy(m->ev_ready);
@@ -220,10 +270,89 @@ int pb_comm_destroy(pb_comm *m) {
 	return PB_OK;
 }
 
+// Collective over the communicator, once: every rank names the landing buffers it will receive into (in the order it will
+// pass them to pb_route_recv, round robin), the rank it receives from and the rank it sends to.  The ranks exchange CUDA IPC
+// handles (over NCCL, a few hundred bytes) and map each other's buffers.  From then on pb_route_send to `peer_out` and
+// pb_route_recv from `peer_in` use the copy engines; anything else (and every failure to map) stays on NCCL.
+int pb_route_attach(pb_comm *m, pb_buf **landing, int n, int peer_in, int peer_out) {
+	if (!m || !landing) return fail(PB_ERR_ARG, "null argument");
+	if (n < 2 || n > 4) return fail(PB_ERR_ARG, "pb_route_attach: 2..4 landing buffers, found %d", n);
+	if (peer_in < 0 || peer_in >= m->world || peer_out < 0 || peer_out >= m->world) return fail(PB_ERR_ARG, "bad peer");
+	if (m->open) return fail(PB_ERR_STATE, "pb_route_attach inside an open exchange");
+	if (m->world < 2 || peer_in == m->rank || peer_out == m->rank || getenv("PB_ROUTE_NCCL_ONLY")) return PB_OK;   // nothing to map: NCCL path
+	DriverOps *ops = driver_ops();
+	if (!ops->wait32 || !ops->write32) return PB_OK;
+	pb_ctx *c = m->ctx;
+	std::lock_guard<std::recursive_mutex> lk(c->mu);
+	CU(cudaSetDevice(c->dev));
+	pb_comm::Ce &ce = m->ce;
+	CU(cudaMalloc(&ce.flags, 64));
+	CU(cudaMemsetAsync(ce.flags, 0, 64, m->rs));
+	struct Packet {
+		cudaIpcMemHandle_t flags, landing[4];
+		int slots, rank;
+		unsigned long long bytes;
+	} mine{}, from_in{}, from_out{};
+	CU(cudaIpcGetMemHandle(&mine.flags, ce.flags));
+	for (int i = 0; i < n; ++i) {
+		pb_buf *b = landing[i];
+		if (!b || b->ctx != c) return fail(PB_ERR_ARG, "landing buffer %d belongs to another context", i);
+		int r = ensure_dev(b);
+		if (r) return r;
+		b->expr.reset();
+		CU(cudaIpcGetMemHandle(&mine.landing[i], b->dev));
+		b->refs.fetch_add(1);
+		ce.landing[i] = b;
+	}
+	mine.slots = n;
+	mine.rank = m->rank;
+	mine.bytes = landing[0]->bytes;
+	Packet *dev = nullptr;
+	CU(cudaMalloc(&dev, 3 * sizeof(Packet)));
+	CU(cudaMemcpyAsync(dev, &mine, sizeof mine, cudaMemcpyHostToDevice, m->rs));
+	// my handles go to both neighbours (peer_in writes my landing buffers and my "ready"; peer_out writes my "credit")
+	NC(nccl()->GroupStart());
+	NC(nccl()->Send(dev, sizeof(Packet), kNcclUint8, peer_in, m->comm, m->rs));
+	NC(nccl()->Send(dev, sizeof(Packet), kNcclUint8, peer_out, m->comm, m->rs));
+	NC(nccl()->Recv(dev + 1, sizeof(Packet), kNcclUint8, peer_out, m->comm, m->rs));   // (same order on every rank: from the rank I send to ...
+	NC(nccl()->Recv(dev + 2, sizeof(Packet), kNcclUint8, peer_in, m->comm, m->rs));    //  ... then from the rank I receive from)
+	NC(nccl()->GroupEnd());
+	CU(cudaMemcpyAsync(&from_out, dev + 1, sizeof(Packet), cudaMemcpyDeviceToHost, m->rs));
+	CU(cudaMemcpyAsync(&from_in, dev + 2, sizeof(Packet), cudaMemcpyDeviceToHost, m->rs));
+	CU(cudaStreamSynchronize(m->rs));
+	cudaFree(dev);
+	bool ok = from_out.rank == peer_out && from_in.rank == peer_in && from_out.slots >= 2 && from_out.slots <= 4 && from_out.bytes == mine.bytes;
+	void *p = nullptr;
+	if (ok && cudaIpcOpenMemHandle(&p, from_out.flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) ce.flags_of_out = (uint32_t *)p;
+	else ok = false;
+	if (ok && peer_in == peer_out) ce.flags_of_in = ce.flags_of_out;   // (two ranks: one neighbour, one mapping)
+	else if (ok && cudaIpcOpenMemHandle(&p, from_in.flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) ce.flags_of_in = (uint32_t *)p;
+	else ok = false;
+	for (int i = 0; ok && i < from_out.slots; ++i) {
+		if (cudaIpcOpenMemHandle(&p, from_out.landing[i], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) ce.remote_landing[i] = p;
+		else ok = false;
+	}
+	cudaGetLastError();   // (a failed mapping is not an error of the library: the NCCL path stays)
+	ce.peer_in = peer_in;
+	ce.peer_out = peer_out;
+	ce.slots = n;
+	ce.on = ok && from_out.slots == n;
+	return PB_OK;
+}
+
+int pb_route_transport(pb_comm *m) { return (m && m->ce.on) ? 1 : 0; }
+
 int pb_route_begin(pb_comm *m) {
 	if (!m) return fail(PB_ERR_ARG, "null comm");
 	if (m->open) return fail(PB_ERR_STATE, "pb_route_begin: an exchange is already open");
 	CU(cudaSetDevice(m->ctx->dev));
+	if (m->ce.on && m->ce.credit_due > m->ce.credit_given) {
+		// the frames that read the exchange(s) waited for since the last begin are queued by now (the contract of pb_route_wait):
+		// when they have run, the sender may overwrite those landing buffers
+		if (driver_ops()->write32(m->ctx->q[PB_QUEUE_PROCESS], (unsigned long long)(uintptr_t)(m->ce.flags_of_in + 1), m->ce.credit_due, 0) != 0)
+			return fail(PB_ERR_CUDA, "cuStreamWriteValue32 (credit) failed");
+		m->ce.credit_given = m->ce.credit_due;
+	}
 	{   // earlier exchanges that have completed give their buffers back; the slot about to be reused has to (normally it
 		// finished several frame periods ago, so this does not block)
 		std::lock_guard<std::recursive_mutex> lk(m->ctx->mu);
@@ -236,6 +365,7 @@ int pb_route_begin(pb_comm *m) {
 			release_gen(m, g);
 		}
 		m->head = next;
+		m->gen_recv_seq[next] = 0;
 	}
 	NC(nccl()->GroupStart());
 	m->open = true;
@@ -254,7 +384,19 @@ int pb_route_send(pb_comm *m, pb_buf *frame, int peer) {
 	if ((r = flush_host(frame, m->ctx->q[PB_QUEUE_PROCESS]))) return r;
 	if (!frame->dev) return fail(PB_ERR_STATE, "routed frame '%s' has no contents", frame->owner.c_str());
 	if ((r = order_after_queues(m))) return r;
-	NC(nccl()->Send(frame->dev, frame->bytes, kNcclUint8, peer, m->comm, m->rs));
+	if (m->ce.on && peer == m->ce.peer_out && frame->bytes == m->ce.landing[0]->bytes) {
+		pb_comm::Ce &ce = m->ce;
+		const uint32_t seq = ++ce.sent;   // 1-based
+		const int slot = (int)((seq - 1) % (uint32_t)ce.slots);
+		DriverOps *ops = driver_ops();
+		// the receiver must be done with what this slot held: exchange seq - slots
+		if (seq > (uint32_t)ce.slots && ops->wait32(m->rs, (unsigned long long)(uintptr_t)(ce.flags + 1), seq - (uint32_t)ce.slots, kWaitGeq) != 0)
+			return fail(PB_ERR_CUDA, "cuStreamWaitValue32 (credit) failed");
+		CU(cudaMemcpyAsync(ce.remote_landing[slot], frame->dev, frame->bytes, cudaMemcpyDeviceToDevice, m->rs));   // copy engines, over NVLink
+		if (ops->write32(m->rs, (unsigned long long)(uintptr_t)(ce.flags_of_out + 0), seq, 0) != 0) return fail(PB_ERR_CUDA, "cuStreamWriteValue32 (ready) failed");
+	} else {
+		NC(nccl()->Send(frame->dev, frame->bytes, kNcclUint8, peer, m->comm, m->rs));
+	}
 	frame->refs.fetch_add(1);
 	m->gen[m->head].held.push_back(frame);
 	m->bytes_sent += frame->bytes;
@@ -272,8 +414,17 @@ int pb_route_recv(pb_comm *m, pb_buf *landing, int peer) {
 	landing->host_dirty = false;
 	int r;
 	if ((r = ensure_dev(landing))) return r;
-	if ((r = order_after_queues(m))) return r;   // earlier readers of the landing buffer finish before it is overwritten
-	NC(nccl()->Recv(landing->dev, landing->bytes, kNcclUint8, peer, m->comm, m->rs));
+	if (m->ce.on && peer == m->ce.peer_in) {
+		// the sender's copy engine fills the buffer; nothing runs here.  The credit protocol keeps the sender off the buffer until
+		// its earlier readers are done; pb_route_wait makes the consumer wait for the "ready" sequence number.
+		pb_comm::Ce &ce = m->ce;
+		if (landing != ce.landing[ce.received % (uint32_t)ce.slots])
+			return fail(PB_ERR_STATE, "pb_route_recv: attached landing buffers are filled in the order they were attached");
+		m->gen_recv_seq[m->head] = ++ce.received;
+	} else {
+		if ((r = order_after_queues(m))) return r;   // earlier readers of the landing buffer finish before it is overwritten
+		NC(nccl()->Recv(landing->dev, landing->bytes, kNcclUint8, peer, m->comm, m->rs));
+	}
 	landing->version = ++m->ctx->version_counter;
 	landing->refs.fetch_add(1);
 	m->gen[m->head].held.push_back(landing);
@@ -299,8 +450,14 @@ int pb_route_wait_age(pb_comm *m, int queue, int age) {
 	if (m->open) return fail(PB_ERR_STATE, "pb_route_wait inside an open exchange");
 	CU(cudaSetDevice(m->ctx->dev));
 	// (an exchange that has been released already has completed; its event still says so)
-	pb_comm::Gen &g = m->gen[(m->head + pb_comm::kRing - age) % pb_comm::kRing];
+	const int gi = (m->head + pb_comm::kRing - age) % pb_comm::kRing;
+	pb_comm::Gen &g = m->gen[gi];
 	CU(cudaStreamWaitEvent(m->ctx->q[queue], g.done, 0));
+	if (m->ce.on && m->gen_recv_seq[gi]) {   // the frame pushed by the peer's copy engine: wait for its sequence number, on the device
+		if (driver_ops()->wait32(m->ctx->q[queue], (unsigned long long)(uintptr_t)(m->ce.flags + 0), m->gen_recv_seq[gi], kWaitGeq) != 0)
+			return fail(PB_ERR_CUDA, "cuStreamWaitValue32 (ready) failed");
+		m->ce.credit_due = std::max(m->ce.credit_due, m->gen_recv_seq[gi]);
+	}
 	return PB_OK;
 }
 

@@ -74,6 +74,13 @@ class RouteComm:
         check(_lib.lib().pb_comm_init(ctx._need(), self.rank, self.world, C.create_string_buffer(unique_id, self.ID_BYTES), C.byref(h)))
         self._h = h.value
 
+    def attach(self, landing, peer_in: int, peer_out: int) -> bool:
+        """collective, once: map the neighbours' landing buffers (CUDA IPC) so that frames cross with the copy engines instead of
+        NCCL's copy kernel.  `landing`: this rank's buffers in the order they will be passed to recv().  -> True if attached"""
+        arr = (C.c_void_p * len(landing))(*[b._h for b in landing])
+        check(_lib.lib().pb_route_attach(self._h, arr, len(landing), int(peer_in), int(peer_out)))
+        return bool(_lib.lib().pb_route_transport(self._h))
+
     def begin(self) -> None:
         check(_lib.lib().pb_route_begin(self._h))
 

@@ -188,7 +188,7 @@ def test_routed_frame_through_the_c_abi_enters_another_channel_as_a_layer():
     assert np.array_equal(ours, ref)
 
 
-def _nccl_worker(rank, world, uid, q, w, h):
+def _nccl_worker(rank, world, uid, q, w, h, attach=False):
     """rank r composes channel r and routes its frame to rank 1 - r; -> channel r with the peer's frame as layer 2"""
     import asyncio
     import sys
@@ -210,6 +210,10 @@ def _nccl_worker(rank, world, uid, q, w, h):
         comm = RouteComm(ctx, rank, world, uid)
         ex = GpuRouteExchange(ctx, comm, RouteTable([(1, 0), (0, 1)]), w, h)
         await ex.init()
+        if attach:   # copy-engine transport: the peer pushes straight into this rank's landing buffers
+            my_in = [i for i, (s, d) in enumerate(ex.table.routes) if d == rank][0]
+            assert comm.attach(ex.landing[my_in], 1 - rank, 1 - rank), "CUDA IPC mapping between the two GPUs failed"
+
         mine = layered_scene(w, h, 2, "noise", "plain", "709", "709", frame_set=rank)
         ha = ChannelHarness(ctx, mine, env.pj, chanID=f"A{rank}")
         await ha.init()
@@ -229,8 +233,10 @@ def _nccl_worker(rank, world, uid, q, w, h):
 
 
 @pytest.mark.gpu
-def test_route_between_two_gpus_over_nccl():
-    """two processes, two GPUs: each channel's frame crosses over NCCL P2P (pb_route_*) and is composited by the other"""
+@pytest.mark.parametrize("transport", ["nccl", "copy_engines"])
+def test_route_between_two_gpus(transport):
+    """two processes, two GPUs: each channel's frame crosses (pb_route_*: NCCL point-to-point, or pushed by the copy engines into
+    the peer's IPC-mapped landing buffer after pb_route_attach) and is composited by the other"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -242,7 +248,7 @@ def test_route_between_two_gpus_over_nccl():
     uid = RouteComm.unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, uid, q, w, h)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, uid, q, w, h, transport == "copy_engines")) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in procs)
