@@ -421,7 +421,10 @@ int pb_chain_end(pb_ctx *c, pb_chain **out) {
 
 int pb_chain_info(pb_chain *ch, int *launches, int *complete) {
 	if (!ch) return fail(PB_ERR_ARG, "null chain");
-	if (launches) *launches = (int)ch->items.size();
+	if (launches) {   // fused launches and the first passes that go with them
+		*launches = 0;
+		for (const auto &it : ch->items) *launches += 1 + (int)it.pre.size();
+	}
 	if (complete) *complete = ch->complete ? 1 : 0;
 	return PB_OK;
 }
@@ -432,7 +435,7 @@ int pb_chain_replay(pb_chain *ch, int queue) {
 	std::lock_guard<std::recursive_mutex> lk(c->mu);
 	CU(cudaSetDevice(c->dev));
 	for (const auto &it : ch->items) {
-		int r = launch_compiled(c, c->q[queue], it.d, it.march, it.out_rgba);
+		int r = launch_compiled(c, c->q[queue], it.d, it.march, it.out_rgba, it.pre.empty() ? nullptr : &it.pre);
 		if (r) return r;
 		c->stats.kernel_launches++;
 		c->stats.fused_launches++;
@@ -449,6 +452,7 @@ int pb_chain_destroy(pb_chain *ch) {
 	for (auto &it : ch->items) {
 		it.keep.clear();
 		if (it.out_buf) buf_release_locked(it.out_buf);
+		for (auto &sc : it.scratch) c->pool.dev_put(sc.second, sc.first);
 	}
 	delete ch;
 	return PB_OK;

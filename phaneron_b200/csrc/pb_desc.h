@@ -44,6 +44,8 @@ enum LeafKind : int {
 	LEAF_YUV422P8 = 6,    // yuv422p8.ts
 	LEAF_YUV420P = 7,     // yuv420p.ts
 	LEAF_NV12 = 8,        // nv12.ts: ptr = Y, ptr_u = interleaved chroma
+	LEAF_LANCZOS_V = 10,  // second pass of a separable Lanczos Transform: ptr = the horizontally filtered rows H (RGBA-f32, h source rows x w output
+	                      // columns, written by k_lanczos_hpass); value = sum_j lz_wy[j] * H(x, lz_j0[y] + j)
 	LEAF_YADIF = 9        // yadifCl.ts:105-167 over three RGBA-f32 frames: ptr = cur, ptr_u = prev, ptr_v = next; Leaf::yadif = parity | tff << 1 | skipSpatial << 2
 };
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
@@ -119,6 +121,7 @@ struct Leaf {
 	int lz_tx, lz_ty;
 	const int *lz_i0, *lz_j0;
 	const float *lz_wx, *lz_wy;
+	int lz_sep;            // march launch: this Lanczos leaf is evaluated separably (launch_desc runs k_lanczos_hpass first and hands the kernel a LEAF_LANCZOS_V)
 	const float *lz_wxt;   // march kernel: the horizontal weights tap-major, [tap][output column]: a warp's lanes (consecutive columns) read one line
 	// strips [s0, s1] and output lines [y0, y1] outside of which every tap of this leaf is a border
 	// texel: the kernel skips the leaf there without touching memory
@@ -158,6 +161,21 @@ enum SinkKind : int {
 	SINK_YUV420P = 5,    // yuv420p.ts:142-238
 	SINK_NV12 = 6,       // nv12.ts:134-240: out = Y, out_u = interleaved chroma
 	SINK_RGBA_F32 = 7    // the composite itself as an RGBA-f32 frame (a deferred frame made real: ROUTE payloads, Yadif inputs, host reads)
+};
+
+// first pass of a separable Lanczos Transform (pb_march.cu k_lanczos_hpass): every source row of a packed leaf that the
+// vertical support of some output line reaches is converted ONCE and filtered horizontally into H (one float4 per output
+// column: the three colour sums and the weight sum of the texels inside the image)
+struct HPassDesc {
+	Leaf lf;             // the packed source leaf with its Lanczos tables and the strip footprints of the consuming launch
+	ReadConsts rc;
+	ReadK rk;
+	LutDesc lut;         // the leaf's gamma table in the one-byte form
+	float4 *out;         // H: lf.h rows x xf_w columns
+	int xf_w;
+	int strip_groups, s0, s1;   // output-column strips as the consuming launch cuts them; [s0, s1] touch the image
+	int j_lo, j_hi;      // source rows needed: [j_lo, j_hi)
+	uint32_t e_magic, lds_koff;
 };
 
 struct FusedDesc {

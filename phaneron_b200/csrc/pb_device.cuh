@@ -338,6 +338,22 @@ __device__ __forceinline__ float4 lanczos_sample(const Leaf &lf, const ReadConst
 
 // value of one leaf at output pixel (x, y)
 __device__ __forceinline__ float4 leaf_value(const Leaf &lf, const ReadConsts *rcs, int x, int y) {
+	if (lf.kind == LEAF_LANCZOS_V) {   // second pass of a separable Lanczos Transform over the filtered rows H
+		const int j0 = __ldg(lf.lz_j0 + y);
+		const float *wy = lf.lz_wy + (size_t)y * lf.lz_ty;
+		const float4 *H = reinterpret_cast<const float4 *>(lf.ptr);
+		float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+		for (int j = max(0, -j0); j < min(lf.lz_ty, lf.h - j0); ++j) {
+			const float4 hv = __ldg(H + (size_t)(j0 + j) * lf.w + x);
+			const float w = __ldg(wy + j);
+			acc.x = fma_(w, hv.x, acc.x);
+			acc.y = fma_(w, hv.y, acc.y);
+			acc.z = fma_(w, hv.z, acc.z);
+			acc.w = fma_(w, hv.w, acc.w);
+		}
+		return acc;
+	}
 	if (!lf.has_xf) return leaf_texel(lf, rcs, x, y);
 	if (lf.lz_tx) return lanczos_sample(lf, rcs, x, y);
 	const float2 p = transform_pos(lf.m, x, y, lf.xf_w, lf.xf_h);

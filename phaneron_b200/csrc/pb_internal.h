@@ -199,6 +199,9 @@ struct pb_ctx {
 	// spinning, and waits for ITS copy only, not for whatever other producers have queued behind it
 	std::vector<cudaEvent_t> copy_events;
 	bool allow_march = true;
+	// first passes (and their intermediates) of the launch launch_desc has just issued, for record_launch to take over
+	std::vector<pb::HPassDesc> pending_pre;
+	std::vector<std::pair<void *, size_t>> pending_scratch;
 	int march_sms = 0;   // SMs the persistent march kernels occupy; fewer than all while a ROUTE communicator needs SMs of its own (pb_route.cu)
 	// gamma tables by content (see lut_table_of)
 	struct LutTable {
@@ -261,6 +264,8 @@ struct pb_chain {
 		void *out_rgba;
 		std::vector<std::shared_ptr<void>> keep;   // expression nodes (hold the leaf buffers)
 		pb_buf *out_buf;                           // addref'd destination
+		std::vector<pb::HPassDesc> pre;            // launches that go before it: first passes of separable Lanczos leaves
+		std::vector<std::pair<void *, size_t>> scratch;   // their intermediates (pool blocks, given back with the chain)
 	};
 	std::vector<Item> items;
 	bool complete = true;
@@ -311,7 +316,7 @@ int lut_table_by_raw(pb_ctx *c, const float *raw);
 // pb_march_prep.cu
 int attach_lanczos(pb_ctx *c, pb::Leaf *lf, int lobes);
 int prepare_march(pb_ctx *c, pb::FusedDesc &d);
-int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool march, void *out_rgba);
+int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool march, void *out_rgba, const std::vector<pb::HPassDesc> *pre = nullptr);
 int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, bool *march_out);
 
 }  // namespace pbrt

@@ -32,6 +32,8 @@ cudaError_t launch_fused(cudaStream_t s, const FusedDesc &d, void *out_rgba);
 // March kernel (pb_march.cu); the descriptor must have been prepared (sampling tables, LUT slots).
 cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms);
 size_t march_smem_bytes(const FusedDesc &d);
+// first pass of a separable Lanczos Transform (see HPassDesc)
+cudaError_t launch_lanczos_hpass(cudaStream_t s, const HPassDesc &h, int num_sms);
 // gamma table -> one-byte-per-entry form (pb_lut.cuh): n_cands candidate models evaluated in one launch
 struct LutFitResult;
 cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *cands_dev, int n_cands, uint8_t *d8_out, void *results_dev);

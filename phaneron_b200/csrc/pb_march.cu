@@ -599,6 +599,32 @@ __device__ __noinline__ void eval_leaf_lanczos(const FusedDesc &d, const Leaf &l
 	}
 }
 
+// second pass of a separable Lanczos Transform: the vertical chain over the horizontally filtered rows H that k_lanczos_hpass
+// wrote (one float4 per output column and source row).  No row buffer: every tap is one coalesced 16-byte load per lane.
+__device__ __forceinline__ void eval_leaf_lanczos_v(const Leaf &lf, int lane, int y, int x_first, int x_last, float4 (&p)[kRounds]) {
+	const int j0 = __ldg(lf.lz_j0 + y);
+	const float *wy = lf.lz_wy + (size_t)y * lf.lz_ty;
+	const float4 *H[kRounds];
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+		H[r] = reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j0 * lf.w + min(x_first + r * 32 + lane, x_last);
+	}
+	const int j_lo = max(0, -j0), j_hi = min(lf.lz_ty, lf.h - j0);
+#pragma unroll 2
+	for (int j = j_lo; j < j_hi; ++j) {
+		const float w = __ldg(wy + j);
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) {
+			const float4 hv = __ldg(H[r] + (size_t)j * lf.w);
+			p[r].x = fma_(w, hv.x, p[r].x);
+			p[r].y = fma_(w, hv.y, p[r].y);
+			p[r].z = fma_(w, hv.z, p[r].z);
+			p[r].w = fma_(w, hv.w, p[r].w);
+		}
+	}
+}
+
 // ---- rgba8 / bgra8 leaves (graphics with alpha: FFmpegProducer 'rgba' / 'bgra' / any rgb format, rgba8.ts) ----------
 // Four planes (the alpha of these sources is data and is sampled like a colour channel), one pass per source row, every tap
 // validated.  Conversion is lane = texel (coalesced 128-byte loads, 3 texels per lane in flight): a texel costs four table
@@ -1116,13 +1142,13 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 					const int oi2 = __ffs(todo2) - 1;
 					const MarchOp &op2 = d.ops[oi2];
 					const Leaf &lf2 = (&d.layers[op2.layer].a)[op2.which];
-					if (lane == 0) {
+					if (lf2.kind == LEAF_V210 && lane == 0) {
 						const uint32_t sc = pf.raw + 2 * kPfRowBytes;
 						asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sc), "l"(lf2.strip_tab + strip2) : "memory");
 						asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sc + 16), "l"(lf2.row_tab + (first_line + k2 * step)) : "memory");
 					}
 					pf_op2 = oi2;
-					pf_stage = true;
+					pf_stage = lf2.kind == LEAF_V210;
 				}
 				int k3 = k2 + stride_k, strip3 = strip2 + stride_s;
 				if (strip3 >= d.n_strips) ++k3;
@@ -1159,6 +1185,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
 			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
+			else if (lf.kind == LEAF_LANCZOS_V) eval_leaf_lanczos_v(lf, lane, y, x_first, x_last, p);
 			else if (kPlanar && lf.lz_tx) eval_leaf_lanczos<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows, kPf>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p, &pf,
 			                                                                                                                  kPf && pf.item == item && pf.op == oi);
@@ -1458,7 +1485,145 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 }
 
 
+// ---- k_lanczos_hpass: first pass of a separable Lanczos Transform (HPassDesc) ---------------------------------------------------
+// Work item = one source row x one strip of output columns: the warp converts the strip's source footprint once (lane = v210
+// group, as everywhere), then every lane takes the horizontal taps of its 3 columns from the row buffer: the ascending fma
+// chain of the filter's definition (oracle/oracle.c), border texels skipped (fma(w, 0, s) == s).  The result row goes to H.
+template <int kReadMode>
+__global__ void __launch_bounds__(kMarchThreads, 1) k_lanczos_hpass(const __grid_constant__ HPassDesc h) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+	uint32_t tid_x;
+	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
+	const int lane = tid_x & 31, warp = tid_x >> 5;
+	SPtr buf;
+	{
+		const uint32_t addr = lut_saddr + 65536u + (uint32_t)warp * (kRowFloats * 4u);
+		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));
+	}
+	{
+		__shared__ __align__(8) unsigned long long lut_bar;
+		const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&lut_bar);
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(65536) : "memory");
+			for (int c = 0; c < 4; ++c)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lut_saddr + c * 16384),
+				             "l"(h.lut.d8 + c * 16384), "r"(16384), "r"(bar)
+				             : "memory");
+		}
+		mbar_wait(bar, 0);
+	}
+	const Leaf &lf = h.lf;
+	LutK<1> lut;
+	lut.raw = h.rc.lut;
+	lut.magic = kTwo23 + (float)lut_saddr;
+	lut.koff = h.lds_koff;
+	const LutParams &lp = h.lut.lp;
+	const uint32_t E = h.e_magic;
+	constexpr int cap = kRowGroups * 6;
+	const int tx = lf.lz_tx, xw = h.xf_w, strip_px = h.strip_groups * 6;
+	const int ns = h.s1 - h.s0 + 1, total = (h.j_hi - h.j_lo) * ns, stride = gridDim.x * kMarchWarps;
+#pragma unroll 1
+	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride) {
+		const int jr = item / ns, strip = h.s0 + (item - jr * ns), row = h.j_lo + jr;
+		const int x_first = strip * strip_px, x_last = min(x_first + strip_px, xw) - 1;
+		const int4 si = __ldg(lf.strip_tab + strip);
+		float4 *o = h.out + (size_t)row * xw;
+		if (!(si.x & 1)) {   // no tap of this strip lies inside the image
+#pragma unroll
+			for (int r = 0; r < kRounds; ++r) {
+				const int x = x_first + r * 32 + lane;
+				if (x <= x_last) o[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			continue;
+		}
+		const int g_lo = si.y, ng = si.z, origin = g_lo * 6;
+		const bool edge = (si.x & 2) != 0;
+		if (lane < ng) {
+			const uint4 w = load_group<true>(lf, row, g_lo + lane);
+			if (w.x >> 31) convert_group_exact(lf, &h.rc, row, g_lo + lane, buf, cap, lane);
+			else convert_group<1, true, kReadMode>(w, lane, E, h.rc, h.rk, lut, lp, buf, cap);
+		}
+		int i0[kRounds];
+		const float *wxp[kRounds];
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) {
+			const int x = min(x_first + r * 32 + lane, x_last);
+			i0[r] = __ldg(lf.lz_i0 + x);
+			wxp[r] = lf.lz_wxt + x;
+		}
+		__syncwarp();
+		const SPtr bufo = buf + (-origin);
+		float4 acc[kRounds];
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (!edge) {
+#pragma unroll 4
+			for (int i = 0; i < tx; ++i) {
+#pragma unroll
+				for (int r = 0; r < kRounds; ++r) {
+					const float w = __ldg(wxp[r] + (size_t)i * xw);
+					const SPtr t = bufo + (i0[r] + i);
+					acc[r].x = fma_(w, t[0], acc[r].x);
+					acc[r].y = fma_(w, t[cap], acc[r].y);
+					acc[r].z = fma_(w, t[2 * cap], acc[r].z);
+					acc[r].w = fma_(w, 1.0f, acc[r].w);
+				}
+			}
+		} else {
+#pragma unroll 2
+			for (int i = 0; i < tx; ++i) {
+#pragma unroll
+				for (int r = 0; r < kRounds; ++r) {
+					const int cidx = i0[r] + i;
+					if ((unsigned)cidx >= (unsigned)lf.w) continue;
+					const float w = __ldg(wxp[r] + (size_t)i * xw);
+					const SPtr t = bufo + cidx;
+					acc[r].x = fma_(w, t[0], acc[r].x);
+					acc[r].y = fma_(w, t[cap], acc[r].y);
+					acc[r].z = fma_(w, t[2 * cap], acc[r].z);
+					acc[r].w = fma_(w, 1.0f, acc[r].w);
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) {
+			const int x = x_first + r * 32 + lane;
+			if (x <= x_last) o[x] = acc[r];
+		}
+		__syncwarp();
+	}
+}
+
 }  // namespace
+
+cudaError_t launch_lanczos_hpass(cudaStream_t s, const HPassDesc &h, int num_sms) {
+	static std::mutex mu;
+	static std::set<int> configured;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (!configured.count(dev)) {
+			cudaError_t e = cudaFuncSetAttribute(k_lanczos_hpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lanczos_hpass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+			if (e != cudaSuccess) return e;
+			configured.insert(dev);
+		}
+	}
+	const int total = (h.j_hi - h.j_lo) * (h.s1 - h.s0 + 1);
+	if (total <= 0) return cudaSuccess;
+	const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
+	const size_t smem = 65536 + (size_t)kMarchWarps * kRowFloats * sizeof(float);
+	if (h.lut.lp.affine == 2) k_lanczos_hpass<2><<<grid, kMarchThreads, smem, s>>>(h);
+	else k_lanczos_hpass<0><<<grid, kMarchThreads, smem, s>>>(h);
+	return cudaGetLastError();
+}
 
 cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *cands_dev, int n_cands, uint8_t *d8_out, void *results_dev) {
 	lut_fit_kernel<<<dim3(65536 / 256, n_cands), 256, 0, s>>>(table, cands_dev, d8_out, reinterpret_cast<LutFitResult *>(results_dev));

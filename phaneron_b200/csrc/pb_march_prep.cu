@@ -393,8 +393,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			const bool rgba = lf.kind == pb::LEAF_RGBA8 || lf.kind == pb::LEAF_BGRA8 || lf.kind == pb::LEAF_RGBA_F32 || lf.kind == pb::LEAF_YADIF;
 			if (lf.kind == pb::LEAF_RGBA_F32 || lf.kind == pb::LEAF_YADIF) any_f32 = true;
 			if (!(ycc || rgba) || lf.w < 6 || (lf.lz_tx && !ycc)) return 0;
-			// (a Lanczos leaf -- the extension of DESIGN.md 4.6 -- takes the general variants: eval_leaf_lanczos)
-			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0 || lf.lz_tx) any_planar = true;   // general load path (formats, partial last groups)
+			// (a Lanczos leaf -- the extension of DESIGN.md 4.6 -- is evaluated separably where its footprints allow: the kernel then
+			// sees only the vertical pass, LEAF_LANCZOS_V, which every variant evaluates; else inside the launch, by the general
+			// variants: eval_leaf_lanczos.  Decided below, once the strip width is known.)
+			lf.lz_sep = 0;
+			if (lf.kind != pb::LEAF_V210 || lf.w % 6 != 0) any_planar = true;   // general load path (formats, partial last groups)
 			if (rgba) any_rgba = true;
 			else rc_ycc[lf.rc] = true;
 			if (lf.has_xf) {
@@ -449,6 +452,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			if (r) return r;
 			if (!lt->fits) return 0;
 			if (lt->fits == 2) big_rows = true;
+			leaves[i]->lz_sep = (lt->fits == 1 && lt->s1 >= lt->s0 && lt->y1 >= lt->y0 && !getenv("PB_LANCZOS_ONE_PASS")) ? 1 : 0;
+			if (!leaves[i]->lz_sep) any_planar = true;   // evaluated inside the launch: the general variants
 			opq[i] = nullptr;
 			tab_of[i] = lt->opq;
 			leaves[i]->col_tab = nullptr;
@@ -769,6 +774,8 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (any_rgba && d.n_luts == 0) return 0;   // rgba8 leaves ride on the big-row variants, which exist for shared-memory tables
 	d.any_planar = any_planar;
 	if (any_planar && !(d.n_luts > 0 && d.sparse_cm)) return 0;   // planar variants exist for the common configuration only
+	for (int i = 0; i < n_leaves; ++i)   // the first pass of a separable Lanczos leaf decodes its table from shared memory
+		if (leaves[i]->lz_sep && !(d.n_luts > 0 && d.sparse_cm && d.rc[leaves[i]->rc].lut_slot >= 0)) return 0;
 	if (rgba_f32_sink && !d.direct_mode) {
 		// A frame made real.  The march kernel pays where packed leaves are sampled through a Transform (every texel converted once
 		// instead of once per tap); a graph of 1:1 packed reads and RGBA-f32 frames is a few gathers per pixel, which the generic
@@ -821,7 +828,13 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 
 // issue the launch(es) of a prepared descriptor: the march or the generic kernel, plus -- after a march launch on a ragged
 // v210 width -- the generic kernel on the tail columns (prepare_march).  Also the replay path of recorded chains.
-int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool march, void *out_rgba) {
+int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool march, void *out_rgba, const std::vector<pb::HPassDesc> *pre) {
+	if (pre)
+		for (const pb::HPassDesc &h : *pre) {   // first passes of separable Lanczos leaves
+			cudaError_t e = pb::launch_lanczos_hpass(s, h, c->march_sms);
+			if (e != cudaSuccess) return fail(PB_ERR_CUDA, "lanczos first pass: %s", cudaGetErrorString(e));
+			c->stats.kernel_launches++;   // the caller counts the main launch
+		}
 	pb::FusedDesc bg_copy;
 	const pb::FusedDesc *dp = &d_in;
 	if (march && d_in.bg_single) {
@@ -858,7 +871,64 @@ int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, boo
 		if (r < 0) return r;
 		march = r == 1;
 	}
-	int r = launch_compiled(c, s, d, march, out_rgba);
+	// Lanczos leaves of a march launch are evaluated separably: a first launch converts every source row the filter reaches
+	// ONCE and filters it horizontally into H (RGBA-f32 rows in HBM / L2); the fused launch then runs the vertical chains over
+	// H.  Evaluating the filter inside the one launch converts every source row once per output line that reaches it (six
+	// times at 0.5x with three lobes): 2.8 ms against 0.x ms for BASELINE.json's config 5 (profiles/r02_bench_config5*.json).
+	// Same fma chains in the same order, so the same bits.  PB_LANCZOS_ONE_PASS=1 keeps the single launch (A/B).
+	for (auto &sc : c->pending_scratch) c->pool.dev_put(sc.second, sc.first);   // (left over by a caller that did not record)
+	c->pending_scratch.clear();
+	c->pending_pre.clear();
+	if (march) {
+		for (int l = 0; l < d.n_layers; ++l) {
+			pb::Layer &ly = d.layers[l];
+			pb::Leaf *ll[3] = {&ly.a, &ly.b, &ly.mask};
+			const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
+			for (int q = 0; q < nleaf; ++q) {
+				pb::Leaf &lf = *ll[q];
+				if (!lf.lz_tx || !lf.lz_sep || lf.kind == pb::LEAF_LANCZOS_V) continue;
+				pb_ctx::LanczosTab *lt = nullptr;
+				for (auto &e : c->lanczos_tabs)
+					if (e.i0 == lf.lz_i0) lt = &e;
+				const int slot = d.rc[lf.rc].lut_slot;
+				if (!lt || lt->strip_groups != d.strip_groups || slot < 0 || d.n_luts <= slot || !d.sparse_cm)
+					return fail(PB_ERR_STATE, "separable lanczos leaf without its tables");
+				pb::HPassDesc h{};
+				h.lf = lf;
+				h.rc = d.rc[lf.rc];
+				h.rk = d.rk[lf.rc];
+				h.lut = d.luts[slot];
+				h.xf_w = lf.xf_w;
+				h.strip_groups = d.strip_groups;
+				h.s0 = lt->s0;
+				h.s1 = lt->s1;
+				h.j_lo = std::max(0, lt->h_j0[lt->y0]);
+				h.j_hi = std::min(lf.h, lt->h_j0[lt->y1] + lt->ty);
+				for (int y = lt->y0; y <= lt->y1; ++y) {   // (not assumed monotone: flips)
+					h.j_lo = std::min(h.j_lo, std::max(0, lt->h_j0[y]));
+					h.j_hi = std::max(h.j_hi, std::min(lf.h, lt->h_j0[y] + lt->ty));
+				}
+				h.e_magic = d.e_magic;
+				h.lds_koff = d.lds_koff;
+				const size_t bytes = (size_t)lf.h * lf.xf_w * sizeof(float4);
+				void *H = nullptr;
+				CU(c->pool.dev_get(bytes, &H));
+				h.out = (float4 *)H;
+				c->pending_pre.push_back(h);
+				c->pending_scratch.push_back({H, bytes});
+				// the consuming launch sees the second pass
+				lf.kind = pb::LEAF_LANCZOS_V;
+				lf.ptr = H;
+				lf.w = lf.xf_w;   // H: source rows x output columns
+			}
+		}
+	}
+	int r = launch_compiled(c, s, d, march, out_rgba, c->pending_pre.empty() ? nullptr : &c->pending_pre);
+	if (!c->recording) {   // (a recording keeps the intermediates: record_launch takes them over)
+		for (auto &sc : c->pending_scratch) c->pool.dev_put(sc.second, sc.first);   // stream-ordered: the next user of a block waits for this launch
+		c->pending_scratch.clear();
+		c->pending_pre.clear();
+	}
 	if (r) return r;
 	if (march_out) *march_out = march;
 	return PB_OK;

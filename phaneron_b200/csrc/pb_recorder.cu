@@ -355,6 +355,10 @@ void record_launch(pb_ctx *c, const Compiler &cc, void *out_rgba, pb_buf *out_bu
 	for (const auto &k : cc.keep) it.keep.push_back(std::static_pointer_cast<void>(k));
 	it.out_buf = out_buf;
 	if (out_buf) out_buf->refs.fetch_add(1);
+	it.pre = std::move(c->pending_pre);
+	it.scratch = std::move(c->pending_scratch);
+	c->pending_pre.clear();
+	c->pending_scratch.clear();
 	c->recording->items.push_back(std::move(it));
 }
 

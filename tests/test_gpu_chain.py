@@ -547,8 +547,9 @@ def test_lanczos_layers_fuse_into_one_launch():
                                            ("yuv420p", "709", _xf(scaleX=0.5, scaleY=0.5, offsetX=-0.25, offsetY=-0.2, filter="lanczos3"))])
     ref = SceneOracle(scene).packed()
     out, st = run(_run_scene_variant(scene, "march"))
-    # Lanczos leaves ride the march kernel (pb_march.cu eval_leaf_lanczos): still ONE launch, now the fast one
-    assert st["kernel_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0 and st["march_launches"] == 1, st
+    # Lanczos leaves ride the march kernel: ONE fused launch, now the fast one, plus the horizontal first pass of each Lanczos
+    # leaf (k_lanczos_hpass: every source row converted once); no RGBA-f32 frame of the reference's kind is written
+    assert st["fused_launches"] == 1 and st["materialised"] == 0 and st["march_launches"] == 1 and 1 <= st["kernel_launches"] <= 3, st
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
     slow, st0 = run(_run_scene_variant(scene, "generic"))
     assert st0["march_launches"] == 0 and np.array_equal(slow, ref)
@@ -575,10 +576,23 @@ def _lanczos_scene(w, h, specs, dissolve=False):
 def test_lanczos_leaves_in_the_march_kernel(name):
     scene = LANCZOS_MARCH_SCENES[name]()
     ref = SceneOracle(scene).packed()
+    passes = {"config5_shape": 1, "two_lobes_upscale_flip": 2, "mostly_outside_and_dissolve": 2, "deep_downscale_big_rows": 1}[name]
     for mode in ("march", "march_nocull"):
         out, st = run(_run_scene_variant(scene, mode))
-        assert st["march_launches"] == 1 and st["kernel_launches"] == 1 and st["materialised"] == 0, (mode, st)
+        # one fused launch + at most one horizontal first pass per Lanczos leaf (where its strip footprints fit a row buffer; a leaf
+        # that is not separable this way is filtered inside the fused launch)
+        assert st["march_launches"] == 1 and st["fused_launches"] == 1 and 1 <= st["kernel_launches"] <= 1 + passes and st["materialised"] == 0, (mode, st)
+        if name == "config5_shape":
+            assert st["kernel_launches"] == 2, st
         assert np.array_equal(out, ref), f"{mode}: {int((out != ref).sum())} bytes differ"
+    import os
+    os.environ["PB_LANCZOS_ONE_PASS"] = "1"   # the filter evaluated inside the one launch (pb_march.cu eval_leaf_lanczos): same bytes
+    try:
+        out, st = run(_run_scene_variant(scene, "march"))
+    finally:
+        del os.environ["PB_LANCZOS_ONE_PASS"]
+    assert st["march_launches"] == 1 and st["kernel_launches"] == 1, st
+    assert np.array_equal(out, ref)
 
 
 # ---- planar YCbCr leaves in the march kernel (gathered into the v210 group layout, pb_march.cu load_group) ----
