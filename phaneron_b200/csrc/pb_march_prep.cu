@@ -782,7 +782,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		// kernel does faster than the row-buffer round trip (a routed channel frame: 17 vs 52 us, profiles/r02_route_launches.txt)
 		bool sampled_packed = false;
 		for (int i = 0; i < n_leaves; ++i) sampled_packed = sampled_packed || (leaves[i]->kind != pb::LEAF_RGBA_F32 && leaves[i]->has_xf);
-		if (!sampled_packed) return 0;
+		if (!sampled_packed && !getenv("PB_RGBA_SINK_MARCH")) return 0;
 	}
 	for (int i = 0; i < d.n_luts; ++i) {
 		d.luts[i].d8 = c->lut_tables[slots[i]].d8;
