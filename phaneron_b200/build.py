@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("PB_LIB_OUT") or os.path.join(HERE, "libphaneron_b200.so")   # PB_LIB_OUT: kernel-variant experiments (load with PB_LIB)
-SOURCES = ["pb_kernels.cu", "pb_fused.cu", "pb_march.cu", "pb_recorder.cu", "pb_lut_cache.cu", "pb_march_prep.cu", "pb_abi.cu", "pb_route.cu", "pb_colour.cpp"]
+SOURCES = ["pb_kernels.cu", "pb_fused.cu", "pb_march.cu", "pb_march_general.cu", "pb_march_bigrows.cu", "pb_recorder.cu", "pb_lut_cache.cu", "pb_march_prep.cu", "pb_abi.cu", "pb_route.cu", "pb_colour.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -207,6 +207,7 @@ struct FusedDesc {
 	int direct_mode;   // one v210 leaf read 1:1 into a v210 sink: the dedicated k_march_direct (192-px strips, all lanes convert)
 	int n_t256;        // 1 KiB tables of rgba8 / bgra8 leaves staged behind the row buffers (ReadConsts::t256_slot)
 	int big_rows;      // row buffers of 64 source groups (a leaf is scaled down below ~0.47); implies any_planar
+	int feat;          // general march variants: abilities this launch needs (pb_march.cu kFeat): 1 Lanczos filtered inside the launch, 2 Yadif leaves, 4 RGBA-f32 sink
 	int march_w;       // output pixels the march kernel writes: out_w rounded down to whole v210 groups
 	int g_first;       // generic kernel, v210 sink: first output group column to write (the ragged tail after a march launch), else 0
 	LutDesc luts[kMaxLuts];   // slot 0 = rc[0]'s table

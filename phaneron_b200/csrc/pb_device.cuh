@@ -261,6 +261,13 @@ __device__ __forceinline__ float4 yadif_texel(const float4 *__restrict__ prev, c
 // ---- leaves -------------------------------------------------------------------------
 // One texel of a leaf as RGBA-f32; texels outside the image are the CLK_ADDRESS_CLAMP
 // border colour (0,0,0,0).
+// (one out-of-line copy per generic kernel instance that evaluates Yadif leaves: a leaf texel is fetched at ~15 places of such a
+// kernel -- four taps of three leaves of a layer, the Lanczos loop -- and inlining the de-interlacer into each made pb_fused.cu
+// a five-minute compile)
+static __device__ __noinline__ float4 yadif_texel_call(const float4 *prev, const float4 *cur, const float4 *next, int w, int h, int flags, int x, int y) {
+	return yadif_texel(prev, cur, next, w, h, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, x, y);
+}
+
 // kYadifLeaves: the kernel is compiled to evaluate LEAF_YADIF texels too.  A de-interlaced texel is 27 float4 reads and two
 // predictors per channel; inlined into every tap of every leaf it takes k_fused_generic from 56 to 150 registers (a third of
 // the resident warps), so only the kernel instances launched for a graph that holds such a leaf carry it.
@@ -271,8 +278,8 @@ __device__ __forceinline__ float4 leaf_texel(const Leaf &lf, const ReadConsts *r
 		return __ldg(reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + i);
 	}
 	if (kYadifLeaves && lf.kind == LEAF_YADIF)   // a de-interlaced field, computed where it is sampled (ptr = cur, ptr_u = prev, ptr_v = next: RGBA-f32 frames)
-		return yadif_texel(reinterpret_cast<const float4 *>(lf.ptr_u), reinterpret_cast<const float4 *>(lf.ptr), reinterpret_cast<const float4 *>(lf.ptr_v),
-		                   lf.w, lf.h, lf.yadif & 1, (lf.yadif >> 1) & 1, (lf.yadif >> 2) & 1, i, j);
+		return yadif_texel_call(reinterpret_cast<const float4 *>(lf.ptr_u), reinterpret_cast<const float4 *>(lf.ptr), reinterpret_cast<const float4 *>(lf.ptr_v),
+		                        lf.w, lf.h, lf.yadif, i, j);
 	if (lf.kind != LEAF_V210) return packed_texel(lf, rcs[lf.rc], i, j);
 	const int g = i / 6, p = i - g * 6;
 	const uint4 w = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);

@@ -67,7 +67,7 @@ struct LutFitResult {
 };
 
 // one candidate parameter set per blockIdx.y
-__global__ void lut_fit_kernel(const float *table, const LutParams *cands, uint8_t *d8_out, LutFitResult *res) {
+static __global__ void lut_fit_kernel(const float *table, const LutParams *cands, uint8_t *d8_out, LutFitResult *res) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= 65536) return;
 	const LutParams lp = cands[blockIdx.y];

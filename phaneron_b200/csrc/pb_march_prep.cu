@@ -774,6 +774,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	if (any_rgba && d.n_luts == 0) return 0;   // rgba8 leaves ride on the big-row variants, which exist for shared-memory tables
 	d.any_planar = any_planar;
 	if (any_planar && !(d.n_luts > 0 && d.sparse_cm)) return 0;   // planar variants exist for the common configuration only
+	d.feat = rgba_f32_sink ? 4 : 0;
+	for (int i = 0; i < n_leaves; ++i) {
+		if (leaves[i]->lz_tx && !leaves[i]->lz_sep) d.feat |= 1;
+		if (leaves[i]->kind == pb::LEAF_YADIF) d.feat |= 2;
+	}
 	for (int i = 0; i < n_leaves; ++i)   // the first pass of a separable Lanczos leaf decodes its table from shared memory
 		if (leaves[i]->lz_sep && !(d.n_luts > 0 && d.sparse_cm && d.rc[leaves[i]->rc].lut_slot >= 0)) return 0;
 	if (rgba_f32_sink && !d.direct_mode) {
