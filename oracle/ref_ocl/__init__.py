@@ -216,6 +216,34 @@ def wipe_mask(in0: np.ndarray, in1: np.ndarray, mask: np.ndarray) -> np.ndarray:
     return _image_op("transition_wipe.cl", "transition_wipe", [in0, in1, mask], w, h)
 
 
+def mix(in0: np.ndarray, in1: np.ndarray, m: float) -> np.ndarray:
+    """mix.ts:24-47 (entry 'mixer')"""
+    h, w, _ = in0.shape
+    return _image_op("mix.cl", "mixer", [in0, in1], w, h, scalar=m)
+
+
+def wipe(in0: np.ndarray, in1: np.ndarray, wipe_: float) -> np.ndarray:
+    """wipe.ts:24-48"""
+    h, w, _ = in0.shape
+    return _image_op("wipe.cl", "wipe", [in0, in1], w, h, scalar=wipe_)
+
+
+def resize(src: np.ndarray, scale: float, offset_x: float, offset_y: float, flip4, w: int, h: int) -> np.ndarray:
+    """resize.ts:24-58: (input image, scale, offsetX, offsetY, flip buffer, output image)"""
+    k = _kernel("resize.cl", "resize")
+    i, o, f = _img(src.shape[1], src.shape[0], src), _img(w, h), _buf(np.asarray(flip4, np.float32))
+    _ck(_lib.ocl_arg_mem(k, 0, i))
+    _ck(_lib.ocl_arg_f32(k, 1, scale))
+    _ck(_lib.ocl_arg_f32(k, 2, offset_x))
+    _ck(_lib.ocl_arg_f32(k, 3, offset_y))
+    _ck(_lib.ocl_arg_mem(k, 4, f))
+    _ck(_lib.ocl_arg_mem(k, 5, o))
+    _ck(_lib.ocl_run(k, 2, w, h, 0))
+    out = _read_img(o, w, h)
+    _free(i, o, f)
+    return out
+
+
 def transform(src: np.ndarray, mat9, w: int, h: int) -> np.ndarray:
     """transform.ts:36-59: (input image, transformMatrix buffer, output image)"""
     k = _kernel("transform.cl", "transform")

@@ -95,6 +95,9 @@ def main():
         "yuv422p8.cl": literal_after(rd("yuv422p8.ts"), "const yuv422p8Kernel ="),
         "yuv420p.cl": literal_after(rd("yuv420p.ts"), "const yuv420pKernel ="),
         "nv12.cl": literal_after(rd("nv12.ts"), "const nv12Kernel ="),
+        "mix.cl": literal_after(rd("mix.ts"), "const mixKernel ="),
+        "wipe.cl": literal_after(rd("wipe.ts"), "const wipeKernel ="),
+        "resize.cl": literal_after(rd("resize.ts"), "const resizeKernel ="),
         "transition_dissolve.cl": gen_transition(rd("transition.ts"), "dissolve"),
         "transition_wipe.cl": gen_transition(rd("transition.ts"), "wipe"),
     }

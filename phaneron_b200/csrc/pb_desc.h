@@ -46,7 +46,8 @@ enum LeafKind : int {
 	LEAF_NV12 = 8,        // nv12.ts: ptr = Y, ptr_u = interleaved chroma
 	LEAF_LANCZOS_V = 10,  // second pass of a separable Lanczos Transform: ptr = the horizontally filtered rows H (RGBA-f32, h source rows x w output
 	                      // columns, written by k_lanczos_hpass); value = sum_j lz_wy[j] * H(x, lz_j0[y] + j)
-	LEAF_YADIF = 9        // yadifCl.ts:105-167 over three RGBA-f32 frames: ptr = cur, ptr_u = prev, ptr_v = next; Leaf::yadif = parity | tff << 1 | skipSpatial << 2
+	LEAF_YADIF = 9        // yadifCl.ts:105-167 over three RGBA-f32 frames: ptr = cur, ptr_u = prev, ptr_v = next; Leaf::yadif = parity | tff << 1 | skipSpatial << 2.
+	                      // What a kernel sees (launch_desc has run the pre-pass, yadif bit 3 set): ptr = cur, ptr_u = the interpolated lines, row j >> 1
 };
 enum LayerKind : int { LAYER_DIRECT = 0, LAYER_DISSOLVE = 1, LAYER_WIPE_MASK = 2 };
 
@@ -176,6 +177,8 @@ struct HPassDesc {
 	int strip_groups, s0, s1;   // output-column strips as the consuming launch cuts them; [s0, s1] touch the image
 	int j_lo, j_hi;      // source rows needed: [j_lo, j_hi)
 	uint32_t e_magic, lds_koff;
+	int pre_kind;        // 0: the Lanczos first pass above.  1: the interpolated lines of a Yadif leaf (lf.ptr_u / ptr / ptr_v = prev / cur /
+	                     // next, lf.yadif = flags) into out: row r of out = line 2 r + (1 - parity) of the field
 };
 
 struct FusedDesc {

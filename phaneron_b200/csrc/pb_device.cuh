@@ -261,25 +261,15 @@ __device__ __forceinline__ float4 yadif_texel(const float4 *__restrict__ prev, c
 // ---- leaves -------------------------------------------------------------------------
 // One texel of a leaf as RGBA-f32; texels outside the image are the CLK_ADDRESS_CLAMP
 // border colour (0,0,0,0).
-// (one out-of-line copy per generic kernel instance that evaluates Yadif leaves: a leaf texel is fetched at ~15 places of such a
-// kernel -- four taps of three leaves of a layer, the Lanczos loop -- and inlining the de-interlacer into each made pb_fused.cu
-// a five-minute compile)
-static __device__ __noinline__ float4 yadif_texel_call(const float4 *prev, const float4 *cur, const float4 *next, int w, int h, int flags, int x, int y) {
-	return yadif_texel(prev, cur, next, w, h, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, x, y);
-}
-
-// kYadifLeaves: the kernel is compiled to evaluate LEAF_YADIF texels too.  A de-interlaced texel is 27 float4 reads and two
-// predictors per channel; inlined into every tap of every leaf it takes k_fused_generic from 56 to 150 registers (a third of
-// the resident warps), so only the kernel instances launched for a graph that holds such a leaf carry it.
-template <bool kYadifLeaves = false>
 __device__ __forceinline__ float4 leaf_texel(const Leaf &lf, const ReadConsts *rcs, int i, int j) {
 	if (i < 0 || j < 0 || i >= lf.w || j >= lf.h) return make_float4(0.f, 0.f, 0.f, 0.f);
 	if (lf.kind == LEAF_RGBA_F32) {
 		return __ldg(reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + i);
 	}
-	if (kYadifLeaves && lf.kind == LEAF_YADIF)   // a de-interlaced field, computed where it is sampled (ptr = cur, ptr_u = prev, ptr_v = next: RGBA-f32 frames)
-		return yadif_texel_call(reinterpret_cast<const float4 *>(lf.ptr_u), reinterpret_cast<const float4 *>(lf.ptr), reinterpret_cast<const float4 *>(lf.ptr_v),
-		                        lf.w, lf.h, lf.yadif, i, j);
+	if (lf.kind == LEAF_YADIF)   // a de-interlaced field: the lines of its own parity are the current frame's (ptr), the interpolated ones
+		// were computed by the launch's pre-pass (k_yadif_rows) into ptr_u, row j >> 1
+		return (j & 1) == (lf.yadif & 1) ? __ldg(reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + i)
+		                                 : __ldg(reinterpret_cast<const float4 *>(lf.ptr_u) + (size_t)(j >> 1) * lf.w + i);
 	if (lf.kind != LEAF_V210) return packed_texel(lf, rcs[lf.rc], i, j);
 	const int g = i / 6, p = i - g * 6;
 	const uint4 w = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(lf.ptr) + (size_t)j * lf.pitch) + g);
@@ -322,7 +312,6 @@ __device__ __forceinline__ float2 transform_pos(const float *m, int x, int y, in
 
 // Lanczos-filtered sample (definition: oracle/oracle.c): sum_j wy_j * (sum_i wx_i * T(i0 + i, j0 + j)), ascending
 // fma chains from +0, weights from the host-built tables; texels outside the image are (0,0,0,0)
-template <bool kYadifLeaves = false>
 __device__ __forceinline__ float4 lanczos_sample(const Leaf &lf, const ReadConsts *rcs, int x, int y) {
 	const int i0 = __ldg(lf.lz_i0 + x), j0 = __ldg(lf.lz_j0 + y);
 	const float *wx = lf.lz_wx + (size_t)x * lf.lz_tx, *wy = lf.lz_wy + (size_t)y * lf.lz_ty;
@@ -332,7 +321,7 @@ __device__ __forceinline__ float4 lanczos_sample(const Leaf &lf, const ReadConst
 		float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
 		for (int i = 0; i < lf.lz_tx; ++i) {
-			const float4 t = leaf_texel<kYadifLeaves>(lf, rcs, i0 + i, j0 + j);
+			const float4 t = leaf_texel(lf, rcs, i0 + i, j0 + j);
 			const float w = __ldg(wx + i);
 			row.x = fma_(w, t.x, row.x);
 			row.y = fma_(w, t.y, row.y);
@@ -349,7 +338,6 @@ __device__ __forceinline__ float4 lanczos_sample(const Leaf &lf, const ReadConst
 }
 
 // value of one leaf at output pixel (x, y)
-template <bool kYadifLeaves = false>
 __device__ __forceinline__ float4 leaf_value(const Leaf &lf, const ReadConsts *rcs, int x, int y) {
 	if (lf.kind == LEAF_LANCZOS_V) {   // second pass of a separable Lanczos Transform over the filtered rows H
 		const int j0 = __ldg(lf.lz_j0 + y);
@@ -367,10 +355,10 @@ __device__ __forceinline__ float4 leaf_value(const Leaf &lf, const ReadConsts *r
 		}
 		return acc;
 	}
-	if (!lf.has_xf) return leaf_texel<kYadifLeaves>(lf, rcs, x, y);
-	if (lf.lz_tx) return lanczos_sample<kYadifLeaves>(lf, rcs, x, y);
+	if (!lf.has_xf) return leaf_texel(lf, rcs, x, y);
+	if (lf.lz_tx) return lanczos_sample(lf, rcs, x, y);
 	const float2 p = transform_pos(lf.m, x, y, lf.xf_w, lf.xf_h);
-	return sample_linear_clamp(lf.w, lf.h, p.x, p.y, [&](int i, int j) { return leaf_texel<kYadifLeaves>(lf, rcs, i, j); });
+	return sample_linear_clamp(lf.w, lf.h, p.x, p.y, [&](int i, int j) { return leaf_texel(lf, rcs, i, j); });
 }
 
 // transition.ts:60-73 / combine.ts:49-59
@@ -402,13 +390,12 @@ __device__ __forceinline__ float4 over4(const float4 &acc, const float4 &l) {
 	return o;
 }
 
-template <bool kYadifLeaves = false>
 __device__ __forceinline__ float4 layer_value(const Layer &ly, const ReadConsts *rcs, int x, int y) {
-	const float4 a = leaf_value<kYadifLeaves>(ly.a, rcs, x, y);
+	const float4 a = leaf_value(ly.a, rcs, x, y);
 	if (ly.kind == LAYER_DIRECT) return a;
-	const float4 b = leaf_value<kYadifLeaves>(ly.b, rcs, x, y);
+	const float4 b = leaf_value(ly.b, rcs, x, y);
 	if (ly.kind == LAYER_DISSOLVE) return dissolve4(a, b, ly.mix);
-	const float4 m = leaf_value<kYadifLeaves>(ly.mask, rcs, x, y);
+	const float4 m = leaf_value(ly.mask, rcs, x, y);
 	return wipe_mask4(a, b, m.x);
 }
 

@@ -16,7 +16,7 @@ namespace pb {
 
 constexpr int kFusedThreads = 128;
 
-template <bool kToRgba, bool kY>
+template <bool kToRgba>
 __global__ void __launch_bounds__(kFusedThreads) k_fused_generic(const __grid_constant__ FusedDesc d, float4 *__restrict__ out_rgba) {
 	const int pitch16 = kToRgba ? (d.out_w + 5) / 6 : d.out_pitch / 16;
 	const int g_first = kToRgba ? 0 : d.g_first, cols = pitch16 - g_first;   // g_first > 0: only the ragged tail columns of each line
@@ -32,9 +32,9 @@ __global__ void __launch_bounds__(kFusedThreads) k_fused_generic(const __grid_co
 #pragma unroll 1
 		for (int p = 0; p < n; ++p) {
 			const int x = x0 + p;
-			float4 acc = layer_value<kY>(d.layers[0], d.rc, x, line);
+			float4 acc = layer_value(d.layers[0], d.rc, x, line);
 #pragma unroll 1
-			for (int l = 1; l < d.n_layers; ++l) acc = over4(acc, layer_value<kY>(d.layers[l], d.rc, x, line));
+			for (int l = 1; l < d.n_layers; ++l) acc = over4(acc, layer_value(d.layers[l], d.rc, x, line));
 			if (kToRgba) {
 				out_rgba[(size_t)line * d.out_w + x] = acc;
 			} else {
@@ -56,20 +56,19 @@ __global__ void __launch_bounds__(kFusedThreads) k_fused_generic(const __grid_co
 }
 
 // the layer graph at one output pixel: bottom layer, then `over` for each layer above (combine.ts:49-59)
-template <bool kY>
 __device__ __forceinline__ float4 composite_px(const FusedDesc &d, int x, int line) {
-	float4 acc = layer_value<kY>(d.layers[0], d.rc, x, line);
+	float4 acc = layer_value(d.layers[0], d.rc, x, line);
 #pragma unroll 1
-	for (int l = 1; l < d.n_layers; ++l) acc = over4(acc, layer_value<kY>(d.layers[l], d.rc, x, line));
+	for (int l = 1; l < d.n_layers; ++l) acc = over4(acc, layer_value(d.layers[l], d.rc, x, line));
 	return acc;
 }
 
 // Fused sinks for the other Writer PackImpls: the same decomposition into threads as the stand-alone writer kernels
 // (pb_kernels.cu), the pixel source being the layer graph instead of an RGBA-f32 frame.
-template <int kSink, bool kY>
+template <int kSink>
 __global__ void __launch_bounds__(kFusedThreads) k_fused_sink(const __grid_constant__ FusedDesc d) {
 	const size_t tid = (size_t)blockIdx.x * kFusedThreads + threadIdx.x;
-	auto px = [&](int x, int line) { return composite_px<kY>(d, x, line); };
+	auto px = [&](int x, int line) { return composite_px(d, x, line); };
 	if (kSink == SINK_RGBA8 || kSink == SINK_BGRA8) {
 		const int lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
 		if (tid >= (size_t)d.out_w * lines) return;
@@ -94,40 +93,29 @@ __global__ void __launch_bounds__(kFusedThreads) k_fused_sink(const __grid_const
 const char *fused_variant(const FusedDesc &) { return "generic"; }
 
 // a graph with a Yadif leaf takes the kernel instances that can evaluate one (see leaf_texel)
-static bool has_yadif_leaf(const FusedDesc &d) {
-	for (int l = 0; l < d.n_layers; ++l)
-		if (d.layers[l].a.kind == LEAF_YADIF || (d.layers[l].kind != LAYER_DIRECT && d.layers[l].b.kind == LEAF_YADIF) ||
-		    (d.layers[l].kind == LAYER_WIPE_MASK && d.layers[l].mask.kind == LEAF_YADIF))
-			return true;
-	return false;
-}
-
 cudaError_t launch_fused(cudaStream_t s, const FusedDesc &d, void *out_rgba) {
 	const int lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
-	const bool yd = has_yadif_leaf(d);
 	if (!out_rgba && d.sink != SINK_V210) {
 		const size_t blocks8 = (size_t)((d.out_w + 7) / 8);
 		size_t n;
 		auto grid = [&](size_t threads) { return (unsigned)((threads + kFusedThreads - 1) / kFusedThreads); };
 		switch (d.sink) {
-			case SINK_RGBA8: n = (size_t)d.out_w * lines; if (yd) k_fused_sink<SINK_RGBA8, true><<<grid(n), kFusedThreads, 0, s>>>(d); else k_fused_sink<SINK_RGBA8, false><<<grid(n), kFusedThreads, 0, s>>>(d); break;
-			case SINK_BGRA8: n = (size_t)d.out_w * lines; if (yd) k_fused_sink<SINK_BGRA8, true><<<grid(n), kFusedThreads, 0, s>>>(d); else k_fused_sink<SINK_BGRA8, false><<<grid(n), kFusedThreads, 0, s>>>(d); break;
-			case SINK_YUV422P10: n = blocks8 * lines; if (yd) k_fused_sink<SINK_YUV422P10, true><<<grid(n), kFusedThreads, 0, s>>>(d); else k_fused_sink<SINK_YUV422P10, false><<<grid(n), kFusedThreads, 0, s>>>(d); break;
-			case SINK_YUV422P8: n = blocks8 * lines; if (yd) k_fused_sink<SINK_YUV422P8, true><<<grid(n), kFusedThreads, 0, s>>>(d); else k_fused_sink<SINK_YUV422P8, false><<<grid(n), kFusedThreads, 0, s>>>(d); break;
-			case SINK_YUV420P: n = blocks8 * (d.out_h / 2); if (yd) k_fused_sink<SINK_YUV420P, true><<<grid(n), kFusedThreads, 0, s>>>(d); else k_fused_sink<SINK_YUV420P, false><<<grid(n), kFusedThreads, 0, s>>>(d); break;
-			case SINK_NV12: n = blocks8 * (d.out_h / 2); if (yd) k_fused_sink<SINK_NV12, true><<<grid(n), kFusedThreads, 0, s>>>(d); else k_fused_sink<SINK_NV12, false><<<grid(n), kFusedThreads, 0, s>>>(d); break;
+			case SINK_RGBA8: n = (size_t)d.out_w * lines; k_fused_sink<SINK_RGBA8><<<grid(n), kFusedThreads, 0, s>>>(d); break;
+			case SINK_BGRA8: n = (size_t)d.out_w * lines; k_fused_sink<SINK_BGRA8><<<grid(n), kFusedThreads, 0, s>>>(d); break;
+			case SINK_YUV422P10: n = blocks8 * lines; k_fused_sink<SINK_YUV422P10><<<grid(n), kFusedThreads, 0, s>>>(d); break;
+			case SINK_YUV422P8: n = blocks8 * lines; k_fused_sink<SINK_YUV422P8><<<grid(n), kFusedThreads, 0, s>>>(d); break;
+			case SINK_YUV420P: n = blocks8 * (d.out_h / 2); k_fused_sink<SINK_YUV420P><<<grid(n), kFusedThreads, 0, s>>>(d); break;
+			case SINK_NV12: n = blocks8 * (d.out_h / 2); k_fused_sink<SINK_NV12><<<grid(n), kFusedThreads, 0, s>>>(d); break;
 			default: return cudaErrorInvalidValue;
 		}
 		return cudaGetLastError();
 	}
 	if (out_rgba) {
 		const size_t n = (size_t)((d.out_w + 5) / 6) * lines;
-		if (yd) k_fused_generic<true, true><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, (float4 *)out_rgba);
-		else k_fused_generic<true, false><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, (float4 *)out_rgba);
+		k_fused_generic<true><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, (float4 *)out_rgba);
 	} else {
 		const size_t n = (size_t)(d.out_pitch / 16 - d.g_first) * lines;
-		if (yd) k_fused_generic<false, true><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, nullptr);
-		else k_fused_generic<false, false><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, nullptr);
+		k_fused_generic<false><<<(unsigned)((n + kFusedThreads - 1) / kFusedThreads), kFusedThreads, 0, s>>>(d, nullptr);
 	}
 	return cudaGetLastError();
 }

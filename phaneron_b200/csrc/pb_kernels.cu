@@ -259,6 +259,17 @@ __global__ void __launch_bounds__(kThreads) k_yadif(const float4 *__restrict__ p
 	out[tid] = yadif_texel(prev, cur, next, w, h, parity, tff, skip, xo, yo);
 }
 
+// The interpolated lines only (the lines of the other parity are the current frame's own: "the primary field is not modified",
+// yadifCl.ts:118-120): the pre-pass of a fused launch that samples a de-interlaced field.  Row r of out = line 2 r + (1 - parity).
+__global__ void __launch_bounds__(kThreads) k_yadif_rows(const float4 *__restrict__ prev, const float4 *__restrict__ cur,
+                                                         const float4 *__restrict__ next, int parity, int tff, int skip,
+                                                         float4 *__restrict__ out, int w, int h) {
+	const int xo = blockIdx.x * kThreads + threadIdx.x;
+	const int yo = 2 * blockIdx.y + (1 - parity);
+	if (xo >= w || yo >= h) return;
+	out[(size_t)blockIdx.y * w + xo] = yadif_texel(prev, cur, next, w, h, parity, tff, skip, xo, yo);
+}
+
 // ---- launchers -----------------------------------------------------------------------------------------
 #define LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
@@ -355,6 +366,15 @@ cudaError_t launch_resize(cudaStream_t s, const void *in, int sw, int sh, float 
                           void *out, int w, int h) {
 	k_resize<<<blocks_for((size_t)w * h), kThreads, 0, s>>>((const float4 *)in, sw, sh, scale, ox, oy, flip4[0], flip4[1], flip4[2],
 	                                                        flip4[3], (float4 *)out, w, h);
+	LAUNCH_CHECK();
+	return cudaSuccess;
+}
+cudaError_t launch_yadif_rows(cudaStream_t s, const void *prev, const void *cur, const void *next, int parity, int tff, int skip,
+                              void *out, int w, int h) {
+	const int rows = (h - (1 - parity) + 1) / 2;   // lines 1 - parity, 3 - parity, ... below h
+	if (rows <= 0 || w <= 0) return cudaSuccess;
+	k_yadif_rows<<<dim3((w + kThreads - 1) / kThreads, rows), kThreads, 0, s>>>((const float4 *)prev, (const float4 *)cur, (const float4 *)next, parity,
+	                                                                          tff, skip, (float4 *)out, w, h);
 	LAUNCH_CHECK();
 	return cudaSuccess;
 }

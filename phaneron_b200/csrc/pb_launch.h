@@ -26,6 +26,10 @@ cudaError_t launch_resize(cudaStream_t s, const void *in, int sw, int sh, float 
 cudaError_t launch_yadif(cudaStream_t s, const void *prev, const void *cur, const void *next, int parity, int tff, int skip,
                          void *out, int w, int h);
 
+// the interpolated lines of a de-interlaced field only, packed: row r of out = line 2 r + (1 - parity)  (pre-pass of fused launches)
+cudaError_t launch_yadif_rows(cudaStream_t s, const void *prev, const void *cur, const void *next, int parity, int tff, int skip,
+                              void *out, int w, int h);
+
 // Fused chain: N layers of (leaf | dissolve | wipe) -> combine -> v210 pack, one launch.
 // out_rgba != nullptr writes the composite as RGBA-f32 instead of packing (materialise).
 cudaError_t launch_fused(cudaStream_t s, const FusedDesc &d, void *out_rgba);

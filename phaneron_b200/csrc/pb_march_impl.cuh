@@ -634,7 +634,6 @@ __device__ __forceinline__ void eval_leaf_lanczos_v(const Leaf &lf, int lane, in
 // Four planes (the alpha of these sources is data and is sampled like a colour channel), one pass per source row, every tap
 // validated.  Conversion is lane = texel (coalesced 128-byte loads, 3 texels per lane in flight): a texel costs four table
 // reads at 256 distinct indices and the 3x3 gamut matrix.
-template <bool kYadif = false>
 __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &lf, SPtr buf, uint32_t t256_saddr, int lane, int strip, int y, int x_first,
                                                int x_last, float4 (&p)[kRounds]) {
 	constexpr int cap = kRowGroups * 6;   // 4 planes x 192 texels x 4 B = 3 KiB: the big row buffers (kernel variants with kBigRows)
@@ -671,22 +670,20 @@ __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &l
 	for (int rr = 0; rr < 2; ++rr) {
 		if (!(rr ? ok1 : ok0)) continue;
 		const uchar4 *line = reinterpret_cast<const uchar4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;   // (rgba8 / bgra8)
-		if (lf.kind == LEAF_RGBA_F32 || (kYadif && lf.kind == LEAF_YADIF)) {   // an RGBA-f32 frame (a materialised sub-expression, a routed frame):
-			// nothing to convert; or a de-interlaced field computed here from its three RGBA-f32 frames (yadifCl.ts:105-167)
-			const float4 *linef = reinterpret_cast<const float4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;
-			const bool yadif = kYadif && lf.kind == LEAF_YADIF;
+		if (lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF) {   // an RGBA-f32 frame (a materialised sub-expression, a routed frame):
+			// nothing to convert.  A de-interlaced field (yadifCl.ts:105-167) is two of them: the lines of its own parity are the
+			// current frame's, the interpolated ones come from the launch's pre-pass (k_yadif_rows), row j >> 1 of ptr_u.
+			const int j = j0 + rr;
+			const float4 *linef = (lf.kind == LEAF_YADIF && (j & 1) != (lf.yadif & 1))
+			                          ? reinterpret_cast<const float4 *>(lf.ptr_u) + (size_t)(j >> 1) * lf.w + origin
+			                          : reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + origin;
 #pragma unroll 1
 			for (int base = 0; base < ntex; base += 64) {
 				float4 v[2];
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
 					const int t = base + k * 32 + lane;
-					if (t >= ntex) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-					else if (yadif)
-						v[k] = yadif_texel(reinterpret_cast<const float4 *>(lf.ptr_u), reinterpret_cast<const float4 *>(lf.ptr),
-						                   reinterpret_cast<const float4 *>(lf.ptr_v), lf.w, lf.h, lf.yadif & 1, (lf.yadif >> 1) & 1, (lf.yadif >> 2) & 1,
-						                   origin + t, j0 + rr);
-					else v[k] = __ldg(linef + t);
+					v[k] = t < ntex ? __ldg(linef + t) : make_float4(0.f, 0.f, 0.f, 0.f);
 				}
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
@@ -1007,12 +1004,13 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(d.n_luts * 65536) : "memory");
-			for (int t = 0; t < d.n_luts; ++t)
-				for (int c = 0; c < 4; ++c)
+			_Pragma("unroll 1") for (int tc = 0; tc < d.n_luts * 4; ++tc) {   // 16 KiB per copy; not unrolled: n_luts x 4 UBLKCP + ELECT blocks were ~15 % of the code
+				const int t = tc >> 2, c = tc & 3;
 					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
 					                 lut_saddr + t * 65536 + c * 16384),
 					             "l"(d.luts[t].d8 + c * 16384), "r"(16384), "r"(bar)
 					             : "memory");
+			}
 		}
 		uint32_t done = 0;
 		while (!done)
@@ -1030,7 +1028,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 // left to a second phase of the same launch, march_single_items<true> (every source row converted once: k_march_single)
 // kFeat (general variants): the rarer abilities, compiled only into the instances a launch that needs one takes (FusedDesc::feat),
 // so that FFmpeg-format / graphics scenes do not carry their registers: 1 = Lanczos leaves filtered inside the launch
-// (eval_leaf_lanczos), 2 = Yadif leaves (yadif_texel inside the four-plane row fill), 4 = the RGBA-f32 sink and its alpha chain
+// (eval_leaf_lanczos), 2 = (unused: Yadif leaves are two RGBA-f32 frames since their interpolated lines come from a pre-pass), 4 = the RGBA-f32 sink and its alpha chain
 template <int kLutMode, bool kSparse, bool kSingleRc, int kPlain = 0, bool kPlanar = false, bool kBigRows = false, bool kBg = false, int kFeat = 0>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1071,12 +1069,13 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(d.n_luts * 65536) : "memory");
-			for (int t = 0; t < d.n_luts; ++t)
-				for (int c = 0; c < 4; ++c)   // 16 KiB per copy
+			_Pragma("unroll 1") for (int tc = 0; tc < d.n_luts * 4; ++tc) {   // 16 KiB per copy; not unrolled: n_luts x 4 UBLKCP + ELECT blocks were ~15 % of the code
+				const int t = tc >> 2, c = tc & 3;
 					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
 					                 lut_saddr + t * 65536 + c * 16384),
 					             "l"(d.luts[t].d8 + c * 16384), "r"(16384), "r"(bar)
 					             : "memory");
+			}
 		}
 		uint32_t done = 0;
 		while (!done)
@@ -1192,7 +1191,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32 || ((kFeat & 2) && lf.kind == LEAF_YADIF))) eval_leaf_rgba<(kFeat & 2) != 0>(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
+			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
 			else if (lf.kind == LEAF_LANCZOS_V) eval_leaf_lanczos_v(lf, lane, y, x_first, x_last, p);
 			else if (kPlanar && (kFeat & 1) && lf.lz_tx) eval_leaf_lanczos<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows, kPf>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p, &pf,
@@ -1375,12 +1374,13 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(d.n_luts * 65536) : "memory");
-			for (int t = 0; t < d.n_luts; ++t)
-				for (int c = 0; c < 4; ++c)
+			_Pragma("unroll 1") for (int tc = 0; tc < d.n_luts * 4; ++tc) {   // 16 KiB per copy; not unrolled: n_luts x 4 UBLKCP + ELECT blocks were ~15 % of the code
+				const int t = tc >> 2, c = tc & 3;
 					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
 					                 lut_saddr + t * 65536 + c * 16384),
 					             "l"(d.luts[t].d8 + c * 16384), "r"(16384), "r"(bar)
 					             : "memory");
+			}
 		}
 		uint32_t done = 0;
 		while (!done)

@@ -777,7 +777,6 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.feat = rgba_f32_sink ? 4 : 0;
 	for (int i = 0; i < n_leaves; ++i) {
 		if (leaves[i]->lz_tx && !leaves[i]->lz_sep) d.feat |= 1;
-		if (leaves[i]->kind == pb::LEAF_YADIF) d.feat |= 2;
 	}
 	for (int i = 0; i < n_leaves; ++i)   // the first pass of a separable Lanczos leaf decodes its table from shared memory
 		if (leaves[i]->lz_sep && !(d.n_luts > 0 && d.sparse_cm && d.rc[leaves[i]->rc].lut_slot >= 0)) return 0;
@@ -835,9 +834,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 // v210 width -- the generic kernel on the tail columns (prepare_march).  Also the replay path of recorded chains.
 int launch_compiled(pb_ctx *c, cudaStream_t s, const pb::FusedDesc &d_in, bool march, void *out_rgba, const std::vector<pb::HPassDesc> *pre) {
 	if (pre)
-		for (const pb::HPassDesc &h : *pre) {   // first passes of separable Lanczos leaves
-			cudaError_t e = pb::launch_lanczos_hpass(s, h, c->march_sms);
-			if (e != cudaSuccess) return fail(PB_ERR_CUDA, "lanczos first pass: %s", cudaGetErrorString(e));
+		for (const pb::HPassDesc &h : *pre) {   // first passes of separable Lanczos leaves, interpolated lines of Yadif leaves
+			cudaError_t e = h.pre_kind == 1 ? pb::launch_yadif_rows(s, h.lf.ptr_u, h.lf.ptr, h.lf.ptr_v, h.lf.yadif & 1, (h.lf.yadif >> 1) & 1,
+			                                                        (h.lf.yadif >> 2) & 1, h.out, h.lf.w, h.lf.h)
+			                                : pb::launch_lanczos_hpass(s, h, c->march_sms);
+			if (e != cudaSuccess) return fail(PB_ERR_CUDA, "%s: %s", h.pre_kind == 1 ? "yadif lines" : "lanczos first pass", cudaGetErrorString(e));
 			c->stats.kernel_launches++;   // the caller counts the main launch
 		}
 	pb::FusedDesc bg_copy;
@@ -884,6 +885,36 @@ int launch_desc(pb_ctx *c, cudaStream_t s, pb::FusedDesc &d, void *out_rgba, boo
 	for (auto &sc : c->pending_scratch) c->pool.dev_put(sc.second, sc.first);   // (left over by a caller that did not record)
 	c->pending_scratch.clear();
 	c->pending_pre.clear();
+	// Yadif leaves (march and generic kernel alike): the interpolated lines of the field -- half of its lines; 27 float4 reads and
+	// two predictors per channel each -- are computed ONCE by a pre-pass into a half-height RGBA-f32 block; the lines of the
+	// field's own parity are read from the current frame where they lie.  Evaluating the filter where the field is sampled
+	// costs it once per tap row (twice per pixel through the Mixer's Transform): 727 against xxx us per 2160p field
+	// (profiles/r02_kbench_yadif.txt).  The consuming launch sees two RGBA-f32 frames: ptr = cur, ptr_u = the block.
+	for (int l = 0; l < d.n_layers; ++l) {
+		pb::Layer &ly = d.layers[l];
+		pb::Leaf *ll[3] = {&ly.a, &ly.b, &ly.mask};
+		const int nleaf = ly.kind == pb::LAYER_DIRECT ? 1 : (ly.kind == pb::LAYER_DISSOLVE ? 2 : 3);
+		for (int q = 0; q < nleaf; ++q) {
+			pb::Leaf &lf = *ll[q];
+			if (lf.kind != pb::LEAF_YADIF || (lf.yadif & 8)) continue;   // (bit 3: ptr_u already is the block of interpolated lines)
+			void *rows = nullptr;
+			for (const pb::HPassDesc &h : c->pending_pre)   // the same field sampled by another leaf of this launch
+				if (h.pre_kind == 1 && h.lf.ptr == lf.ptr && h.lf.ptr_u == lf.ptr_u && h.lf.ptr_v == lf.ptr_v && h.lf.yadif == lf.yadif) rows = h.out;
+			if (!rows) {
+				pb::HPassDesc h{};
+				h.pre_kind = 1;
+				h.lf = lf;
+				const size_t bytes = (size_t)((lf.h + 1) / 2) * lf.w * sizeof(float4);
+				CU(c->pool.dev_get(bytes, &rows));
+				h.out = (float4 *)rows;
+				c->pending_pre.push_back(h);
+				c->pending_scratch.push_back({rows, bytes});
+			}
+			lf.ptr_u = rows;
+			lf.ptr_v = nullptr;
+			lf.yadif |= 8;
+		}
+	}
 	if (march) {
 		for (int l = 0; l < d.n_layers; ++l) {
 			pb::Layer &ly = d.layers[l];

@@ -989,7 +989,8 @@ def test_interlaced_source_through_yadif_composites_on_the_march_kernel(use_marc
 def test_yadif_fields_are_fused_into_the_composite_launch(mode):
     """Interlaced v210 frames -> ToRGBA -> Yadif (yadif.ts:88-145) -> Mixer Transform -> Combine with a PiP -> FromRGBA.
     Each ToRGBA output is made real ONCE (one direct-kernel launch per input frame: the window re-reads it for six fields);
-    the de-interlaced field itself never exists in HBM: it is computed inside the ONE march launch of its output frame.
+    the de-interlaced field is a leaf of the ONE march launch of its output frame: only its interpolated lines (half a frame)
+    are computed, once, by that launch's pre-pass; the lines of its own parity are read from the current frame in place.
     Bit-exact against the oracle's stage-by-stage chain (v210 read x3 -> yadif -> transform -> combine -> v210 write)."""
     from phaneron_b200.process import v210 as v210m
     from phaneron_b200.process.combine import Combine
@@ -1075,7 +1076,7 @@ def test_yadif_fields_are_fused_into_the_composite_launch(mode):
     # launch structure
     for kind, st in stats:
         if kind == "compose":
-            assert st["kernel_launches"] == 1 and st["march_launches"] == 1 and st["materialised"] == 0, st
+            assert st["kernel_launches"] == 2 and st["march_launches"] == 1 and st["fused_launches"] == 1 and st["materialised"] == 0, st
         else:   # producer side: frames are made real when the window first needs them (one direct-kernel launch each), nothing else
             assert st["kernel_launches"] == st["materialised"] == st["march_launches"], st
     assert sum(st["materialised"] for kind, st in stats if kind == "deinterlace") == 4   # each input frame exactly once

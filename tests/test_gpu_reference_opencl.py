@@ -127,3 +127,25 @@ def test_oracle_rgba8_bit_exact_vs_reference_kernels():
     ref = ref_ocl.rgba8_read(src, w, h, lut_r, gamut)
     assert np.array_equal(_bits(ref), _bits(oracle.rgba8_read(src, w, h, lut_r, gamut)))
     assert np.array_equal(ref_ocl.rgba8_write(ref, w, h, 0, lut_w), oracle.rgba8_write(ref, w, h, 0, lut_w))
+
+
+def test_oracle_mix_and_wipe_bit_exact_vs_reference_kernels():
+    """mix.ts:24-47 ('mixer': fma(in0, mix, in1 * (1 - mix))) and wipe.ts:24-48 (x > w * wipe): point-sampled, so every bit must agree"""
+    rng = np.random.default_rng(15)
+    a, b = (rng.random((135, 240, 4), dtype=np.float32) for _ in range(2))
+    for m in (0.0, 0.25, 0.37, 1.0):
+        assert np.array_equal(_bits(ref_ocl.mix(a, b, m)), _bits(oracle.mix(a, b, m)))
+    for wp in (0.0, 0.3, 0.5, 0.999, 1.0):
+        assert np.array_equal(_bits(ref_ocl.wipe(a, b, wp)), _bits(oracle.wipe(a, b, wp)))
+
+
+def test_resize_differs_from_reference_only_by_the_hardware_sampler():
+    """resize.ts:24-58 samples with normalised coordinates + CLK_FILTER_LINEAR: as for transform, the driver's tex.2d quantises the
+    filter weights to 1/256; the restatement follows the OpenCL 1.2 formula and must sit within one weight step of it"""
+    rng = np.random.default_rng(16)
+    im = rng.random((135, 240, 4), dtype=np.float32)
+    for scale, ox, oy, flip in ((1.0, 0.0, 0.0, (0.0, 1.0, 0.0, 1.0)), (0.5, 0.1, -0.2, (0.0, 1.0, 0.0, 1.0)), (1.7, 0.0, 0.25, (1.0, -1.0, 0.0, 1.0)),
+                                (0.8, -0.3, 0.0, (1.0, -1.0, 1.0, -1.0))):
+        ref = ref_ocl.resize(im, scale, ox, oy, flip, 240, 135)
+        got = oracle.resize(im, scale, ox, oy, flip, 240, 135)
+        assert float(np.abs(ref - got).max()) < 1.0 / 128

@@ -5,9 +5,10 @@
 
   python tools/kbench_yadif.py [--size 1920x1080] [--frames 100]
 
-fused : the product's deferred mode.  Per input frame: ONE direct-kernel launch makes the new ToRGBA output real, then ONE march
-        launch per output frame computes the de-interlaced field where it is sampled (no yadif output in HBM).  Timed by replaying
-        the recorded launches of one input frame (CUDA events).
+fused : the product's deferred mode.  Per input frame: ONE direct-kernel launch makes the new ToRGBA output real; per output frame
+        a pre-pass computes the interpolated lines of the field (half a frame, each pixel once) and ONE march launch composites,
+        reading the field's other lines from the current frame in place.  Timed by replaying the recorded launches of one input
+        frame (CUDA events).
 eager : the reference's launch structure (one kernel per job, RGBA-f32 frames between all stages): sum of the per-job kernel
         times the library reports (RunTimings.kernelExec, CUDA events around each launch), host time excluded.
 """
@@ -134,12 +135,15 @@ async def main():
     ctx = clContext({"deviceIndex": 0, "deferred": False})
     await ctx.initialise()
     total = {"us": 0, "n": 0}
+    per = {}
     orig = ctx.runProgram
 
     async def timed_run(program, params, queue, timed=False):
         t = await orig(program, params, queue, timed=True)
         total["us"] += t.kernelExec
         total["n"] += 1
+        name = getattr(program, "name", None) or getattr(program, "op_name", None) or str(program)
+        per[name] = per.get(name, 0) + t.kernelExec
         return t
     ctx.runProgram = timed_run
     rig = Rig(ctx, w, h)
@@ -147,11 +151,13 @@ async def main():
     for _ in range(4):
         await rig.input_frame()
     total.update(us=0, n=0)
+    per.clear()
     m = max(10, a.frames // 5)
     for _ in range(m):
         await rig.input_frame()
     print(f"yadif eager  {w}x{h}: {total['us'] / m:8.1f} us per input frame = {total['us'] / m / 2:7.1f} us per output field; kernels per input frame "
           f"{total['n'] / m:.0f} (sum of per-kernel CUDA-event times, host time excluded)", flush=True)
+    print("             per input frame: " + ", ".join(f"{k} {v / m:.1f}" for k, v in sorted(per.items(), key=lambda kv: -kv[1])), flush=True)
     ctx.close()
 
 asyncio.run(main())
