@@ -630,6 +630,73 @@ __device__ __forceinline__ void eval_leaf_lanczos_v(const Leaf &lf, int lane, in
 	}
 }
 
+// ---- RGBA-f32 leaves (routed channel frames, materialised sub-expressions, de-interlaced fields) ---------------------------
+// Nothing to convert, so nothing to stage: every lane fetches the four taps of each of its pixels straight from global memory
+// (L1 serves the overlap between neighbouring lanes and between the two rows), all twelve 16-byte loads of a leaf in flight at
+// once.  The row-buffer form this replaces (four planes through shared memory, one pass per source row) exposed the load
+// latency four times per leaf and item and needed the 64-group buffers: 220 us for the composite of a 2160p de-interlaced field.
+// Same weights, same fma chain as eval_leaf_rgba: w(1-a)(1-b) t00 -> + a(1-b) t10 -> + (1-a)b t01 -> + ab t11, from +0.
+// A de-interlaced field (yadifCl.ts:105-167) is two frames: the lines of its own parity are the current frame's (ptr), the
+// interpolated ones come from the launch's pre-pass (k_yadif_rows), row j >> 1 of ptr_u.
+__device__ __forceinline__ void eval_leaf_f32(const Leaf &lf, int lane, int strip, int y, int x_first, int x_last, float4 (&p)[kRounds]) {
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+	const int4 si = __ldg(lf.strip_tab + strip);
+	const int2 rt = __ldg(lf.row_tab + y);
+	if (!(si.x & 1)) return;
+	const int j0 = rt.x;
+	const bool has_xf = lf.has_xf != 0;
+	const bool ok0 = (unsigned)j0 < (unsigned)lf.h, ok1 = has_xf && (unsigned)(j0 + 1) < (unsigned)lf.h;
+	if (!ok0 && !ok1) return;
+	auto row = [&](int j) {
+		return (lf.kind == LEAF_YADIF && (j & 1) != (lf.yadif & 1)) ? reinterpret_cast<const float4 *>(lf.ptr_u) + (size_t)(j >> 1) * lf.w
+		                                                            : reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w;
+	};
+	const float4 *r0 = row(ok0 ? j0 : j0 + 1), *r1 = row(ok1 ? j0 + 1 : j0);
+	const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (!has_xf) {   // 1:1 read of texel (x, y): exact passthrough, alpha included
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) p[r] = __ldg(r0 + min(x_first + r * 32 + lane, x_last));
+		return;
+	}
+	int i0[kRounds];
+	float ca[kRounds];
+	float4 t00[kRounds], t10[kRounds], t01[kRounds], t11[kRounds];
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		const int2 ct = __ldg(lf.col_tab + min(x_first + r * 32 + lane, x_last));
+		i0[r] = ct.x;
+		ca[r] = __int_as_float(ct.y);
+	}
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		const bool f0 = (unsigned)i0[r] < (unsigned)lf.w, f1 = (unsigned)(i0[r] + 1) < (unsigned)lf.w;
+		t00[r] = (ok0 && f0) ? __ldg(r0 + i0[r]) : zero;
+		t10[r] = (ok0 && f1) ? __ldg(r0 + i0[r] + 1) : zero;
+		t01[r] = (ok1 && f0) ? __ldg(r1 + i0[r]) : zero;
+		t11[r] = (ok1 && f1) ? __ldg(r1 + i0[r] + 1) : zero;
+	}
+	const float b = __int_as_float(rt.y), rb = sub(1.0f, b);
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		const float ra = sub(1.0f, ca[r]);
+		if (ok0) {
+			const float w0 = mul(ra, rb), w1 = mul(ca[r], rb);
+			p[r].x = fma_(w1, t10[r].x, fma_(w0, t00[r].x, p[r].x));
+			p[r].y = fma_(w1, t10[r].y, fma_(w0, t00[r].y, p[r].y));
+			p[r].z = fma_(w1, t10[r].z, fma_(w0, t00[r].z, p[r].z));
+			p[r].w = fma_(w1, t10[r].w, fma_(w0, t00[r].w, p[r].w));
+		}
+		if (ok1) {
+			const float w0 = mul(ra, b), w1 = mul(ca[r], b);
+			p[r].x = fma_(w1, t11[r].x, fma_(w0, t01[r].x, p[r].x));
+			p[r].y = fma_(w1, t11[r].y, fma_(w0, t01[r].y, p[r].y));
+			p[r].z = fma_(w1, t11[r].z, fma_(w0, t01[r].z, p[r].z));
+			p[r].w = fma_(w1, t11[r].w, fma_(w0, t01[r].w, p[r].w));
+		}
+	}
+}
+
 // ---- rgba8 / bgra8 leaves (graphics with alpha: FFmpegProducer 'rgba' / 'bgra' / any rgb format, rgba8.ts) ----------
 // Four planes (the alpha of these sources is data and is sampled like a colour channel), one pass per source row, every tap
 // validated.  Conversion is lane = texel (coalesced 128-byte loads, 3 texels per lane in flight): a texel costs four table
@@ -670,34 +737,6 @@ __device__ __forceinline__ void eval_leaf_rgba(const FusedDesc &d, const Leaf &l
 	for (int rr = 0; rr < 2; ++rr) {
 		if (!(rr ? ok1 : ok0)) continue;
 		const uchar4 *line = reinterpret_cast<const uchar4 *>(lf.ptr) + (size_t)(j0 + rr) * lf.w + origin;   // (rgba8 / bgra8)
-		if (lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF) {   // an RGBA-f32 frame (a materialised sub-expression, a routed frame):
-			// nothing to convert.  A de-interlaced field (yadifCl.ts:105-167) is two of them: the lines of its own parity are the
-			// current frame's, the interpolated ones come from the launch's pre-pass (k_yadif_rows), row j >> 1 of ptr_u.
-			const int j = j0 + rr;
-			const float4 *linef = (lf.kind == LEAF_YADIF && (j & 1) != (lf.yadif & 1))
-			                          ? reinterpret_cast<const float4 *>(lf.ptr_u) + (size_t)(j >> 1) * lf.w + origin
-			                          : reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + origin;
-#pragma unroll 1
-			for (int base = 0; base < ntex; base += 64) {
-				float4 v[2];
-#pragma unroll
-				for (int k = 0; k < 2; ++k) {
-					const int t = base + k * 32 + lane;
-					v[k] = t < ntex ? __ldg(linef + t) : make_float4(0.f, 0.f, 0.f, 0.f);
-				}
-#pragma unroll
-				for (int k = 0; k < 2; ++k) {
-					const int t = base + k * 32 + lane;
-					if (t < ntex) {
-						const uint32_t a = buf.a + 4u * (uint32_t)t;
-						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v[k].x) : "memory");
-						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 4u * cap), "f"(v[k].y) : "memory");
-						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 8u * cap), "f"(v[k].z) : "memory");
-						asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 12u * cap), "f"(v[k].w) : "memory");
-					}
-				}
-			}
-		} else
 #pragma unroll 1
 		for (int base = 0; base < ntex; base += 96) {
 			uchar4 px[3];
@@ -1028,7 +1067,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 // left to a second phase of the same launch, march_single_items<true> (every source row converted once: k_march_single)
 // kFeat (general variants): the rarer abilities, compiled only into the instances a launch that needs one takes (FusedDesc::feat),
 // so that FFmpeg-format / graphics scenes do not carry their registers: 1 = Lanczos leaves filtered inside the launch
-// (eval_leaf_lanczos), 2 = (unused: Yadif leaves are two RGBA-f32 frames since their interpolated lines come from a pre-pass), 4 = the RGBA-f32 sink and its alpha chain
+// (eval_leaf_lanczos), 2 = RGBA-f32 / Yadif leaves (eval_leaf_f32), 4 = the RGBA-f32 sink and its alpha chain
 template <int kLutMode, bool kSparse, bool kSingleRc, int kPlain = 0, bool kPlanar = false, bool kBigRows = false, bool kBg = false, int kFeat = 0>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1191,7 +1230,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8 || lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
+			if (kPlanar && (kFeat & 2) && (lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_f32(lf, lane, strip, y, x_first, x_last, p);
+			else if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
 			else if (lf.kind == LEAF_LANCZOS_V) eval_leaf_lanczos_v(lf, lane, y, x_first, x_last, p);
 			else if (kPlanar && (kFeat & 1) && lf.lz_tx) eval_leaf_lanczos<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);
 			else eval_leaf<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kPlanar, kBigRows, kPf>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p, &pf,

@@ -467,11 +467,11 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
 		if (r) return r;
 		if (!fits) return 0;
-		const bool leaf_rgba = leaves[i]->kind == pb::LEAF_RGBA8 || leaves[i]->kind == pb::LEAF_BGRA8 || leaves[i]->kind == pb::LEAF_RGBA_F32 ||
-		                       leaves[i]->kind == pb::LEAF_YADIF;
-		if (leaf_rgba && fits != 1) return 0;   // four planes: 32 source groups per row at most
-		if (fits == 2 || leaf_rgba) big_rows = true;
-		opq[i] = leaf_rgba ? nullptr : t->opq;   // the alpha of an rgba8 leaf is data: never certifiably opaque
+		const bool leaf_f32 = leaves[i]->kind == pb::LEAF_RGBA_F32 || leaves[i]->kind == pb::LEAF_YADIF;   // taps straight from global memory: no row buffer
+		const bool leaf_rgba = leaves[i]->kind == pb::LEAF_RGBA8 || leaves[i]->kind == pb::LEAF_BGRA8 || leaf_f32;
+		if (leaf_rgba && !leaf_f32 && fits != 1) return 0;   // four planes: 32 source groups per row at most
+		if (!leaf_f32 && (fits == 2 || leaf_rgba)) big_rows = true;
+		opq[i] = leaf_rgba ? nullptr : t->opq;   // the alpha of an rgba8 / RGBA-f32 leaf is data: never certifiably opaque
 		tab_of[i] = t->opq;
 		leaves[i]->col_tab = t->dcol;
 		leaves[i]->row_tab = t->drow;
@@ -777,6 +777,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	d.feat = rgba_f32_sink ? 4 : 0;
 	for (int i = 0; i < n_leaves; ++i) {
 		if (leaves[i]->lz_tx && !leaves[i]->lz_sep) d.feat |= 1;
+		if (leaves[i]->kind == pb::LEAF_RGBA_F32 || leaves[i]->kind == pb::LEAF_YADIF) d.feat |= 2;
 	}
 	for (int i = 0; i < n_leaves; ++i)   // the first pass of a separable Lanczos leaf decodes its table from shared memory
 		if (leaves[i]->lz_sep && !(d.n_luts > 0 && d.sparse_cm && d.rc[leaves[i]->rc].lut_slot >= 0)) return 0;
