@@ -276,11 +276,12 @@ def test_resize():
 
 @pytest.mark.parametrize("deferred", [False, True])
 @pytest.mark.parametrize("mode,tff", [("send_frame", True), ("send_field", True), ("send_field", False), ("send_field_nospatial", True)])
-def test_yadif_window(mode, tff, deferred):
+@pytest.mark.parametrize("size", [(96, 40), (150, 37), (7, 5)])   # (deferred: the tiled pre-pass k_yadif_rows -- 64 x 8 tiles -- at ragged widths, odd heights, frames smaller than its halo)
+def test_yadif_window(mode, tff, deferred, size):
     """yadif.ts:115-145: 3-frame window, 1 or 2 outputs per input, parity rule of yadif.ts:104"""
     async def go():
         async with Env(deferred) as env:
-            w, h = 96, 40
+            w, h = size
             frames = [rand_rgba(h, w, 40 + i) for i in range(5)]
             yad = Yadif(env.ctx, env.jobs, w, h, {"mode": mode, "tff": tff}, True)
             await yad.init()
