@@ -98,8 +98,8 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		const size_t smem_single = (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
 		const bool poly = d.luts[d.rc[d.layers[0].a.rc].lut_slot].lp.affine == 2;   // the layer's read table in the MUFU-free model
 		const bool plain_fmt = d.layers[0].a.kind == LEAF_V210 && d.sink == SINK_V210;
-		(plain_fmt ? (poly ? k_march_single<false, 2> : k_march_single<false, 0>) : (poly ? k_march_single<true, 2> : k_march_single<true, 0>))<<<grid, kMarchThreads, smem_single, s>>>(d);
-		return cudaGetLastError();
+		return launch_pdl(plain_fmt ? (poly ? k_march_single<false, 2> : k_march_single<false, 0>) : (poly ? k_march_single<true, 2> : k_march_single<true, 0>), grid,
+		                  kMarchThreads, smem_single, s, d);
 	}
 	if (d.direct_mode) {   // one v210 source 1:1 into a v210 output (prepare_march checks the conditions)
 		static std::mutex mu;
@@ -121,13 +121,11 @@ cudaError_t launch_fused_march(cudaStream_t s, const FusedDesc &d, int num_sms) 
 		const int grid = max(1, min(num_sms, (total + kDirectWarps - 1) / kDirectWarps));
 		const size_t smem_direct = (size_t)d.n_luts * 65536 + (size_t)kDirectWarps * kRowFloats * sizeof(float);
 		if (d.direct_mode == 2) {   // an RGBA-f32 frame packed to v210
-			k_march_direct<0, false, true><<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
-			return cudaGetLastError();
+			return launch_pdl(k_march_direct<0, false, true>, grid, kDirectWarps * 32, smem_direct, s, d);
 		}
 		const bool poly = d.luts[d.rc[0].lut_slot].lp.affine == 2;
-		if (d.sink == SINK_RGBA_F32) (poly ? k_march_direct<2, true> : k_march_direct<0, true>)<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
-		else (poly ? k_march_direct<2, false> : k_march_direct<0, false>)<<<grid, kDirectWarps * 32, smem_direct, s>>>(d);
-		return cudaGetLastError();
+		if (d.sink == SINK_RGBA_F32) return launch_pdl(poly ? k_march_direct<2, true> : k_march_direct<0, true>, grid, kDirectWarps * 32, smem_direct, s, d);
+		return launch_pdl(poly ? k_march_direct<2, false> : k_march_direct<0, false>, grid, kDirectWarps * 32, smem_direct, s, d);
 	}
 	const bool single = d.n_rc == 1;
 	if (d.n_luts > 0) {

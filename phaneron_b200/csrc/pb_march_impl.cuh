@@ -39,6 +39,7 @@
 // table fit has already absorbed, so results are bit-identical to the generic kernel
 // (pb_fused.cu) and to the oracle.
 #pragma once
+#include <cstdlib>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -56,6 +57,14 @@ constexpr float kTwo23 = 8388608.0f;
 // Keeps the three pixel pairs of a v210 group from being interleaved: fewer table lookups in flight at once means
 // fewer live registers, and registers (not ILP) bound the number of resident warps (profiles/r01_kbench_warps_fence.txt).
 #define PB_PAIR_FENCE() asm volatile("" ::: "memory")
+
+// Programmatic dependent launch (PDL): consecutive frames are independent launches on one stream.  A kernel lets its successor's
+// CTAs become resident as its own exit (pdl_trigger at entry), and does everything that does not depend on earlier launches --
+// the TMA load of the gamma tables: 128 KiB per CTA, 19 MB per launch, constant data -- before pdl_wait, which returns when every
+// earlier grid has completed and its writes are visible.  No frame data is read and nothing is written before it.  The
+// successor's prologue and launch latency thus hide under the predecessor's tail.  (No-ops in a launch without the attribute.)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
@@ -1023,6 +1032,7 @@ __device__ __forceinline__ void march_single_items(const FusedDesc &d, SPtr buf,
 
 template <bool kPlanarSrc, int kReadMode>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_constant__ FusedDesc d) {
+	pdl_trigger();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
 	uint32_t tid_x;
@@ -1055,6 +1065,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 		while (!done)
 			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
 	}
+	pdl_wait();   // from here on: frame data
 	march_single_items<false, kPlanarSrc, kReadMode>(d, buf, lut_saddr, lane, warp);
 }
 
@@ -1070,6 +1081,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 // (eval_leaf_lanczos), 2 = RGBA-f32 / Yadif leaves (eval_leaf_f32), 4 = the RGBA-f32 sink and its alpha chain
 template <int kLutMode, bool kSparse, bool kSingleRc, int kPlain = 0, bool kPlanar = false, bool kBigRows = false, bool kBg = false, int kFeat = 0>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
+	pdl_trigger();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(lut_s);
@@ -1120,6 +1132,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		while (!done)
 			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
 	}
+	pdl_wait();   // from here on: frame data
 
 	const int step = d.interlace == 0 ? 1 : 2;
 	const int first_line = d.interlace == 3 ? 1 : 0;
@@ -1394,6 +1407,7 @@ constexpr int kDirectWarps = PB_DIRECT_WARPS;   // 69 registers per thread: more
 // an RGBA-f32 frame (a routed channel frame, a Yadif output, a host-written image) that FromRGBA packs: v210.ts:113-195 alone.
 template <int kReadMode, bool kRgbaOut = false, bool kRgbaIn = false>
 __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __grid_constant__ FusedDesc d) {
+	pdl_trigger();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
 	uint32_t tid_x;
@@ -1426,6 +1440,7 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 		while (!done)
 			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
 	}
+	pdl_wait();   // from here on: frame data
 	const Leaf &lf = d.layers[0].a;
 	const ReadConsts &rc = d.rc[0];
 	const ReadK &rk = d.rk[0];
@@ -1651,6 +1666,23 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_lanczos_hpass(const __grid
 }  // namespace
 
 // opt in to > 48 KiB of dynamic shared memory once per (kernel, device) -- the attribute is per context -- and launch one
+// a launch that may start while its predecessor on the stream drains (see pdl_trigger / pdl_wait); PB_NO_PDL=1 for A/B runs
+template <typename Kernel>
+inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t s, const FusedDesc &d) {
+	static const bool pdl = getenv("PB_NO_PDL") == nullptr;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)grid);
+	cfg.blockDim = dim3((unsigned)block);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = s;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, d);
+}
+
 // persistent CTA per SM
 template <typename Kernel>
 inline cudaError_t march_launch(Kernel kernel, cudaStream_t s, const FusedDesc &d, int num_sms, size_t smem) {
@@ -1669,8 +1701,7 @@ inline cudaError_t march_launch(Kernel kernel, cudaStream_t s, const FusedDesc &
 	const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
 	const int total = n_lines * d.n_strips;
 	const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
-	kernel<<<grid, kMarchThreads, smem, s>>>(d);
-	return cudaGetLastError();
+	return launch_pdl(kernel, grid, kMarchThreads, smem, s, d);
 }
 
 // the general variants live in their own translation units
