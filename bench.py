@@ -219,7 +219,7 @@ def ncu_traffic(kernel, inputs):
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_march_ncu_summary.json")), reverse=True):
         try:
             with open(path) as f:
-                v = json.load(f).get(f"{kernel}_{inputs}", {}).get("dram_bytes_per_launch")
+                v = json.load(f).get(f"{kernel}_{inputs}" + (f"_lanczos{LANCZOS}" if LANCZOS else ""), {}).get("dram_bytes_per_launch")
             if v:
                 return v
         except Exception:
@@ -484,7 +484,7 @@ async def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.kernel, args.inputs), "peak_kind": f"of {peak_kind}", "frac_of_nominal_8TBps": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": alg_bytes // launches_per_frame, "bytes_moved_per_launch": moved,
-                         "launch_us": launch_ms * 1e3},
+                         "launch_us": launch_ms * 1e3, "launches_per_frame": launches_per_frame, "frame_us": launch_ms * 1e3 * launches_per_frame},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": n_in * frame_bytes * E2E_FRAMES_PER_STEP,
                     "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // e2e_steps, "frames_per_step": E2E_FRAMES_PER_STEP,
                     "steps": e2e_steps, "parity_checked": e2e_parity},

@@ -18,6 +18,7 @@ constexpr int kFusedThreads = 128;
 
 template <bool kToRgba>
 __global__ void __launch_bounds__(kFusedThreads) k_fused_generic(const __grid_constant__ FusedDesc d, float4 *__restrict__ out_rgba) {
+	asm volatile("griddepcontrol.launch_dependents;");   // a march launch behind this one may load its tables meanwhile (pb_march_impl.cuh pdl_wait)
 	const int pitch16 = kToRgba ? (d.out_w + 5) / 6 : d.out_pitch / 16;
 	const int g_first = kToRgba ? 0 : d.g_first, cols = pitch16 - g_first;   // g_first > 0: only the ragged tail columns of each line
 	const int lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
@@ -67,6 +68,7 @@ __device__ __forceinline__ float4 composite_px(const FusedDesc &d, int x, int li
 // (pb_kernels.cu), the pixel source being the layer graph instead of an RGBA-f32 frame.
 template <int kSink>
 __global__ void __launch_bounds__(kFusedThreads) k_fused_sink(const __grid_constant__ FusedDesc d) {
+	asm volatile("griddepcontrol.launch_dependents;");   // a march launch behind this one may load its tables meanwhile (pb_march_impl.cuh pdl_wait)
 	const size_t tid = (size_t)blockIdx.x * kFusedThreads + threadIdx.x;
 	auto px = [&](int x, int line) { return composite_px(d, x, line); };
 	if (kSink == SINK_RGBA8 || kSink == SINK_BGRA8) {

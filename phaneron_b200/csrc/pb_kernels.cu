@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(kThreads) k_yadif_rows(const float4 *__restric
 	// lines of the interpolated parity, y - 2, y, y + 2, of the two frames around the field in time (yadifCl.ts prev2 / next2)
 	__shared__ float p2[4][kYOwnRows][kYTileW];
 	__shared__ float n2[4][kYOwnRows][kYTileW];
+	asm volatile("griddepcontrol.launch_dependents;");   // the fused launch behind this pre-pass may load its tables meanwhile (it waits before it reads)
 	const int second = !(parity ^ tff);
 	const float4 *f_p2 = second ? cur : prev, *f_n2 = second ? next : cur;
 	const int x0 = blockIdx.x * kYTileW, r0 = blockIdx.y * kYTileR;

@@ -1554,6 +1554,7 @@ __global__ void __launch_bounds__(kDirectWarps * 32, 1) k_march_direct(const __g
 // chain of the filter's definition (oracle/oracle.c), border texels skipped (fma(w, 0, s) == s).  The result row goes to H.
 template <int kReadMode>
 __global__ void __launch_bounds__(kMarchThreads, 1) k_lanczos_hpass(const __grid_constant__ HPassDesc h) {
+	pdl_trigger();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
 	uint32_t tid_x;
