@@ -197,7 +197,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    fps, dt, native = cpu_reference_fps(args.steps, max(args.warmup, 1), args.inputs, threads)
+    fps, dt, native = cpu_reference_fps(args.steps, max(args.warmup, 3), args.inputs, threads)   # (>= 3: the first frames page in 1.5 GB of intermediates)
     sample = (f"{args.steps} steps, each ONE whole {WIDTH}x{HEIGHT} frame through the full unfused chain (a v210 read + transform per source, "
               f"{'dissolve, ' if VARIANT == 'mix' else ''}combine_{LAYERS}, v210 write, RGBA-f32 intermediates), oracle/ built {'-O3 -march=native on this host' if native else '-O3'}, {dt:.1f} s")
     line = {
