@@ -127,6 +127,10 @@ struct Leaf {
 	// strips [s0, s1] and output lines [y0, y1] outside of which every tap of this leaf is a border
 	// texel: the kernel skips the leaf there without touching memory
 	int s0, s1, y0, y1;
+	// RGBA-f32 leaves: the raw gamma table of the packed source this frame was made from by the library itself (a rotated source
+	// made real by the recorder), else null.  Host only: a frame known to hold table values times a gamut matrix is finite, so
+	// the launch may keep its occlusion culling (NaN * 0 != 0 is the reason frames of unknown origin switch it off).
+	const float *finite_lut;
 };
 
 struct Layer {

@@ -647,7 +647,19 @@ __device__ __forceinline__ void eval_leaf_lanczos_v(const Leaf &lf, int lane, in
 // Same weights, same fma chain as eval_leaf_rgba: w(1-a)(1-b) t00 -> + a(1-b) t10 -> + (1-a)b t01 -> + ab t11, from +0.
 // A de-interlaced field (yadifCl.ts:105-167) is two frames: the lines of its own parity are the current frame's (ptr), the
 // interpolated ones come from the launch's pre-pass (k_yadif_rows), row j >> 1 of ptr_u.
-__device__ __forceinline__ void eval_leaf_f32(const Leaf &lf, int lane, int strip, int y, int x_first, int x_last, float4 (&p)[kRounds]) {
+__device__ __forceinline__ void eval_leaf_f32(const Leaf &lf, const ReadConsts *, int lane, int strip, int y, int x_first, int x_last, float4 (&p)[kRounds]) {
+	if (lf.has_xf == 2) {   // rotation / shear: the position of every pixel from the matrix, as the generic kernel does (pb_device.cuh leaf_value)
+#pragma unroll
+		for (int r = 0; r < kRounds; ++r) {
+			const float2 pos = transform_pos(lf.m, min(x_first + r * 32 + lane, x_last), y, lf.xf_w, lf.xf_h);
+			p[r] = sample_linear_clamp(lf.w, lf.h, pos.x, pos.y, [&](int i, int j) {   // (leaf_texel restricted to the two kinds this function sees)
+				if (i < 0 || j < 0 || i >= lf.w || j >= lf.h) return make_float4(0.f, 0.f, 0.f, 0.f);
+				return (lf.kind == LEAF_YADIF && (j & 1) != (lf.yadif & 1)) ? __ldg(reinterpret_cast<const float4 *>(lf.ptr_u) + (size_t)(j >> 1) * lf.w + i)
+				                                                            : __ldg(reinterpret_cast<const float4 *>(lf.ptr) + (size_t)j * lf.w + i);
+			});
+		}
+		return;
+	}
 #pragma unroll
 	for (int r = 0; r < kRounds; ++r) p[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 	const int4 si = __ldg(lf.strip_tab + strip);
@@ -1243,7 +1255,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 			todo &= todo - 1;
 			const MarchOp &op = d.ops[oi];
 			const Leaf &lf = (&d.layers[op.layer].a)[op.which];
-			if (kPlanar && (kFeat & 2) && (lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_f32(lf, lane, strip, y, x_first, x_last, p);
+			if (kPlanar && (kFeat & 2) && (lf.kind == LEAF_RGBA_F32 || lf.kind == LEAF_YADIF)) eval_leaf_f32(lf, d.rc, lane, strip, y, x_first, x_last, p);
 			else if (kBigRows && (lf.kind == LEAF_RGBA8 || lf.kind == LEAF_BGRA8)) eval_leaf_rgba(d, lf, buf, t256_saddr, lane, strip, y, x_first, x_last, p);
 			else if (lf.kind == LEAF_LANCZOS_V) eval_leaf_lanczos_v(lf, lane, y, x_first, x_last, p);
 			else if (kPlanar && (kFeat & 1) && lf.lz_tx) eval_leaf_lanczos<kLutMode, kSparse, kSingleRc, (kPlain == 2 ? 2 : kPlain == 1 ? 0 : -1), kBigRows>(d, lf, lut_saddr, buf, lane, strip, y, x_first, x_last, p);

@@ -403,7 +403,10 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			if (lf.has_xf) {
 				for (float v : lf.m)
 					if (!(v == v) || v > 1e30f || v < -1e30f) return 0;
-				if (lf.m[1] != 0.0f || lf.m[3] != 0.0f) return 0;   // rotation / shear
+				if (lf.m[1] != 0.0f || lf.m[3] != 0.0f) {   // rotation / shear: RGBA-f32 frames only (sampled per pixel, no row buffers, no tables)
+					if (!(lf.kind == pb::LEAF_RGBA_F32 || lf.kind == pb::LEAF_YADIF) || lf.lz_tx) return 0;
+					lf.has_xf = 2;
+				}
 				if (lf.xf_w != d.out_w || lf.xf_h != d.out_h) return 0;
 				any_xf = true;
 			} else if (lf.w != d.out_w || lf.h != d.out_h) {
@@ -462,6 +465,36 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			leaves[i]->s0 = lt->s0; leaves[i]->s1 = lt->s1; leaves[i]->y0 = lt->y0; leaves[i]->y1 = lt->y1;
 			continue;
 		}
+		if (leaves[i]->has_xf == 2) {   // general affine position of an RGBA-f32 frame: only the bounding box of where it can be non-zero
+			// transform.ts:54-57: (s, t) = M . (x/W - 1/2, y/H - 1/2, 1) + 1/2; a tap is inside the image only for s in
+			// [-1/2sw, 1 + 1/2sw) (t alike).  Map the corners of that square, widened to two texels, back to output pixels.
+			const pb::Leaf &lf = *leaves[i];
+			const double det = (double)lf.m[0] * lf.m[4] - (double)lf.m[1] * lf.m[3];
+			int x_lo = 0, x_hi = d.out_w - 1, y_lo = 0, y_hi = d.out_h - 1;
+			if (std::fabs(det) > 1e-9) {
+				double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+				for (int k = 0; k < 4; ++k) {
+					const double sN = (k & 1) ? 1.0 + 2.0 / lf.w : -2.0 / lf.w, tN = (k & 2) ? 1.0 + 2.0 / lf.h : -2.0 / lf.h;
+					const double bs = sN - 0.5 - lf.m[2], bt = tN - 0.5 - lf.m[5];
+					const double ix = (bs * lf.m[4] - lf.m[1] * bt) / det, iy = (lf.m[0] * bt - lf.m[3] * bs) / det;
+					const double x = (ix + 0.5) * d.out_w, y = (iy + 0.5) * d.out_h;
+					xmin = std::min(xmin, x); xmax = std::max(xmax, x);
+					ymin = std::min(ymin, y); ymax = std::max(ymax, y);
+				}
+				xmin = std::max(xmin - 3.0, -1.0); ymin = std::max(ymin - 3.0, -1.0);
+				xmax = std::min(xmax + 3.0, (double)d.out_w); ymax = std::min(ymax + 3.0, (double)d.out_h);
+				x_lo = std::max(0, (int)std::floor(xmin)); x_hi = std::min(d.out_w - 1, (int)std::ceil(xmax));
+				y_lo = std::max(0, (int)std::floor(ymin)); y_hi = std::min(d.out_h - 1, (int)std::ceil(ymax));
+			}
+			opq[i] = nullptr;
+			tab_of[i] = nullptr;
+			leaves[i]->col_tab = nullptr;
+			leaves[i]->row_tab = nullptr;
+			leaves[i]->strip_tab = nullptr;
+			if (x_hi < x_lo || y_hi < y_lo) { leaves[i]->s0 = 1; leaves[i]->s1 = 0; leaves[i]->y0 = 1; leaves[i]->y1 = 0; }   // nowhere
+			else { leaves[i]->s0 = x_lo / (d.strip_groups * 6); leaves[i]->s1 = x_hi / (d.strip_groups * 6); leaves[i]->y0 = y_lo; leaves[i]->y1 = y_hi; }
+			continue;
+		}
 		pb_ctx::SampleTab *t;
 		int fits = 0;
 		int r = get_tabs(c, *leaves[i], d.out_w, d.out_h, d.strip_groups, &t, &fits);
@@ -500,7 +533,12 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 	}
 	// exact occlusion culling: which layers are opaque (alpha == 1.0f) over whole strips / whole lines.
 	// Needs finite values below (NaN * 0 != 0): every read table must lie in [0, 1].
-	bool cull = !(c->flags & PB_CTX_NO_CULL) && !any_f32;   // (an RGBA-f32 frame may hold NaN / inf: NaN * 0 != 0)
+	bool cull = !(c->flags & PB_CTX_NO_CULL);
+	for (int i = 0; i < n_leaves && cull && any_f32; ++i) {   // an RGBA-f32 frame may hold NaN / inf (NaN * 0 != 0) unless the library made it
+		if (leaves[i]->kind != pb::LEAF_RGBA_F32 && leaves[i]->kind != pb::LEAF_YADIF) continue;   // from a packed source itself
+		const int t = leaves[i]->finite_lut ? lut_table_by_raw(c, leaves[i]->finite_lut) : -1;
+		cull = t >= 0 && c->lut_tables[t].unit_range;
+	}
 	for (int i = 0; i < d.n_rc && cull; ++i) {
 		const int t = lut_table_by_raw(c, d.rc[i].lut);
 		cull = t >= 0 && c->lut_tables[t].unit_range;
@@ -807,6 +845,7 @@ int prepare_march(pb_ctx *c, pb::FusedDesc &d) {
 			int li = 0;   // index of the op's leaf in leaves[] / opq[]
 			for (int l = 0; l < d.ops[oi].layer; ++l) li += layer_n_ops[l];
 			li += d.ops[oi].which;
+			if (!tab_of[li]) continue;   // (a rotated RGBA-f32 leaf: no tables; not a packed source either)
 			const auto &o = *tab_of[li];
 			for (int sidx = 0; sidx < d.n_strips; ++sidx) {
 				if (!o.strip_ng[sidx]) continue;

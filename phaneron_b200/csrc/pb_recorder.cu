@@ -245,9 +245,16 @@ struct Compiler {
 		if (0 == set_basic_leaf(n, lf)) return PB_OK;
 		if (n->kind == N_TRANSFORM) {
 			const NodeP &child = n->in[0];
-			if (0 != set_basic_leaf(child, lf)) {
+			// A rotated / sheared Transform (the Mixer's DVE rotation) of a packed source: no kernel can share conversions between
+			// output pixels there (the generic kernel converts every tap: four conversions per pixel and leaf), so the source is
+			// made real once as RGBA-f32 (the direct kernel: 31 us at 2160p) and sampled as a frame -- by the march kernel too,
+			// which takes the taps of RGBA-f32 leaves straight from global memory at any affine position (eval_leaf_f32).
+			const bool rotated = (n->mat[1] != 0.0f || n->mat[3] != 0.0f) && !n->lanczos && (c->flags & PB_CTX_DEFER);
+			const bool packed_child = child->kind == N_LEAF_V210 || child->kind == N_LEAF_PACKED;
+			if ((rotated && packed_child) || 0 != set_basic_leaf(child, lf)) {
 				int r = as_rgba_leaf(child, lf);
 				if (r) return r;
+				if (rotated && packed_child) lf->finite_lut = child->rc.lut;   // table values x gamut matrix: finite if the table is
 			}
 			lf->has_xf = 1;
 			lf->xf_w = n->w;

@@ -73,7 +73,8 @@ def test_rotated_and_scaled_layers():
     scene["layers"][2]["xf"] = dict(IDENTITY_XF, scaleX=1.3, scaleY=0.7, offsetX=0.11, flipH=True)
     out, st = run(_run_scene(scene))
     assert np.array_equal(out, SceneOracle(scene).packed())
-    assert st["kernel_launches"] == 1
+    # the rotated layer's source is made real once (RGBA-f32, the direct kernel) and sampled as a frame by the one composite launch
+    assert st["kernel_launches"] == 2 and st["materialised"] == 1 and st["march_launches"] == 2, st
 
 
 def test_sources_of_different_sizes():
@@ -323,13 +324,37 @@ def test_gamma_tables_are_deduplicated_and_compressed():
 
 
 def test_march_kernel_declines_what_it_cannot_do():
-    """rotation and a deep downscale (footprint wider than a row buffer) fall back to the generic kernel"""
+    """a deep downscale (footprint wider than a row buffer) falls back to the generic kernel; a rotated packed source is made real
+    as RGBA-f32 first (one launch of the direct kernel) and then sampled by the march kernel at its affine positions"""
     rot = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(rotate=0.01)])
     deep = _with_xf(layered_scene(480, 270, 2, "noise", "plain"), [_xf(), _xf(scaleX=0.2, scaleY=0.2)])
-    for scene in (rot, deep):
-        out, st = run(_run_scene_variant(scene, "march"))
-        assert st["march_launches"] == 0 and st["fused_launches"] == 1
-        assert np.array_equal(out, SceneOracle(scene).packed())
+    out, st = run(_run_scene_variant(deep, "march"))
+    assert st["march_launches"] == 0 and st["fused_launches"] == 1, st
+    assert np.array_equal(out, SceneOracle(deep).packed())
+    out, st = run(_run_scene_variant(rot, "march"))
+    assert st["march_launches"] == 2 and st["fused_launches"] == 2 and st["materialised"] == 1 and st["kernel_launches"] == 2, st
+    assert np.array_equal(out, SceneOracle(rot).packed())
+    out, st = run(_run_scene_variant(rot, "generic"))
+    assert st["march_launches"] == 0 and np.array_equal(out, SceneOracle(rot).packed())
+
+
+@pytest.mark.parametrize("angle,scale,ox,oy", [(0.04, 0.6, 0.2, 0.1), (-0.31, 1.0, 0.0, 0.0), (0.25, 0.35, -0.3, 0.3), (0.5, 1.4, 0.4, -0.45), (0.013, 0.5, 0.9, 0.9)])
+def test_rotated_layers_on_the_march_kernel(angle, scale, ox, oy):
+    """DVE rotation (transform.ts:132-171 builds rotate into the matrix): layers 2 and 3 rotated -- one of them in a dissolve --
+    over a full-frame layer: bounding boxes of the rotated quads (incl. mostly / entirely outside the frame), bit-exact against
+    the oracle, and march == generic"""
+    w, h = 480, 270
+    scene = layered_scene(w, h, 3, "noise", "mix", "709", "2020")
+    scene["layers"][1]["xf"] = dict(pip(scale, ox, oy), rotate=angle)
+    xf2 = dict(pip(0.5, 0.3, 0.25), rotate=-angle * 0.5)
+    scene["layers"][2]["xf"] = xf2
+    scene["layers"][2]["transition"]["xf"] = xf2
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+    assert st["materialised"] == 3 and st["march_launches"] == 4, st   # three rotated sources made real, one composite
+    slow, st2 = run(_run_scene_variant(scene, "generic"))
+    assert st2["march_launches"] == 0 and np.array_equal(slow, ref)
 
 
 # ---- widths that are not whole v210 groups / 48-pixel blocks: 1280-wide 720p (213 groups + 2 pixels per line) ----
@@ -492,8 +517,9 @@ def test_packed_source_formats_fuse_into_one_launch(name):
     ref = SceneOracle(scene).packed()
     out, st = run(_run_scene_variant(scene, "march"))
     tail = 1 if (st["march_launches"] and scene["width"] % 48) else 0   # ragged v210 widths: march kernel + line-tail launch
-    assert st["kernel_launches"] == 1 + tail and st["fused_launches"] == 1 and st["materialised"] == 0, st
-    assert st["march_launches"] == (0 if name == "bgra8_over_v210" else 1), st   # (rotation: generic kernel)
+    rot = 1 if name == "bgra8_over_v210" else 0   # a rotated packed source is made real (RGBA-f32) before it is sampled
+    assert st["kernel_launches"] == 1 + tail + rot and st["fused_launches"] == 1 + rot and st["materialised"] == rot, st
+    assert st["march_launches"] >= 1, st
     assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
     slow, st2 = run(_run_scene_variant(scene, "generic"))
     assert st2["march_launches"] == 0 and np.array_equal(slow, ref)

@@ -33,6 +33,10 @@ def make_scene(kind, w, h, inputs, fs):
         return single_layer_scene(w, h, inputs, False, "709", "709", frame_set=fs)
     if kind == "single_xf":
         return single_layer_scene(w, h, inputs, True, "709", "709", frame_set=fs)
+    if kind == "rot":   # the bench scene with its second layer rotated (the Mixer's DVE rotation)
+        sc = layered_scene(w, h, 4, inputs, "mix", "709", "2020", frame_set=fs)
+        sc["layers"][1]["xf"] = dict(sc["layers"][1]["xf"], rotate=0.04)
+        return sc
     if kind == "overlay":   # 3 video layers + a full-frame rgba8 graphic with alpha
         return overlay_scene(w, h, inputs, "709", "2020", frame_set=fs)
     if kind.startswith("planar1:"):   # e.g. planar1:yuv422p10 -- one FFmpegProducer-format clip through the Mixer's identity Transform
