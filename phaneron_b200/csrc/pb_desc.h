@@ -21,6 +21,13 @@ constexpr int kMaxLuts = 3;          // march kernel: distinct gamma tables resi
 #endif
 constexpr int kMarchWarps = PB_MARCH_WARPS;  // warps per CTA; one persistent CTA per SM
 constexpr int kMarchThreads = kMarchWarps * 32;
+// The general variants of the march kernel (planar / rgba8 / RGBA-f32 leaves, the other sinks, big rows) carry more live state:
+// at 20 warps x 96 registers they spill 200-600 bytes per thread; 16 warps x 128 registers do not (2160p: FFmpeg-format 4-layer
+// scene 193 -> 179 us, rgba8 overlay scene 340 -> 292 us; the fast v210 variant loses 10 % that way and keeps 20 x 96).
+#ifndef PB_GENERAL_WARPS
+#define PB_GENERAL_WARPS 16
+#endif
+constexpr int kGeneralWarps = PB_GENERAL_WARPS;
 #ifndef PB_MARCH_ROUNDS
 #define PB_MARCH_ROUNDS 3
 #endif

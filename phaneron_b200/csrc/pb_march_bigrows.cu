@@ -5,7 +5,7 @@
 namespace pb {
 
 cudaError_t launch_fused_march_bigrows(cudaStream_t s, const FusedDesc &d, int num_sms, size_t smem, int plain, bool single) {
-	auto launch = [&](void (*kernel)(const FusedDesc)) -> cudaError_t { return march_launch(kernel, s, d, num_sms, smem); };
+	auto launch = [&](void (*kernel)(const FusedDesc)) -> cudaError_t { return march_launch(kernel, s, d, num_sms, smem, kGeneralWarps); };
 	const bool extras = d.feat != 0;   // Lanczos-in-launch / Yadif leaves / RGBA-f32 sink: the instances that carry them
 		if (d.feat == 2 && plain != 2) {   // RGBA-f32 / Yadif leaves only (the frames of a de-interlacing channel, routed layers)
 			if (plain) return single ? launch(k_fused_march<1, true, true, 1, true, true, false, 2>) : launch(k_fused_march<1, true, false, 1, true, true, false, 2>);

@@ -1092,7 +1092,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_march_single(const __grid_
 // so that FFmpeg-format / graphics scenes do not carry their registers: 1 = Lanczos leaves filtered inside the launch
 // (eval_leaf_lanczos), 2 = RGBA-f32 / Yadif leaves (eval_leaf_f32), 4 = the RGBA-f32 sink and its alpha chain
 template <int kLutMode, bool kSparse, bool kSingleRc, int kPlain = 0, bool kPlanar = false, bool kBigRows = false, bool kBg = false, int kFeat = 0>
-__global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
+__global__ void __launch_bounds__(((kPlanar || kBigRows) ? kGeneralWarps : kMarchWarps) * 32, 1) k_fused_march(const __grid_constant__ FusedDesc d) {
+	constexpr int kW = (kPlanar || kBigRows) ? kGeneralWarps : kMarchWarps;   // warps of this variant (pb_desc.h)
 	pdl_trigger();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint8_t *lut_s = reinterpret_cast<uint8_t *>(smem_raw);
@@ -1108,12 +1109,12 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 		asm volatile("mov.u32 %0, %1;" : "=r"(buf.a) : "r"(addr));   // opaque: keep it in a register, do not re-derive it
 	}
 
-	const uint32_t t256_saddr = buf.a - (uint32_t)warp * ((kBigRows ? 2u : 1u) * kRowFloats * 4u) + (uint32_t)kMarchWarps * ((kBigRows ? 2u : 1u) * kRowFloats * 4u);
+	const uint32_t t256_saddr = buf.a - (uint32_t)warp * ((kBigRows ? 2u : 1u) * kRowFloats * 4u) + (uint32_t)kW * ((kBigRows ? 2u : 1u) * kRowFloats * 4u);
 	if (kBigRows && d.n_t256) {   // 256-entry tables of the rgba8 / bgra8 leaves: gammaLut[c * 257], behind the row buffers
 		for (int i = 0; i < d.n_rc; ++i) {
 			const int slot = d.rc[i].t256_slot;
 			if (slot < 0) continue;
-			for (uint32_t cidx = tid_x; cidx < 256u; cidx += kMarchThreads) {
+			for (uint32_t cidx = tid_x; cidx < 256u; cidx += (kW * 32)) {
 				const float v = __ldg(d.rc[i].lut + cidx * 257u);
 				asm volatile("st.shared.f32 [%0], %1;" ::"r"(t256_saddr + (uint32_t)slot * 1024u + cidx * 4u), "f"(v) : "memory");
 			}
@@ -1160,9 +1161,9 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 
 	// TMA row prefetch (see RowPf): the fast variants only (v210 leaves with whole groups, 32-group row buffers)
 	constexpr bool kPf = kLutMode == 1 && !kPlanar && !kBigRows && !kBg;
-	__shared__ __align__(8) unsigned long long pf_bars[kPf ? kMarchWarps : 1];
+	__shared__ __align__(8) unsigned long long pf_bars[kPf ? kW : 1];
 	RowPf pf;
-	pf.raw = lut_saddr + (uint32_t)d.n_luts * 65536u + (uint32_t)kMarchWarps * (kRowFloats * 4u) + (uint32_t)warp * kPfBytes;
+	pf.raw = lut_saddr + (uint32_t)d.n_luts * 65536u + (uint32_t)kW * (kRowFloats * 4u) + (uint32_t)warp * kPfBytes;
 	pf.bar = (uint32_t)__cvta_generic_to_shared(&pf_bars[kPf ? warp : 0]);
 	pf.parity = 0;
 	pf.item = -1;
@@ -1180,15 +1181,15 @@ __global__ void __launch_bounds__(kMarchThreads, 1) k_fused_march(const __grid_c
 	}
 
 	// item -> (line k, strip) is kept incrementally: no integer division per item
-	const int stride = gridDim.x * kMarchWarps, stride_k = stride / d.n_strips, stride_s = stride - stride_k * d.n_strips;
-	int k = (blockIdx.x * kMarchWarps + warp) / d.n_strips, strip = (blockIdx.x * kMarchWarps + warp) - k * d.n_strips;
+	const int stride = gridDim.x * kW, stride_k = stride / d.n_strips, stride_s = stride - stride_k * d.n_strips;
+	int k = (blockIdx.x * kW + warp) / d.n_strips, strip = (blockIdx.x * kW + warp) - k * d.n_strips;
 	if (kPf && pf_on) {   // the line mask of this warp's second item
 		int k2 = k + stride_k, strip2 = strip + stride_s;
 		if (strip2 >= d.n_strips) ++k2;
-		if (blockIdx.x * kMarchWarps + warp + stride < total) lo_next = __ldg(d.line_ops + first_line + k2 * step);
+		if (blockIdx.x * kW + warp + stride < total) lo_next = __ldg(d.line_ops + first_line + k2 * step);
 	}
 #pragma unroll 1
-	for (int item = blockIdx.x * kMarchWarps + warp; item < total; item += stride, k += stride_k, strip += stride_s) {
+	for (int item = blockIdx.x * kW + warp; item < total; item += stride, k += stride_k, strip += stride_s) {
 		if (strip >= d.n_strips) {
 			strip -= d.n_strips;
 			++k;
@@ -1698,7 +1699,7 @@ inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, c
 
 // persistent CTA per SM
 template <typename Kernel>
-inline cudaError_t march_launch(Kernel kernel, cudaStream_t s, const FusedDesc &d, int num_sms, size_t smem) {
+inline cudaError_t march_launch(Kernel kernel, cudaStream_t s, const FusedDesc &d, int num_sms, size_t smem, int warps = kMarchWarps) {
 	static std::mutex mu;
 	static std::set<std::pair<const void *, int>> configured;
 	int dev = 0;
@@ -1713,8 +1714,8 @@ inline cudaError_t march_launch(Kernel kernel, cudaStream_t s, const FusedDesc &
 	}
 	const int n_lines = d.interlace == 0 ? d.out_h : d.out_h / 2;
 	const int total = n_lines * d.n_strips;
-	const int grid = max(1, min(num_sms, (total + kMarchWarps - 1) / kMarchWarps));
-	return launch_pdl(kernel, grid, kMarchThreads, smem, s, d);
+	const int grid = max(1, min(num_sms, (total + warps - 1) / warps));
+	return launch_pdl(kernel, grid, warps * 32, smem, s, d);
 }
 
 // the general variants live in their own translation units
