@@ -167,6 +167,28 @@ def cpu_reference_fps(steps, warmup, inputs, threads):
     return steps / dt, dt, native
 
 
+def yadif_outputs_match_oracle(window, pip_frame, pip_xf, main_xf, w, h, produced):
+    """--config yadif, untimed: the two output frames of one input frame against the oracle's unfused chain (v210 read x3 + PiP
+    source, yadif for both fields, transform, combine_2, v210 write), byte for byte"""
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from scene_oracle import xf_matrix
+    oracle.use_native()
+    oracle.set_threads(os.cpu_count() or 1)
+    cm_r, lut_r, gam = oracle.ycbcr2rgb_matrix("709"), oracle.gamma2linear_lut("709"), oracle.rgb2rgb_matrix("709", "2020")
+    cm_w, lut_w = oracle.rgb2ycbcr_matrix("2020"), oracle.linear2gamma_lut("2020")
+    win = [oracle.v210_read(f, w, h, cm_r, lut_r, gam) for f in window]
+    lb = oracle.transform(oracle.v210_read(pip_frame, w, h, cm_r, lut_r, gam), xf_matrix(w, h, pip_xf), w, h)
+    ok = len(produced) == 2
+    for k, second in enumerate((False, True)):
+        parity = 1 ^ (0 if second else 1)   # tff: (tff ? 1 : 0) ^ (!isSecond ? 1 : 0), yadif.ts:104
+        deint = oracle.yadif(win[0], win[1], win[2], parity, True, False)
+        la = oracle.transform(deint, xf_matrix(w, h, main_xf), w, h)
+        ref = oracle.v210_write(oracle.combine([la, lb]), w, h, 0, cm_w, lut_w)
+        ok = ok and np.array_equal(produced[k], ref)
+    return ok
+
+
 def reference_kernels_on_gpu(inputs, frames=6):
     """Baseline A: the reference's OWN OpenCL kernels (extracted from its .ts sources into the
     git-ignored oracle/_ref/) launched in the reference's unfused sequence on the same B200 through NVIDIA's
@@ -518,10 +540,13 @@ def main():
     ap.add_argument("--no-culling", action="store_true", help="evaluate layers hidden under opaque ones too (A/B)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle comparison of the replayed and downloaded frames")
     ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP, help="frames per device-resident step (profiling runs use a few)")
-    ap.add_argument("--config", default="3", choices=["3", "route", "5"],
+    ap.add_argument("--config", default="3", choices=["3", "route", "5", "yadif"],
                     help="3: BASELINE.json configs[2], the 2160p 4-layer composite (default, the headline metric); route: configs[3], 1080p "
-                         "channels one per GPU with ROUTE cross-feed over NCCL; 5: configs[4], 4320p 2-layer composite with a Lanczos-3 PiP")
+                         "channels one per GPU with ROUTE cross-feed over NCCL; 5: configs[4], 4320p 2-layer composite with a Lanczos-3 PiP; "
+                         "yadif: the reference's own operating point, a 1080i50 source de-interlaced and composited")
     ap.add_argument("--route-frames-per-step", type=int, default=200)
+    ap.add_argument("--yadif-inputs-per-step", type=int, default=100)
+    ap.add_argument("--yadif-size", default="1920x1080")
     ap.add_argument("--kernel", default="march", choices=["march", "march_raw", "generic"],
                     help="march: fused kernel, gamma tables in shared memory (default); march_raw: same kernel gathering "
                          "from the raw tables; generic: the fallback fused kernel")
@@ -532,7 +557,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if world > 1 or "route" in sys.argv:
+    if world > 1 or "route" in sys.argv or "yadif" in sys.argv:
         # libraries (NCCL's version banner, torchrun notices) write to fd 1: everything but the JSON line goes to stderr
         global _JSON_OUT
         sys.stdout.flush()
@@ -548,6 +573,11 @@ def main():
     if args.config == "route":
         from phaneron_b200 import bench_route
         asyncio.run(bench_route.run(args, rank, world, local_rank, emit, ClockSampler, measured_peak))
+        return
+    if args.config == "yadif":
+        from phaneron_b200 import bench_yadif
+        yw, yh = (int(v) for v in args.yadif_size.split("x"))
+        asyncio.run(bench_yadif.run(args, rank, world, local_rank, emit, ClockSampler, measured_peak, yadif_outputs_match_oracle, yw, yh))
         return
     asyncio.run(run_ours(args, rank, world, local_rank))
 
