@@ -1011,8 +1011,8 @@ def test_interlaced_source_through_yadif_composites_on_the_march_kernel(use_marc
     assert st["march_launches"] == (1 if use_march else 0) and st["fused_launches"] == 1 and st["kernel_launches"] == 1, st
 
 
-@pytest.mark.parametrize("mode", ["send_field", "send_frame_nospatial"])
-def test_yadif_fields_are_fused_into_the_composite_launch(mode):
+@pytest.mark.parametrize("mode,size", [("send_field", (480, 136)), ("send_frame_nospatial", (480, 136)), ("send_field", (1920, 1080))])
+def test_yadif_fields_are_fused_into_the_composite_launch(mode, size):
     """Interlaced v210 frames -> ToRGBA -> Yadif (yadif.ts:88-145) -> Mixer Transform -> Combine with a PiP -> FromRGBA.
     Each ToRGBA output is made real ONCE (one direct-kernel launch per input frame: the window re-reads it for six fields);
     the de-interlaced field is a leaf of the ONE march launch of its output frame: only its interpolated lines (half a frame)
@@ -1025,7 +1025,7 @@ def test_yadif_fields_are_fused_into_the_composite_launch(mode):
     from phaneron_b200.process.transform import Transform
     from phaneron_b200.process.yadif import Yadif
     from scene_oracle import xf_matrix
-    w, h = 480, 136
+    w, h = size   # (1920 x 1080: the reference's own operating point, 1080i50 channels, at full size)
     frames = [make_frame("noise", w, h, 170 + i) for i in range(4)]
     pip_src = make_frame("noise", w, h, 180)
     pip_xf = pip(0.5, 0.3, 0.2)
