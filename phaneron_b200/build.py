@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
     "-Xptxas", "-v",
 ]
-for _k in ("PB_MARCH_WARPS", "PB_MARCH_ROUNDS", "PB_DIRECT_WARPS", "PB_EXP"):   # kernel-variant experiments
+for _k in ("PB_MARCH_WARPS", "PB_GENERAL_WARPS", "PB_MARCH_ROUNDS", "PB_DIRECT_WARPS", "PB_EXP", "PB_EXP_ROW_PREFETCH"):   # kernel-variant experiments
     if os.environ.get(_k):
         NVCC_FLAGS += [f"-D{_k}={int(os.environ[_k])}"]
 

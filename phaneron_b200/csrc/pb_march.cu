@@ -70,7 +70,11 @@ cudaError_t launch_lut_fit(cudaStream_t s, const float *table, const LutParams *
 
 size_t march_smem_bytes(const FusedDesc &d) {
 	if (d.bg_single) return (size_t)d.n_luts * 65536 + (size_t)kMarchWarps * kSingleRowFloats * sizeof(float);
+#ifdef PB_EXP_ROW_PREFETCH
 	const size_t pf_tiles = (d.n_luts > 0 && !d.any_planar && !d.big_rows) ? (size_t)kMarchWarps * kPfBytes : 0;   // TMA row prefetch of the fast variants
+#else
+	const size_t pf_tiles = 0;
+#endif
 	const size_t warps = (d.n_luts > 0 && (d.any_planar || d.big_rows)) ? kGeneralWarps : kMarchWarps;   // (as launch_fused_march dispatches)
 	return (size_t)d.n_luts * 65536 + warps * (d.big_rows ? 2 : 1) * kRowFloats * sizeof(float) + (size_t)d.n_t256 * 1024 + pf_tiles;
 }

@@ -1160,7 +1160,11 @@ __global__ void __launch_bounds__(((kPlanar || kBigRows) ? kGeneralWarps : kMarc
 	const LutParams &wlp = d.wlp;
 
 	// TMA row prefetch (see RowPf): the fast variants only (v210 leaves with whole groups, 32-group row buffers)
+#ifdef PB_EXP_ROW_PREFETCH   // the TMA row prefetch experiment (exact, 6-9 % slower): compiled only into experiment builds
 	constexpr bool kPf = kLutMode == 1 && !kPlanar && !kBigRows && !kBg;
+#else
+	constexpr bool kPf = false;
+#endif
 	__shared__ __align__(8) unsigned long long pf_bars[kPf ? kW : 1];
 	RowPf pf;
 	pf.raw = lut_saddr + (uint32_t)d.n_luts * 65536u + (uint32_t)kW * (kRowFloats * 4u) + (uint32_t)warp * kPfBytes;
