@@ -1,0 +1,66 @@
+"""Seeded random layer graphs through the public operator surface, fused (march kernel and generic kernel) against the oracle's
+unfused chain, byte for byte: layer counts 1-6, every Transform flavour the Mixer can produce (none, identity, scales 0.3-1.7,
+offsets that push layers partly or wholly out of frame, flips, small and large rotations), dissolve and wipe transitions on any
+layer, three frame sizes (ragged strip counts, odd heights), random colour-spec pairs."""
+import os
+
+import numpy as np
+import pytest
+
+from phaneron_b200.scenes import IDENTITY_XF, layered_scene, make_frame, ramp_frame
+
+from gpu_util import run
+from scene_oracle import SceneOracle
+from test_gpu_chain import _run_scene_variant
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(480, 270), (528, 97), (960, 136)]
+SPECS = ["601_525", "709", "2020"]
+
+
+def _random_xf(rng):
+    kind = rng.integers(0, 6)
+    if kind == 0:
+        return None                      # ToRGBA output straight into the combiner
+    if kind == 1:
+        return dict(IDENTITY_XF)         # the Mixer's identity Transform (half-texel blur: transform.ts samples at x/w)
+    xf = dict(IDENTITY_XF)
+    s = float(rng.choice([0.3, 0.5, 0.62, 0.75, 1.0, 1.25, 1.7]))
+    xf["scaleX"], xf["scaleY"] = s, float(s * rng.choice([1.0, 1.0, 0.8, 1.3]))
+    xf["offsetX"], xf["offsetY"] = float(rng.uniform(-0.7, 0.7)), float(rng.uniform(-0.7, 0.7))
+    if kind == 3:
+        xf["flipH"], xf["flipV"] = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    if kind >= 4:
+        xf["rotate"] = float(rng.choice([0.01, -0.04, 0.25, -0.5, 0.125]))
+    if rng.integers(0, 4) == 0:
+        xf["anchorX"], xf["anchorY"] = float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.3, 0.3))
+    return xf
+
+
+def _random_scene(seed):
+    rng = np.random.default_rng(1000 + seed)
+    w, h = SIZES[seed % len(SIZES)]
+    n = int(rng.integers(1, 7))
+    spec_r, spec_w = str(rng.choice(SPECS)), str(rng.choice(SPECS))
+    scene = layered_scene(w, h, n, "noise", "plain", spec_r, spec_w, frame_set=seed)
+    for i, L in enumerate(scene["layers"]):
+        L["xf"] = _random_xf(rng) if (i > 0 or rng.integers(0, 3)) else dict(IDENTITY_XF)
+        t = rng.integers(0, 5)
+        if t == 0:
+            L["transition"] = dict(type="dissolve", mix=float(rng.choice([0.0, 0.25, 0.5, 0.9, 1.0])), src=make_frame("noise", w, h, 500 + seed * 8 + i),
+                                   sw=w, sh=h, xf=L["xf"] if rng.integers(0, 2) else _random_xf(rng))
+        elif t == 1:
+            L["transition"] = dict(type="wipe", src=make_frame("noise", w, h, 600 + seed * 8 + i), sw=w, sh=h, xf=L["xf"],
+                                   mask=ramp_frame(w, h, 13 + i), mask_sw=w, mask_sh=h, mask_xf=dict(IDENTITY_XF) if rng.integers(0, 2) else None)
+    return scene
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("PB_FUZZ_FIRST", "0")), int(os.environ.get("PB_FUZZ_FIRST", "0")) + int(os.environ.get("PB_FUZZ_SEEDS", "24"))))
+def test_random_layer_graphs_match_the_oracle(seed):
+    scene = _random_scene(seed)
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert np.array_equal(out, ref), f"march path, seed {seed}: {int((out != ref).sum())} bytes differ ({st})"
+    slow, _ = run(_run_scene_variant(scene, "generic"))
+    assert np.array_equal(slow, ref), f"generic path, seed {seed}: {int((slow != ref).sum())} bytes differ"
