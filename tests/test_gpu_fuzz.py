@@ -64,3 +64,39 @@ def test_random_layer_graphs_match_the_oracle(seed):
     assert np.array_equal(out, ref), f"march path, seed {seed}: {int((out != ref).sum())} bytes differ ({st})"
     slow, _ = run(_run_scene_variant(scene, "generic"))
     assert np.array_equal(slow, ref), f"generic path, seed {seed}: {int((slow != ref).sum())} bytes differ"
+
+
+FORMATS = [("v210", None), ("yuv422p10", "709"), ("yuv422p8", "709"), ("yuv420p", "709"), ("nv12", "601_525"), ("rgba8", "sRGB"), ("bgra8", "sRGB")]
+SINKS = [None, "yuv422p10", "yuv422p8", "yuv420p", "nv12", "rgba8", "bgra8"]
+
+
+def _random_format_scene(seed):
+    from test_gpu_chain import _mixed_format_scene
+    rng = np.random.default_rng(5000 + seed)
+    w, h = [(480, 270), (960, 136), (528, 98)][seed % 3]   # (4:2:0 formats need an even height)
+    n = int(rng.integers(1, 5))
+    specs = []
+    for i in range(n):
+        fmt, col = FORMATS[int(rng.integers(0, len(FORMATS)))]
+        xf = _random_xf(rng)
+        if xf is not None and rng.integers(0, 5) == 0 and "rotate" not in xf and fmt not in ("rgba8", "bgra8"):
+            xf["filter"] = f"lanczos{int(rng.choice([2, 3]))}"   # the extension of DESIGN.md 4.6 (axis-aligned, YCbCr sources)
+        specs.append((fmt, col, xf))
+    scene = _mixed_format_scene(w, h, specs)
+    sink = SINKS[int(rng.integers(0, len(SINKS)))]
+    if sink:
+        scene["outFmt"] = sink
+        if sink in ("rgba8", "bgra8"):
+            scene["colWrite"] = "sRGB"
+    return scene
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("PB_FUZZ_FIRST", "0")), int(os.environ.get("PB_FUZZ_FIRST", "0")) + int(os.environ.get("PB_FUZZ_SEEDS", "24"))))
+def test_random_source_and_consumer_formats_match_the_oracle(seed):
+    """every Reader format as a layer (planar 4:2:2 / 4:2:0, rgba8 with its alpha), every Writer format as the sink, Lanczos on some"""
+    scene = _random_format_scene(seed)
+    ref = SceneOracle(scene).packed()
+    out, st = run(_run_scene_variant(scene, "march"))
+    assert out.shape == ref.shape and np.array_equal(out, ref), f"march path, seed {seed}: {int((out != ref).sum())} bytes differ ({st})"
+    slow, _ = run(_run_scene_variant(scene, "generic"))
+    assert np.array_equal(slow, ref), f"generic path, seed {seed}: {int((slow != ref).sum())} bytes differ"
