@@ -100,3 +100,38 @@ def test_random_source_and_consumer_formats_match_the_oracle(seed):
     assert out.shape == ref.shape and np.array_equal(out, ref), f"march path, seed {seed}: {int((out != ref).sum())} bytes differ ({st})"
     slow, _ = run(_run_scene_variant(scene, "generic"))
     assert np.array_equal(slow, ref), f"generic path, seed {seed}: {int((slow != ref).sum())} bytes differ"
+
+
+def test_interleaved_replays_of_different_chains_stay_exact():
+    """Eight different frames (random layer graphs and random formats: fast, general, single-layer, direct, rotated and Lanczos
+    launches, pre-passes included) recorded as chains in ONE context and replayed 160 times in random order with no
+    synchronisation in between: consecutive launches of different kernels overlap their prologues (programmatic dependent launch),
+    scratch blocks cycle through the pool.  Every chain's destination must still hold its oracle frame."""
+    from phaneron_b200.harness import ChannelHarness
+    from gpu_util import Env
+
+    scenes = [_random_scene(s) for s in (3, 7, 11, 18)] + [_random_format_scene(s) for s in (2, 5, 9, 14)]
+    refs = [SceneOracle(sc).packed() for sc in scenes]
+
+    async def go():
+        async with Env(True) as env:
+            hs, chains, dests = [], [], []
+            for i, sc in enumerate(scenes):
+                h = ChannelHarness(env.ctx, sc, env.pj, chanID=f"fz{i}")
+                await h.init()
+                chain, d = await h.record_chain()
+                assert chain.complete, f"scene {i} is not replayable"
+                hs.append(h); chains.append(chain); dests.append(d)
+            order = np.random.default_rng(77).integers(0, len(scenes), 160)
+            for k in order:
+                chains[int(k)].replay()
+            await env.ctx.waitFinish(env.ctx.queue.process)
+            outs = []
+            for h, d in zip(hs, dests):
+                await h.fromRGBA.saveFrame(d, env.ctx.queue.unload)
+                await env.ctx.waitFinish(env.ctx.queue.unload)
+                outs.append(d[0].host.copy() if len(d) == 1 else np.concatenate([b.host for b in d]))   # (as ChannelHarness.run_frame)
+            return outs
+    outs = run(go())
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        assert o.shape == r.shape and np.array_equal(o, r), f"chain {i}: {int((o != r).sum()) if o.shape == r.shape else 'shape'} bytes differ"
