@@ -570,6 +570,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     select_config(args.config)
     if args.impl == "reference":
+        if args.config in ("route", "yadif"):   # (the CPU arm exists for the composite configurations: 3 and 5)
+            if rank == 0:
+                emit({"impl": "reference", "unavailable": f"no CPU arm for --config {args.config}: run it for the default config or --config 5"})
+            return
         run_reference(args, rank, world)
         return
     if args.frames_per_step == 240:
